@@ -1,0 +1,70 @@
+"""Seeded synthetic "planted-peaky" log-posteriors.
+
+The reference treats -1000.0 as minus infinity (forced_alignment.py:23), so flat
+random posteriors are invalid inputs (every path scores below the sentinel).
+Valid synthetic inputs plant a monotone alignment: 2N+1 slots
+(blank, ph_0, blank, ph_1, ... blank) with random durations summing to T, a
++peak logit on the planted class of each frame, then log_softmax -- the same
+thing core.py:898-899 produces from CUPE logits.
+
+Pure torch, vectorised over the batch, runs on CPU or CUDA.  Used by tests,
+bench.py and smoke(); it has no dependency on oracle/.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def planted_batch(B, T, N, C, *, seed=0, peak=8.0, blank_id=None, silence_id=0, sil_every=0,
+                  sil_frames=15, device="cpu", dtype=torch.float32):
+    """Returns (log_probs [B,T,C] f32, targets [B,N] i64, planted [B,T] i64).
+
+    targets are drawn from [1, blank_id) (never SIL=0, never blank) unless
+    sil_every>0, in which case every sil_every-th target is silence_id and its
+    slot is at least sil_frames long (drives silence-anchored segmentation).
+    """
+    if blank_id is None:
+        blank_id = C - 1
+    g = torch.Generator(device="cpu").manual_seed(int(seed))
+    tgt = torch.randint(1, blank_id, (B, N), generator=g)
+    if sil_every and N > sil_every:
+        tgt[:, sil_every::sil_every] = silence_id
+    nslot = 2 * N + 1
+    w = torch.rand(B, nslot, generator=g) + 0.2
+    w[:, 0::2] *= 0.5  # blanks shorter than phonemes
+    slot_class = torch.full((B, nslot), blank_id, dtype=torch.long)
+    slot_class[:, 1::2] = tgt
+    min_len = torch.zeros(B, nslot)
+    min_len[:, 1::2] = 1.0  # every phoneme gets at least one frame
+    if sil_every:
+        min_len[slot_class == silence_id] = float(sil_frames)
+    free = (T - min_len.sum(1, keepdim=True)).clamp_min(0.0)
+    dur = min_len + w / w.sum(1, keepdim=True) * free
+    edges = torch.cumsum(dur, 1)
+    edges[:, -1] = T + 1.0
+    frames = torch.arange(T, dtype=torch.float32).expand(B, T) + 0.5
+    slot_of_frame = torch.searchsorted(edges.contiguous(), frames.contiguous(), right=False).clamp_max(nslot - 1)
+    planted = torch.gather(slot_class, 1, slot_of_frame)
+    planted = planted.to(device)
+    gd = torch.Generator(device=device).manual_seed(int(seed) + 7919)
+    logits = torch.randn(B, T, C, generator=gd, device=device, dtype=torch.float32)
+    logits.scatter_add_(2, planted.unsqueeze(-1), torch.full((B, T, 1), float(peak), device=device))
+    logp = torch.log_softmax(logits, dim=2).to(dtype)
+    return logp, tgt.to(device), planted
+
+
+def ragged_batch(B, *, C=66, t_range=(60, 1800), n_range=(4, 120), seed=0, peak=10.0, device="cpu"):
+    """Ragged corpus of config 4: T~U[t_range], N~U[n_range] with N <= T/5 mostly,
+    plus a tail (every 16th utterance) that lands on strides 3/2/1.
+    Returns a list of (log_probs [T,C], targets [N]) per utterance."""
+    g = torch.Generator().manual_seed(int(seed))
+    out = []
+    for u in range(B):
+        T = int(torch.randint(t_range[0], t_range[1] + 1, (1,), generator=g))
+        nmax = max(n_range[0], min(n_range[1], T // 5))
+        N = int(torch.randint(n_range[0], nmax + 1, (1,), generator=g))
+        if u % 16 == 15:  # dense tail: stride 3 / 2 / 1
+            N = min(n_range[1], max(n_range[0], int(T / (1.2 + 2.5 * float(torch.rand(1, generator=g))))))
+        lp, tgt, _ = planted_batch(1, T, N, C, seed=seed * 100003 + u, peak=peak, device=device)
+        out.append((lp[0], tgt[0]))
+    return out

@@ -1,0 +1,1 @@
+"""Parity oracle -- TEST INFRASTRUCTURE ONLY (see oracle/oracle.py)."""
