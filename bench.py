@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- aligned frames/sec of the batched forced-alignment path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                     (CPU arm: the oracle port on the host cores)
+
+A step = one pass of the whole hot path (row stats -> device planner -> Viterbi fill + back-trace ->
+timestamps + confidences) over one batch of synthetic planted-peaky log-posteriors of the metric
+shape B=4096, T=600, N=40, C=66 (BASELINE.json `metric`; `configs[1]` is the same shape at B=1024).
+`value` = frames all ranks aligned / max-over-ranks CUDA-event time with inputs resident in HBM.
+`e2e`   = the same through the host-buffer C-ABI entry (bfa_align_batch_host): pinned host inputs,
+          H2D + kernels + D2H inside the timed region.
+Only the cpu_baseline / --impl reference legs touch oracle/ (as the thing being timed ON THE CPU arm,
+never on the product path).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "aligned frames/sec at T=600,N=40,P=66,batch=4096; 1/2/4/8 GPU vs CPU ref"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--T", type=int, default=600)
+    ap.add_argument("--N", type=int, default=40)
+    ap.add_argument("--C", type=int, default=66)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_config(a, extra=None):
+    cfg = {"workload": f"synthetic planted-peaky fp32 log-posteriors, batch={a.batch} utterances/GPU, T={a.T}, N={a.N}, C={a.C}, "
+                       f"full decode_alignments path (boost+floor+silence-anchor check, Viterbi, assort, confidences)",
+           "batch_per_gpu": a.batch, "T": a.T, "N": a.N, "C": a.C, "L": 4 * a.N + 1,
+           "l2_policy": "inputs larger than L2 (649 MB/GPU per step vs 126 MB L2), no flush needed"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(B, T, N, C):
+    """per frame 4*C read + 8 written; per utterance 24*N (targets + stamp records)."""
+    return B * (T * (4 * C + 8) + 24 * N)
+
+
+def measured_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_arm(a, n_utts, steps, warmup, seed=1234):
+    """Time the oracle port (oracle/bfa_oracle.c, all host threads) on a bounded sample of the workload."""
+    import numpy as np
+    import torch
+    from bfa_b200 import synth
+    from oracle import oracle as orc
+
+    threads = orc.n_host_threads()
+    lp, tgt, _ = synth.planted_batch(n_utts, a.T, a.N, a.C, seed=seed)
+    p = orc.params(a.C - 1, 0)
+    lp_np = lp.numpy(); tg = tgt.numpy().astype(np.int32).reshape(-1)
+    row_off = np.arange(n_utts, dtype=np.int64) * a.T * a.C
+    Ts = np.full(n_utts, a.T, np.int32); toff = np.arange(n_utts + 1, dtype=np.int64) * a.N
+    run = lambda: orc.align_batch(p, lp_np, row_off, Ts, a.C, tg, toff, max_stamps=2 * a.N + 8, n_threads=threads)
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = time.perf_counter() - t0
+    return {"value": n_utts * a.T * steps / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"{n_utts} utterances of the workload shape x {steps} passes, oracle/bfa_oracle.c (C restatement of "
+                      f"forced_alignment.py + utils._calculate_confidences), {threads} pthreads, {dt:.2f} s wall"}, dt / steps
+
+
+def reference_main(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as orc
+    threads = orc.n_host_threads()
+    n = a.cpu_sample or a.batch
+    base, step_s = cpu_arm(a, n, a.steps, a.warmup)
+    out = {"metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "impl": "reference", "config": workload_config(a, {"cpu_sample_utterances": n}),
+           "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return reference_main(a)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import bfa_b200
+    from bfa_b200 import _cabi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback on the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.lib()
+
+    B, T, N, Cc = a.batch, a.T, a.N, a.C
+    lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=4242 + 1000 * rank, device=dev)
+    au = bfa_b200.AlignmentUtils(blank_id=Cc - 1, silence_id=0, silence_anchors=10, ignore_noise=True, truly_forced=True)
+    dec = au.viterbi_decoder
+    params = dec._params(True, True, True)
+    row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T * Cc)
+    tgt32 = tgt.to(torch.int32).reshape(-1).contiguous()
+    Ts, Ns = [T] * B, [N] * B
+    gather_bufs = None
+
+    def step():
+        r = dec.align_batch(lp, row_off, Ts, Cc, tgt32, Ns, params=params, want_stamps=True, want_conf=True)
+        if world > 1:  # final gather of the timestamp arrays (the path's only exchange)
+            nonlocal gather_bufs
+            if gather_bufs is None:
+                gather_bufs = [torch.empty((world,) + tuple(x.shape), dtype=x.dtype, device=dev) for x in (r.stamps, r.conf, r.n_stamps)]
+            for g, x in zip(gather_bufs, (r.stamps, r.conf, r.n_stamps)):
+                dist.all_gather_into_tensor(g, x)
+        return r
+
+    for _ in range(max(a.warmup, 3)):
+        r = step()
+    torch.cuda.synchronize()
+    assert int((r.status[:B] & 7 != 0).sum()) == 0, "unexpected non-OK status on the synthetic workload"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = lib.bfa_launch_count()
+    lib.bfa_profile_enable(1)
+    lib.bfa_profile_read(None, None)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    dom_ms, dom_n = C.c_float(), C.c_int32()
+    lib.bfa_profile_read(C.byref(dom_ms), C.byref(dom_n))
+    lib.bfa_profile_enable(0)
+    time.sleep(0.15)
+    clocks = sampler.stop()
+    launches = lib.bfa_launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * T * a.steps / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel (Viterbi fill + back-trace), timed by CUDA events on its stream
+    peak, peak_src = measured_peak()
+    alg = algorithmic_bytes(B, T, N, Cc)
+    dom_avg_ms = dom_ms.value / max(dom_n.value, 1)
+    achieved = alg / (dom_avg_ms / 1e3) / 1e9 if dom_avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "viterbi_generic_kernel<0>", "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_avg_ms / (ms / a.steps),
+                "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}
+    tf = ROOT / "profiles" / "traffic_latest.json"
+    if tf.exists():
+        try:
+            roofline["traffic"] = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e through the host-buffer C-ABI entry (pinned host memory in, results out)
+    e2e = None
+    if not a.no_e2e:
+        lp_h = torch.empty((B, T, Cc), dtype=torch.float32, pin_memory=True); lp_h.copy_(lp)
+        tgt_h = torch.empty(B * N, dtype=torch.int32, pin_memory=True); tgt_h.copy_(tgt32)
+        ms_stamps = 2 * N + 8
+        out = {k: torch.empty(s, dtype=d, pin_memory=True).numpy() for k, s, d in (
+            ("frame_ph", (B * T,), torch.int32), ("frame_idx", (B * T,), torch.int32), ("dp_final", (B,), torch.float32),
+            ("status", (B,), torch.int32), ("stamps", (B, ms_stamps, 4), torch.int32), ("n_stamps", (B,), torch.int32),
+            ("conf", (B, ms_stamps), torch.float32))}
+        ro_h = np.arange(B, dtype=np.int64) * T * Cc; T_h = np.full(B, T, np.int32); to_h = np.arange(B + 1, dtype=np.int64) * N
+        run = lambda: bfa_b200.align_host(params, lp_h.numpy(), ro_h, T_h, Cc, tgt_h.numpy(), to_h, max_stamps=ms_stamps,
+                                          device=local, chunk_utts=512, out=out)
+        for _ in range(3):
+            run()
+        barrier()
+        ke = max(3, min(a.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            run()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = lp_h.numel() * 4 + tgt_h.numel() * 4 + B * 8 + B * 4 + 2 * (B + 1) * 8
+        d2h = sum(v.nbytes for v in out.values())
+        e2e = {"value": world * B * T * ke / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": ke, "ms_per_step": dt / ke * 1e3, "api": "bfa_align_batch_host (pinned host buffers, 512-utterance chunks, 2 streams)"}
+        lib.bfa_host_release()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import oracle as orc
+        n = a.cpu_sample or B
+        cpu_baseline, _ = cpu_arm(a, n, 3, 1)
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+               "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "impl": "b200",
+               "config": workload_config(a, {"sharding": f"{world} rank(s) x {B} utterances, no data-path collective; "
+                                                         f"final all_gather of stamp arrays inside the step when n_gpus>1"}),
+               "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,13 @@
+"""bfa_b200 -- importable name of the package that lives in `bournemouth-forced-aligner_b200/`
+(the directory name required by the repo layout is not a valid Python identifier)."""
+import os as _os
+
+_impl = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "bournemouth-forced-aligner_b200")
+__path__.append(_impl)
+
+from ._cabi import BfaError, BfaParams, BfaShape, default_params  # noqa: E402,F401
+from .aligner import (AlignmentUtils, BatchResult, ViterbiDecoder, _calculate_confidences,  # noqa: E402,F401
+                      align_host)
+
+__all__ = ["AlignmentUtils", "ViterbiDecoder", "_calculate_confidences", "align_host", "BatchResult",
+           "BfaError", "BfaParams", "BfaShape", "default_params"]

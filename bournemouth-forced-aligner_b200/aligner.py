@@ -1,0 +1,381 @@
+"""Host-side mirror of the reference's alignment interface, backed by libbfa_b200.so.
+
+Same class names, constructor arguments, method signatures, return types and error behaviour as
+  bournemouth_aligner/forced_alignment.py   ViterbiDecoder (:11), AlignmentUtils (:836)
+  bournemouth_aligner/utils.py              _calculate_confidences (:70)
+so core.py:256-257 / :902-937 / :1028 can switch imports.  torch is used for device memory and
+streams only; every computation on the path runs in the CUDA library.  There is no CPU fallback:
+without a CUDA device or without the built library the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import BfaError, BfaParams, BfaShape
+
+Stamp = Tuple[int, int, int, int]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise BfaError(f"{what} must be a CUDA tensor (got {t.device}); use align_host() for host buffers")
+
+
+class _Workspace:
+    """Grow-only device scratch, one per (aligner, device)."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        key = str(device)
+        b = self.buf.get(key)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(int(nbytes * 1.1) + 256, dtype=torch.uint8, device=device)
+            self.buf[key] = b
+        return b
+
+
+class BatchResult:
+    """Device-resident result arrays of one batched alignment call (C-ABI layout)."""
+
+    def __init__(self, frame_ph, frame_idx, frame_off, dp_final, status, stamps, conf, n_stamps, T, max_stamps):
+        self.frame_ph, self.frame_idx, self.frame_off = frame_ph, frame_idx, frame_off
+        self.dp_final, self.status = dp_final, status
+        self.stamps, self.conf, self.n_stamps = stamps, conf, n_stamps
+        self.T, self.max_stamps = T, max_stamps
+
+    def stamp_lists(self, with_conf: bool = False) -> List[List[tuple]]:
+        """list[B] of list[(phoneme, start, end_exclusive, target_idx[, conf])] -- forced_alignment.py:871-872."""
+        n = self.n_stamps.cpu().numpy()
+        st = self.stamps.cpu().numpy()
+        cf = self.conf.cpu().numpy() if (with_conf and self.conf is not None) else None
+        out = []
+        for b in range(n.shape[0]):
+            rows = st[b, : n[b]].tolist()
+            if cf is None:
+                out.append([tuple(r) for r in rows])
+            else:
+                out.append([tuple(r) + (float(c),) for r, c in zip(rows, cf[b, : n[b]].tolist())])
+        return out
+
+
+class ViterbiDecoder:
+    """forced_alignment.py:11-834 (same constructor signature, :16)."""
+
+    def __init__(self, blank_id, silence_id, silence_anchors=3, min_phoneme_prob=1e-8, ignore_noise=True, truly_forced=False):
+        self.blank_id = blank_id
+        self.silence_id = silence_id
+        self.silence_anchors = silence_anchors
+        self.min_phoneme_prob = min_phoneme_prob
+        self.ignore_noise = ignore_noise
+        self.truly_forced = truly_forced
+        self._neg_inf = -1000.0
+        self._ws = _Workspace()
+
+    def set_blank_id(self, blank_id):
+        self.blank_id = blank_id
+
+    # ---- parameter block -------------------------------------------------------------------
+    def _params(self, boost_targets=True, enforce_minimum=True, anchor_pauses=True, mode=_cabi.MODE_FULL) -> BfaParams:
+        if self.blank_id is None:
+            raise ValueError("Blank ID not set. Call set_blank_id first.")  # forced_alignment.py:104-105
+        p = _cabi.default_params(self.blank_id, self.silence_id)
+        p.silence_anchors = int(self.silence_anchors) if anchor_pauses else 0
+        p.ignore_noise = int(bool(self.ignore_noise))
+        p.truly_forced = int(bool(self.truly_forced))
+        p.boost_targets = int(bool(boost_targets))
+        p.enforce_minimum = int(bool(enforce_minimum))
+        p.min_log_prob = float(np.log(np.float32(self.min_phoneme_prob)))
+        p.neg_inf = float(self._neg_inf)
+        p.mode = mode
+        return p
+
+    # ---- batched core ----------------------------------------------------------------------
+    def align_batch(self, log_probs: torch.Tensor, row_off: torch.Tensor, T: Sequence[int], C_: int, tgt: torch.Tensor,
+                    N: Sequence[int], *, params: BfaParams, want_stamps=True, want_conf=True, max_stamps=None) -> BatchResult:
+        """Ragged batch through bfa_align_batch.  log_probs: flat/any-shape fp32 CUDA tensor holding the rows,
+        row_off int64[B] element offsets (CUDA), T/N python sequences, tgt flat int32 CUDA targets."""
+        _require_cuda(log_probs, "log_probs")
+        dev = log_probs.device
+        if log_probs.dtype != torch.float32 or not log_probs.is_contiguous():
+            raise BfaError("log_probs must be contiguous float32")
+        B = len(T)
+        T_np = np.asarray(T, np.int32)
+        N_np = np.asarray(N, np.int64)
+        frame_off_np = np.zeros(B + 1, np.int64); np.cumsum(T_np, out=frame_off_np[1:])
+        tgt_off_np = np.zeros(B + 1, np.int64); np.cumsum(N_np, out=tgt_off_np[1:])
+        total = int(frame_off_np[-1])
+        max_T = int(T_np.max()) if B else 0
+        max_N = int(N_np.max()) if B else 0
+        if max_stamps is None:
+            max_stamps = (2 * max_N + 8) if params.ignore_noise else max(max_T, 1)
+        shape = BfaShape(B, C_, max_T, max_N, total, int(max_stamps), 0)
+        meta = torch.from_numpy(np.concatenate([frame_off_np, tgt_off_np])).to(dev, non_blocking=True)
+        frame_off, tgt_off = meta[: B + 1], meta[B + 1:]
+        T_dev = torch.from_numpy(T_np).to(dev, non_blocking=True)
+        frame_ph = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        frame_idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        dp_final = torch.empty(max(B, 1), dtype=torch.float32, device=dev)
+        status = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
+        stamps = conf = n_stamps = None
+        if want_stamps:
+            stamps = torch.empty((max(B, 1), max_stamps, 4), dtype=torch.int32, device=dev)
+            n_stamps = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
+            if want_conf:
+                conf = torch.empty((max(B, 1), max_stamps), dtype=torch.float32, device=dev)
+        l = _cabi.lib()
+        with torch.cuda.device(dev):
+            ws_bytes = l.bfa_workspace_bytes(C.byref(params), C.byref(shape))
+            if ws_bytes == 0 and B > 0:
+                _cabi.check(_cabi.BFA_E_UNSUPPORTED)
+            ws = self._ws.get(max(ws_bytes, 256), dev)
+            rc = l.bfa_align_batch(C.byref(params), C.byref(shape), _ptr(log_probs), _ptr(row_off), _ptr(T_dev), _ptr(tgt),
+                                   _ptr(tgt_off), _ptr(frame_ph), _ptr(frame_idx), _ptr(frame_off), _ptr(dp_final), _ptr(status),
+                                   _ptr(stamps), _ptr(conf), _ptr(n_stamps), _ptr(ws), ws.numel(), _stream(dev))
+        _cabi.check(rc)
+        return BatchResult(frame_ph, frame_idx, frame_off, dp_final, status, stamps, conf, n_stamps, T_np, max_stamps)
+
+    @staticmethod
+    def _raise_if_too_short(status_np, T, N):
+        bad = np.nonzero((status_np & 7) == _cabi.ST_TOO_SHORT)[0]
+        if bad.size:
+            i = int(bad[0])
+            raise ValueError(  # same text as forced_alignment.py:162-165
+                f"Audio too short to align: {int(N[i])} phonemes cannot be fit into "
+                f"{int(T[i])} frames (need at least 1 frame per phoneme)."
+            )
+
+    # ---- reference methods -----------------------------------------------------------------
+    def decode_with_forced_alignment(self, log_probs, true_sequence, return_scores=False, boost_targets=True,
+                                     enforce_minimum=True, anchor_pauses=True, debug=False):
+        """forced_alignment.py:87-199.  Returns (frame_phonemes i64[T], frame_phonemes_idx i64[T], score|None)."""
+        _require_cuda(log_probs, "log_probs")
+        lp = log_probs.contiguous().float()
+        T, C_ = lp.shape
+        seq = true_sequence.to(lp.device)
+        N = int(seq.shape[0])
+        p = self._params(boost_targets, enforce_minimum, anchor_pauses)
+        r = self.align_batch(lp, torch.zeros(1, dtype=torch.int64, device=lp.device), [T], C_, seq.to(torch.int32).contiguous(),
+                             [N], params=p, want_stamps=False)
+        self._raise_if_too_short(r.status[:1].cpu().numpy(), [T], [N])
+        fp, fi = r.frame_ph[:T].long(), r.frame_idx[:T].long()
+        score = self._calculate_alignment_score(lp, fp) if return_scores else None
+        return fp, fi, score
+
+    def _viterbi_decode(self, log_probs, ctc_path, ctc_len, ctc_path_true_idx=None, band_width=0, debug=False):
+        """forced_alignment.py:563-703 on an explicit CTC path."""
+        r = self.viterbi_paths(log_probs.contiguous().float(), [log_probs.shape[0]], [0], ctc_path[:ctc_len], ctc_path_true_idx,
+                               [int(ctc_len)], [int(band_width)])
+        fp = r["frame_ph"].long()
+        return fp, (r["frame_idx"].long() if ctc_path_true_idx is not None else None)
+
+    def viterbi_paths(self, log_probs, T: Sequence[int], row_off: Sequence[int], path, true_idx, L: Sequence[int],
+                      band: Sequence[int]):
+        """Batched bfa_viterbi_paths: item i uses rows at row_off[i] (elements), path[path_off[i]: +L[i]]."""
+        _require_cuda(log_probs, "log_probs")
+        dev = log_probs.device
+        C_ = int(log_probs.shape[-1])
+        n = len(T)
+        T_np = np.asarray(T, np.int32); L_np = np.asarray(L, np.int32)
+        f_off = np.zeros(n + 1, np.int64); np.cumsum(T_np, out=f_off[1:])
+        p_off = np.zeros(n + 1, np.int64); np.cumsum(L_np, out=p_off[1:])
+        i64 = lambda a: torch.from_numpy(np.asarray(a, np.int64)).to(dev)
+        i32 = lambda a: torch.from_numpy(np.asarray(a, np.int32)).to(dev)
+        path_d = path.to(dev).to(torch.int32).contiguous()
+        tidx_d = None if true_idx is None else true_idx.to(dev).to(torch.int32).contiguous()
+        total = int(f_off[-1])
+        frame_ph = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        frame_idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        dp_final = torch.empty(n, dtype=torch.float32, device=dev)
+        fstate = torch.empty(n, dtype=torch.int32, device=dev)
+        row_off_d, T_d, p_off_d, L_d, band_d, f_off_d = i64(row_off), i32(T_np), i64(p_off), i32(L_np), i32(band), i64(f_off)
+        p = self._params(False, False, False)
+        l = _cabi.lib()
+        with torch.cuda.device(dev):
+            max_T, max_L = int(T_np.max()), int(L_np.max())
+            if max_L > _cabi.MAX_L:
+                _cabi.check(_cabi.BFA_E_UNSUPPORTED)
+            ws_bytes = l.bfa_viterbi_paths_workspace_bytes(n, max_T, max_L)
+            ws = self._ws.get(max(ws_bytes, 256), dev)
+            rc = l.bfa_viterbi_paths(C.byref(p), n, C_, max_T, max_L, _ptr(log_probs), _ptr(row_off_d), _ptr(T_d), _ptr(path_d),
+                                     _ptr(tidx_d), _ptr(p_off_d), _ptr(L_d), _ptr(band_d), _ptr(frame_ph), _ptr(frame_idx),
+                                     _ptr(f_off_d), _ptr(dp_final), _ptr(fstate), _ptr(ws), ws.numel(), _stream(dev))
+        _cabi.check(rc)
+        return dict(frame_ph=frame_ph[:total], frame_idx=frame_idx[:total], frame_off=f_off, dp_final=dp_final, final_state=fstate)
+
+    def _calculate_alignment_score(self, log_probs, frame_phonemes):
+        """forced_alignment.py:767-773 (off the hot path: core.py passes return_scores=False)."""
+        valid = frame_phonemes < log_probs.shape[1]
+        g = log_probs.gather(1, frame_phonemes.clamp_max(log_probs.shape[1] - 1).unsqueeze(1)).squeeze(1)
+        return float((g.double() * valid).sum().item())
+
+    def assort_frames(self, frame_phonemes, frame_phonemes_idx, max_blanks=10) -> List[Stamp]:
+        """forced_alignment.py:777-834."""
+        if len(frame_phonemes) == 0:
+            return []
+        fp = torch.as_tensor(frame_phonemes)
+        fi = torch.as_tensor(frame_phonemes_idx)
+        dev = fp.device if fp.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        if not torch.cuda.is_available():
+            raise BfaError("assort_frames needs a CUDA device")
+        fp = fp.to(dev).to(torch.int32).contiguous(); fi = fi.to(dev).to(torch.int32).contiguous()
+        T = int(fp.shape[0])
+        p = self._params(False, False, False)
+        p.max_blanks = int(max_blanks)
+        ms = T
+        stamps = torch.empty((1, ms, 4), dtype=torch.int32, device=dev)
+        n_st = torch.empty(1, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        T_d = torch.tensor([T], dtype=torch.int32, device=dev)
+        f_off = torch.tensor([0, T], dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().bfa_assort_batch(C.byref(p), 1, _ptr(T_d), _ptr(f_off), _ptr(fp), _ptr(fi), _ptr(status), _ptr(stamps),
+                                              _ptr(n_st), ms, _stream(dev))
+        _cabi.check(rc)
+        n = int(n_st.item())
+        return [tuple(r) for r in stamps[0, :n].cpu().tolist()]
+
+
+class AlignmentUtils:
+    """forced_alignment.py:836-986 (same constructor signature, :841)."""
+
+    def __init__(self, blank_id, silence_id, silence_anchors=10, ignore_noise=True, truly_forced=True):
+        self.blank_id = blank_id
+        self.silence_id = silence_id
+        self.silence_anchors = silence_anchors
+        self.truly_forced = truly_forced
+        self.viterbi_decoder = ViterbiDecoder(blank_id, silence_id, silence_anchors=self.silence_anchors,
+                                              ignore_noise=ignore_noise, truly_forced=self.truly_forced)
+        self.last_result: Optional[BatchResult] = None
+
+    @staticmethod
+    def _lens(x, B, default):
+        if x is None:
+            return [default] * B
+        if isinstance(x, torch.Tensor):
+            return [int(v) for v in x.tolist()]
+        return [int(v) for v in x]
+
+    def _dense_batch(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf):
+        _require_cuda(log_probs, "log_probs")
+        lp = log_probs if (log_probs.dtype == torch.float32 and log_probs.is_contiguous()) else log_probs.contiguous().float()
+        B, T_max, C_ = lp.shape
+        dev = lp.device
+        T = self._lens(pred_lens, B, T_max)
+        S = int(true_seqs.shape[1]) if true_seqs.dim() == 2 else 0
+        N = self._lens(true_seqs_lens, B, S)
+        seqs = true_seqs.to(dev)
+        N_dev = torch.tensor(N, dtype=torch.int64, device=dev)
+        mask = torch.arange(S, device=dev)[None, :] < N_dev[:, None]
+        tgt = seqs[mask].to(torch.int32).contiguous()
+        row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T_max * C_)
+        r = self.viterbi_decoder.align_batch(lp, row_off, T, C_, tgt, N, params=params, want_stamps=True, want_conf=want_conf)
+        self.last_result = r
+        self.viterbi_decoder._raise_if_too_short(r.status[:B].cpu().numpy(), T, N)
+        return r
+
+    def decode_alignments(self, log_probs, true_seqs=None, pred_lens=None, true_seqs_lens=None, forced_alignment=True,
+                          boost_targets=True, enforce_minimum=True, debug=False, with_confidence=False):
+        """forced_alignment.py:856-928.  Returns list[B] of list[(phoneme, start, end, target_idx)].
+        with_confidence=True (extension) appends utils._calculate_confidences' score to each tuple."""
+        if forced_alignment:
+            if (true_seqs is None) or (true_seqs_lens is None):
+                raise ValueError("Phoneme sequences and lengths required for forced alignment")  # :878-879
+            p = self.viterbi_decoder._params(boost_targets, enforce_minimum, self.silence_anchors > 0)
+            r = self._dense_batch(log_probs, true_seqs, pred_lens, true_seqs_lens, p, with_confidence)
+            return r.stamp_lists(with_conf=with_confidence)
+        # free decoding (:912-928): frame-wise argmax then assort; returns ONE flat list like the reference
+        _require_cuda(log_probs, "log_probs")
+        B = log_probs.shape[0]
+        T = self._lens(pred_lens, B, log_probs.shape[1])
+        pred = torch.argmax(log_probs, dim=2)
+        out = []
+        for i in range(B):
+            fp = pred[i, : T[i]]
+            out.extend(self.viterbi_decoder.assort_frames(fp, torch.full_like(fp, -1)))
+        return out
+
+    def decode_alignments_simple(self, log_probs, true_seqs, pred_lens=None, true_seqs_lens=None):
+        """forced_alignment.py:932-986: no boost, no floor, no anchoring."""
+        p = self.viterbi_decoder._params(False, False, False, mode=_cabi.MODE_SIMPLE)
+        r = self._dense_batch(log_probs, true_seqs, pred_lens, true_seqs_lens, p, False)
+        return r.stamp_lists()
+
+
+def _calculate_confidences(log_probs: torch.Tensor, framestamps):
+    """utils.py:70-113.  framestamps: 5-tuples (phoneme, start, end, target_idx, is_estimated);
+    returns 6-tuples with avg_confidence appended."""
+    _require_cuda(log_probs, "log_probs")
+    lp = log_probs.contiguous().float()
+    T, C_ = lp.shape
+    n = len(framestamps)
+    if n == 0:
+        return []
+    dev = lp.device
+    for (ph, s, e, _i, est) in framestamps:
+        s2, e2 = max(0, int(s)), min(T, int(e))
+        if est and not (s2 < T and e2 <= T):  # utils.py:88-91
+            raise ValueError(f"Invalid frame range for estimated timestamp: start_frame={s2}, end_frame={e2}, "
+                             f"log_probs shape={tuple(lp.shape)}, is_estimated={est}, phoneme_id={ph}")
+    st = torch.tensor([[int(f[0]), int(f[1]), int(f[2]), int(f[3])] for f in framestamps], dtype=torch.int32, device=dev)
+    conf = torch.empty(n, dtype=torch.float32, device=dev)
+    i64 = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+    row_off, T_d, n_d = i64([0]), i32([T]), i32([n])
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().bfa_confidence_batch(1, C_, _ptr(lp), _ptr(row_off), _ptr(T_d), _ptr(st), _ptr(n_d), n, _ptr(conf),
+                                              _stream(dev))
+    _cabi.check(rc)
+    c = conf.cpu().tolist()
+    return [(f[0], max(0, int(f[1])), min(T, int(f[2])), f[3], f[4], c[i]) for i, f in enumerate(framestamps)]
+
+
+def align_host(params: BfaParams, log_probs: np.ndarray, row_off: np.ndarray, T: np.ndarray, C_: int, tgt: np.ndarray,
+               tgt_off: np.ndarray, *, max_stamps: Optional[int] = None, want_conf=True, device=0, chunk_utts=0, out=None):
+    """bfa_align_batch_host: every buffer is a HOST numpy array (pin them for full PCIe speed).
+    Returns dict of numpy arrays.  `out` may carry pre-allocated (pinned) output arrays."""
+    T = np.ascontiguousarray(T, np.int32); B = T.shape[0]
+    row_off = np.ascontiguousarray(row_off, np.int64); tgt_off = np.ascontiguousarray(tgt_off, np.int64)
+    tgt = np.ascontiguousarray(tgt, np.int32)
+    assert log_probs.dtype == np.float32 and log_probs.flags.c_contiguous
+    frame_off = np.zeros(B + 1, np.int64); np.cumsum(T, out=frame_off[1:])
+    total = int(frame_off[-1])
+    N = np.diff(tgt_off)
+    max_T, max_N = (int(T.max()), int(N.max())) if B else (0, 0)
+    if max_stamps is None:
+        max_stamps = (2 * max_N + 8) if params.ignore_noise else max(max_T, 1)
+    shape = BfaShape(B, C_, max_T, max_N, total, int(max_stamps), 0)
+    o = out if out is not None else {}
+
+    def buf(name, shp, dt):
+        a = o.get(name)
+        if a is None or a.shape != tuple(shp) or a.dtype != dt:
+            a = np.empty(shp, dt); o[name] = a
+        return a
+
+    frame_ph = buf("frame_ph", (max(total, 1),), np.int32); frame_idx = buf("frame_idx", (max(total, 1),), np.int32)
+    dp_final = buf("dp_final", (max(B, 1),), np.float32); status = buf("status", (max(B, 1),), np.int32)
+    stamps = buf("stamps", (max(B, 1), max_stamps, 4), np.int32); n_stamps = buf("n_stamps", (max(B, 1),), np.int32)
+    conf = buf("conf", (max(B, 1), max_stamps), np.float32) if want_conf else None
+    vp = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+    rc = _cabi.lib().bfa_align_batch_host(C.byref(params), C.byref(shape), vp(log_probs), vp(row_off), vp(T), vp(tgt), vp(tgt_off),
+                                          vp(frame_ph), vp(frame_idx), vp(frame_off), vp(dp_final), vp(status), vp(stamps), vp(conf),
+                                          vp(n_stamps), int(device), int(chunk_utts))
+    _cabi.check(rc, host=True)
+    o["frame_off"] = frame_off
+    o["max_stamps"] = max_stamps
+    return o

@@ -1,0 +1,354 @@
+// bfa_api.cu -- C-ABI entry points of libbfa_b200.so (see include/bfa_b200.h).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <type_traits>
+#include <vector>
+
+#include "assort.cuh"
+#include "bfa_common.cuh"
+#include "plan.cuh"
+#include "viterbi_generic.cuh"
+
+using namespace bfa;
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+thread_local char g_cuda_err[256] = "";
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "%s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return BFA_E_CUDA;                                                                      \
+        }                                                                                           \
+    } while (0)
+
+#define LAUNCH_CHECK()                                   \
+    do {                                                 \
+        g_launches.fetch_add(1, std::memory_order_relaxed); \
+        CUDA_TRY(cudaGetLastError());                    \
+    } while (0)
+
+// Optional timing of the dominant (Viterbi) kernel with CUDA events recorded on the launch stream.
+struct Prof {
+    std::mutex mu;
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+} g_prof;
+
+struct DeviceInfo {
+    int sms = 0;
+    int vg_ctas_per_sm = 0;      // short-path class (L <= 256)
+    int vg_ctas_per_sm_big = 0;  // long-path class
+    bool ok = false;
+};
+
+int device_info(DeviceInfo& out) {
+    static std::mutex mu;
+    static DeviceInfo cache[64];
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    DeviceInfo& d = cache[dev & 63];
+    if (!d.ok) {
+        CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+        const size_t smem = sizeof(WarpSmem) * VG_WARPS;
+        CUDA_TRY(cudaFuncSetAttribute(viterbi_generic_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(viterbi_generic_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.vg_ctas_per_sm, viterbi_generic_kernel<0>, VG_WARPS * 32, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.vg_ctas_per_sm_big, viterbi_generic_kernel<1>, VG_WARPS * 32, smem));
+        if (d.vg_ctas_per_sm < 1) d.vg_ctas_per_sm = 1;
+        if (d.vg_ctas_per_sm_big < 1) d.vg_ctas_per_sm_big = 1;
+        d.ok = true;
+    }
+    out = d;
+    return BFA_OK;
+}
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// Workspace carve-up shared by bfa_workspace_bytes and bfa_align_batch.
+struct Layout {
+    bool segmenting;
+    int item_cap, gmax, amax, anchor_words, list_ints, max_L, bp_words_per_lane;
+    int resident_warps;
+    long long slab_words;
+    size_t off_tmask, off_rowstat, off_items_local, off_items, off_lists, off_padded, off_anchors, off_counters, off_bp, total;
+};
+
+int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layout& L) {
+    if (s.B < 0 || s.C <= 0 || s.max_T < 0 || s.max_N < 0) return BFA_E_INVALID;
+    if (s.C > BFA_MAX_C) return BFA_E_UNSUPPORTED;
+    L.segmenting = (p.mode == BFA_MODE_FULL && p.silence_anchors > 0 && p.silence_id >= 0);
+    L.gmax = L.segmenting ? s.max_N / 2 + 1 : 0;
+    L.amax = L.segmenting ? s.max_T / 2 + 2 : 0;
+    L.item_cap = L.segmenting ? L.gmax + 1 : 1;
+    L.anchor_words = L.segmenting ? (s.max_T + 6 * L.item_cap) / 8 + L.item_cap + 1 : 0;
+    L.list_ints = L.segmenting ? 14 * L.gmax + 4 * L.amax + 16 : 0;
+    // longest CTC path: stride*N+1 <= 4*max_N+1; the non-simple paths also guarantee L <= 1.2*(T+6)
+    long long maxL = 4LL * s.max_N + 1;
+    if (p.mode == BFA_MODE_FULL) {
+        long long byT = (long long)(1.2 * (double)(s.max_T + 2 * p.boundary_pad)) + 1;
+        if (byT < maxL) maxL = byT;
+    }
+    if (maxL > BFA_MAX_L) return BFA_E_UNSUPPORTED;
+    L.max_L = (int)maxL;
+    L.bp_words_per_lane = (maxL > 512) ? 2 : 1;
+    L.resident_warps = d.sms * d.vg_ctas_per_sm * VG_WARPS;
+    L.slab_words = (long long)(s.max_T + 2) * 32 * L.bp_words_per_lane;
+    size_t o = 0;
+    L.off_tmask = o; o = align_up(o + (size_t)s.B * MAX_WORDS * 4);
+    L.off_rowstat = o; o = align_up(o + (p.boost_targets && p.mode == BFA_MODE_FULL ? (size_t)s.total_frames * 8 : 0));
+    L.off_items_local = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
+    L.off_items = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
+    L.off_lists = o; o = align_up(o + (size_t)s.B * L.list_ints * 4);
+    L.off_padded = o; o = align_up(o + (L.segmenting ? (size_t)s.B * (s.max_T + 16) * 4 : 0));
+    L.off_anchors = o; o = align_up(o + (size_t)s.B * L.anchor_words * 4);
+    L.off_counters = o; o = align_up(o + 64);
+    L.off_bp = o; o = align_up(o + (size_t)L.resident_warps * L.slab_words * 4);
+    L.total = o;
+    return BFA_OK;
+}
+
+// max_L: upper bound of the path length of any item; the long-path kernel is only launched when
+// an item can need it.  Both classes use the same per-warp slabs (kernels are stream-ordered).
+int launch_viterbi(VitArgs& va, int max_items, int max_L, const DeviceInfo& d, cudaStream_t st) {
+    int want = (max_items + VG_WARPS - 1) / VG_WARPS;
+    if (want < 1) want = 1;
+    int ctas = want < d.sms * d.vg_ctas_per_sm ? want : d.sms * d.vg_ctas_per_sm;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_prof.mu);
+        if (g_prof.on) { e0 = g_prof.get(); e1 = g_prof.get(); }
+    }
+    if (e0) cudaEventRecord(e0, st);
+    viterbi_generic_kernel<0><<<ctas, VG_WARPS * 32, sizeof(WarpSmem) * VG_WARPS, st>>>(va);
+    LAUNCH_CHECK();
+    if (e0) {
+        cudaEventRecord(e1, st);
+        std::lock_guard<std::mutex> lk(g_prof.mu);
+        g_prof.pending.emplace_back(e0, e1);
+    }
+    if (max_L > 256) {
+        ctas = want < d.sms * d.vg_ctas_per_sm_big ? want : d.sms * d.vg_ctas_per_sm_big;
+        viterbi_generic_kernel<1><<<ctas, VG_WARPS * 32, sizeof(WarpSmem) * VG_WARPS, st>>>(va);
+        LAUNCH_CHECK();
+    }
+    return BFA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bfa_version(void) { return BFA_VERSION; }
+
+const char* bfa_strerror(int code) {
+    switch (code) {
+        case BFA_OK: return "ok";
+        case BFA_E_INVALID: return "invalid argument";
+        case BFA_E_UNSUPPORTED: return "shape outside compiled limits (C > 256 or CTC path longer than 1024 states)";
+        case BFA_E_WORKSPACE: return "workspace too small";
+        case BFA_E_CUDA: return "CUDA runtime error";
+        default: return "unknown error";
+    }
+}
+
+const char* bfa_last_cuda_error(void) { return g_cuda_err; }
+int bfa_sizeof_params(void) { return (int)sizeof(BfaParams); }
+int64_t bfa_launch_count(void) { return (int64_t)g_launches.load(); }
+
+void bfa_default_params(BfaParams* p, int32_t blank_id, int32_t silence_id) {
+    memset(p, 0, sizeof(*p));
+    p->blank_id = blank_id;
+    p->silence_id = silence_id;
+    p->silence_anchors = 10;   // AlignmentUtils.__init__ (forced_alignment.py:841)
+    p->ignore_noise = 1;
+    p->truly_forced = 1;
+    p->boost_targets = 1;      // decode_alignments defaults (:858)
+    p->enforce_minimum = 1;
+    p->max_blanks = 10;        // assort_frames (:777)
+    p->boost_factor = 5.0f;    // :29
+    p->min_log_prob = logf(1e-8f);  // torch.log(torch.tensor(1e-8)) (:70)
+    p->neg_inf = -1000.0f;     // :23
+    p->sub_boost = 5.0f;       // :418
+    p->boundary_pad = 3;       // :269
+    p->min_speech_frames = 20; // :269
+    p->mode = BFA_MODE_FULL;
+}
+
+size_t bfa_workspace_bytes(const BfaParams* p, const BfaShape* shape) {
+    if (!p || !shape) return 0;
+    DeviceInfo d;
+    if (device_info(d) != BFA_OK) return 0;
+    Layout L;
+    if (make_layout(*p, *shape, d, L) != BFA_OK) return 0;
+    return L.total;
+}
+
+int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp, const int64_t* row_off, const int32_t* T,
+                    const int32_t* tgt, const int64_t* tgt_off, int32_t* frame_ph, int32_t* frame_idx,
+                    const int64_t* frame_off, float* dp_final, int32_t* status, BfaStamp* stamps, float* conf,
+                    int32_t* n_stamps, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!p || !shape || !logp || !row_off || !T || !tgt_off || !frame_ph || !frame_idx || !frame_off || !status) return BFA_E_INVALID;
+    if ((stamps == nullptr) != (n_stamps == nullptr)) return BFA_E_INVALID;
+    if (p->blank_id < 0 || p->blank_id >= shape->C) return BFA_E_INVALID;
+    if (shape->B == 0) return BFA_OK;
+    if (!tgt && shape->max_N > 0) return BFA_E_INVALID;
+    DeviceInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    Layout L;
+    rc = make_layout(*p, *shape, d, L);
+    if (rc) return rc;
+    if (!workspace || workspace_bytes < L.total) return BFA_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    const int B = shape->B, C = shape->C;
+    const bool boost = p->boost_targets && p->mode == BFA_MODE_FULL;
+
+    uint32_t* tmask = (uint32_t*)(ws + L.off_tmask);
+    float2* rowstat = boost ? (float2*)(ws + L.off_rowstat) : nullptr;
+    int* counters = (int*)(ws + L.off_counters);
+    CUDA_TRY(cudaMemsetAsync(counters, 0, 64, st));
+
+    tmask_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, C, p->blank_id, tgt, (const long long*)tgt_off, tmask);
+    LAUNCH_CHECK();
+    if (boost && shape->max_T > 0) {
+        dim3 grid((shape->max_T + 7) / 8, B);
+        rowstat_kernel<<<grid, 256, 0, st>>>(C, p->boost_factor, logp, (const long long*)row_off, T, (const long long*)frame_off, tmask, rowstat);
+        LAUNCH_CHECK();
+    }
+    PlanArgs pa;
+    pa.p = *p; pa.B = B; pa.C = C; pa.max_T = shape->max_T; pa.max_N = shape->max_N;
+    pa.logp = logp; pa.row_off = (const long long*)row_off; pa.T = T; pa.tgt = tgt; pa.tgt_off = (const long long*)tgt_off;
+    pa.frame_off = (const long long*)frame_off; pa.rowstat = rowstat; pa.tmask = tmask;
+    pa.frame_ph = frame_ph; pa.frame_idx = frame_idx; pa.dp_final = dp_final; pa.status = status;
+    pa.item_cap = L.item_cap; pa.gmax = L.gmax; pa.amax = L.amax; pa.anchor_words = L.anchor_words;
+    pa.items_local = (Item*)(ws + L.off_items_local); pa.items = (Item*)(ws + L.off_items);
+    pa.n_items = counters; pa.lists = (int32_t*)(ws + L.off_lists); pa.list_ints = L.list_ints;
+    pa.padded = (float*)(ws + L.off_padded); pa.anchors = (uint32_t*)(ws + L.off_anchors);
+    plan_kernel<<<(B + 3) / 4, 128, 0, st>>>(pa);
+    LAUNCH_CHECK();
+
+    VitArgs va;
+    va.p = *p; va.C = C; va.logp = logp; va.rowstat = rowstat; va.tmask = tmask; va.tgt = tgt;
+    va.path = nullptr; va.true_idx = nullptr; va.anchors = pa.anchors; va.items = pa.items;
+    va.n_items = counters; va.work_counter = counters + 1;
+    va.frame_ph = frame_ph; va.frame_idx = frame_idx; va.dp_final = dp_final; va.status = status; va.final_state = nullptr;
+    va.bp_scratch = (uint32_t*)(ws + L.off_bp); va.bp_slab_words = L.slab_words;
+    long long max_items = (long long)B * L.item_cap;
+    rc = launch_viterbi(va, (int)(max_items > (1 << 30) ? (1 << 30) : max_items), L.max_L, d, st);
+    if (rc) return rc;
+
+    if (stamps) {
+        AssortArgs aa;
+        aa.p = *p; aa.B = B; aa.C = C; aa.max_stamps = shape->max_stamps; aa.logp = logp; aa.row_off = (const long long*)row_off;
+        aa.T = T; aa.frame_off = (const long long*)frame_off; aa.frame_ph = frame_ph; aa.frame_idx = frame_idx;
+        aa.status = status; aa.stamps = stamps; aa.conf = conf; aa.n_stamps = n_stamps;
+        if (shape->max_stamps <= 0) return BFA_E_INVALID;
+        assort_confidence_kernel<<<(B + 3) / 4, 128, 0, st>>>(aa);
+        LAUNCH_CHECK();
+    }
+    return BFA_OK;
+}
+
+size_t bfa_viterbi_paths_workspace_bytes(int32_t n_items, int32_t max_T, int32_t max_L) {
+    DeviceInfo d;
+    if (device_info(d) != BFA_OK) return 0;
+    size_t warps = (size_t)d.sms * d.vg_ctas_per_sm * VG_WARPS;
+    size_t slab = (size_t)(max_T + 2) * 32 * (max_L > 512 ? 2 : 1) * 4;
+    return align_up((size_t)n_items * sizeof(Item)) + align_up(64) + align_up(warps * slab);
+}
+
+int bfa_viterbi_paths(const BfaParams* p, int32_t n_items, int32_t C, int32_t max_T, int32_t max_L, const float* logp,
+                      const int64_t* row_off, const int32_t* T, const int32_t* path, const int32_t* true_idx,
+                      const int64_t* path_off, const int32_t* Lp, const int32_t* band, int32_t* frame_ph, int32_t* frame_idx,
+                      const int64_t* frame_off, float* dp_final, int32_t* final_state, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+    if (!p || !logp || !row_off || !T || !path || !path_off || !Lp || !band || !frame_ph || !frame_idx || !frame_off) return BFA_E_INVALID;
+    if (n_items <= 0) return n_items == 0 ? BFA_OK : BFA_E_INVALID;
+    if (C <= 0 || C > BFA_MAX_C || max_L > BFA_MAX_L) return BFA_E_UNSUPPORTED;
+    if (p->blank_id < 0 || p->blank_id >= C) return BFA_E_INVALID;
+    DeviceInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    if (!workspace || workspace_bytes < bfa_viterbi_paths_workspace_bytes(n_items, max_T, max_L)) return BFA_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    Item* items = (Item*)ws;
+    int* counters = (int*)(ws + align_up((size_t)n_items * sizeof(Item)));
+    uint32_t* bp = (uint32_t*)((char*)counters + align_up(64));
+    CUDA_TRY(cudaMemsetAsync(counters, 0, 64, st));
+    items_from_arrays_kernel<<<(n_items + 127) / 128, 128, 0, st>>>(n_items, C, (const long long*)row_off, T, (const long long*)path_off,
+                                                                    Lp, band, (const long long*)frame_off, items, counters);
+    LAUNCH_CHECK();
+    VitArgs va;
+    va.p = *p; va.C = C; va.logp = logp; va.rowstat = nullptr; va.tmask = nullptr; va.tgt = nullptr;
+    va.path = path; va.true_idx = true_idx; va.anchors = nullptr; va.items = items;
+    va.n_items = counters; va.work_counter = counters + 1;
+    va.frame_ph = frame_ph; va.frame_idx = frame_idx; va.dp_final = dp_final; va.status = nullptr; va.final_state = final_state;
+    va.bp_scratch = bp; va.bp_slab_words = (long long)(max_T + 2) * 32 * (max_L > 512 ? 2 : 1);
+    return launch_viterbi(va, n_items, max_L, d, st);
+}
+
+int bfa_confidence_batch(int32_t B, int32_t C, const float* logp, const int64_t* row_off, const int32_t* T_conf,
+                         const BfaStamp* stamps, const int32_t* n_stamps, int32_t max_stamps, float* conf, void* stream) {
+    if (!logp || !row_off || !T_conf || !stamps || !n_stamps || !conf || C <= 0 || max_stamps <= 0) return BFA_E_INVALID;
+    if (B <= 0) return B == 0 ? BFA_OK : BFA_E_INVALID;
+    confidence_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(B, C, logp, (const long long*)row_off, T_conf, stamps, n_stamps,
+                                                                     max_stamps, conf);
+    LAUNCH_CHECK();
+    return BFA_OK;
+}
+
+void bfa_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.on = on != 0;
+}
+
+// Sum of the device time of the dominant kernel launches recorded since the last read; blocks on them.
+int bfa_profile_read(float* dominant_ms, int32_t* n_launches) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    float total = 0.f;
+    int n = 0;
+    for (auto& pr : g_prof.pending) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventSynchronize(pr.second));
+        CUDA_TRY(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        total += ms; ++n;
+        g_prof.pool.push_back(pr.first); g_prof.pool.push_back(pr.second);
+    }
+    g_prof.pending.clear();
+    if (dominant_ms) *dominant_ms = total;
+    if (n_launches) *n_launches = n;
+    return BFA_OK;
+}
+
+int bfa_assort_batch(const BfaParams* p, int32_t B, const int32_t* T, const int64_t* frame_off, const int32_t* frame_ph,
+                     const int32_t* frame_idx, int32_t* status, BfaStamp* stamps, int32_t* n_stamps, int32_t max_stamps,
+                     void* stream) {
+    if (!p || !T || !frame_off || !frame_ph || !frame_idx || !status || !stamps || !n_stamps || max_stamps <= 0) return BFA_E_INVALID;
+    if (B <= 0) return B == 0 ? BFA_OK : BFA_E_INVALID;
+    AssortArgs aa;
+    aa.p = *p; aa.B = B; aa.C = 0; aa.max_stamps = max_stamps; aa.logp = nullptr; aa.row_off = nullptr; aa.T = T;
+    aa.frame_off = (const long long*)frame_off; aa.frame_ph = frame_ph; aa.frame_idx = frame_idx; aa.status = status;
+    aa.stamps = stamps; aa.conf = nullptr; aa.n_stamps = n_stamps;
+    assort_confidence_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(aa);
+    LAUNCH_CHECK();
+    return BFA_OK;
+}
+
+}  // extern "C"

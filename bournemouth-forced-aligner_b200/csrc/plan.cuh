@@ -1,0 +1,447 @@
+// plan.cuh -- per-utterance planning on the device: target masks, row statistics, silence
+// scan + silence-anchored segmentation, and emission of DP work items.
+//
+// Restates the control logic of ViterbiDecoder.decode_with_forced_alignment
+// (forced_alignment.py:87-199), _segmented_viterbi_decode (:268-469), _find_target_sil_groups
+// (:203-224), _match_silences (:226-266), _detect_silence_segments (:471-541) and
+// AlignmentUtils.decode_alignments_simple (:932-986).  One warp per utterance; list logic is
+// executed redundantly by all lanes (uniform control flow), lane 0 writes, the frame-parallel
+// parts (exp / prefix sums / fills) use all 32 lanes.  No host round trip: the work-item list and
+// its length stay on the device.
+#pragma once
+#include "bfa_common.cuh"
+
+namespace bfa {
+
+struct PlanArgs {
+    BfaParams p;
+    int B, C, max_T, max_N;
+    const float* logp;
+    const long long* row_off;
+    const int32_t* T;
+    const int32_t* tgt;
+    const long long* tgt_off;
+    const long long* frame_off;
+    const float2* rowstat;     // valid when p.boost_targets
+    uint32_t* tmask;           // [B][MAX_WORDS]
+    int32_t* frame_ph;
+    int32_t* frame_idx;
+    float* dp_final;
+    int32_t* status;
+    // scratch
+    int item_cap;              // local item slots per utterance
+    int gmax, amax;            // list capacities per utterance
+    int anchor_words;          // anchor words per utterance
+    Item* items_local;         // [B][item_cap]
+    Item* items;               // compacted list
+    int* n_items;              // device counter
+    int32_t* lists;            // [B][list_ints]
+    int list_ints;
+    float* padded;             // [B][max_T + 16]
+    uint32_t* anchors;         // [B][anchor_words]
+};
+
+// ---- target-class bitmask: unique_targets = set(seq) - {blank, -100}, p < C (:44-49) ----
+__global__ void tmask_kernel(int B, int C, int blank_id, const int32_t* tgt, const long long* tgt_off, uint32_t* tmask) {
+    int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (u >= B) return;
+    uint32_t w[MAX_WORDS];
+#pragma unroll
+    for (int i = 0; i < MAX_WORDS; ++i) w[i] = 0;
+    long long b = tgt_off[u], e = tgt_off[u + 1];
+    for (long long j = b + lane; j < e; j += 32) {
+        int c = tgt[j];
+        if (c == blank_id || c == -100 || c < 0 || c >= C) continue;
+#pragma unroll
+        for (int i = 0; i < MAX_WORDS; ++i)
+            if ((c >> 5) == i) w[i] |= 1u << (c & 31);
+    }
+#pragma unroll
+    for (int i = 0; i < MAX_WORDS; ++i) {
+        uint32_t v = w[i];
+        for (int d = 16; d >= 1; d >>= 1) v |= __shfl_xor_sync(FULL, v, d);
+        if (lane == 0) tmask[(size_t)u * MAX_WORDS + i] = v;
+    }
+}
+
+// ---- row statistics of the boosted row: max and log(sum exp(x - max)) (:51-54) ----
+// grid = (ceil(max_T / rows_per_cta), B); one warp per row.
+__global__ void rowstat_kernel(int C, float boost, const float* __restrict__ logp, const long long* row_off, const int32_t* T,
+                               const long long* frame_off, const uint32_t* tmask, float2* rowstat) {
+    const int u = blockIdx.y, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= T[u]) return;
+    const float* row = logp + row_off[u] + (long long)t * C;
+    float v[MAX_WORDS];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < MAX_WORDS; ++i) {
+        int c = lane + 32 * i;
+        v[i] = -INFINITY;
+        if (c < C) {
+            bool tg = (tmask[(size_t)u * MAX_WORDS + i] >> lane) & 1u;
+            v[i] = row[c] + (tg ? boost : 0.0f);
+            mx = fmaxf(mx, v[i]);
+        }
+    }
+    mx = warp_max(mx);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_WORDS; ++i)
+        if (lane + 32 * i < C) s += expf(v[i] - mx);
+    s = warp_sum(s);
+    if (lane == 0) rowstat[frame_off[u] + t] = make_float2(mx, logf(s));
+}
+
+// ------------------------------------------------------------------------------------------
+struct UttCtx {
+    const PlanArgs* a;
+    int u, lane, T, N;
+    const float* lp;         // utterance rows
+    const int32_t* seq;
+    const float2* stat;      // utterance row stats (or null)
+    bool sil_is_target;
+    float* padded;
+};
+
+// exp(modified_lp[row, silence_id]) (:503-504)
+__device__ __forceinline__ float sil_prob(const UttCtx& c, int row) {
+    const BfaParams& p = c.a->p;
+    float x = c.lp[(long long)row * c.a->C + p.silence_id];
+    float m = 0.f, ls = 0.f;
+    if (p.boost_targets) { float2 s = c.stat[row]; m = s.x; ls = s.y; }
+    x = mod_value(x, c.sil_is_target, p.boost_targets != 0, p.enforce_minimum != 0, p.boost_factor, m, ls, p.min_log_prob);
+    return expf(x);
+}
+
+// _detect_silence_segments (:471-541) over rows [r0, r0+Tn).  Writes (start,end) pairs to out
+// (lane 0) and returns the count (uniform).  k-frame moving average through a prefix sum that is
+// accumulated in fp64 and stored as fp32, like torch.cumsum on CPU.
+__device__ int detect_silence(const UttCtx& c, int r0, int Tn, float thr, int k, int32_t* out, int max_out) {
+    const BfaParams& p = c.a->p;
+    if (p.silence_id >= c.a->C) return 0;   // :497
+    if (Tn < k || Tn <= 0) return 0;        // :499
+    const int lane = c.lane;
+    float* padded = c.padded;
+    if (k > 1) {
+        double carry = 0.0;
+        if (lane == 0) padded[0] = 0.0f;
+        for (int base = 0; base < Tn; base += 32) {
+            int t = base + lane;
+            double v = (t < Tn) ? (double)sil_prob(c, r0 + t) : 0.0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                double o = __shfl_up_sync(FULL, v, d);
+                if (lane >= d) v += o;
+            }
+            v += carry;
+            if (t < Tn) padded[t + 1] = (float)v;
+            carry = __shfl_sync(FULL, v, 31);
+        }
+        __syncwarp();
+    }
+    const int nwin = (k > 1) ? Tn - k + 1 : Tn;
+    int n = 0, in_sil = 0, start = 0;
+    for (int base = 0; base < nwin; base += 32) {
+        int i = base + lane;
+        bool sil = false;
+        if (i < nwin) {
+            float avg = (k > 1) ? (padded[i + k] - padded[i]) / (float)k : sil_prob(c, r0 + i);   // :510-512
+            sil = avg >= thr;                                                                      // :517
+        }
+        uint32_t bits = __ballot_sync(FULL, sil);
+        uint32_t vmask = (nwin - base >= 32) ? FULL : ((1u << (nwin - base)) - 1u);
+        uint32_t trans = (bits ^ ((bits << 1) | (in_sil ? 1u : 0u))) & vmask;
+        while (trans) {                                                                           // :524-533
+            int b = __ffs(trans) - 1;
+            trans &= trans - 1;
+            int i2 = base + b;
+            if (!in_sil) { in_sil = 1; start = i2; }
+            else {
+                in_sil = 0;
+                int e = min(i2 + k - 1, Tn);
+                if (e - start >= k && n < max_out) {
+                    if (lane == 0) { out[2 * n] = start; out[2 * n + 1] = e; }
+                    ++n;
+                }
+            }
+        }
+    }
+    if (in_sil && Tn - start >= k && n < max_out) {                                              // :536-539
+        if (lane == 0) { out[2 * n] = start; out[2 * n + 1] = Tn; }
+        ++n;
+    }
+    __syncwarp();
+    return n;
+}
+
+__device__ __forceinline__ void fill_frames(const UttCtx& c, long long o0, long long olim, int nf, int ph, int idx) {
+    for (int f = c.lane; f < nf; f += 32)
+        if (o0 + f < olim) { c.a->frame_ph[o0 + f] = ph; c.a->frame_idx[o0 + f] = idx; }
+}
+
+__device__ __forceinline__ int band_rule(int L, int div, int floor_) { return (L > 60) ? max(L / div, floor_) : 0; }
+
+// _segmented_viterbi_decode (:268-469).  Returns the number of local items on success, -1 when the
+// reference returns ([], []) and the caller must fall back to a single Viterbi.
+__device__ int plan_segmented(const UttCtx& c, Item* loc, int32_t* lists, uint32_t* anchors) {
+    const PlanArgs& a = *c.a;
+    const BfaParams& p = a.p;
+    const int lane = c.lane, T = c.T, N = c.N, C = a.C;
+    int32_t* grp = lists;                      // [2*gmax]
+    int32_t* asil = grp + 2 * a.gmax;          // [2*amax]
+    int32_t* mt = asil + 2 * a.amax;           // [2*gmax]
+    int32_t* segs = mt + 2 * a.gmax;           // [5*(2*gmax+2)]
+    int32_t* sub = segs + 5 * (2 * a.gmax + 2);// [2*amax]
+
+    // Step 1: target SIL groups (:203-224)
+    int ng = 0;
+    for (int i = 0; i < N;) {
+        if (c.seq[i] == p.silence_id) {
+            int s = i;
+            while (i < N && c.seq[i] == p.silence_id) ++i;
+            if (lane == 0) { grp[2 * ng] = s; grp[2 * ng + 1] = i; }
+            ++ng;
+        } else ++i;
+    }
+    if (ng == 0) return -1;                                                       // :293-295
+    int k = p.silence_anchors;                                                    // :296
+    int na = detect_silence(c, 0, T, 0.9f, k, asil, a.amax);                      // :297
+    if (na == 0 && N > 200) {                                                     // :298-304
+        double nt = 1.0 - (0.09 * (double)k);
+        if (nt < 0.05) nt = 0.05;
+        na = detect_silence(c, 0, T, (float)nt, k, asil, a.amax);
+    }
+    if (na == 0 && N > 200 && k > 3) {                                            // :305-308
+        k = 3;
+        na = detect_silence(c, 0, T, 0.9f, k, asil, a.amax);
+    }
+    if (na == 0) return -1;                                                       // :315-320
+    __syncwarp();
+
+    // Step 2: _match_silences (:226-266)
+    int nm = 0, audio_idx = 0;
+    for (int g = 0; g < ng; ++g) {
+        double tpos = (double)(grp[2 * g] + grp[2 * g + 1]) / 2.0 / (double)N;
+        int best = -1;
+        double bd = INFINITY;
+        for (int ai = audio_idx; ai < na; ++ai) {
+            double apos = (double)(asil[2 * ai] + asil[2 * ai + 1]) / 2.0 / (double)T;
+            double d = fabs(tpos - apos);
+            if (d < bd) { bd = d; best = ai; }
+            else if (d > bd) break;
+        }
+        if (best >= 0 && bd < 0.3) {
+            if (lane == 0) { mt[2 * nm] = g; mt[2 * nm + 1] = best; }
+            ++nm;
+            audio_idx = best + 1;
+        }
+    }
+    if (nm == 0) return -1;                                                       // :324-325
+    __syncwarp();
+
+    // Step 3 + 3b: segment list with short-speech merge (:327-369); built in registers, lane 0 stores
+    int ns = 0, pa = 0, pt = 0;
+    auto push = [&](int a0, int a1, int t0, int t1, int sil) {
+        // merge rule (:363-366): short non-silence segment with phonemes joins the previous entry
+        if (!sil && (t1 - t0) > 0 && (a1 - a0) < p.min_speech_frames && ns > 0) {
+            if (lane == 0) { segs[5 * (ns - 1) + 1] = a1; segs[5 * (ns - 1) + 3] = t1; segs[5 * (ns - 1) + 4] = 0; }
+        } else {
+            if (lane == 0) { int32_t* s = segs + 5 * ns; s[0] = a0; s[1] = a1; s[2] = t0; s[3] = t1; s[4] = sil; }
+            ++ns;
+        }
+    };
+    for (int m = 0; m < nm; ++m) {
+        int tg0 = grp[2 * mt[2 * m]], tg1 = grp[2 * mt[2 * m] + 1];
+        int as0 = asil[2 * mt[2 * m + 1]], as1 = asil[2 * mt[2 * m + 1] + 1];
+        if (pa < as0 && pt < tg0) push(pa, as0, pt, tg0, 0);
+        else if (pa < as0) push(pa, as0, pt, pt, 0);
+        push(as0, as1, tg0, tg1, 1);
+        pa = as1;
+        pt = tg1;
+    }
+    if (pa < T && pt < N) push(pa, T, pt, N, 0);
+    else if (pa < T) push(pa, T, pt, pt, 0);
+    __syncwarp();
+
+    // Step 4 (:377-451)
+    const long long o_base = a.frame_off[c.u], o_lim = a.frame_off[c.u + 1];
+    int w = 0, n_items = 0, anc_used = 0;
+    for (int i = 0; i < ns; ++i) {
+        const int a0 = segs[5 * i], a1 = segs[5 * i + 1], t0 = segs[5 * i + 2], t1 = segs[5 * i + 3], sil = segs[5 * i + 4];
+        const int nf = a1 - a0;
+        if (nf <= 0) continue;
+        if (sil) {                                                                // :382-397
+            const int nsil = t1 - t0;
+            fill_frames(c, o_base + w, o_lim, nf, p.silence_id, -1);
+            __syncwarp();
+            if (nsil > 0) {
+                double fps = (double)nf / (double)nsil;
+                for (int q = 0; q < nsil; ++q) {
+                    int f0 = (int)((double)q * fps), f1 = min((int)((double)(q + 1) * fps), nf);
+                    for (int f = f0 + lane; f < f1; f += 32)
+                        if (o_base + w + f < o_lim) a.frame_idx[o_base + w + f] = t0 + q;
+                    __syncwarp();
+                }
+            }
+            w += nf;
+            continue;
+        }
+        const int n = t1 - t0;
+        if (n == 0) {                                                             // :409-412
+            fill_frames(c, o_base + w, o_lim, nf, p.blank_id, -1);
+            w += nf;
+            continue;
+        }
+        const int p0 = max(0, a0 - p.boundary_pad), p1 = min(T, a1 + p.boundary_pad);   // :401-403
+        const int Ts = p1 - p0;
+        // sub-silence anchoring (:415-419): counts per frame, 4 bits each
+        const int nss = detect_silence(c, p0, Ts, 0.8f, k, sub, a.amax);
+        const int words = (Ts + 7) / 8;
+        int flags_anchor = 0;
+        if (nss > 0 && anc_used + words <= a.anchor_words) {
+            for (int wd = lane; wd < words; wd += 32) {
+                uint32_t v = 0;
+                for (int q = 0; q < 8; ++q) {
+                    int f = wd * 8 + q, cnt = 0;
+                    for (int s = 0; s < nss; ++s) cnt += (f >= sub[2 * s] && f < sub[2 * s + 1]);
+                    v |= (uint32_t)min(cnt, 15) << (4 * q);
+                }
+                anchors[anc_used + wd] = v;
+            }
+            flags_anchor = ITEM_ANCHOR;
+        }
+        int stride = 4;                                                           // :423-426
+        if ((double)(stride * n + 1) > (double)Ts * 0.9) stride = 3;
+        if ((double)(stride * n + 1) > (double)Ts * 0.8) stride = 2;
+        const int L = stride * n + 1;
+        if ((double)L > (double)Ts * 1.2) return -1;                              // :427-429
+        if (n_items >= a.item_cap) return -1;  // cannot happen (item_cap = gmax + 1); defensive
+        if (lane == 0) {
+            Item it;
+            it.lp_off = a.row_off[c.u] + (long long)p0 * C;
+            it.stat_off = a.frame_off[c.u] + p0;
+            it.out_off = o_base + w;
+            it.out_lim = o_lim;
+            it.seq_off = a.tgt_off[c.u] + t0;
+            it.T = Ts; it.L = L; it.band = band_rule(L, 3, 30);                   // :441
+            it.stride = stride; it.n = n; it.idx0 = t0;
+            it.trim = a0 - p0; it.n_out = nf;                                     // :447-448
+            it.utt = c.u;
+            it.anchor_off = (int)((size_t)c.u * a.anchor_words) + anc_used;
+            it.flags = (p.boost_targets ? ITEM_STATS : 0) | (p.enforce_minimum ? ITEM_FLOOR : 0) | flags_anchor;
+            it.pad = 0;
+            loc[n_items] = it;
+        }
+        if (flags_anchor) anc_used += words;
+        ++n_items;
+        w += nf;
+    }
+    if (w == 0) return -1;                                                        // :454-455
+    // tail padding with blanks if short (:461-464); over-long output is clipped by out_lim
+    if (w < T) fill_frames(c, o_base + w, o_lim, T - w, p.blank_id, -1);
+    __syncwarp();
+    return n_items;
+}
+
+__global__ void plan_kernel(PlanArgs a) {
+    const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (u >= a.B) return;
+    const BfaParams& p = a.p;
+    UttCtx c;
+    c.a = &a; c.u = u; c.lane = lane;
+    c.T = a.T[u];
+    c.N = (int)(a.tgt_off[u + 1] - a.tgt_off[u]);
+    c.lp = a.logp + a.row_off[u];
+    c.seq = a.tgt + a.tgt_off[u];
+    c.stat = a.rowstat ? a.rowstat + a.frame_off[u] : nullptr;
+    c.padded = a.padded + (size_t)u * (a.max_T + 16);
+    c.sil_is_target = false;
+    if (p.silence_id >= 0 && p.silence_id < a.C)
+        c.sil_is_target = (a.tmask[(size_t)u * MAX_WORDS + (p.silence_id >> 5)] >> (p.silence_id & 31)) & 1u;
+    const int T = c.T, N = c.N;
+    const long long o_base = a.frame_off[u], o_lim = a.frame_off[u + 1];
+    Item* loc = a.items_local + (size_t)u * a.item_cap;
+    int st = BFA_ST_OK, n_items = 0;
+    if (lane == 0 && a.dp_final) a.dp_final[u] = 0.0f;
+
+    if (N == 0) {                                                                 // :894-897 / :112-118
+        fill_frames(c, o_base, o_lim, T, p.blank_id, -1);
+        st = BFA_ST_EMPTY_TARGET;
+    } else {
+        bool done = false;
+        if (p.mode == BFA_MODE_FULL && p.silence_anchors > 0 && p.silence_id >= 0 && T > 0) {   // :133
+            int r = plan_segmented(c, loc, a.lists + (size_t)u * a.list_ints, a.anchors + (size_t)u * a.anchor_words);
+            if (r >= 0) { n_items = r; st = BFA_ST_SEGMENTED; done = true; }
+        }
+        if (!done) {
+            int stride = 4;
+            bool ok = true;
+            if (p.mode == BFA_MODE_SIMPLE) {                                      // :963-968
+                if ((double)(stride * N + 1) > (double)T * 0.9) stride = 3;
+                if ((double)(stride * N + 1) > (double)T * 0.8) stride = 2;
+            } else {                                                              // :153-157
+                if (stride * N + 1 > T) stride = 3;
+                if (stride * N + 1 > T) stride = 2;
+                if (stride * N + 1 > T) stride = 1;
+                if (stride * N + 1 > T) {                                         // :159-176
+                    ok = false;
+                    if (T < N) {
+                        st = BFA_ST_TOO_SHORT;
+                        fill_frames(c, o_base, o_lim, T, p.blank_id, -1);
+                    } else {
+                        st = BFA_ST_PROPORTIONAL;
+                        for (int t = lane; t < T; t += 32) {
+                            int j = (int)(((long long)t * N) / T);
+                            a.frame_ph[o_base + t] = c.seq[j];
+                            a.frame_idx[o_base + t] = j;
+                        }
+                    }
+                }
+            }
+            if (ok && T > 0) {
+                const int L = stride * N + 1;
+                if (lane == 0) {
+                    Item it;
+                    it.lp_off = a.row_off[u];
+                    it.stat_off = a.frame_off[u];
+                    it.out_off = o_base; it.out_lim = o_lim;
+                    it.seq_off = a.tgt_off[u];
+                    it.T = T; it.L = L; it.band = band_rule(L, 4, 20);            // :190 / :976
+                    it.stride = stride; it.n = N; it.idx0 = 0; it.trim = 0; it.n_out = T;
+                    it.utt = u; it.anchor_off = 0;
+                    it.flags = ITEM_FINAL;
+                    if (p.mode == BFA_MODE_FULL)
+                        it.flags |= (p.boost_targets ? ITEM_STATS : 0) | (p.enforce_minimum ? ITEM_FLOOR : 0);
+                    it.pad = 0;
+                    loc[0] = it;
+                }
+                n_items = 1;
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) a.status[u] = st;
+    // publish this utterance's items into the compact global list
+    int base = 0;
+    if (lane == 0 && n_items > 0) base = atomicAdd(a.n_items, n_items);
+    base = __shfl_sync(FULL, base, 0);
+    for (int i = lane; i < n_items; i += 32) a.items[base + i] = loc[i];
+}
+
+// Build explicit-path items from parallel arrays (bfa_viterbi_paths entry).
+__global__ void items_from_arrays_kernel(int n, int C, const long long* row_off, const int32_t* T, const long long* path_off,
+                                         const int32_t* L, const int32_t* band, const long long* frame_off, Item* items,
+                                         int* n_items) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *n_items = n;
+    if (i >= n) return;
+    Item it;
+    it.lp_off = row_off[i]; it.stat_off = 0; it.out_off = frame_off[i]; it.out_lim = frame_off[i] + T[i];
+    it.seq_off = path_off[i];
+    it.T = T[i]; it.L = L[i]; it.band = band[i]; it.stride = 0; it.n = 0; it.idx0 = 0; it.trim = 0; it.n_out = T[i];
+    it.utt = i; it.anchor_off = 0; it.flags = ITEM_FINAL; it.pad = 0;
+    items[i] = it;
+}
+
+}  // namespace bfa

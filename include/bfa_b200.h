@@ -1,0 +1,200 @@
+/*
+ * bfa_b200.h -- C ABI of libbfa_b200.so, the B200 (sm_100a) forced-alignment engine.
+ *
+ * Drop-in boundary for ONE path of tabahi/bournemouth-forced-aligner: the batched
+ * monotonic Viterbi aligner + per-phoneme confidence pass
+ *   bournemouth_aligner/forced_alignment.py   AlignmentUtils / ViterbiDecoder
+ *   bournemouth_aligner/utils.py:70-113       _calculate_confidences
+ * called from core.py:902-922 (decode_alignments), :1028 (decode_alignments_simple) and
+ * :936-937 (_calculate_confidences).  The reference has no FFI layer for this path (it is
+ * plain Python over torch); these entry points are what a ctypes binding in core.py would
+ * call instead (INTEGRATION.md shows that binding).
+ *
+ * Conventions
+ *  - plain pointers and sizes, no torch types.  Pointers marked [dev] are device pointers,
+ *    [host] host pointers.  All buffers are caller-owned; inputs are never modified (the
+ *    reference clones before mutating, forced_alignment.py:121).
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no
+ *    hidden synchronisation and allocates nothing, except the *_host convenience entry.
+ *  - return value: 0 on success, negative BFA_E_* on argument/launch errors.  Data conditions
+ *    are reported per utterance in status[] (BFA_ST_*), mirroring the reference's exceptions
+ *    (ValueError "Audio too short to align", forced_alignment.py:161-165).
+ *  - log-posteriors are fp32, row-major [T_u, C] per utterance at logp + row_off[u]
+ *    (elements).  Dense [B, T_max, C] is the special case row_off[u] = u*T_max*C.
+ */
+#ifndef BFA_B200_H
+#define BFA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFA_VERSION 100 /* 0.1.0 */
+
+/* return codes */
+#define BFA_OK 0
+#define BFA_E_INVALID (-1)     /* null pointer / bad size / C <= blank_id */
+#define BFA_E_UNSUPPORTED (-2) /* shape outside compiled limits (C > 256, L > BFA_MAX_L) */
+#define BFA_E_WORKSPACE (-3)   /* workspace too small: call bfa_workspace_bytes */
+#define BFA_E_CUDA (-4)        /* CUDA runtime error, see bfa_last_cuda_error */
+
+/* per-utterance status (low 3 bits = branch taken, bit 3 = degenerate score) */
+#define BFA_ST_OK 0            /* single Viterbi over the utterance (forced_alignment.py:153-193) */
+#define BFA_ST_EMPTY_TARGET 1  /* N == 0 (:894-897 / :112-118) */
+#define BFA_ST_TOO_SHORT 2     /* T < N: the reference raises ValueError (:161-165) */
+#define BFA_ST_PROPORTIONAL 3  /* T == N proportional assignment (:170-176) */
+#define BFA_ST_SEGMENTED 4     /* silence-anchored segmentation accepted (:133-145) */
+#define BFA_ST_DEGENERATE 8    /* flag: winning DP score <= -1000 (the reference's "-inf") */
+#define BFA_ST_STAMP_OVERFLOW 16 /* flag: more than max_stamps runs; stamps truncated */
+
+#define BFA_MODE_FULL 0   /* AlignmentUtils.decode_alignments        (:856-910) */
+#define BFA_MODE_SIMPLE 1 /* AlignmentUtils.decode_alignments_simple (:932-986) */
+
+#define BFA_MAX_C 256
+#define BFA_MAX_L 1024  /* CTC-path states per DP problem (N <= 255 at stride 4) */
+
+/* Constants of ViterbiDecoder/AlignmentUtils (forced_alignment.py:16-23, :29, :226, :269, :418,
+ * :777, :841).  Replaces the reference's constructor arguments + hard-coded literals. */
+typedef struct BfaParams {
+    int32_t blank_id;
+    int32_t silence_id;       /* < 0 : None */
+    int32_t silence_anchors;  /* 0 disables silence anchoring */
+    int32_t ignore_noise;
+    int32_t truly_forced;
+    int32_t boost_targets;
+    int32_t enforce_minimum;
+    int32_t max_blanks;       /* 10 */
+    float boost_factor;       /* 5.0 */
+    float min_log_prob;       /* float32 log(1e-8) = -18.420681 */
+    float neg_inf;            /* -1000.0 */
+    float sub_boost;          /* 5.0 */
+    int32_t boundary_pad;     /* 3 */
+    int32_t min_speech_frames;/* 20 */
+    int32_t mode;             /* BFA_MODE_* */
+    int32_t reserved;
+} BfaParams;
+
+/* framestamp tuple (phoneme_id, start_frame, end_frame_exclusive, target_seq_idx)
+ * = the 4-tuples returned by ViterbiDecoder.assort_frames (forced_alignment.py:777-834). */
+typedef struct BfaStamp {
+    int32_t phoneme;
+    int32_t start;
+    int32_t end;
+    int32_t target_idx;
+} BfaStamp;
+
+/* Shape summary the host must provide (it owns pred_lens / true_seqs_lens anyway). */
+typedef struct BfaShape {
+    int32_t B;            /* utterances */
+    int32_t C;            /* classes (66 / 67 / 17 ...) */
+    int32_t max_T;        /* max frames of any utterance */
+    int32_t max_N;        /* max target length of any utterance */
+    int64_t total_frames; /* sum of T_u */
+    int32_t max_stamps;   /* row pitch of stamps/conf (>= max_N, or >= max_T if !ignore_noise) */
+    int32_t reserved;
+} BfaShape;
+
+int bfa_version(void);
+const char *bfa_strerror(int code);
+const char *bfa_last_cuda_error(void);
+int bfa_sizeof_params(void);
+
+/* == ViterbiDecoder.__init__/AlignmentUtils.__init__ defaults (forced_alignment.py:16-23, :841-853) */
+void bfa_default_params(BfaParams *p, int32_t blank_id, int32_t silence_id);
+
+/* Bytes of device scratch bfa_align_batch needs for this shape on the current device. */
+size_t bfa_workspace_bytes(const BfaParams *p, const BfaShape *shape);
+
+/*
+ * == AlignmentUtils.decode_alignments(forced_alignment=True) (forced_alignment.py:856-910)
+ *    or decode_alignments_simple (:932-986) when p->mode == BFA_MODE_SIMPLE,
+ *    followed (if conf != NULL) by utils._calculate_confidences (utils.py:70-113) on the ORIGINAL
+ *    log-posteriors, exactly as core.py:935-937 does.
+ *
+ *  logp      [dev] fp32 log-posteriors, utterance u at logp + row_off[u], T[u] rows of C
+ *  row_off   [dev] int64[B]      T [dev] int32[B]
+ *  tgt       [dev] int32 flat target ids; utterance u = tgt[tgt_off[u] .. tgt_off[u+1])
+ *  tgt_off   [dev] int64[B+1]
+ *  frame_ph/frame_idx [dev] int32[total_frames]: per-frame phoneme / target index (-1 on blanks),
+ *            utterance u at frame_off[u]   (the tensors decode_with_forced_alignment returns)
+ *  frame_off [dev] int64[B+1]
+ *  dp_final  [dev] float[B] or NULL: winning DP score (unsegmented utterances; 0 otherwise)
+ *  status    [dev] int32[B]  BFA_ST_*
+ *  stamps    [dev] BfaStamp[B * max_stamps], n_stamps [dev] int32[B]
+ *  conf      [dev] float[B * max_stamps] or NULL
+ */
+int bfa_align_batch(const BfaParams *p, const BfaShape *shape,
+                    const float *logp, const int64_t *row_off, const int32_t *T,
+                    const int32_t *tgt, const int64_t *tgt_off,
+                    int32_t *frame_ph, int32_t *frame_idx, const int64_t *frame_off,
+                    float *dp_final, int32_t *status,
+                    BfaStamp *stamps, float *conf, int32_t *n_stamps,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * == ViterbiDecoder._viterbi_decode (forced_alignment.py:563-703) on explicit CTC paths, one DP
+ *    problem per item (white-box entry used by parity tests and by callers that build their own
+ *    paths).  Item i: rows logp + row_off[i] (T[i] x C), path/true_idx at path_off[i] (L[i] states),
+ *    band[i]; outputs at frame_off[i].  final_state [dev] int32[n] or NULL.
+ */
+int bfa_viterbi_paths(const BfaParams *p, int32_t n_items, int32_t C, int32_t max_T, int32_t max_L,
+                      const float *logp, const int64_t *row_off, const int32_t *T,
+                      const int32_t *path, const int32_t *true_idx, const int64_t *path_off,
+                      const int32_t *L, const int32_t *band,
+                      int32_t *frame_ph, int32_t *frame_idx, const int64_t *frame_off,
+                      float *dp_final, int32_t *final_state,
+                      void *workspace, size_t workspace_bytes, void *stream);
+size_t bfa_viterbi_paths_workspace_bytes(int32_t n_items, int32_t max_T, int32_t max_L);
+
+/*
+ * == utils._calculate_confidences (utils.py:70-113) for a batch: utterance u has n_stamps[u]
+ *    stamps at stamps + u*max_stamps; T_conf[u] is the row count used for clamping (core.py:936
+ *    passes the un-sliced [T_max, C] matrix).
+ */
+int bfa_confidence_batch(int32_t B, int32_t C, const float *logp, const int64_t *row_off,
+                         const int32_t *T_conf, const BfaStamp *stamps, const int32_t *n_stamps,
+                         int32_t max_stamps, float *conf, void *stream);
+
+/*
+ * Host-buffer convenience entry (what a CPU-side caller binds): same semantics as bfa_align_batch
+ * with every pointer a HOST pointer.  Copies inputs host->device in chunks of utterances on two
+ * streams (copy of chunk i+1 overlaps the kernels of chunk i), runs the device pipeline, copies
+ * results back, and synchronises before returning.  Device memory is taken from an internal
+ * grow-only arena (released by bfa_host_release).  device = CUDA device ordinal.
+ */
+int bfa_align_batch_host(const BfaParams *p, const BfaShape *shape,
+                         const float *logp, const int64_t *row_off, const int32_t *T,
+                         const int32_t *tgt, const int64_t *tgt_off,
+                         int32_t *frame_ph, int32_t *frame_idx, const int64_t *frame_off,
+                         float *dp_final, int32_t *status,
+                         BfaStamp *stamps, float *conf, int32_t *n_stamps,
+                         int32_t device, int32_t chunk_utts);
+void bfa_host_release(void);
+const char *bfa_host_last_error(void);
+
+/*
+ * == ViterbiDecoder.assort_frames (forced_alignment.py:777-834) for a batch of per-frame
+ *    (phoneme, target index) arrays.  status [dev] int32[B] is in/out: utterances whose low bits
+ *    are EMPTY_TARGET / TOO_SHORT produce no stamps; BFA_ST_STAMP_OVERFLOW is or-ed in when a
+ *    row needs more than max_stamps entries.
+ */
+int bfa_assort_batch(const BfaParams *p, int32_t B, const int32_t *T, const int64_t *frame_off,
+                     const int32_t *frame_ph, const int32_t *frame_idx, int32_t *status,
+                     BfaStamp *stamps, int32_t *n_stamps, int32_t max_stamps, void *stream);
+
+/* Measurement hook: when enabled, bfa_align_batch / bfa_viterbi_paths bracket the dominant kernel
+ * (the Viterbi fill+back-trace) with CUDA events on the launch stream; bfa_profile_read waits for
+ * them and returns the summed device time and the number of launches since the previous read. */
+void bfa_profile_enable(int on);
+int bfa_profile_read(float *dominant_ms, int32_t *n_launches);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+int64_t bfa_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFA_B200_H */

@@ -1,0 +1,290 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the golden vectors from the
+reference and against the C oracle on seeded corpora.
+
+Bar: per-frame indices, stamps and final states bit-exact; fp32 DP scores bit-exact when both
+sides consume identical log-probs (the DP is single fp32 adds), 1e-4 relative where expf/logf
+are involved (boost+log_softmax, confidences) -- the tolerance north_star states."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def bfa():
+    import bfa_b200
+    return bfa_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def _cases(npz):
+    return [str(c) for c in npz["__cases__"]]
+
+
+# ------------------------------------------------------------------------------------------------
+def test_viterbi_core_golden_bit_exact(golden, bfa, dev):
+    """bfa_viterbi_paths == _viterbi_decode (forced_alignment.py:563-703) incl. degenerate wrap cases."""
+    g = golden("viterbi_core")
+    for forced in (True, False):
+        names = [n for n in _cases(g) if bool(g[f"{n}/meta"][2]) == forced]
+        by_c = {}
+        for n in names:
+            by_c.setdefault((g[f"{n}/lp"].shape[1], int(g[f"{n}/meta"][1])), []).append(n)
+        for (Cc, blank), group in by_c.items():
+            dec = bfa.ViterbiDecoder(blank, 0, silence_anchors=10, ignore_noise=True, truly_forced=forced)
+            lps = [torch.from_numpy(g[f"{n}/lp"]) for n in group]
+            T = [int(x.shape[0]) for x in lps]
+            row_off = np.concatenate([[0], np.cumsum([t * Cc for t in T])[:-1]])
+            flat = torch.cat([x.reshape(-1) for x in lps]).to(dev)
+            path = torch.cat([torch.from_numpy(g[f"{n}/path"]) for n in group])
+            tidx = torch.cat([torch.from_numpy(g[f"{n}/tidx"]) for n in group])
+            L = [int(g[f"{n}/path"].shape[0]) for n in group]
+            band = [int(g[f"{n}/meta"][0]) for n in group]
+            r = dec.viterbi_paths(flat.view(-1, Cc), T, row_off, path, tidx, L, band)
+            fo = r["frame_off"]
+            fph, fix = r["frame_ph"].cpu().numpy(), r["frame_idx"].cpu().numpy()
+            dpf, fs = r["dp_final"].cpu().numpy(), r["final_state"].cpu().numpy()
+            for i, n in enumerate(group):
+                fstate = int(g[f"{n}/meta"][3])
+                assert fs[i] == fstate, n
+                np.testing.assert_array_equal(fph[fo[i]:fo[i + 1]], g[f"{n}/frame_ph"], err_msg=n)
+                np.testing.assert_array_equal(fix[fo[i]:fo[i + 1]], g[f"{n}/frame_idx"], err_msg=n)
+                assert dpf[i].tobytes() == g[f"{n}/dp_last"][fstate].tobytes(), n
+
+
+def test_single_viterbi_decode_method(golden, bfa, dev):
+    g = golden("viterbi_core")
+    n = "cfg1_T60_N8_C67"
+    dec = bfa.ViterbiDecoder(66, 0, truly_forced=True)
+    fp, fi = dec._viterbi_decode(torch.from_numpy(g[f"{n}/lp"]).to(dev), torch.from_numpy(g[f"{n}/path"]).long(),
+                                 len(g[f"{n}/path"]), torch.from_numpy(g[f"{n}/tidx"]).long(), band_width=0)
+    assert fp.dtype == torch.int64 and fi.dtype == torch.int64
+    np.testing.assert_array_equal(fp.cpu().numpy(), g[f"{n}/frame_ph"])
+    np.testing.assert_array_equal(fi.cpu().numpy(), g[f"{n}/frame_idx"])
+
+
+def test_decode_forced_golden(golden, bfa, dev):
+    """decode_with_forced_alignment (forced_alignment.py:87-199): every branch in the fixture set."""
+    g = golden("decode_forced")
+    for name in _cases(g):
+        blank, sil, anchors, forced, boost, floor, err, segmented = (int(v) for v in g[f"{name}/meta"])
+        dec = bfa.ViterbiDecoder(blank, None if sil < 0 else sil, silence_anchors=anchors, ignore_noise=True, truly_forced=bool(forced))
+        lp = torch.from_numpy(g[f"{name}/lp"]).to(dev)
+        seq = torch.from_numpy(g[f"{name}/seq"]).long()
+        if err:
+            with pytest.raises(ValueError, match="Audio too short to align"):
+                dec.decode_with_forced_alignment(lp, seq, boost_targets=bool(boost), enforce_minimum=bool(floor), anchor_pauses=anchors > 0)
+            continue
+        fp, fi, sc = dec.decode_with_forced_alignment(lp, seq, boost_targets=bool(boost), enforce_minimum=bool(floor),
+                                                      anchor_pauses=anchors > 0)
+        assert sc is None and fp.dtype == torch.int64
+        np.testing.assert_array_equal(fp.cpu().numpy(), g[f"{name}/frame_ph"], err_msg=name)
+        np.testing.assert_array_equal(fi.cpu().numpy(), g[f"{name}/frame_idx"], err_msg=name)
+        stamps = dec.assort_frames(fp, fi)
+        np.testing.assert_array_equal(np.array(stamps, np.int32).reshape(-1, 4), g[f"{name}/stamps"], err_msg=name)
+        conf = bfa._calculate_confidences(lp, [s + (False,) for s in stamps])
+        np.testing.assert_allclose([c[5] for c in conf], g[f"{name}/conf"], rtol=RTOL, atol=1e-6, err_msg=name)
+
+
+def test_batch_api_golden(golden, bfa, dev):
+    """AlignmentUtils.decode_alignments / decode_alignments_simple on a padded batch with ragged lengths,
+    an empty target, ignore_noise=False and the C=17 group head."""
+    g = golden("batch_api")
+    lp = torch.from_numpy(g["batch/lp"]).to(dev); tgt = torch.from_numpy(g["batch/tgt"]).long().to(dev)
+    pred = torch.from_numpy(g["batch/pred_lens"]).long()
+    au = bfa.AlignmentUtils(66, 0, silence_anchors=10, ignore_noise=True, truly_forced=True)
+    res = au.decode_alignments(lp, true_seqs=tgt, pred_lens=pred, true_seqs_lens=torch.from_numpy(g["batch/seq_lens"]).long(),
+                               with_confidence=True)
+    for i, r in enumerate(res):
+        np.testing.assert_array_equal(np.array([x[:4] for x in r], np.int32).reshape(-1, 4), g[f"batch/stamps{i}"], err_msg=str(i))
+        np.testing.assert_allclose([x[4] for x in r], g[f"batch/conf{i}"], rtol=RTOL, atol=1e-6)
+    res = au.decode_alignments_simple(lp, tgt, pred_lens=pred, true_seqs_lens=torch.from_numpy(g["simple/seq_lens"]).long())
+    for i, r in enumerate(res):
+        np.testing.assert_array_equal(np.array(r, np.int32).reshape(-1, 4), g[f"simple/stamps{i}"], err_msg=f"simple{i}")
+    au2 = bfa.AlignmentUtils(66, 0, silence_anchors=0, ignore_noise=False, truly_forced=True)
+    res = au2.decode_alignments(lp, true_seqs=tgt, pred_lens=pred, true_seqs_lens=torch.from_numpy(g["noise/seq_lens"]).long())
+    for i, r in enumerate(res):
+        np.testing.assert_array_equal(np.array(r, np.int32).reshape(-1, 4), g[f"noise/stamps{i}"], err_msg=f"noise{i}")
+    aug = bfa.AlignmentUtils(16, 0)
+    res = aug.decode_alignments(torch.from_numpy(g["group/lp"]).to(dev), true_seqs=torch.from_numpy(g["group/tgt"]).long(),
+                                pred_lens=torch.tensor([150, 140, 100]), true_seqs_lens=torch.tensor([14, 14, 9]))
+    for i, r in enumerate(res):
+        np.testing.assert_array_equal(np.array(r, np.int32).reshape(-1, 4), g[f"group/stamps{i}"], err_msg=f"group{i}")
+
+
+def test_missing_sequences_raise(bfa, dev):
+    au = bfa.AlignmentUtils(66, 0)
+    with pytest.raises(ValueError, match="required for forced alignment"):
+        au.decode_alignments(torch.zeros(1, 4, 67, device=dev))
+
+
+# ------------------------------------------------------------------------------------------------
+def _oracle_batch(orc, p, lp, tgt, T, N, Cc, threads=8):
+    B, Tm = lp.shape[0], lp.shape[1]
+    tflat = np.concatenate([tgt[i, :N[i]] for i in range(B)]).astype(np.int32) if B else np.zeros(0, np.int32)
+    toff = np.zeros(B + 1, np.int64); np.cumsum(N, out=toff[1:])
+    return orc.align_batch(p, lp, np.arange(B, dtype=np.int64) * Tm * Cc, np.asarray(T, np.int32), Cc, tflat, toff,
+                           max_stamps=2 * int(max(N)) + 8, n_threads=threads)
+
+
+def _compare_with_oracle(bfa, orc, dev, lp, tgt, T, N, Cc, blank, **kw):
+    au = bfa.AlignmentUtils(blank, 0, **kw)
+    p = orc.params(blank, 0, kw.get("silence_anchors", 10), kw.get("ignore_noise", True), kw.get("truly_forced", True))
+    dparams = au.viterbi_decoder._params(True, True, au.silence_anchors > 0)
+    B, Tm = lp.shape[0], lp.shape[1]
+    lp_d = lp.to(dev)
+    seqs = tgt.to(dev)
+    Nd = torch.tensor(N, device=dev)
+    mask = torch.arange(tgt.shape[1], device=dev)[None, :] < Nd[:, None]
+    r = au.viterbi_decoder.align_batch(lp_d, torch.arange(B, dtype=torch.int64, device=dev) * Tm * Cc, T, Cc,
+                                       seqs[mask].to(torch.int32).contiguous(), N, params=dparams)
+    o = _oracle_batch(orc, p, lp.numpy(), tgt.numpy(), T, N, Cc)
+    st = r.status[:B].cpu().numpy()
+    np.testing.assert_array_equal(st & 15, o["status"] & 15)
+    fph, fix = r.frame_ph.cpu().numpy(), r.frame_idx.cpu().numpy()
+    fo = o["frame_off"]
+    bad = [b for b in range(B) if not (np.array_equal(fph[fo[b]:fo[b + 1]], o["frame_ph"][fo[b]:fo[b + 1]])
+                                      and np.array_equal(fix[fo[b]:fo[b + 1]], o["frame_idx"][fo[b]:fo[b + 1]]))]
+    assert not bad, f"{len(bad)} of {B} utterances differ from the oracle, first {bad[:5]}"
+    nst = r.n_stamps[:B].cpu().numpy()
+    np.testing.assert_array_equal(nst, o["n_stamps"])
+    stamps = r.stamps.cpu().numpy(); conf = r.conf.cpu().numpy()
+    for b in range(B):
+        n = nst[b]
+        want = np.stack([o["stamps"][b][f][:n] for f in ("phoneme", "start", "end", "target_idx")], 1)
+        np.testing.assert_array_equal(stamps[b, :n], want)
+        np.testing.assert_allclose(conf[b, :n], o["conf"][b, :n], rtol=RTOL, atol=1e-6)
+    unseg = (st & 7) == 0
+    np.testing.assert_allclose(r.dp_final[:B].cpu().numpy()[unseg], o["dp_final"][unseg], rtol=RTOL)
+    return st
+
+
+def test_metric_shape_vs_oracle(bfa, orc, dev):
+    """B=256 of the metric shape T=600,N=40,C=66 (full mode: boost + floor + anchoring enabled)."""
+    from bfa_b200 import synth
+    lp, tgt, _ = synth.planted_batch(256, 600, 40, 66, seed=101)
+    st = _compare_with_oracle(bfa, orc, dev, lp, tgt, [600] * 256, [40] * 256, 66, 65)
+    assert (st == 0).all()
+
+
+def test_segmented_long_form_vs_oracle(bfa, orc, dev):
+    """config 3 shape: T=3600, N=200 with SIL anchors -> silence-anchored segmentation on the device."""
+    from bfa_b200 import synth
+    lp, tgt, _ = synth.planted_batch(12, 3600, 200, 66, seed=102, peak=12.0, sil_every=40, sil_frames=18)
+    st = _compare_with_oracle(bfa, orc, dev, lp, tgt, [3600] * 12, [200] * 12, 66, 65)
+    assert ((st & 7) == 4).sum() >= 10
+
+
+def test_segmented_mixed_vs_oracle(bfa, orc, dev):
+    from bfa_b200 import synth
+    for seed, (T, N, Cc, every, frames, anchors, forced) in enumerate([
+            (900, 60, 67, 12, 22, 10, True), (400, 60, 67, 10, 14, 10, True), (420, 100, 67, 9, 12, 10, False),
+            (300, 24, 17, 6, 16, 10, True), (700, 40, 67, 8, 25, 3, True), (500, 50, 30, 5, 8, 3, True)]):
+        lp, tgt, _ = synth.planted_batch(24, T, N, Cc, seed=200 + seed, peak=10.0, sil_every=every, sil_frames=frames)
+        _compare_with_oracle(bfa, orc, dev, lp, tgt, [T] * 24, [N] * 24, Cc, Cc - 1, silence_anchors=anchors, truly_forced=forced)
+
+
+def test_ragged_lengths_and_strides_vs_oracle(bfa, orc, dev):
+    """Padded batch with ragged pred_lens / true_seqs_lens hitting strides 4/3/2/1, T==N, N==0."""
+    from bfa_b200 import synth
+    rng = np.random.default_rng(7)
+    B, Tm, Nm, Cc = 96, 400, 120, 67
+    lp, tgt, _ = synth.planted_batch(B, Tm, Nm, Cc, seed=300, peak=10.0)
+    T = rng.integers(60, Tm + 1, B).tolist()
+    N = [int(min(Nm, max(1, t // d))) for t, d in zip(T, rng.choice([1, 2, 3, 4, 6, 12], B))]
+    N[5] = 0; T[6] = N[6] = 77
+    # planted alignment does not match the shortened targets; re-plant per utterance
+    for b in range(B):
+        if N[b] > 0:
+            l, t2, _ = synth.planted_batch(1, T[b], N[b], Cc, seed=1000 + b, peak=10.0)
+            lp[b, :T[b]] = l[0]; tgt[b, :N[b]] = t2[0]
+    st = _compare_with_oracle(bfa, orc, dev, lp, tgt, T, N, Cc, Cc - 1)
+    assert (st & 7 == 3).any() and (st & 7 == 1).any()
+
+
+def test_degenerate_inputs_vs_oracle(bfa, orc, dev):
+    """Flat random posteriors: every path below -1000, masked candidates win, back-pointers wrap."""
+    g = torch.Generator().manual_seed(11)
+    B, T, N, Cc = 32, 600, 40, 66
+    lp = torch.log_softmax(torch.randn(B, T, Cc, generator=g) * 3.0, -1)
+    tgt = torch.randint(1, Cc - 1, (B, N), generator=g)
+    st = _compare_with_oracle(bfa, orc, dev, lp, tgt, [T] * B, [N] * B, Cc, Cc - 1, silence_anchors=0)
+    assert (st & 8).all()
+
+
+def test_too_short_raises_like_reference(bfa, dev):
+    from bfa_b200 import synth
+    lp, tgt, _ = synth.planted_batch(2, 30, 40, 67, seed=5)
+    au = bfa.AlignmentUtils(66, 0)
+    with pytest.raises(ValueError, match="40 phonemes cannot be fit into 30 frames"):
+        au.decode_alignments(lp.to(dev), true_seqs=tgt, pred_lens=torch.tensor([30, 30]), true_seqs_lens=torch.tensor([40, 40]))
+
+
+# ---- size-independent properties at BASELINE.json's full batch -------------------------------------
+def test_full_batch_properties(bfa, orc, dev):
+    """B=4096, T=600, N=40, C=66: (i) dp_final equals the sequential fp32 sum of the modified log-probs along
+    the returned path, (ii) target indices are monotone and cover all 40 phonemes, (iii) a
+    random sample of utterances is bit-identical to the oracle."""
+    from bfa_b200 import synth
+    B, T, N, Cc = 4096, 600, 40, 66
+    lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=77, device=dev)
+    au = bfa.AlignmentUtils(Cc - 1, 0)
+    dec = au.viterbi_decoder
+    p = dec._params(True, True, True)
+    r = dec.align_batch(lp, torch.arange(B, dtype=torch.int64, device=dev) * T * Cc, [T] * B, Cc,
+                        tgt.to(torch.int32).reshape(-1).contiguous(), [N] * B, params=p)
+    assert (r.status[:B] == 0).all()
+    fph = r.frame_ph.view(B, T).long(); fix = r.frame_idx.view(B, T).long()
+    # (ii)
+    idx = fix.clone(); idx[idx < 0] = 0
+    run = torch.cummax(idx, dim=1).values
+    assert ((fix < 0) | (fix == run)).all()
+    assert (r.n_stamps[:B] == N).all()
+    assert (r.stamps[:, :N, 3] == torch.arange(N, device=dev, dtype=torch.int32)[None, :]).all()
+    # (iii) + (i) on a sample, oracle-side
+    sample = list(range(0, B, 173))
+    lp_s = lp[sample].cpu(); tgt_s = tgt[sample].cpu()
+    o = _oracle_batch(orc, orc.params(Cc - 1, 0), lp_s.numpy(), tgt_s.numpy(), [T] * len(sample), [N] * len(sample), Cc)
+    np.testing.assert_array_equal(fph[sample].cpu().numpy().reshape(-1), o["frame_ph"])
+    np.testing.assert_array_equal(fix[sample].cpu().numpy().reshape(-1), o["frame_idx"])
+    dpf = r.dp_final[sample].cpu().numpy()
+    for i in range(len(sample)):
+        m = orc.prep(lp_s[i].numpy(), tgt_s[i].numpy().astype(np.int32), orc.params(Cc - 1, 0))
+        acc = np.float32(m[0, o["frame_ph"][i * T]])
+        for t in range(1, T):
+            acc = np.float32(acc + m[t, o["frame_ph"][i * T + t]])
+        assert abs(dpf[i] - acc) <= RTOL * abs(acc)
+
+
+def test_host_entry_matches_device_entry(bfa, dev):
+    """bfa_align_batch_host (host buffers, chunked copies) == bfa_align_batch on the same data."""
+    from bfa_b200 import synth
+    B, T, N, Cc = 300, 200, 20, 67
+    lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=55, peak=10.0, sil_every=7, sil_frames=14)
+    au = bfa.AlignmentUtils(Cc - 1, 0)
+    p = au.viterbi_decoder._params(True, True, True)
+    r = au.viterbi_decoder.align_batch(lp.to(dev), torch.arange(B, dtype=torch.int64, device=dev) * T * Cc, [T] * B, Cc,
+                                       tgt.to(torch.int32).reshape(-1).to(dev), [N] * B, params=p)
+    h = bfa.align_host(p, lp.numpy(), np.arange(B, dtype=np.int64) * T * Cc, np.full(B, T, np.int32), Cc,
+                       tgt.numpy().astype(np.int32).reshape(-1), np.arange(B + 1, dtype=np.int64) * N, chunk_utts=64)
+    np.testing.assert_array_equal(h["frame_ph"], r.frame_ph.cpu().numpy())
+    np.testing.assert_array_equal(h["frame_idx"], r.frame_idx.cpu().numpy())
+    np.testing.assert_array_equal(h["status"], r.status.cpu().numpy())
+    np.testing.assert_array_equal(h["n_stamps"], r.n_stamps.cpu().numpy())
+    n = h["n_stamps"]
+    for b in range(B):
+        np.testing.assert_array_equal(h["stamps"][b, :n[b]], r.stamps[b, :n[b]].cpu().numpy())
+        np.testing.assert_array_equal(h["conf"][b, :n[b]], r.conf[b, :n[b]].cpu().numpy())
