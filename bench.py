@@ -284,7 +284,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         h2d = lp_h.numel() * 4 + tgt_h.numel() * 4 + B * 8 + B * 4 + 2 * (B + 1) * 8
-        d2h = sum(v.nbytes for v in out.values())
+        d2h = sum(v.nbytes for v in out.values() if hasattr(v, 'nbytes') and v is not out.get('frame_off'))
         e2e = {"value": world * B * T * ke / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": ke, "ms_per_step": dt / ke * 1e3, "api": "bfa_align_batch_host (pinned host buffers, 512-utterance chunks, 2 streams)"}
         lib.bfa_host_release()
