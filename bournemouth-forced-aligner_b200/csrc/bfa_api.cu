@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <type_traits>
@@ -12,6 +13,7 @@
 #include "assort.cuh"
 #include "bfa_common.cuh"
 #include "plan.cuh"
+#include "viterbi_band.cuh"
 #include "viterbi_generic.cuh"
 
 using namespace bfa;
@@ -52,8 +54,15 @@ struct DeviceInfo {
     int sms = 0;
     int vg_ctas_per_sm = 0;      // short-path class (L <= 256)
     int vg_ctas_per_sm_big = 0;  // long-path class
+    bool band_ok = false;        // banded kernel usable (dynamic smem attribute set)
     bool ok = false;
 };
+
+inline int band_rec_words(int G) { return 6 * G + 1; }
+inline int band_smem_bytes_per_warp(int C, int G) {
+    size_t b = (size_t)BK_NST * BK_UPW * BK_ROWS * C * 4 + BK_PAD * 4 + BK_NST * BK_UPW * 8 + (size_t)band_rec_words(G) * 32 * 4;
+    return (int)((b + 127) / 128 * 128);
+}
 
 int device_info(DeviceInfo& out) {
     static std::mutex mu;
@@ -71,6 +80,9 @@ int device_info(DeviceInfo& out) {
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.vg_ctas_per_sm_big, viterbi_generic_kernel<1>, VG_WARPS * 32, smem));
         if (d.vg_ctas_per_sm < 1) d.vg_ctas_per_sm = 1;
         if (d.vg_ctas_per_sm_big < 1) d.vg_ctas_per_sm_big = 1;
+        const int band_smem_max = band_smem_bytes_per_warp(72, 4) * BK_WARPS;
+        d.band_ok = cudaFuncSetAttribute(viterbi_band_kernel<3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_max) == cudaSuccess &&
+                    cudaFuncSetAttribute(viterbi_band_kernel<4, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_max) == cudaSuccess;
         d.ok = true;
     }
     out = d;
@@ -85,8 +97,12 @@ struct Layout {
     int item_cap, gmax, amax, anchor_words, list_ints, max_L, bp_words_per_lane;
     int resident_warps;
     long long slab_words;
-    size_t off_tmask, off_rowstat, off_items_local, off_items, off_lists, off_padded, off_anchors, off_counters, off_bp, total;
+    int band_grid, band_smem_per_warp[2];
+    long long band_slab_words[2];
+    size_t off_tmask, off_tgtok, off_need, off_rowstat, off_items_local, off_items, off_fast[2], off_lists, off_padded, off_anchors, off_counters,
+        off_bp, total;
 };
+
 
 int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layout& L) {
     if (s.B < 0 || s.C <= 0 || s.max_T < 0 || s.max_N < 0) return BFA_E_INVALID;
@@ -108,30 +124,43 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
     L.bp_words_per_lane = (maxL > 512) ? 2 : 1;
     L.resident_warps = d.sms * d.vg_ctas_per_sm * VG_WARPS;
     L.slab_words = (long long)(s.max_T + 2) * 32 * L.bp_words_per_lane;
+    L.band_grid = d.sms;
+    size_t band_bytes = 0;
+    for (int v = 0; v < 2; ++v) {
+        const int G = 3 + v;
+        L.band_smem_per_warp[v] = band_smem_bytes_per_warp(s.C, G);
+        L.band_slab_words[v] = (long long)((s.max_T + 31) / 32 + 1) * band_rec_words(G) * 32;
+        band_bytes = std::max<size_t>(band_bytes, (size_t)L.band_grid * BK_WARPS * (size_t)L.band_slab_words[v] * 4);
+    }
     size_t o = 0;
     L.off_tmask = o; o = align_up(o + (size_t)s.B * MAX_WORDS * 4);
-    L.off_rowstat = o; o = align_up(o + (p.boost_targets && p.mode == BFA_MODE_FULL ? (size_t)s.total_frames * 8 : 0));
+    L.off_tgtok = o; o = align_up(o + (size_t)s.B * 4);
+    L.off_need = o; o = align_up(o + (size_t)s.B * 4);
+    L.off_rowstat = o; o = align_up(o + (p.boost_targets && L.segmenting ? (size_t)s.total_frames * 8 : 0));
     L.off_items_local = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
     L.off_items = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
+    L.off_fast[0] = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
+    L.off_fast[1] = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
     L.off_lists = o; o = align_up(o + (size_t)s.B * L.list_ints * 4);
     L.off_padded = o; o = align_up(o + (L.segmenting ? (size_t)s.B * (s.max_T + 16) * 4 : 0));
     L.off_anchors = o; o = align_up(o + (size_t)s.B * L.anchor_words * 4);
     L.off_counters = o; o = align_up(o + 64);
-    L.off_bp = o; o = align_up(o + (size_t)L.resident_warps * L.slab_words * 4);
+    // the banded and the generic kernels are stream-ordered, so their back-pointer slabs share one region
+    L.off_bp = o; o = align_up(o + std::max<size_t>((size_t)L.resident_warps * (size_t)L.slab_words * 4, band_bytes));
     L.total = o;
     return BFA_OK;
 }
 
 // max_L: upper bound of the path length of any item; the long-path kernel is only launched when
 // an item can need it.  Both classes use the same per-warp slabs (kernels are stream-ordered).
-int launch_viterbi(VitArgs& va, int max_items, int max_L, const DeviceInfo& d, cudaStream_t st) {
+int launch_viterbi(VitArgs& va, int max_items, int max_L, const DeviceInfo& d, cudaStream_t st, bool profile = true) {
     int want = (max_items + VG_WARPS - 1) / VG_WARPS;
     if (want < 1) want = 1;
     int ctas = want < d.sms * d.vg_ctas_per_sm ? want : d.sms * d.vg_ctas_per_sm;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_prof.mu);
-        if (g_prof.on) { e0 = g_prof.get(); e1 = g_prof.get(); }
+        if (g_prof.on && profile) { e0 = g_prof.get(); e1 = g_prof.get(); }
     }
     if (e0) cudaEventRecord(e0, st);
     viterbi_generic_kernel<0><<<ctas, VG_WARPS * 32, sizeof(WarpSmem) * VG_WARPS, st>>>(va);
@@ -220,15 +249,21 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     const bool boost = p->boost_targets && p->mode == BFA_MODE_FULL;
 
     uint32_t* tmask = (uint32_t*)(ws + L.off_tmask);
-    float2* rowstat = boost ? (float2*)(ws + L.off_rowstat) : nullptr;
+    float2* rowstat = (boost && L.segmenting) ? (float2*)(ws + L.off_rowstat) : nullptr;
     int* counters = (int*)(ws + L.off_counters);
     CUDA_TRY(cudaMemsetAsync(counters, 0, 64, st));
 
-    tmask_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, C, p->blank_id, tgt, (const long long*)tgt_off, tmask);
+    uint32_t* tgt_ok = (uint32_t*)(ws + L.off_tgtok);
+    uint32_t* need_stats = (uint32_t*)(ws + L.off_need);
+    tmask_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, C, p->blank_id, p->silence_id, L.segmenting ? 1 : 0, tgt, (const long long*)tgt_off, tmask,
+                                              tgt_ok, need_stats);
     LAUNCH_CHECK();
-    if (boost && shape->max_T > 0) {
-        dim3 grid((shape->max_T + 7) / 8, B);
-        rowstat_kernel<<<grid, 256, 0, st>>>(C, p->boost_factor, logp, (const long long*)row_off, T, (const long long*)frame_off, tmask, rowstat);
+    // Row statistics are only materialised for the planner's silence scan (utterances whose target holds
+    // SIL); the Viterbi kernels fuse boost + log_softmax + floor into their row loads.
+    if (rowstat && shape->max_T > 0) {
+        dim3 grid((shape->max_T + 63) / 64, B);
+        rowstat_kernel<<<grid, 256, 0, st>>>(C, p->boost_factor, logp, (const long long*)row_off, T, (const long long*)frame_off, tmask,
+                                             need_stats, rowstat);
         LAUNCH_CHECK();
     }
     PlanArgs pa;
@@ -239,18 +274,48 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     pa.item_cap = L.item_cap; pa.gmax = L.gmax; pa.amax = L.amax; pa.anchor_words = L.anchor_words;
     pa.items_local = (Item*)(ws + L.off_items_local); pa.items = (Item*)(ws + L.off_items);
     pa.n_items = counters; pa.lists = (int32_t*)(ws + L.off_lists); pa.list_ints = L.list_ints;
+    const bool fast = (p->reserved & 1) == 0 && C <= 72 && d.band_ok;
+    for (int v = 0; v < 2; ++v) { pa.fast_items[v] = (Item*)(ws + L.off_fast[v]); pa.n_fast[v] = counters + 3 + 2 * v; }
+    pa.fast_enable = fast ? 1 : 0; pa.tgt_ok = tgt_ok;
     pa.padded = (float*)(ws + L.off_padded); pa.anchors = (uint32_t*)(ws + L.off_anchors);
     plan_kernel<<<(B + 3) / 4, 128, 0, st>>>(pa);
     LAUNCH_CHECK();
 
+    long long max_items = (long long)B * L.item_cap;
+    if (fast) {
+        BandArgs ba;
+        ba.p = *p; ba.C = C; ba.logp = logp; ba.tgt = tgt; ba.tmask = tmask;
+        ba.retry_items = pa.items; ba.n_retry = counters;
+        ba.frame_ph = frame_ph; ba.frame_idx = frame_idx; ba.dp_final = dp_final;
+        ba.bp_scratch = (uint32_t*)(ws + L.off_bp); ba.seg_stride = BK_ROWS * C;
+        for (int v = 0; v < 2; ++v) {
+            ba.items = pa.fast_items[v]; ba.n_items = pa.n_fast[v];
+            ba.bp_slab_words = L.band_slab_words[v]; ba.smem_per_warp = L.band_smem_per_warp[v];
+            const size_t smem = (size_t)ba.smem_per_warp * BK_WARPS;
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (v == 0) {
+                std::lock_guard<std::mutex> lk(g_prof.mu);
+                if (g_prof.on) { e0 = g_prof.get(); e1 = g_prof.get(); }
+            }
+            if (e0) cudaEventRecord(e0, st);
+            if (v == 0) viterbi_band_kernel<3, 9><<<L.band_grid, BK_WARPS * 32, smem, st>>>(ba);
+            else viterbi_band_kernel<4, 9><<<L.band_grid, BK_WARPS * 32, smem, st>>>(ba);
+            LAUNCH_CHECK();
+            if (e0) {
+                cudaEventRecord(e1, st);
+                std::lock_guard<std::mutex> lk(g_prof.mu);
+                g_prof.pending.emplace_back(e0, e1);
+            }
+        }
+    }
+
     VitArgs va;
-    va.p = *p; va.C = C; va.logp = logp; va.rowstat = rowstat; va.tmask = tmask; va.tgt = tgt;
+    va.p = *p; va.C = C; va.logp = logp; va.tmask = tmask; va.tgt = tgt;
     va.path = nullptr; va.true_idx = nullptr; va.anchors = pa.anchors; va.items = pa.items;
     va.n_items = counters; va.work_counter = counters + 1;
     va.frame_ph = frame_ph; va.frame_idx = frame_idx; va.dp_final = dp_final; va.status = status; va.final_state = nullptr;
     va.bp_scratch = (uint32_t*)(ws + L.off_bp); va.bp_slab_words = L.slab_words;
-    long long max_items = (long long)B * L.item_cap;
-    rc = launch_viterbi(va, (int)(max_items > (1 << 30) ? (1 << 30) : max_items), L.max_L, d, st);
+    rc = launch_viterbi(va, (int)(max_items > (1 << 30) ? (1 << 30) : max_items), L.max_L, d, st, !fast);
     if (rc) return rc;
 
     if (stamps) {
@@ -296,7 +361,7 @@ int bfa_viterbi_paths(const BfaParams* p, int32_t n_items, int32_t C, int32_t ma
                                                                     Lp, band, (const long long*)frame_off, items, counters);
     LAUNCH_CHECK();
     VitArgs va;
-    va.p = *p; va.C = C; va.logp = logp; va.rowstat = nullptr; va.tmask = nullptr; va.tgt = nullptr;
+    va.p = *p; va.C = C; va.logp = logp; va.tmask = nullptr; va.tgt = nullptr;
     va.path = path; va.true_idx = true_idx; va.anchors = nullptr; va.items = items;
     va.n_items = counters; va.work_counter = counters + 1;
     va.frame_ph = frame_ph; va.frame_idx = frame_idx; va.dp_final = dp_final; va.status = nullptr; va.final_state = final_state;

@@ -83,6 +83,31 @@ __device__ __forceinline__ int warp_max_i(int v) {
     return v;
 }
 
+// Row statistics of the boosted row (forced_alignment.py:51-54): (max, log sum exp(x + b - max)).
+// One warp per row, lane owns classes lane + 32*i; `get(c)` returns the raw value of class c.  Shared by
+// rowstat_kernel (planner's silence scan) and the generic Viterbi kernel so both see identical bits.
+template <typename Get>
+__device__ __forceinline__ float2 row_stats_warp(Get get, int C, int lane, uint32_t tbits, float boost) {
+    float v[MAX_WORDS];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < MAX_WORDS; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = -INFINITY;
+        if (c < C) {
+            v[i] = get(c) + (((tbits >> i) & 1u) ? boost : 0.0f);
+            mx = fmaxf(mx, v[i]);
+        }
+    }
+    mx = warp_max(mx);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_WORDS; ++i)
+        if (lane + 32 * i < C) s += expf(v[i] - mx);
+    s = warp_sum(s);
+    return make_float2(mx, logf(s));
+}
+
 // Modified log-prob of one class of one row = what the reference materialises at
 // forced_alignment.py:121-129:  boost (+5 on target classes) -> log_softmax -> floor at log(1e-8).
 // (m, ls) are the row's max and log-sum-exp of the boosted row (rowstat kernel).

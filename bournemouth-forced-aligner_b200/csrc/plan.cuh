@@ -10,6 +10,7 @@
 // its length stay on the device.
 #pragma once
 #include "bfa_common.cuh"
+#include "viterbi_band.cuh"
 
 namespace bfa {
 
@@ -33,8 +34,12 @@ struct PlanArgs {
     int gmax, amax;            // list capacities per utterance
     int anchor_words;          // anchor words per utterance
     Item* items_local;         // [B][item_cap]
-    Item* items;               // compacted list
+    Item* items;               // compacted list for the exact generic kernel
     int* n_items;              // device counter
+    Item* fast_items[2];       // compacted lists for the banded kernel (window 24 / 32 groups)
+    int* n_fast[2];
+    int fast_enable;
+    uint32_t* tgt_ok;          // [B] 1 when every target id is a valid non-blank class
     int32_t* lists;            // [B][list_ints]
     int list_ints;
     float* padded;             // [B][max_T + 16]
@@ -42,16 +47,18 @@ struct PlanArgs {
 };
 
 // ---- target-class bitmask: unique_targets = set(seq) - {blank, -100}, p < C (:44-49) ----
-__global__ void tmask_kernel(int B, int C, int blank_id, const int32_t* tgt, const long long* tgt_off, uint32_t* tmask) {
+__global__ void tmask_kernel(int B, int C, int blank_id, int silence_id, int segmenting, const int32_t* tgt,
+                             const long long* tgt_off, uint32_t* tmask, uint32_t* tgt_ok, uint32_t* need_stats) {
     int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (u >= B) return;
     uint32_t w[MAX_WORDS];
 #pragma unroll
     for (int i = 0; i < MAX_WORDS; ++i) w[i] = 0;
     long long b = tgt_off[u], e = tgt_off[u + 1];
+    bool all_ok = true;
     for (long long j = b + lane; j < e; j += 32) {
         int c = tgt[j];
-        if (c == blank_id || c == -100 || c < 0 || c >= C) continue;
+        if (c == blank_id || c == -100 || c < 0 || c >= C) { all_ok = false; continue; }
 #pragma unroll
         for (int i = 0; i < MAX_WORDS; ++i)
             if ((c >> 5) == i) w[i] |= 1u << (c & 31);
@@ -62,35 +69,45 @@ __global__ void tmask_kernel(int B, int C, int blank_id, const int32_t* tgt, con
         for (int d = 16; d >= 1; d >>= 1) v |= __shfl_xor_sync(FULL, v, d);
         if (lane == 0) tmask[(size_t)u * MAX_WORDS + i] = v;
     }
+    all_ok = __all_sync(FULL, all_ok);
+    // silence scan (and its row statistics) only when the target holds SIL (forced_alignment.py:291-295)
+    bool has_sil = false;
+    if (segmenting && silence_id >= 0 && silence_id < C) {
+        for (long long j = b + lane; j < e; j += 32) has_sil |= (tgt[j] == silence_id);
+        has_sil = __any_sync(FULL, has_sil);
+    }
+    if (lane == 0) { tgt_ok[u] = all_ok ? 1u : 0u; need_stats[u] = has_sil ? 1u : 0u; }
+}
+
+// Which kernel runs an item: 0 / 1 = banded kernel with a 24 / 32-group window, -1 = exact generic kernel.
+__device__ __forceinline__ int fast_class(const Item& it, int C, const float* logp, bool tgt_ok, int fast_enable) {
+    if (!fast_enable || !tgt_ok) return -1;
+    if (it.stride != 4 || (it.flags & ITEM_ANCHOR) || C > 72 || it.T < 2 || it.L > it.T) return -1;
+    if (((unsigned long long)(logp + it.lp_off) & 15ull) != 0) return -1;   // bulk copies need 16-B aligned rows
+    if (band_window_fits(it.n, it.band, 24)) return 0;
+    if (band_window_fits(it.n, it.band, 32)) return 1;
+    return -1;
 }
 
 // ---- row statistics of the boosted row: max and log(sum exp(x - max)) (:51-54) ----
-// grid = (ceil(max_T / rows_per_cta), B); one warp per row.
+// Only the planner's silence scan needs them materialised (the Viterbi kernels fuse them), i.e. only
+// utterances whose target contains SIL while silence anchoring is on: need[u].
+// grid = (ceil(max_T / 64), B); 8 warps per CTA, 8 rows per warp.
 __global__ void rowstat_kernel(int C, float boost, const float* __restrict__ logp, const long long* row_off, const int32_t* T,
-                               const long long* frame_off, const uint32_t* tmask, float2* rowstat) {
-    const int u = blockIdx.y, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (t >= T[u]) return;
-    const float* row = logp + row_off[u] + (long long)t * C;
-    float v[MAX_WORDS];
-    float mx = -INFINITY;
+                               const long long* frame_off, const uint32_t* tmask, const uint32_t* need, float2* rowstat) {
+    const int u = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (!need[u]) return;
+    const int Tu = T[u];
+    uint32_t tbits = 0;
 #pragma unroll
-    for (int i = 0; i < MAX_WORDS; ++i) {
-        int c = lane + 32 * i;
-        v[i] = -INFINITY;
-        if (c < C) {
-            bool tg = (tmask[(size_t)u * MAX_WORDS + i] >> lane) & 1u;
-            v[i] = row[c] + (tg ? boost : 0.0f);
-            mx = fmaxf(mx, v[i]);
-        }
+    for (int i = 0; i < MAX_WORDS; ++i) tbits |= ((tmask[(size_t)u * MAX_WORDS + i] >> lane) & 1u) << i;
+    for (int r = 0; r < 8; ++r) {
+        const int t = blockIdx.x * 64 + warp * 8 + r;
+        if (t >= Tu) return;
+        const float* row = logp + row_off[u] + (long long)t * C;
+        float2 st = row_stats_warp([&](int c) { return row[c]; }, C, lane, tbits, boost);
+        if (lane == 0) rowstat[frame_off[u] + t] = st;
     }
-    mx = warp_max(mx);
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAX_WORDS; ++i)
-        if (lane + 32 * i < C) s += expf(v[i] - mx);
-    s = warp_sum(s);
-    if (lane == 0) rowstat[frame_off[u] + t] = make_float2(mx, logf(s));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -422,11 +439,24 @@ __global__ void plan_kernel(PlanArgs a) {
     }
     __syncwarp();
     if (lane == 0) a.status[u] = st;
-    // publish this utterance's items into the compact global list
-    int base = 0;
-    if (lane == 0 && n_items > 0) base = atomicAdd(a.n_items, n_items);
-    base = __shfl_sync(FULL, base, 0);
-    for (int i = lane; i < n_items; i += 32) a.items[base + i] = loc[i];
+    // publish this utterance's items into the compact global lists (banded kernels / exact kernel)
+    const bool tok = a.tgt_ok[u] != 0;
+    for (int i0 = 0; i0 < n_items; i0 += 32) {
+        const int i = i0 + lane;
+        int cl = -2;
+        if (i < n_items) cl = fast_class(loc[i], a.C, a.logp, tok, a.fast_enable);
+#pragma unroll
+        for (int c = -1; c <= 1; ++c) {
+            const unsigned m = __ballot_sync(FULL, cl == c);
+            if (!m) continue;
+            int* cnt = (c < 0) ? a.n_items : a.n_fast[c];
+            Item* dst = (c < 0) ? a.items : a.fast_items[c];
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cnt, __popc(m));
+            base = __shfl_sync(FULL, base, 0);
+            if (cl == c) dst[base + __popc(m & ((1u << lane) - 1u))] = loc[i];
+        }
+    }
 }
 
 // Build explicit-path items from parallel arrays (bfa_viterbi_paths entry).

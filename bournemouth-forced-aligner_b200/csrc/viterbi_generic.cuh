@@ -24,7 +24,6 @@ struct VitArgs {
     BfaParams p;
     int C;
     const float* logp;
-    const float2* rowstat;      // (max, log-sum-exp) of the boosted row, per global frame; may be null
     const uint32_t* tmask;      // [B][MAX_WORDS] target-class bitmask; may be null (explicit items)
     const int32_t* tgt;         // flat targets (structured items)
     const int32_t* path;        // explicit path arrays (explicit items)
@@ -156,7 +155,6 @@ __device__ void run_item(const VitArgs& a, const Item& it, WarpSmem& sm, Stream&
         st.ready = 0;
     }
 
-    float2 stat_blk = make_float2(0.f, 0.f);   // lane q holds the row stats of frame (blk*32 + q)
     uint32_t anc_blk = 0;                       // lane q holds anchor word q of the current 256-frame block
 
     // transform row t into rowbuf[t & 1]
@@ -164,11 +162,11 @@ __device__ void run_item(const VitArgs& a, const Item& it, WarpSmem& sm, Stream&
         int pos = st.shift + t * C;
         stream_advance(sm, st, pos, pos + C - 1, lane, pol);
         __syncwarp();
-        if (use_stats && (t & 31) == 0) {
-            int tt = t + lane;
-            if (tt < T) stat_blk = a.rowstat[it.stat_off + tt];
+        float m = 0.f, ls = 0.f;
+        if (use_stats) {   // boost + log_softmax statistics of this row (:51-54), same bits as rowstat_kernel
+            float2 st2 = row_stats_warp([&](int c) { return sm.ring[(pos + c) & (RING - 1)]; }, C, lane, tbits, a.p.boost_factor);
+            m = st2.x; ls = st2.y;
         }
-        float m = __shfl_sync(FULL, stat_blk.x, t & 31), ls = __shfl_sync(FULL, stat_blk.y, t & 31);
         int cnt = 0;
         if (has_anchor) {
             if ((t & 255) == 0) {
