@@ -73,6 +73,28 @@ class BatchResult:
         return out
 
 
+class BatchPlan:
+    """Device-resident shape metadata of one ragged batch (frame / target offsets, lengths, BfaShape)."""
+
+    def __init__(self, T, N, C_, params, dev, max_stamps=None):
+        B = len(T)
+        self.T_np = np.asarray(T, np.int32)
+        N_np = np.asarray(N, np.int64)
+        frame_off_np = np.zeros(B + 1, np.int64); np.cumsum(self.T_np, out=frame_off_np[1:])
+        tgt_off_np = np.zeros(B + 1, np.int64); np.cumsum(N_np, out=tgt_off_np[1:])
+        self.B, self.total = B, int(frame_off_np[-1])
+        max_T = int(self.T_np.max()) if B else 0
+        max_N = int(N_np.max()) if B else 0
+        if max_stamps is None:
+            max_stamps = (2 * max_N + 8) if params.ignore_noise else max(max_T, 1)
+        self.max_stamps = int(max_stamps)
+        self.shape = BfaShape(B, C_, max_T, max_N, self.total, self.max_stamps, 0)
+        meta = torch.from_numpy(np.concatenate([frame_off_np, tgt_off_np])).to(dev)
+        self.frame_off, self.tgt_off = meta[: B + 1], meta[B + 1:]
+        self.T_dev = torch.from_numpy(self.T_np).to(dev)
+        self.ws_bytes = None
+
+
 class ViterbiDecoder:
     """forced_alignment.py:11-834 (same constructor signature, :16)."""
 
@@ -105,49 +127,48 @@ class ViterbiDecoder:
         return p
 
     # ---- batched core ----------------------------------------------------------------------
+    def plan_batch(self, T: Sequence[int], N: Sequence[int], C_: int, *, params: BfaParams, device, max_stamps=None) -> "BatchPlan":
+        """Shape metadata of a ragged batch, uploaded once; reusable for every call with the same (T, N)."""
+        return BatchPlan(T, N, C_, params, torch.device(device), max_stamps)
+
     def align_batch(self, log_probs: torch.Tensor, row_off: torch.Tensor, T: Sequence[int], C_: int, tgt: torch.Tensor,
-                    N: Sequence[int], *, params: BfaParams, want_stamps=True, want_conf=True, max_stamps=None) -> BatchResult:
+                    N: Sequence[int], *, params: BfaParams, want_stamps=True, want_conf=True, max_stamps=None,
+                    plan: Optional["BatchPlan"] = None, out: Optional[BatchResult] = None) -> BatchResult:
         """Ragged batch through bfa_align_batch.  log_probs: flat/any-shape fp32 CUDA tensor holding the rows,
-        row_off int64[B] element offsets (CUDA), T/N python sequences, tgt flat int32 CUDA targets."""
+        row_off int64[B] element offsets (CUDA), T/N python sequences, tgt flat int32 CUDA targets.
+        `plan` (from plan_batch) skips the per-call metadata upload, `out` reuses a previous result's buffers."""
         _require_cuda(log_probs, "log_probs")
         dev = log_probs.device
         if log_probs.dtype != torch.float32 or not log_probs.is_contiguous():
             raise BfaError("log_probs must be contiguous float32")
-        B = len(T)
-        T_np = np.asarray(T, np.int32)
-        N_np = np.asarray(N, np.int64)
-        frame_off_np = np.zeros(B + 1, np.int64); np.cumsum(T_np, out=frame_off_np[1:])
-        tgt_off_np = np.zeros(B + 1, np.int64); np.cumsum(N_np, out=tgt_off_np[1:])
-        total = int(frame_off_np[-1])
-        max_T = int(T_np.max()) if B else 0
-        max_N = int(N_np.max()) if B else 0
-        if max_stamps is None:
-            max_stamps = (2 * max_N + 8) if params.ignore_noise else max(max_T, 1)
-        shape = BfaShape(B, C_, max_T, max_N, total, int(max_stamps), 0)
-        meta = torch.from_numpy(np.concatenate([frame_off_np, tgt_off_np])).to(dev, non_blocking=True)
-        frame_off, tgt_off = meta[: B + 1], meta[B + 1:]
-        T_dev = torch.from_numpy(T_np).to(dev, non_blocking=True)
-        frame_ph = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-        frame_idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-        dp_final = torch.empty(max(B, 1), dtype=torch.float32, device=dev)
-        status = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
-        stamps = conf = n_stamps = None
-        if want_stamps:
-            stamps = torch.empty((max(B, 1), max_stamps, 4), dtype=torch.int32, device=dev)
-            n_stamps = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
-            if want_conf:
-                conf = torch.empty((max(B, 1), max_stamps), dtype=torch.float32, device=dev)
+        if plan is None:
+            plan = BatchPlan(T, N, C_, params, dev, max_stamps)
+        B, total, ms = plan.B, plan.total, plan.max_stamps
+        if out is None:
+            frame_ph = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+            frame_idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+            dp_final = torch.empty(max(B, 1), dtype=torch.float32, device=dev)
+            status = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
+            stamps = conf = n_stamps = None
+            if want_stamps:
+                stamps = torch.empty((max(B, 1), ms, 4), dtype=torch.int32, device=dev)
+                n_stamps = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
+                if want_conf:
+                    conf = torch.empty((max(B, 1), ms), dtype=torch.float32, device=dev)
+            out = BatchResult(frame_ph, frame_idx, plan.frame_off, dp_final, status, stamps, conf, n_stamps, plan.T_np, ms)
         l = _cabi.lib()
         with torch.cuda.device(dev):
-            ws_bytes = l.bfa_workspace_bytes(C.byref(params), C.byref(shape))
-            if ws_bytes == 0 and B > 0:
-                _cabi.check(_cabi.BFA_E_UNSUPPORTED)
-            ws = self._ws.get(max(ws_bytes, 256), dev)
-            rc = l.bfa_align_batch(C.byref(params), C.byref(shape), _ptr(log_probs), _ptr(row_off), _ptr(T_dev), _ptr(tgt),
-                                   _ptr(tgt_off), _ptr(frame_ph), _ptr(frame_idx), _ptr(frame_off), _ptr(dp_final), _ptr(status),
-                                   _ptr(stamps), _ptr(conf), _ptr(n_stamps), _ptr(ws), ws.numel(), _stream(dev))
+            if plan.ws_bytes is None:
+                plan.ws_bytes = l.bfa_workspace_bytes(C.byref(params), C.byref(plan.shape))
+                if plan.ws_bytes == 0 and B > 0:
+                    _cabi.check(_cabi.BFA_E_UNSUPPORTED)
+            ws = self._ws.get(max(plan.ws_bytes, 256), dev)
+            rc = l.bfa_align_batch(C.byref(params), C.byref(plan.shape), _ptr(log_probs), _ptr(row_off), _ptr(plan.T_dev), _ptr(tgt),
+                                   _ptr(plan.tgt_off), _ptr(out.frame_ph), _ptr(out.frame_idx), _ptr(plan.frame_off), _ptr(out.dp_final),
+                                   _ptr(out.status), _ptr(out.stamps), _ptr(out.conf), _ptr(out.n_stamps), _ptr(ws), ws.numel(),
+                                   _stream(dev))
         _cabi.check(rc)
-        return BatchResult(frame_ph, frame_idx, frame_off, dp_final, status, stamps, conf, n_stamps, T_np, max_stamps)
+        return out
 
     @staticmethod
     def _raise_if_too_short(status_np, T, N):

@@ -60,7 +60,8 @@ struct DeviceInfo {
 
 inline int band_rec_words(int G) { return 6 * G + 1; }
 inline int band_smem_bytes_per_warp(int C, int G) {
-    size_t b = (size_t)BK_NST * BK_UPW * BK_ROWS * C * 4 + BK_PAD * 4 + BK_NST * BK_UPW * 8 + (size_t)band_rec_words(G) * 32 * 4;
+    // stage buffers + zero pad + mbarriers + back-trace staging ([UPW][8G*4 cells] x 8 B + 32 shift-flag words)
+    size_t b = (size_t)BK_NST * BK_UPW * BK_ROWS * C * 4 + BK_PAD * 4 + BK_NST * BK_UPW * 8 + (size_t)BK_UPW * 8 * G * 4 * 8 + 32 * 4;
     return (int)((b + 127) / 128 * 128);
 }
 
@@ -253,17 +254,11 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     int* counters = (int*)(ws + L.off_counters);
     CUDA_TRY(cudaMemsetAsync(counters, 0, 64, st));
 
-    uint32_t* tgt_ok = (uint32_t*)(ws + L.off_tgtok);
-    uint32_t* need_stats = (uint32_t*)(ws + L.off_need);
-    tmask_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, C, p->blank_id, p->silence_id, L.segmenting ? 1 : 0, tgt, (const long long*)tgt_off, tmask,
-                                              tgt_ok, need_stats);
-    LAUNCH_CHECK();
     // Row statistics are only materialised for the planner's silence scan (utterances whose target holds
     // SIL); the Viterbi kernels fuse boost + log_softmax + floor into their row loads.
     if (rowstat && shape->max_T > 0) {
-        dim3 grid((shape->max_T + 63) / 64, B);
-        rowstat_kernel<<<grid, 256, 0, st>>>(C, p->boost_factor, logp, (const long long*)row_off, T, (const long long*)frame_off, tmask,
-                                             need_stats, rowstat);
+        rowstat_kernel<<<B, 256, 0, st>>>(C, p->blank_id, p->silence_id, p->boost_factor, logp, (const long long*)row_off, T, tgt,
+                                          (const long long*)tgt_off, (const long long*)frame_off, rowstat);
         LAUNCH_CHECK();
     }
     PlanArgs pa;
@@ -276,7 +271,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     pa.n_items = counters; pa.lists = (int32_t*)(ws + L.off_lists); pa.list_ints = L.list_ints;
     const bool fast = (p->reserved & 1) == 0 && C <= 72 && d.band_ok;
     for (int v = 0; v < 2; ++v) { pa.fast_items[v] = (Item*)(ws + L.off_fast[v]); pa.n_fast[v] = counters + 3 + 2 * v; }
-    pa.fast_enable = fast ? 1 : 0; pa.tgt_ok = tgt_ok;
+    pa.fast_enable = fast ? 1 : 0;
     pa.padded = (float*)(ws + L.off_padded); pa.anchors = (uint32_t*)(ws + L.off_anchors);
     plan_kernel<<<(B + 3) / 4, 128, 0, st>>>(pa);
     LAUNCH_CHECK();

@@ -39,7 +39,6 @@ struct PlanArgs {
     Item* fast_items[2];       // compacted lists for the banded kernel (window 24 / 32 groups)
     int* n_fast[2];
     int fast_enable;
-    uint32_t* tgt_ok;          // [B] 1 when every target id is a valid non-blank class
     int32_t* lists;            // [B][list_ints]
     int list_ints;
     float* padded;             // [B][max_T + 16]
@@ -47,36 +46,32 @@ struct PlanArgs {
 };
 
 // ---- target-class bitmask: unique_targets = set(seq) - {blank, -100}, p < C (:44-49) ----
-__global__ void tmask_kernel(int B, int C, int blank_id, int silence_id, int segmenting, const int32_t* tgt,
-                             const long long* tgt_off, uint32_t* tmask, uint32_t* tgt_ok, uint32_t* need_stats) {
-    int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (u >= B) return;
+// Warp-cooperative; returns this lane's view: w[i] = mask word i (all lanes), all_ok = every id is a valid
+// non-blank class, has_sil = the target holds silence_id.
+struct TgtInfo {
     uint32_t w[MAX_WORDS];
+    bool all_ok, has_sil;
+};
+__device__ __forceinline__ TgtInfo target_info(const int32_t* tgt, long long b, long long e, int C, int blank_id, int silence_id,
+                                               int lane) {
+    TgtInfo r;
 #pragma unroll
-    for (int i = 0; i < MAX_WORDS; ++i) w[i] = 0;
-    long long b = tgt_off[u], e = tgt_off[u + 1];
-    bool all_ok = true;
+    for (int i = 0; i < MAX_WORDS; ++i) r.w[i] = 0;
+    bool all_ok = true, has_sil = false;
     for (long long j = b + lane; j < e; j += 32) {
-        int c = tgt[j];
+        const int c = tgt[j];
+        has_sil |= (c == silence_id);
         if (c == blank_id || c == -100 || c < 0 || c >= C) { all_ok = false; continue; }
 #pragma unroll
         for (int i = 0; i < MAX_WORDS; ++i)
-            if ((c >> 5) == i) w[i] |= 1u << (c & 31);
+            if ((c >> 5) == i) r.w[i] |= 1u << (c & 31);
     }
 #pragma unroll
-    for (int i = 0; i < MAX_WORDS; ++i) {
-        uint32_t v = w[i];
-        for (int d = 16; d >= 1; d >>= 1) v |= __shfl_xor_sync(FULL, v, d);
-        if (lane == 0) tmask[(size_t)u * MAX_WORDS + i] = v;
-    }
-    all_ok = __all_sync(FULL, all_ok);
-    // silence scan (and its row statistics) only when the target holds SIL (forced_alignment.py:291-295)
-    bool has_sil = false;
-    if (segmenting && silence_id >= 0 && silence_id < C) {
-        for (long long j = b + lane; j < e; j += 32) has_sil |= (tgt[j] == silence_id);
-        has_sil = __any_sync(FULL, has_sil);
-    }
-    if (lane == 0) { tgt_ok[u] = all_ok ? 1u : 0u; need_stats[u] = has_sil ? 1u : 0u; }
+    for (int i = 0; i < MAX_WORDS; ++i)
+        for (int d = 16; d >= 1; d >>= 1) r.w[i] |= __shfl_xor_sync(FULL, r.w[i], d);
+    r.all_ok = __all_sync(FULL, all_ok);
+    r.has_sil = __any_sync(FULL, has_sil);
+    return r;
 }
 
 // Which kernel runs an item: 0 / 1 = banded kernel with a 24 / 32-group window, -1 = exact generic kernel.
@@ -91,19 +86,19 @@ __device__ __forceinline__ int fast_class(const Item& it, int C, const float* lo
 
 // ---- row statistics of the boosted row: max and log(sum exp(x - max)) (:51-54) ----
 // Only the planner's silence scan needs them materialised (the Viterbi kernels fuse them), i.e. only
-// utterances whose target contains SIL while silence anchoring is on: need[u].
-// grid = (ceil(max_T / 64), B); 8 warps per CTA, 8 rows per warp.
-__global__ void rowstat_kernel(int C, float boost, const float* __restrict__ logp, const long long* row_off, const int32_t* T,
-                               const long long* frame_off, const uint32_t* tmask, const uint32_t* need, float2* rowstat) {
-    const int u = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (!need[u]) return;
+// utterances whose target contains SIL while silence anchoring is on (forced_alignment.py:291-297).
+// One CTA per utterance (8 warps, one row per warp per step); other utterances exit at once.
+__global__ void rowstat_kernel(int C, int blank_id, int silence_id, float boost, const float* __restrict__ logp,
+                               const long long* row_off, const int32_t* T, const int32_t* tgt, const long long* tgt_off,
+                               const long long* frame_off, float2* rowstat) {
+    const int u = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TgtInfo ti = target_info(tgt, tgt_off[u], tgt_off[u + 1], C, blank_id, silence_id, lane);
+    if (!ti.has_sil) return;
     const int Tu = T[u];
     uint32_t tbits = 0;
 #pragma unroll
-    for (int i = 0; i < MAX_WORDS; ++i) tbits |= ((tmask[(size_t)u * MAX_WORDS + i] >> lane) & 1u) << i;
-    for (int r = 0; r < 8; ++r) {
-        const int t = blockIdx.x * 64 + warp * 8 + r;
-        if (t >= Tu) return;
+    for (int i = 0; i < MAX_WORDS; ++i) tbits |= ((ti.w[i] >> lane) & 1u) << i;
+    for (int t = warp; t < Tu; t += (blockDim.x >> 5)) {
         const float* row = logp + row_off[u] + (long long)t * C;
         float2 st = row_stats_warp([&](int c) { return row[c]; }, C, lane, tbits, boost);
         if (lane == 0) rowstat[frame_off[u] + t] = st;
@@ -373,9 +368,20 @@ __global__ void plan_kernel(PlanArgs a) {
     c.seq = a.tgt + a.tgt_off[u];
     c.stat = a.rowstat ? a.rowstat + a.frame_off[u] : nullptr;
     c.padded = a.padded + (size_t)u * (a.max_T + 16);
+    const TgtInfo ti = target_info(a.tgt, a.tgt_off[u], a.tgt_off[u + 1], a.C, p.blank_id, p.silence_id, lane);
+    if (lane < MAX_WORDS) {
+        uint32_t wv = 0;
+#pragma unroll
+        for (int i = 0; i < MAX_WORDS; ++i)
+            if (i == lane) wv = ti.w[i];
+        a.tmask[(size_t)u * MAX_WORDS + lane] = wv;      // consumed by the Viterbi kernels
+    }
     c.sil_is_target = false;
-    if (p.silence_id >= 0 && p.silence_id < a.C)
-        c.sil_is_target = (a.tmask[(size_t)u * MAX_WORDS + (p.silence_id >> 5)] >> (p.silence_id & 31)) & 1u;
+    if (p.silence_id >= 0 && p.silence_id < a.C) {
+#pragma unroll
+        for (int i = 0; i < MAX_WORDS; ++i)
+            if (i == (p.silence_id >> 5)) c.sil_is_target = (ti.w[i] >> (p.silence_id & 31)) & 1u;
+    }
     const int T = c.T, N = c.N;
     const long long o_base = a.frame_off[u], o_lim = a.frame_off[u + 1];
     Item* loc = a.items_local + (size_t)u * a.item_cap;
@@ -440,7 +446,7 @@ __global__ void plan_kernel(PlanArgs a) {
     __syncwarp();
     if (lane == 0) a.status[u] = st;
     // publish this utterance's items into the compact global lists (banded kernels / exact kernel)
-    const bool tok = a.tgt_ok[u] != 0;
+    const bool tok = ti.all_ok;
     for (int i0 = 0; i0 < n_items; i0 += 32) {
         const int i = i0 + lane;
         int cl = -2;

@@ -168,6 +168,7 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
     if (l8 == 0) B3[0] = 0.0f;        // virtual frame -1: only state 0 is alive, with score 0
     int next_crel = (seg_on ? group_class(S::W) : blank) - l8;   // class of the group that enters at the next shift (lane 7)
     const int brel = blank - l8;
+    const bool seg_first = l8 == 0;
 
     // ---- log-sum-exp constants: this lane sums classes l8 + 8*i; out-of-range classes get weight 0 ----
     float kk[NI];
@@ -187,6 +188,7 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
     float fin_val = NEG;
     int fin_g = 0, fin_k = 3, fin_base = 0;
     float emax = -INFINITY;                                        // raw mode: emissions must be <= 0 (log-probabilities)
+    float lse_chk = 0.f;                                           // running sum of the rows' log-sum-exp (finite <=> all rows sane)
 
     for (int c = 0; c < n_chunks; ++c) {
         const int t0 = c * BK_ROWS;
@@ -236,30 +238,61 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
         const int fin_r = T - 1 - t0;                                                         // row of the last frame if it is in this chunk
         const bool fin_here = __any_sync(FULL, fin_r >= 0 && fin_r < BK_ROWS);
 
+        // ---- fused boost + log_softmax statistics (:51-54) of the 8 rows, up front: 72 independent exps per lane,
+        //      tree sums and batched shuffles instead of one dependent chain per frame ----
+        float lnS8[BK_ROWS];
+#pragma unroll
+        for (int r = 0; r < BK_ROWS; ++r) lnS8[r] = 0.f;
+        if (warp_stats) {   // uniform: every item of a call shares the mode
+#pragma unroll
+            for (int r = 0; r < BK_ROWS; ++r) {
+                const float* rp = rowp0 + r * C;
+                float e[NI];
+#pragma unroll
+                for (int i = 0; i < NI; ++i) e[i] = ex2_approx(fmaf(rp[8 * i], LOG2E, kk[i]));
+#pragma unroll
+                for (int w = 1; w < NI; w <<= 1)
+#pragma unroll
+                    for (int i = 0; i + w < NI; i += 2 * w) e[i] += e[i + w];
+                lnS8[r] = e[0];
+            }
+#pragma unroll
+            for (int d = 1; d < BK_LPU; d <<= 1)
+#pragma unroll
+                for (int r = 0; r < BK_ROWS; ++r) lnS8[r] += __shfl_xor_sync(FULL, lnS8[r], d);
+#pragma unroll
+            for (int r = 0; r < BK_ROWS; ++r) {
+                lnS8[r] = lg2_approx(lnS8[r]) * LN2;   // log sum exp(x + b - boost)
+                lse_chk += lnS8[r];                    // any zero / overflowing / NaN sum leaves a non-finite trace here
+            }
+        }
+        // raw emissions of the next frame are fetched one frame ahead
+        float xb_n = rowp0[brel], xp_n[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) xp_n[g] = rowp0[crel[g]];
+
         auto frame = [&](const int r, auto check_fin) {
             constexpr bool CHECK = decltype(check_fin)::value;
             const float* rowp = rowp0 + r * C;
             const bool active = CHECK ? (r <= fin_r) : (t0 < T);
-            // ---- fused boost + log_softmax statistics (:51-54) ----
-            float lnS = 0.f, lse = 0.f;
-            if (warp_stats) {   // uniform: every item of a call shares the mode
-                float s = 0.f;
+            float lnS = lnS8[0];
+            if (CHECK) {
 #pragma unroll
-                for (int i = 0; i < NI; ++i) s += ex2_approx(fmaf(rowp[8 * i], LOG2E, kk[i]));
-                s += __shfl_xor_sync(FULL, s, 1);
-                s += __shfl_xor_sync(FULL, s, 2);
-                s += __shfl_xor_sync(FULL, s, 4);
-                if (use_stats) {
-                    if (active && !(s > 0.f && s < 3.0e38f)) bad = true;
-                    lnS = lg2_approx(s) * LN2;     // log sum exp(x + b - boost)
-                    lse = lnS + boostv;
-                }
+                for (int q = 1; q < BK_ROWS; ++q) lnS = (r == q) ? lnS8[q] : lnS;
+            } else {
+                lnS = lnS8[r];
             }
+            const float lse = warp_stats ? lnS + boostv : 0.f;
             // emissions: blank is never a target (x - lse); phoneme classes are boosted targets (x + boost - lse = x - lnS)
-            const float eb = rowp[brel] - lse;
+            const float eb = xb_n - lse;
             float ep[G];
 #pragma unroll
-            for (int g = 0; g < G; ++g) ep[g] = fmaxf(rowp[crel[g]] - lnS, min_lp);
+            for (int g = 0; g < G; ++g) ep[g] = fmaxf(xp_n[g] - lnS, min_lp);
+            if (r + 1 < BK_ROWS) {
+                xb_n = rowp[C + brel];
+#pragma unroll
+                for (int g = 0; g < G; ++g) xp_n[g] = rowp[C + crel[g]];
+            }
             if (!warp_stats) {
                 float m = eb;
 #pragma unroll
@@ -296,13 +329,16 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
                     base += 1;
                     if (last) next_crel = group_class(base + S::W) - l8;
 #pragma unroll
-                    for (int g = 0; g < G; ++g) ep[g] = fmaxf(rowp[crel[g]] - lnS, min_lp);   // emissions follow their groups
+                    for (int g = 0; g < G; ++g) {   // emissions follow their groups (this frame and the prefetched next one)
+                        ep[g] = fmaxf(rowp[crel[g]] - lnS, min_lp);
+                        if (r + 1 < BK_ROWS) xp_n[g] = rowp[C + crel[g]];
+                    }
                 }
             }
 
             // ---- DP update, right-most group first so that left neighbours are still frame t-1 ----
             float l2 = __shfl_up_sync(FULL, B2[G - 1], 1), l3 = __shfl_up_sync(FULL, B3[G - 1], 1);
-            if (l8 == 0) { l2 = -INFINITY; l3 = -INFINITY; }   // nothing (or a dropped, invalid group) to the left
+            if (seg_first) { l2 = -INFINITY; l3 = -INFINITY; }   // nothing (or a dropped, invalid group) to the left
 #pragma unroll
             for (int g = G - 1; g >= 0; --g) {
                 const float Lb2 = (g > 0) ? B2[(g > 0) ? g - 1 : 0] : l2;
@@ -381,7 +417,7 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
         };
 
         if (!fin_here) {
-#pragma unroll 4
+#pragma unroll
             for (int r = 0; r < BK_ROWS; ++r) frame(r, std::false_type{});
         } else {
 #pragma unroll 1
@@ -397,6 +433,7 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
     }
     __syncwarp();
     if (emax > 0.f) bad = true;
+    if (use_stats && !(fabsf(lse_chk) < 3.0e38f)) bad = true;
     {   // make `bad` uniform per segment
         const unsigned m = __ballot_sync(FULL, bad);
         bad = ((m >> (seg * BK_LPU)) & 0xffu) != 0;
@@ -411,39 +448,46 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
     }
 
     // ---- back-trace (:686-703) ----
+    // A cell is addressed by its window-relative state ci = 4*(g' - base) + k.  Staging lays the record
+    // out as bt2[seg][ci] = (first decision word, second decision word or 0), so one 64-bit shared load
+    // per frame yields (b0, b1) and every transition is  ci -= b1 ? 2 : b0  (p: skip = -2 / advance = -1,
+    // b1: advance = -1, b2: skip = -2 / advance = -1, b3: advance = -1); a window shift adds 4.
     const bool walk = seg_on && !bad && T > 0;
-    int gp = fin_g, k = fin_k, bbase = fin_base;   // window position of frame T-1
-    int keep_g = 0, keep_k = 3;
+    int ci = 4 * (fin_g - fin_base) + fin_k;
+    int sabs0 = 4 * fin_base - 3;          // state of ci = 0 at the current frame
+    int keep_s = 0;
+    uint2* bt2 = reinterpret_cast<uint2*>(bt);                 // [UPW][W*4] (b0 word, b1 word)
+    uint32_t* sfw_s = bt + BK_UPW * S::W * 4 * 2;              // [32] shift-flag words
     const int nblk = (Tmax + 31) >> 5;
     for (int b = nblk - 1; b >= 0; --b) {
         __syncwarp();
         {
             const uint32_t* rec = slab + (size_t)b * S::REC * 32 + lane;
+            uint32_t w[S::REC];
 #pragma unroll
-            for (int i = 0; i < S::REC; ++i) bt[i * 32 + lane] = rec[i * 32];
+            for (int i = 0; i < S::REC; ++i) w[i] = rec[i * 32];
+            uint4* dst = reinterpret_cast<uint4*>(bt2 + seg * S::W * 4 + l8 * G * 4);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                dst[2 * g + 0] = make_uint4(w[6 * g + 0], w[6 * g + 1], w[6 * g + 2], 0u);   // p: (A0, A1)   b1: (A2, 0)
+                dst[2 * g + 1] = make_uint4(w[6 * g + 3], w[6 * g + 4], w[6 * g + 5], 0u);   // b2: (A3, A4)  b3: (A5, 0)
+            }
+            sfw_s[lane] = w[S::ACC];
         }
         __syncwarp();
-        const uint32_t sfw = bt[S::ACC * 32 + lane];
+        const uint32_t sfw = sfw_s[lane];
+        const uint2* cell = bt2 + seg * S::W * 4;
+#pragma unroll 8
         for (int q = 31; q >= 0; --q) {
             const int t = b * 32 + q;
             if (walk && t < T) {
-                if ((t & 7) == l8) { keep_g = gp; keep_k = k; }
+                if ((q & 7) == l8) keep_s = sabs0 + ci;
                 if (t >= 1) {
-                    // decisions of cell (gp, k): first bit id {p:0, b1:2, b2:3, b3:5}; p and b2 own a second bit
-                    const int w = gp - bbase;
-                    const int lw = w / G, sl = w - lw * G;
-                    const int kb2 = (0x5320 >> (4 * k)) & 15;
-                    const uint32_t* wp = bt + (sl * 6 + kb2) * 32 + seg * BK_LPU + lw;
-                    const uint32_t b0 = (wp[0] >> (31 - q)) & 1u, b1 = (wp[32] >> (31 - q)) & 1u;
-                    // branch-free transition: idx = 4k + 2*b1 + b0 -> (new k, group decrement)
-                    //  p : b1 -> (g-1, b2)  else b0 -> (g-1, b3)      b1: b0 -> p
-                    //  b2: b1 -> p          else b0 -> b1             b3: b0 -> b2
-                    const int idx = 4 * k + 2 * (int)b1 + (int)b0;
-                    constexpr uint32_t NEWK = (0u << 0) | (3u << 2) | (2u << 4) | (2u << 6) | (1u << 8) | (0u << 10) | (1u << 12) | (0u << 14) |
-                                              (2u << 16) | (1u << 18) | (0u << 20) | (0u << 22) | (3u << 24) | (2u << 26) | (3u << 28) | (2u << 30);
-                    k = (int)((NEWK >> (2 * idx)) & 3u);
-                    gp -= (int)((0xEu >> idx) & 1u);
-                    bbase -= (int)((sfw >> (31 - q)) & 1u);
+                    const uint2 wv = cell[ci];
+                    const uint32_t b0 = (wv.x >> (31 - q)) & 1u, b1 = (wv.y >> (31 - q)) & 1u;
+                    const uint32_t sf = (sfw >> (31 - q)) & 1u;
+                    ci += (int)(4u * sf) - (int)(b1 ? 2u : b0);
+                    sabs0 -= (int)(4u * sf);
                 }
             }
             if ((q & 7) == 0) {
@@ -453,9 +497,10 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
                     const int rel = tf - trim;
                     const long long o = out_off + rel;
                     if (rel >= 0 && rel < n_out && o < out_lim) {
-                        const bool ph = keep_k == 0;
-                        a.frame_ph[o] = ph ? seq[keep_g - 1] : blank;
-                        a.frame_idx[o] = ph ? idx0 + keep_g - 1 : -1;
+                        const bool ph = ((keep_s + 3) & 3) == 0;      // state s = 4g'-3+k is a phoneme state iff k == 0
+                        const int gi = (keep_s + 3) >> 2;
+                        a.frame_ph[o] = ph ? seq[gi - 1] : blank;
+                        a.frame_idx[o] = ph ? idx0 + gi - 1 : -1;
                     }
                 }
             }
