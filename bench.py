@@ -191,6 +191,8 @@ def main():
     au = bfa_b200.AlignmentUtils(blank_id=Cc - 1, silence_id=0, silence_anchors=10, ignore_noise=True, truly_forced=True)
     dec = au.viterbi_decoder
     params = dec._params(True, True, True)
+    if not bool((tgt == 0).any()):
+        params.reserved |= _cabi.HINT_NO_SIL   # host-side knowledge of the targets (they come from the phonemizer on the host)
     row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T * Cc)
     tgt32 = tgt.to(torch.int32).reshape(-1).contiguous()
     Ts, Ns = [T] * B, [N] * B

@@ -299,6 +299,13 @@ class AlignmentUtils:
         T = self._lens(pred_lens, B, T_max)
         S = int(true_seqs.shape[1]) if true_seqs.dim() == 2 else 0
         N = self._lens(true_seqs_lens, B, S)
+        if not true_seqs.is_cuda and params.silence_id >= 0 and S > 0:
+            # targets still live on the host (core.py builds them there): a free check lets the library skip the
+            # row-statistics pass that only the silence scan needs (BFA_HINT_NO_SIL; purely a performance hint)
+            lens = torch.as_tensor(N)[:, None]
+            has_sil = bool(((true_seqs == params.silence_id) & (torch.arange(S)[None, :] < lens)).any())
+            if not has_sil:
+                params.reserved |= _cabi.HINT_NO_SIL
         seqs = true_seqs.to(dev)
         N_dev = torch.tensor(N, dtype=torch.int64, device=dev)
         mask = torch.arange(S, device=dev)[None, :] < N_dev[:, None]

@@ -31,6 +31,29 @@ __device__ __forceinline__ float stamp_confidence(const float* lp, int T, int C,
     return avg;
 }
 
+// Same as stamp_confidence, but lp[f, ph] comes from the per-frame array the Viterbi kernels gathered
+// (valid because every frame of a stamp was assigned the stamp's phoneme).
+__device__ __forceinline__ float stamp_confidence_path(const float* plp, int T, int start, int end) {
+    int s = max(0, start), e = min(T, end);
+    float avg = expf(plp[s]);
+    if (s < e) {
+        const float half = avg / 2.0f;
+        int good = 1;
+        float mx = 0.f;
+        for (int f = s + 1; f < e; ++f) {
+            float pr = expf(plp[f]);
+            mx = fmaxf(mx, pr);
+            if (pr > half || pr > 0.1f) { avg += pr; ++good; }
+        }
+        if (good > 1) {
+            avg /= (float)good;
+            mx = fmaxf(mx, avg);
+            if (avg < mx / 2.0f) avg = mx;
+        }
+    }
+    return avg;
+}
+
 struct AssortArgs {
     BfaParams p;
     int B, C, max_stamps;
@@ -44,6 +67,7 @@ struct AssortArgs {
     BfaStamp* stamps;
     float* conf;       // may be null
     int32_t* n_stamps;
+    const float* path_lp;   // per-frame gathered lp (or null: gather from logp)
 };
 
 __global__ void assort_confidence_kernel(AssortArgs a) {
@@ -125,7 +149,9 @@ __global__ void assort_confidence_kernel(AssortArgs a) {
         const float* lp = a.logp + a.row_off[u];
         for (int i = lane; i < n; i += 32) {
             BfaStamp s = out[i];
-            a.conf[(size_t)u * a.max_stamps + i] = stamp_confidence(lp, T, a.C, s.phoneme, s.start, s.end);
+            a.conf[(size_t)u * a.max_stamps + i] = (a.path_lp && s.phoneme < a.C)
+                                                       ? stamp_confidence_path(a.path_lp + a.frame_off[u], T, s.start, s.end)
+                                                       : stamp_confidence(lp, T, a.C, s.phoneme, s.start, s.end);
         }
     }
 }

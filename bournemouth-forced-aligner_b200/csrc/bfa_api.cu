@@ -94,14 +94,14 @@ inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 // Workspace carve-up shared by bfa_workspace_bytes and bfa_align_batch.
 struct Layout {
-    bool segmenting;
+    bool segmenting, want_rowstat;
     int item_cap, gmax, amax, anchor_words, list_ints, max_L, bp_words_per_lane;
     int resident_warps;
     long long slab_words;
     int band_grid, band_smem_per_warp[2];
     long long band_slab_words[2];
     size_t off_tmask, off_tgtok, off_need, off_rowstat, off_items_local, off_items, off_fast[2], off_lists, off_padded, off_anchors, off_counters,
-        off_bp, total;
+        off_pathlp, off_bp, total;
 };
 
 
@@ -137,7 +137,8 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
     L.off_tmask = o; o = align_up(o + (size_t)s.B * MAX_WORDS * 4);
     L.off_tgtok = o; o = align_up(o + (size_t)s.B * 4);
     L.off_need = o; o = align_up(o + (size_t)s.B * 4);
-    L.off_rowstat = o; o = align_up(o + (p.boost_targets && L.segmenting ? (size_t)s.total_frames * 8 : 0));
+    L.want_rowstat = p.boost_targets && L.segmenting && !(p.reserved & BFA_HINT_NO_SIL);
+    L.off_rowstat = o; o = align_up(o + (L.want_rowstat ? (size_t)s.total_frames * 8 : 0));
     L.off_items_local = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
     L.off_items = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
     L.off_fast[0] = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
@@ -146,6 +147,7 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
     L.off_padded = o; o = align_up(o + (L.segmenting ? (size_t)s.B * (s.max_T + 16) * 4 : 0));
     L.off_anchors = o; o = align_up(o + (size_t)s.B * L.anchor_words * 4);
     L.off_counters = o; o = align_up(o + 64);
+    L.off_pathlp = o; o = align_up(o + (size_t)s.total_frames * 4);
     // the banded and the generic kernels are stream-ordered, so their back-pointer slabs share one region
     L.off_bp = o; o = align_up(o + std::max<size_t>((size_t)L.resident_warps * (size_t)L.slab_words * 4, band_bytes));
     L.total = o;
@@ -250,7 +252,8 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     const bool boost = p->boost_targets && p->mode == BFA_MODE_FULL;
 
     uint32_t* tmask = (uint32_t*)(ws + L.off_tmask);
-    float2* rowstat = (boost && L.segmenting) ? (float2*)(ws + L.off_rowstat) : nullptr;
+    float2* rowstat = L.want_rowstat ? (float2*)(ws + L.off_rowstat) : nullptr;
+    float* path_lp = (stamps && conf) ? (float*)(ws + L.off_pathlp) : nullptr;
     int* counters = (int*)(ws + L.off_counters);
     CUDA_TRY(cudaMemsetAsync(counters, 0, 64, st));
 
@@ -271,7 +274,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     pa.n_items = counters; pa.lists = (int32_t*)(ws + L.off_lists); pa.list_ints = L.list_ints;
     const bool fast = (p->reserved & 1) == 0 && C <= 72 && d.band_ok;
     for (int v = 0; v < 2; ++v) { pa.fast_items[v] = (Item*)(ws + L.off_fast[v]); pa.n_fast[v] = counters + 3 + 2 * v; }
-    pa.fast_enable = fast ? 1 : 0;
+    pa.fast_enable = fast ? 1 : 0; pa.path_lp = path_lp;
     pa.padded = (float*)(ws + L.off_padded); pa.anchors = (uint32_t*)(ws + L.off_anchors);
     plan_kernel<<<(B + 3) / 4, 128, 0, st>>>(pa);
     LAUNCH_CHECK();
@@ -281,7 +284,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         BandArgs ba;
         ba.p = *p; ba.C = C; ba.logp = logp; ba.tgt = tgt; ba.tmask = tmask;
         ba.retry_items = pa.items; ba.n_retry = counters;
-        ba.frame_ph = frame_ph; ba.frame_idx = frame_idx; ba.dp_final = dp_final;
+        ba.frame_ph = frame_ph; ba.frame_idx = frame_idx; ba.dp_final = dp_final; ba.path_lp = path_lp;
         ba.bp_scratch = (uint32_t*)(ws + L.off_bp); ba.seg_stride = BK_ROWS * C;
         for (int v = 0; v < 2; ++v) {
             ba.items = pa.fast_items[v]; ba.n_items = pa.n_fast[v];
@@ -309,6 +312,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     va.path = nullptr; va.true_idx = nullptr; va.anchors = pa.anchors; va.items = pa.items;
     va.n_items = counters; va.work_counter = counters + 1;
     va.frame_ph = frame_ph; va.frame_idx = frame_idx; va.dp_final = dp_final; va.status = status; va.final_state = nullptr;
+    va.path_lp = path_lp;
     va.bp_scratch = (uint32_t*)(ws + L.off_bp); va.bp_slab_words = L.slab_words;
     rc = launch_viterbi(va, (int)(max_items > (1 << 30) ? (1 << 30) : max_items), L.max_L, d, st, !fast);
     if (rc) return rc;
@@ -317,7 +321,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         AssortArgs aa;
         aa.p = *p; aa.B = B; aa.C = C; aa.max_stamps = shape->max_stamps; aa.logp = logp; aa.row_off = (const long long*)row_off;
         aa.T = T; aa.frame_off = (const long long*)frame_off; aa.frame_ph = frame_ph; aa.frame_idx = frame_idx;
-        aa.status = status; aa.stamps = stamps; aa.conf = conf; aa.n_stamps = n_stamps;
+        aa.status = status; aa.stamps = stamps; aa.conf = conf; aa.n_stamps = n_stamps; aa.path_lp = path_lp;
         if (shape->max_stamps <= 0) return BFA_E_INVALID;
         assort_confidence_kernel<<<(B + 3) / 4, 128, 0, st>>>(aa);
         LAUNCH_CHECK();
@@ -360,6 +364,7 @@ int bfa_viterbi_paths(const BfaParams* p, int32_t n_items, int32_t C, int32_t ma
     va.path = path; va.true_idx = true_idx; va.anchors = nullptr; va.items = items;
     va.n_items = counters; va.work_counter = counters + 1;
     va.frame_ph = frame_ph; va.frame_idx = frame_idx; va.dp_final = dp_final; va.status = nullptr; va.final_state = final_state;
+    va.path_lp = nullptr;
     va.bp_scratch = bp; va.bp_slab_words = (long long)(max_T + 2) * 32 * (max_L > 512 ? 2 : 1);
     return launch_viterbi(va, n_items, max_L, d, st);
 }
@@ -405,7 +410,7 @@ int bfa_assort_batch(const BfaParams* p, int32_t B, const int32_t* T, const int6
     AssortArgs aa;
     aa.p = *p; aa.B = B; aa.C = 0; aa.max_stamps = max_stamps; aa.logp = nullptr; aa.row_off = nullptr; aa.T = T;
     aa.frame_off = (const long long*)frame_off; aa.frame_ph = frame_ph; aa.frame_idx = frame_idx; aa.status = status;
-    aa.stamps = stamps; aa.conf = nullptr; aa.n_stamps = n_stamps;
+    aa.stamps = stamps; aa.conf = nullptr; aa.n_stamps = n_stamps; aa.path_lp = nullptr;
     assort_confidence_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(aa);
     LAUNCH_CHECK();
     return BFA_OK;

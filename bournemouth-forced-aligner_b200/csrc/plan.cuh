@@ -43,6 +43,7 @@ struct PlanArgs {
     int list_ints;
     float* padded;             // [B][max_T + 16]
     uint32_t* anchors;         // [B][anchor_words]
+    float* path_lp;            // [total_frames] raw log-prob of the class each frame was assigned to (for confidences), or null
 };
 
 // ---- target-class bitmask: unique_targets = set(seq) - {blank, -100}, p < C (:44-49) ----
@@ -114,6 +115,7 @@ struct UttCtx {
     const float2* stat;      // utterance row stats (or null)
     bool sil_is_target;
     float* padded;
+    uint32_t tw[MAX_WORDS];  // target-class mask words
 };
 
 // exp(modified_lp[row, silence_id]) (:503-504)
@@ -121,7 +123,18 @@ __device__ __forceinline__ float sil_prob(const UttCtx& c, int row) {
     const BfaParams& p = c.a->p;
     float x = c.lp[(long long)row * c.a->C + p.silence_id];
     float m = 0.f, ls = 0.f;
-    if (p.boost_targets) { float2 s = c.stat[row]; m = s.x; ls = s.y; }
+    if (p.boost_targets) {
+        if (c.stat) { float2 s = c.stat[row]; m = s.x; ls = s.y; }
+        else {   // no materialised statistics: this lane walks its own row (slow path, same formula)
+            const float* r = c.lp + (long long)row * c.a->C;
+            const int Cn = c.a->C;
+            m = -INFINITY;
+            for (int q = 0; q < Cn; ++q) m = fmaxf(m, r[q] + (((c.tw[q >> 5] >> (q & 31)) & 1u) ? p.boost_factor : 0.0f));
+            float sum = 0.f;
+            for (int q = 0; q < Cn; ++q) sum += expf(r[q] + (((c.tw[q >> 5] >> (q & 31)) & 1u) ? p.boost_factor : 0.0f) - m);
+            ls = logf(sum);
+        }
+    }
     x = mod_value(x, c.sil_is_target, p.boost_targets != 0, p.enforce_minimum != 0, p.boost_factor, m, ls, p.min_log_prob);
     return expf(x);
 }
@@ -188,8 +201,12 @@ __device__ int detect_silence(const UttCtx& c, int r0, int Tn, float thr, int k,
 }
 
 __device__ __forceinline__ void fill_frames(const UttCtx& c, long long o0, long long olim, int nf, int ph, int idx) {
+    const long long ob = c.a->frame_off[c.u];
     for (int f = c.lane; f < nf; f += 32)
-        if (o0 + f < olim) { c.a->frame_ph[o0 + f] = ph; c.a->frame_idx[o0 + f] = idx; }
+        if (o0 + f < olim) {
+            c.a->frame_ph[o0 + f] = ph; c.a->frame_idx[o0 + f] = idx;
+            if (c.a->path_lp && ph >= 0 && ph < c.a->C && o0 + f - ob < c.T) c.a->path_lp[o0 + f] = c.lp[(o0 + f - ob) * c.a->C + ph];
+        }
 }
 
 __device__ __forceinline__ int band_rule(int L, int div, int floor_) { return (L > 60) ? max(L / div, floor_) : 0; }
@@ -376,6 +393,8 @@ __global__ void plan_kernel(PlanArgs a) {
             if (i == lane) wv = ti.w[i];
         a.tmask[(size_t)u * MAX_WORDS + lane] = wv;      // consumed by the Viterbi kernels
     }
+#pragma unroll
+    for (int i = 0; i < MAX_WORDS; ++i) c.tw[i] = ti.w[i];
     c.sil_is_target = false;
     if (p.silence_id >= 0 && p.silence_id < a.C) {
 #pragma unroll
@@ -418,6 +437,7 @@ __global__ void plan_kernel(PlanArgs a) {
                             int j = (int)(((long long)t * N) / T);
                             a.frame_ph[o_base + t] = c.seq[j];
                             a.frame_idx[o_base + t] = j;
+                            if (a.path_lp && c.seq[j] >= 0 && c.seq[j] < a.C) a.path_lp[o_base + t] = c.lp[(long long)t * a.C + c.seq[j]];
                         }
                     }
                 }

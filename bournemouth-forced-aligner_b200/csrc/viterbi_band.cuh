@@ -60,6 +60,7 @@ struct BandArgs {
     int32_t* frame_ph;
     int32_t* frame_idx;
     float* dp_final;
+    float* path_lp;            // [total_frames] raw log-prob of the assigned class per frame (confidence input), or null
     uint32_t* bp_scratch;
     long long bp_slab_words;
     int seg_stride;            // floats per (stage, utterance) buffer = BK_ROWS * C
@@ -455,7 +456,10 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
     const bool walk = seg_on && !bad && T > 0;
     int ci = 4 * (fin_g - fin_base) + fin_k;
     int sabs0 = 4 * fin_base - 3;          // state of ci = 0 at the current frame
-    int keep_s = 0;
+    long long pend_o[4] = {-1, -1, -1, -1};   // outputs of the previous 32-frame block, stored one block late
+    int pend_cls[4] = {0, 0, 0, 0}, pend_idx[4] = {0, 0, 0, 0};
+    float pend_x[4] = {0.f, 0.f, 0.f, 0.f};
+    bool pend_gather[4] = {false, false, false, false};
     uint2* bt2 = reinterpret_cast<uint2*>(bt);                 // [UPW][W*4] (b0 word, b1 word)
     uint32_t* sfw_s = bt + BK_UPW * S::W * 4 * 2;              // [32] shift-flag words
     const int nblk = (Tmax + 31) >> 5;
@@ -477,35 +481,60 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
         __syncwarp();
         const uint32_t sfw = sfw_s[lane];
         const uint2* cell = bt2 + seg * S::W * 4;
-#pragma unroll 8
+        const int qhi = walk ? min(31, T - 1 - b * 32) : -1;   // last frame of this utterance inside the block
+        int keep4[4] = {0, 0, 0, 0};                            // states of frames 32b + 8i + l8
+#pragma unroll
         for (int q = 31; q >= 0; --q) {
-            const int t = b * 32 + q;
-            if (walk && t < T) {
-                if ((q & 7) == l8) keep_s = sabs0 + ci;
-                if (t >= 1) {
+            if (q <= qhi) {
+                if ((q & 7) == l8) keep4[q >> 3] = sabs0 + ci;
+                if (q > 0 || b > 0) {                      // frame 0 has no predecessor
                     const uint2 wv = cell[ci];
-                    const uint32_t b0 = (wv.x >> (31 - q)) & 1u, b1 = (wv.y >> (31 - q)) & 1u;
-                    const uint32_t sf = (sfw >> (31 - q)) & 1u;
-                    ci += (int)(4u * sf) - (int)(b1 ? 2u : b0);
-                    sabs0 -= (int)(4u * sf);
-                }
-            }
-            if ((q & 7) == 0) {
-                // lanes of the segment hold frames t .. t+7 (t = b*32+q); write them out
-                const int tf = t + l8;
-                if (walk && tf < T) {
-                    const int rel = tf - trim;
-                    const long long o = out_off + rel;
-                    if (rel >= 0 && rel < n_out && o < out_lim) {
-                        const bool ph = ((keep_s + 3) & 3) == 0;      // state s = 4g'-3+k is a phoneme state iff k == 0
-                        const int gi = (keep_s + 3) >> 2;
-                        a.frame_ph[o] = ph ? seq[gi - 1] : blank;
-                        a.frame_idx[o] = ph ? idx0 + gi - 1 : -1;
-                    }
+                    const uint32_t bit = 1u << (31 - q);
+                    const int d = (wv.y & bit) ? 2 : ((wv.x & bit) ? 1 : 0);
+                    ci -= d;
+                    if (sfw & bit) { ci += 4; sabs0 -= 4; }   // the window slid before this frame was computed
                 }
             }
         }
+        // ---- output of the block, software-pipelined by one block: the loads it needs (target ids, gathered
+        //      log-probs for the confidences) are issued now, four independent chains per lane, and consumed
+        //      after the next block's walk, so their latency never stalls the warp ----
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (pend_o[i] >= 0) {
+                a.frame_ph[pend_o[i]] = pend_cls[i];
+                a.frame_idx[pend_o[i]] = pend_idx[i];
+                if (pend_gather[i]) a.path_lp[pend_o[i]] = pend_x[i];
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            pend_o[i] = -1;
+            const int tf = b * 32 + 8 * i + l8;
+            if (walk && tf < T) {
+                const int rel = tf - trim;
+                const long long o = out_off + rel;
+                if (rel >= 0 && rel < n_out && o < out_lim) {
+                    const bool ph = ((keep4[i] + 3) & 3) == 0;      // state s = 4g'-3+k is a phoneme state iff k == 0
+                    const int gi = (keep4[i] + 3) >> 2;
+                    pend_o[i] = o;
+                    pend_cls[i] = ph ? seq[gi - 1] : blank;
+                    pend_idx[i] = ph ? idx0 + gi - 1 : -1;
+                    pend_gather[i] = a.path_lp && (ph || !a.p.ignore_noise);
+                }
+            }
+        }
+        // confidences (utils.py:89-103) read lp[f, phoneme of the stamp]: gather it here, once per frame
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (pend_o[i] >= 0 && pend_gather[i]) pend_x[i] = __ldg(my_src + (long long)(b * 32 + 8 * i + l8) * C + pend_cls[i]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (pend_o[i] >= 0) {
+            a.frame_ph[pend_o[i]] = pend_cls[i];
+            a.frame_idx[pend_o[i]] = pend_idx[i];
+            if (pend_gather[i]) a.path_lp[pend_o[i]] = pend_x[i];
+        }
     __syncwarp();
 }
 

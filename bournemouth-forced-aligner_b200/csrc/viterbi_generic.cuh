@@ -34,6 +34,7 @@ struct VitArgs {
     int* work_counter;          // device scalar, zeroed before launch
     int32_t* frame_ph;
     int32_t* frame_idx;
+    float* path_lp;             // [total_frames] raw log-prob of the assigned class per frame, or null
     float* dp_final;            // per utterance (FINAL items) -- or per item for explicit entry
     int32_t* status;            // per utterance: DEGENERATE flag or-ed in
     int32_t* final_state;       // per item, may be null
@@ -334,8 +335,10 @@ __device__ void run_item(const VitArgs& a, const Item& it, WarpSmem& sm, Stream&
             int rel = t - it.trim;
             long long o = it.out_off + rel;
             if (rel >= 0 && rel < it.n_out && o < it.out_lim) {
-                a.frame_ph[o] = state_class(a, it, keep);
+                const int cls = state_class(a, it, keep);
+                a.frame_ph[o] = cls;
                 a.frame_idx[o] = state_tidx(a, it, keep);
+                if (a.path_lp && cls >= 0 && cls < C) a.path_lp[o] = a.logp[it.lp_off + (long long)t * C + cls];
             }
         }
         keep = -1;

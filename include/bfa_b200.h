@@ -74,8 +74,14 @@ typedef struct BfaParams {
     int32_t boundary_pad;     /* 3 */
     int32_t min_speech_frames;/* 20 */
     int32_t mode;             /* BFA_MODE_* */
-    int32_t reserved;
+    int32_t reserved;         /* BFA_HINT_* / BFA_FLAG_* bits, 0 by default */
 } BfaParams;
+
+/* bits of BfaParams.reserved */
+#define BFA_FLAG_EXACT_ONLY 1 /* run every item through the exact generic kernel (disables the banded fast path) */
+#define BFA_HINT_NO_SIL 2     /* caller asserts that no target contains silence_id: skips the row-statistics pass that
+                                 only the silence scan needs.  A pure performance hint: if it is wrong the planner
+                                 recomputes what it needs (slower), results are unchanged. */
 
 /* framestamp tuple (phoneme_id, start_frame, end_frame_exclusive, target_seq_idx)
  * = the 4-tuples returned by ViterbiDecoder.assort_frames (forced_alignment.py:777-834). */

@@ -288,3 +288,47 @@ def test_host_entry_matches_device_entry(bfa, dev):
     for b in range(B):
         np.testing.assert_array_equal(h["stamps"][b, :n[b]], r.stamps[b, :n[b]].cpu().numpy())
         np.testing.assert_array_equal(h["conf"][b, :n[b]], r.conf[b, :n[b]].cpu().numpy())
+
+
+def test_no_sil_hint_is_only_a_hint(bfa, dev):
+    """BFA_HINT_NO_SIL skips the row-statistics pass; asserting it wrongly (targets DO hold SIL) must not
+    change any result (the planner recomputes what it needs)."""
+    from bfa_b200 import synth, _cabi
+    B, T, N, Cc = 16, 400, 40, 67
+    lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=91, peak=10.0, sil_every=8, sil_frames=16)
+    dec = bfa.AlignmentUtils(Cc - 1, 0).viterbi_decoder
+    row_off = torch.arange(B, dtype=torch.int64, device=dev) * T * Cc
+    tg = tgt.to(torch.int32).reshape(-1).to(dev)
+    outs = []
+    for hint in (0, _cabi.HINT_NO_SIL):
+        p = dec._params(True, True, True)
+        p.reserved |= hint
+        r = dec.align_batch(lp.to(dev), row_off, [T] * B, Cc, tg, [N] * B, params=p)
+        outs.append((r.frame_ph.cpu().numpy(), r.frame_idx.cpu().numpy(), r.status.cpu().numpy(), r.conf.cpu().numpy(), r.n_stamps.cpu().numpy()))
+    assert ((outs[0][2] & 7) == 4).sum() >= B // 2            # segmentation really happened
+    for a_, b_ in zip(outs[0][:3], outs[1][:3]):
+        np.testing.assert_array_equal(a_, b_)
+    n = outs[0][4]
+    for b in range(B):
+        np.testing.assert_allclose(outs[0][3][b, :n[b]], outs[1][3][b, :n[b]], rtol=1e-5)
+
+
+def test_exact_only_flag_matches_fast_path(bfa, dev):
+    """BFA_FLAG_EXACT_ONLY routes everything through the generic exact kernel; on valid inputs the banded fast
+    kernel must produce the same frames (scores within fp tolerance of the fused log-sum-exp)."""
+    from bfa_b200 import synth, _cabi
+    B, T, N, Cc = 64, 600, 40, 66
+    lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=92)
+    dec = bfa.AlignmentUtils(Cc - 1, 0).viterbi_decoder
+    row_off = torch.arange(B, dtype=torch.int64, device=dev) * T * Cc
+    tg = tgt.to(torch.int32).reshape(-1).to(dev)
+    res = []
+    for flag in (0, _cabi.FLAG_EXACT_ONLY):
+        p = dec._params(True, True, True)
+        p.reserved |= flag
+        r = dec.align_batch(lp.to(dev), row_off, [T] * B, Cc, tg, [N] * B, params=p)
+        res.append(r)
+    np.testing.assert_array_equal(res[0].frame_ph.cpu().numpy(), res[1].frame_ph.cpu().numpy())
+    np.testing.assert_array_equal(res[0].frame_idx.cpu().numpy(), res[1].frame_idx.cpu().numpy())
+    np.testing.assert_allclose(res[0].dp_final.cpu().numpy(), res[1].dp_final.cpu().numpy(), rtol=RTOL)
+    np.testing.assert_allclose(res[0].conf.cpu().numpy()[:, :N], res[1].conf.cpu().numpy()[:, :N], rtol=1e-5)
