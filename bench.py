@@ -206,7 +206,8 @@ def main():
         if world > 1:  # final gather of the timestamp arrays (the path's only exchange)
             nonlocal gather_bufs
             if gather_bufs is None:
-                gather_bufs = [torch.empty((world,) + tuple(x.shape), dtype=x.dtype, device=dev) for x in (r.stamps, r.conf, r.n_stamps)]
+                gather_bufs = [torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)
+                               for x in (r.stamps, r.conf, r.n_stamps)]
             for g, x in zip(gather_bufs, (r.stamps, r.conf, r.n_stamps)):
                 dist.all_gather_into_tensor(g, x)
         return r

@@ -1,0 +1,63 @@
+"""Multi-GPU sharding of a corpus of utterances.
+
+Every utterance is an independent DP problem (the reference's batch loop, forced_alignment.py:885-905,
+carries nothing between iterations), so ranks take contiguous utterance ranges balanced by estimated work
+and never exchange posteriors.  The only collective is the final gather of the fixed-pitch result arrays
+(stamps / confidences / counts / status).  Works with any torch.distributed backend: NCCL on GPUs, gloo in
+the CPU tests."""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def work_estimate(T: Sequence[int], N: Sequence[int]) -> np.ndarray:
+    """Relative cost of aligning each utterance: frames x live states (band-limited path width)."""
+    T = np.asarray(T, np.int64); N = np.asarray(N, np.int64)
+    L = 4 * N + 1
+    band = np.where(L > 60, np.maximum(L // 4, 20), L)
+    return T * np.minimum(L, 2 * band + 1) + 64
+
+
+def shard_ranges(T: Sequence[int], N: Sequence[int], world: int) -> List[Tuple[int, int]]:
+    """Contiguous [start, end) utterance ranges per rank, balanced by cumulative work."""
+    w = work_estimate(T, N)
+    B = len(w)
+    if world <= 1 or B == 0:
+        return [(0, B)] + [(B, B)] * (max(world, 1) - 1)
+    cum = np.concatenate([[0], np.cumsum(w)])
+    bounds = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        bounds.append(int(np.searchsorted(cum, target, side="left")))
+    bounds.append(B)
+    bounds = np.maximum.accumulate(np.minimum(bounds, B))
+    return [(int(bounds[r]), int(bounds[r + 1])) for r in range(world)]
+
+
+def gather_results(stamps: torch.Tensor, conf: torch.Tensor, n_stamps: torch.Tensor, status: torch.Tensor, counts: Sequence[int],
+                   group=None):
+    """All-gather the per-rank result arrays.  Ranks may own different numbers of utterances (`counts[r]`);
+    rows are padded to max(counts) for the collective and trimmed afterwards.
+    stamps [B_r, P, 4] i32, conf [B_r, P] f32, n_stamps/status [B_r] i32 -> tensors over all utterances."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    bmax = int(max(counts)) if len(counts) else 0
+    P = stamps.shape[1]
+
+    def pad(x, shape_tail):
+        out = x.new_zeros((bmax,) + tuple(shape_tail))
+        out[: counts[rank]] = x[: counts[rank]]
+        return out
+
+    packs = [pad(stamps, (P, 4)), pad(conf, (P,)), pad(n_stamps, ()), pad(status, ())]
+    outs = []
+    for x in packs:
+        buf = x.new_empty((world * bmax,) + tuple(x.shape[1:]))   # concatenated layout: accepted by NCCL and gloo
+        dist.all_gather_into_tensor(buf, x.contiguous(), group=group)
+        buf = buf.view((world, bmax) + tuple(x.shape[1:]))
+        outs.append(torch.cat([buf[r, : counts[r]] for r in range(world)], dim=0))
+    return tuple(outs)

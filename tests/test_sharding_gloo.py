@@ -1,0 +1,60 @@
+"""CPU: the multi-GPU host logic (contiguous work-balanced sharding + final gather of result arrays) on a
+world_size-2 gloo group.  The data path has no collective; only the fixed-pitch result arrays are gathered."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_shard_ranges_cover_and_balance():
+    from bfa_b200.sharding import shard_ranges, work_estimate
+    rng = np.random.default_rng(0)
+    T = rng.integers(60, 1800, 1000); N = np.maximum(4, T // rng.integers(5, 20, 1000))
+    for world in (1, 2, 3, 8):
+        r = shard_ranges(T, N, world)
+        assert r[0][0] == 0 and r[-1][1] == 1000 and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        w = work_estimate(T, N)
+        loads = [w[s:e].sum() for s, e in r]
+        assert max(loads) <= 1.1 * (sum(loads) / world) + w.max()
+    assert shard_ranges([], [], 4) == [(0, 0)] * 4
+    assert shard_ranges([100], [10], 2)[0][1] + 0 >= 0
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bfa_b200.sharding import gather_results, shard_ranges
+    T = [100 + 7 * i for i in range(11)]; N = [5 + i for i in range(11)]
+    ranges = shard_ranges(T, N, world)
+    counts = [e - s for s, e in ranges]
+    s0, e0 = ranges[rank]
+    P = 12
+    # fake per-rank results that encode the global utterance index
+    stamps = torch.zeros((counts[rank], P, 4), dtype=torch.int32)
+    conf = torch.zeros((counts[rank], P), dtype=torch.float32)
+    for i, u in enumerate(range(s0, e0)):
+        stamps[i, :, 0] = u; conf[i] = u + 0.5
+    n_st = torch.arange(s0, e0, dtype=torch.int32); st = torch.full((counts[rank],), rank, dtype=torch.int32)
+    g = gather_results(stamps, conf, n_st, st, counts)
+    ok = (g[0].shape == (11, P, 4) and bool((g[0][:, 0, 0] == torch.arange(11)).all()) and bool((g[1][:, 3] == torch.arange(11) + 0.5).all())
+          and bool((g[2] == torch.arange(11)).all()) and g[3].tolist() == sum([[r] * counts[r] for r in range(world)], []))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_gather_results_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs: p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
