@@ -58,10 +58,15 @@ struct DeviceInfo {
     bool ok = false;
 };
 
+// The two banded-kernel variants launched per call: 16 lanes per utterance, window 32 / 64 groups.
+constexpr int BAND_LPU = 16, BAND_NI = 5;
+constexpr int BAND_G[2] = {2, 4};
+constexpr int BAND_WARPS = BandShape<BAND_LPU, 2>::WARPS;
 inline int band_rec_words(int G) { return 6 * G + 1; }
 inline int band_smem_bytes_per_warp(int C, int G) {
-    // stage buffers + zero pad + mbarriers + back-trace staging ([UPW][8G*4 cells] x 8 B + 32 shift-flag words)
-    size_t b = (size_t)BK_NST * BK_UPW * BK_ROWS * C * 4 + BK_PAD * 4 + BK_NST * BK_UPW * 8 + (size_t)BK_UPW * 8 * G * 4 * 8 + 32 * 4;
+    // stage buffers + zero pad + mbarriers + back-trace staging ([UPW][LPU*G*4 cells] x 8 B + 32 shift-flag words)
+    const int upw = 32 / BAND_LPU;
+    size_t b = (size_t)BK_NST * upw * BK_ROWS * C * 4 + BK_PAD * 4 + BK_NST * upw * 8 + (size_t)upw * BAND_LPU * G * 4 * 8 + 32 * 4;
     return (int)((b + 127) / 128 * 128);
 }
 
@@ -81,9 +86,9 @@ int device_info(DeviceInfo& out) {
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.vg_ctas_per_sm_big, viterbi_generic_kernel<1>, VG_WARPS * 32, smem));
         if (d.vg_ctas_per_sm < 1) d.vg_ctas_per_sm = 1;
         if (d.vg_ctas_per_sm_big < 1) d.vg_ctas_per_sm_big = 1;
-        const int band_smem_max = band_smem_bytes_per_warp(72, 4) * BK_WARPS;
-        d.band_ok = cudaFuncSetAttribute(viterbi_band_kernel<3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_max) == cudaSuccess &&
-                    cudaFuncSetAttribute(viterbi_band_kernel<4, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_max) == cudaSuccess;
+        const int band_smem_max = band_smem_bytes_per_warp(72, 4) * BAND_WARPS;
+        d.band_ok = cudaFuncSetAttribute(viterbi_band_kernel<BAND_LPU, 2, BAND_NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_max) == cudaSuccess &&
+                    cudaFuncSetAttribute(viterbi_band_kernel<BAND_LPU, 4, BAND_NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_max) == cudaSuccess;
         d.ok = true;
     }
     out = d;
@@ -128,10 +133,10 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
     L.band_grid = d.sms;
     size_t band_bytes = 0;
     for (int v = 0; v < 2; ++v) {
-        const int G = 3 + v;
+        const int G = BAND_G[v];
         L.band_smem_per_warp[v] = band_smem_bytes_per_warp(s.C, G);
         L.band_slab_words[v] = (long long)((s.max_T + 31) / 32 + 1) * band_rec_words(G) * 32;
-        band_bytes = std::max<size_t>(band_bytes, (size_t)L.band_grid * BK_WARPS * (size_t)L.band_slab_words[v] * 4);
+        band_bytes = std::max<size_t>(band_bytes, (size_t)L.band_grid * BAND_WARPS * (size_t)L.band_slab_words[v] * 4);
     }
     size_t o = 0;
     L.off_tmask = o; o = align_up(o + (size_t)s.B * MAX_WORDS * 4);
@@ -289,15 +294,15 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         for (int v = 0; v < 2; ++v) {
             ba.items = pa.fast_items[v]; ba.n_items = pa.n_fast[v];
             ba.bp_slab_words = L.band_slab_words[v]; ba.smem_per_warp = L.band_smem_per_warp[v];
-            const size_t smem = (size_t)ba.smem_per_warp * BK_WARPS;
+            const size_t smem = (size_t)ba.smem_per_warp * BAND_WARPS;
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (v == 0) {
                 std::lock_guard<std::mutex> lk(g_prof.mu);
                 if (g_prof.on) { e0 = g_prof.get(); e1 = g_prof.get(); }
             }
             if (e0) cudaEventRecord(e0, st);
-            if (v == 0) viterbi_band_kernel<3, 9><<<L.band_grid, BK_WARPS * 32, smem, st>>>(ba);
-            else viterbi_band_kernel<4, 9><<<L.band_grid, BK_WARPS * 32, smem, st>>>(ba);
+            if (v == 0) viterbi_band_kernel<BAND_LPU, 2, BAND_NI><<<L.band_grid, BAND_WARPS * 32, smem, st>>>(ba);
+            else viterbi_band_kernel<BAND_LPU, 4, BAND_NI><<<L.band_grid, BAND_WARPS * 32, smem, st>>>(ba);
             LAUNCH_CHECK();
             if (e0) {
                 cudaEventRecord(e1, st);

@@ -36,7 +36,7 @@ struct PlanArgs {
     Item* items_local;         // [B][item_cap]
     Item* items;               // compacted list for the exact generic kernel
     int* n_items;              // device counter
-    Item* fast_items[2];       // compacted lists for the banded kernel (window 24 / 32 groups)
+    Item* fast_items[2];       // compacted lists for the banded kernel (window 32 / 64 groups)
     int* n_fast[2];
     int fast_enable;
     int32_t* lists;            // [B][list_ints]
@@ -75,13 +75,13 @@ __device__ __forceinline__ TgtInfo target_info(const int32_t* tgt, long long b, 
     return r;
 }
 
-// Which kernel runs an item: 0 / 1 = banded kernel with a 24 / 32-group window, -1 = exact generic kernel.
+// Which kernel runs an item: 0 / 1 = banded kernel with a 32 / 64-group window, -1 = exact generic kernel.
 __device__ __forceinline__ int fast_class(const Item& it, int C, const float* logp, bool tgt_ok, int fast_enable) {
     if (!fast_enable || !tgt_ok) return -1;
     if (it.stride != 4 || (it.flags & ITEM_ANCHOR) || C > 72 || it.T < 2 || it.L > it.T) return -1;
     if (((unsigned long long)(logp + it.lp_off) & 15ull) != 0) return -1;   // bulk copies need 16-B aligned rows
-    if (band_window_fits(it.n, it.band, 24)) return 0;
-    if (band_window_fits(it.n, it.band, 32)) return 1;
+    if (band_window_fits(it.n, it.band, 32)) return 0;
+    if (band_window_fits(it.n, it.band, 64)) return 1;
     return -1;
 }
 

@@ -40,9 +40,9 @@
 
 namespace bfa {
 
-constexpr int BK_WARPS = 8;       // warps per CTA (one CTA per SM: tasks are dealt round-robin over SMs, then warps)
-constexpr int BK_LPU = 8;         // lanes per utterance
-constexpr int BK_UPW = 4;         // utterances per warp
+// LPU lanes own one utterance (template parameter: 16 -> 2 utterances per warp, 8 -> 4).  A warp-task is latency
+// bound (one task takes the same time whether the SM holds 2 or 14 of them), so the default is the small task:
+// LPU = 16 halves the instructions per warp-frame and doubles the number of independent warps.
 constexpr int BK_NST = 2;         // pipeline stages
 constexpr int BK_ROWS = 8;        // rows per stage per utterance (8*C*4 bytes is always a multiple of 16)
 constexpr int BK_PAD = 128;       // zeroed floats after the last stage buffer (LSE lanes may read past a row)
@@ -67,11 +67,14 @@ struct BandArgs {
     int smem_per_warp;         // bytes
 };
 
-template <int G>
+template <int LPU, int G>
 struct BandShape {
-    static constexpr int W = BK_LPU * G;    // groups in the window
+    static constexpr int UPW = 32 / LPU;    // utterances per warp
+    static constexpr int W = LPU * G;       // groups in the window
     static constexpr int ACC = 6 * G;       // decision accumulators per lane
     static constexpr int REC = ACC + 1;     // + window-shift flag word
+    static constexpr int FPL = 32 / LPU;    // frames of a 32-frame block each lane writes out
+    static constexpr int WARPS = (LPU == 16) ? 14 : 8;   // warps per CTA, one CTA per SM
 };
 
 // window eligibility: groups spanned by band(t-1) U band(t) must fit (see header comment)
@@ -95,13 +98,14 @@ __device__ __forceinline__ void push_gt(uint32_t& acc, float earlier, float late
     acc = __funnelshift_l(__float_as_uint(earlier - later), acc, 1);
 }
 
-template <int G, int NI>
+template <int LPU, int G, int NI>
 __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned char* smem_warp, uint32_t* slab, uint32_t& phase,
                           int lane, uint64_t pol) {
-    using S = BandShape<G>;
+    using S = BandShape<LPU, G>;
+    constexpr int BK_LPU = LPU, BK_UPW = S::UPW;
     constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
     constexpr int SENT = 1 << 29;
-    const int seg = lane >> 3, l8 = lane & 7;
+    const int seg = lane / LPU, l8 = lane % LPU;   // l8: lane inside the segment (0..LPU-1)
     const int C = a.C;
     const float NEG = a.p.neg_inf;
     const int blank = a.p.blank_id;
@@ -171,11 +175,11 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
     const int brel = blank - l8;
     const bool seg_first = l8 == 0;
 
-    // ---- log-sum-exp constants: this lane sums classes l8 + 8*i; out-of-range classes get weight 0 ----
+    // ---- log-sum-exp constants: this lane sums classes l8 + LPU*i; out-of-range classes get weight 0 ----
     float kk[NI];
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-        const int c = l8 + 8 * i;
+        const int c = l8 + LPU * i;
         const bool ok = c < C;
         const bool tg = ok && seg_on && ((a.tmask[(size_t)utt * MAX_WORDS + (c >> 5)] >> (c & 31)) & 1u);
         kk[i] = ok ? (tg ? 0.0f : -a.p.boost_factor * LOG2E) : -INFINITY;   // (x + b - boost) * log2(e)
@@ -208,7 +212,8 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
         __syncwarp();                                  // tail floats written by the issuing lane become visible
 
         // ---- band schedule of frames t0..t0+7 (:650-652), frame t0+l8 on lane l8, and the event masks ----
-        const int j = t0 + l8;
+        const int r8 = l8 & 7;            // lanes 8..15 of a 16-lane segment mirror lanes 0..7 (their bits are masked out)
+        const int j = t0 + r8;
         int s_lo = -SENT, s_hi = SENT;
         if (use_band) {
             const double center = (double)j * pace;
@@ -216,8 +221,8 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
             s_hi = __float2int_rd((float)(center + bandd));   // largest  s with (float)s <= hi
         }
         int p1_lo = __shfl_up_sync(FULL, s_lo, 1), p2_lo = __shfl_up_sync(FULL, s_lo, 2), p1_hi = __shfl_up_sync(FULL, s_hi, 1);
-        if (l8 == 0) { p1_lo = carry_lo1; p2_lo = carry_lo2; p1_hi = carry_hi1; }
-        if (l8 == 1) p2_lo = carry_lo1;
+        if (r8 == 0) { p1_lo = carry_lo1; p2_lo = carry_lo2; p1_hi = carry_hi1; }
+        if (r8 == 1) p2_lo = carry_lo1;
         // kill before frame j: the lower edge moved at j-1, or the upper edge rises at j
         const bool kill_j = use_band && j >= 1 && ((j >= 2 && p1_lo > p2_lo) || s_hi > p1_hi);
         // window base used for frame j = group of s_lo(j-1), clamped
@@ -225,15 +230,15 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
         const int want_m = (use_band && j >= 2) ? min(max((p2_lo + 3) >> 2, 0), base_max) : 0;
         const bool shift_j = want_j > want_m;
         const unsigned kb = __ballot_sync(FULL, kill_j), sb = __ballot_sync(FULL, shift_j);
-        const unsigned my_kill8 = (kb >> (seg * 8)) & 0xffu, my_shift8 = (sb >> (seg * 8)) & 0xffu;
-        unsigned ev8 = kb | sb;
-        ev8 |= ev8 >> 16;
-        ev8 = (ev8 | (ev8 >> 8)) & 0xffu;                          // frames of this chunk in which any segment has an event
+        const unsigned my_kill8 = (kb >> (seg * LPU)) & 0xffu, my_shift8 = (sb >> (seg * LPU)) & 0xffu;
+        unsigned ev8 = 0;                                          // frames of this chunk in which any segment has an event
+#pragma unroll
+        for (int q = 0; q < BK_UPW; ++q) ev8 |= ((kb | sb) >> (q * LPU)) & 0xffu;
         shift_acc = (shift_acc << 8) | (__brev(my_shift8) >> 24);  // frame order: t0 in the highest of the 8 bits
         // s_lo(t-1) / s_hi(t-1) as seen by frame r of this chunk live on lane r of the segment (p1_*)
-        carry_lo1 = __shfl_sync(FULL, s_lo, seg * 8 + 7);
-        carry_lo2 = __shfl_sync(FULL, s_lo, seg * 8 + 6);
-        carry_hi1 = __shfl_sync(FULL, s_hi, seg * 8 + 7);
+        carry_lo1 = __shfl_sync(FULL, s_lo, seg * LPU + 7);
+        carry_lo2 = __shfl_sync(FULL, s_lo, seg * LPU + 6);
+        carry_hi1 = __shfl_sync(FULL, s_hi, seg * LPU + 7);
 
         const float* rowp0 = stage_buf + (c & 1) * stage_floats + seg * a.seg_stride + l8;   // lane's pointer into row 0
         const int fin_r = T - 1 - t0;                                                         // row of the last frame if it is in this chunk
@@ -250,7 +255,7 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
                 const float* rp = rowp0 + r * C;
                 float e[NI];
 #pragma unroll
-                for (int i = 0; i < NI; ++i) e[i] = ex2_approx(fmaf(rp[8 * i], LOG2E, kk[i]));
+                for (int i = 0; i < NI; ++i) e[i] = ex2_approx(fmaf(rp[LPU * i], LOG2E, kk[i]));
 #pragma unroll
                 for (int w = 1; w < NI; w <<= 1)
 #pragma unroll
@@ -303,8 +308,8 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
 
             // ---- events (rare): kill cells outside band(t-1); slide the window to the group of s_lo(t-1) ----
             if (ev8 & (1u << r)) {
-                const int slo_p = __shfl_sync(FULL, p1_lo, seg * 8 + r);
-                const int shi_p = __shfl_sync(FULL, p1_hi, seg * 8 + r);
+                const int slo_p = __shfl_sync(FULL, p1_lo, seg * LPU + r);
+                const int shi_p = __shfl_sync(FULL, p1_hi, seg * LPU + r);
                 if ((my_kill8 >> r) & 1u) {
                     const unsigned span = (unsigned)(shi_p - slo_p);
 #pragma unroll
@@ -437,7 +442,7 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
     if (use_stats && !(fabsf(lse_chk) < 3.0e38f)) bad = true;
     {   // make `bad` uniform per segment
         const unsigned m = __ballot_sync(FULL, bad);
-        bad = ((m >> (seg * BK_LPU)) & 0xffu) != 0;
+        bad = ((m >> (seg * BK_LPU)) & ((LPU == 32) ? 0xffffffffu : ((1u << LPU) - 1u))) != 0;
     }
     if (seg_on && l8 == 0) {
         if (bad) {
@@ -456,10 +461,12 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
     const bool walk = seg_on && !bad && T > 0;
     int ci = 4 * (fin_g - fin_base) + fin_k;
     int sabs0 = 4 * fin_base - 3;          // state of ci = 0 at the current frame
-    long long pend_o[4] = {-1, -1, -1, -1};   // outputs of the previous 32-frame block, stored one block late
-    int pend_cls[4] = {0, 0, 0, 0}, pend_idx[4] = {0, 0, 0, 0};
-    float pend_x[4] = {0.f, 0.f, 0.f, 0.f};
-    bool pend_gather[4] = {false, false, false, false};
+    long long pend_o[S::FPL];   // outputs of the previous 32-frame block, stored one block late
+    int pend_cls[S::FPL], pend_idx[S::FPL];
+    float pend_x[S::FPL];
+    bool pend_gather[S::FPL];
+#pragma unroll
+    for (int i = 0; i < S::FPL; ++i) { pend_o[i] = -1; pend_cls[i] = 0; pend_idx[i] = 0; pend_x[i] = 0.f; pend_gather[i] = false; }
     uint2* bt2 = reinterpret_cast<uint2*>(bt);                 // [UPW][W*4] (b0 word, b1 word)
     uint32_t* sfw_s = bt + BK_UPW * S::W * 4 * 2;              // [32] shift-flag words
     const int nblk = (Tmax + 31) >> 5;
@@ -482,11 +489,13 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
         const uint32_t sfw = sfw_s[lane];
         const uint2* cell = bt2 + seg * S::W * 4;
         const int qhi = walk ? min(31, T - 1 - b * 32) : -1;   // last frame of this utterance inside the block
-        int keep4[4] = {0, 0, 0, 0};                            // states of frames 32b + 8i + l8
+        int keep4[S::FPL];                                      // states of frames 32b + LPU*i + l8
+#pragma unroll
+        for (int i = 0; i < S::FPL; ++i) keep4[i] = 0;
 #pragma unroll
         for (int q = 31; q >= 0; --q) {
             if (q <= qhi) {
-                if ((q & 7) == l8) keep4[q >> 3] = sabs0 + ci;
+                if ((q % LPU) == l8) keep4[q / LPU] = sabs0 + ci;
                 if (q > 0 || b > 0) {                      // frame 0 has no predecessor
                     const uint2 wv = cell[ci];
                     const uint32_t bit = 1u << (31 - q);
@@ -497,19 +506,19 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
             }
         }
         // ---- output of the block, software-pipelined by one block: the loads it needs (target ids, gathered
-        //      log-probs for the confidences) are issued now, four independent chains per lane, and consumed
+        //      log-probs for the confidences) are issued now, independent chains per lane, and consumed
         //      after the next block's walk, so their latency never stalls the warp ----
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < S::FPL; ++i)
             if (pend_o[i] >= 0) {
                 a.frame_ph[pend_o[i]] = pend_cls[i];
                 a.frame_idx[pend_o[i]] = pend_idx[i];
                 if (pend_gather[i]) a.path_lp[pend_o[i]] = pend_x[i];
             }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < S::FPL; ++i) {
             pend_o[i] = -1;
-            const int tf = b * 32 + 8 * i + l8;
+            const int tf = b * 32 + LPU * i + l8;
             if (walk && tf < T) {
                 const int rel = tf - trim;
                 const long long o = out_off + rel;
@@ -525,11 +534,11 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
         }
         // confidences (utils.py:89-103) read lp[f, phoneme of the stamp]: gather it here, once per frame
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (pend_o[i] >= 0 && pend_gather[i]) pend_x[i] = __ldg(my_src + (long long)(b * 32 + 8 * i + l8) * C + pend_cls[i]);
+        for (int i = 0; i < S::FPL; ++i)
+            if (pend_o[i] >= 0 && pend_gather[i]) pend_x[i] = __ldg(my_src + (long long)(b * 32 + LPU * i + l8) * C + pend_cls[i]);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < S::FPL; ++i)
         if (pend_o[i] >= 0) {
             a.frame_ph[pend_o[i]] = pend_cls[i];
             a.frame_idx[pend_o[i]] = pend_idx[i];
@@ -538,31 +547,32 @@ __device__ void band_task(const BandArgs& a, int first, int n_valid, unsigned ch
     __syncwarp();
 }
 
-template <int G, int NI>
-__global__ void __launch_bounds__(BK_WARPS * 32, 1) viterbi_band_kernel(BandArgs a) {
+template <int LPU, int G, int NI>
+__global__ void __launch_bounds__(BandShape<LPU, G>::WARPS * 32, 1) viterbi_band_kernel(BandArgs a) {
+    using S = BandShape<LPU, G>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* smem_warp = smem_raw + (size_t)warp * a.smem_per_warp;
     {
         float* stage_buf = reinterpret_cast<float*>(smem_warp);
-        const int nfl = BK_NST * BK_UPW * a.seg_stride + BK_PAD;
+        const int nfl = BK_NST * S::UPW * a.seg_stride + BK_PAD;
         for (int i = lane; i < nfl; i += 32) stage_buf[i] = 0.0f;   // never-loaded slots must hold finite values
         unsigned long long* bars = reinterpret_cast<unsigned long long*>(stage_buf + nfl);
         if (lane == 0)
-            for (int i = 0; i < BK_NST * BK_UPW; ++i) mbar_init(smem_u32(&bars[i]), 1);
+            for (int i = 0; i < BK_NST * S::UPW; ++i) mbar_init(smem_u32(&bars[i]), 1);
         fence_mbar_init();   // also orders the generic-proxy zero fill before the first async copy
     }
     __syncwarp();
     const uint64_t pol = policy_evict_first();
     uint32_t phase = 0;
-    const int gwarp = blockIdx.x * BK_WARPS + warp;
+    const int gwarp = blockIdx.x * S::WARPS + warp;
     uint32_t* slab = a.bp_scratch + (size_t)gwarp * a.bp_slab_words;
     const int n_items = *a.n_items;
-    const int n_tasks = (n_items + BK_UPW - 1) / BK_UPW;
-    // static deal: task j -> CTA j % grid, warp (j / grid) % BK_WARPS.  With one CTA per SM this spreads
+    const int n_tasks = (n_items + S::UPW - 1) / S::UPW;
+    // static deal: task j -> CTA j % grid, warp (j / grid) % WARPS.  With one CTA per SM this spreads
     // ceil(n_tasks / SMs) tasks evenly over the SMs and over the four schedulers of each SM.
-    for (int j = blockIdx.x + gridDim.x * warp; j < n_tasks; j += gridDim.x * BK_WARPS)
-        band_task<G, NI>(a, j * BK_UPW, min(BK_UPW, n_items - j * BK_UPW), smem_warp, slab, phase, lane, pol);
+    for (int j = blockIdx.x + gridDim.x * warp; j < n_tasks; j += gridDim.x * S::WARPS)
+        band_task<LPU, G, NI>(a, j * S::UPW, min(S::UPW, n_items - j * S::UPW), smem_warp, slab, phase, lane, pol);
 }
 
 }  // namespace bfa
