@@ -13,7 +13,7 @@
 #include "assort.cuh"
 #include "bfa_common.cuh"
 #include "plan.cuh"
-#include "viterbi_band.cuh"
+#include "viterbi_band3.cuh"
 #include "viterbi_generic.cuh"
 
 using namespace bfa;
@@ -58,16 +58,24 @@ struct DeviceInfo {
     bool ok = false;
 };
 
-// The two banded-kernel variants launched per call: 16 lanes per utterance, window 32 / 64 groups.
-constexpr int BAND_LPU = 16, BAND_NI = 5;
-constexpr int BAND_G[2] = {2, 4};
-constexpr int BAND_WARPS = BandShape<BAND_LPU, 2>::WARPS;
-inline int band_rec_words(int G) { return 6 * G + 1; }
-inline int band_smem_bytes_per_warp(int C, int G) {
-    // stage buffers + zero pad + mbarriers + back-trace staging ([UPW][LPU*G*4 cells] x 8 B + 32 shift-flag words)
-    const int upw = 32 / BAND_LPU;
-    size_t b = (size_t)BK_NST * upw * BK_ROWS * C * 4 + BK_PAD * 4 + BK_NST * upw * 8 + (size_t)upw * BAND_LPU * G * 4 * 8 + 32 * 4;
-    return (int)((b + 127) / 128 * 128);
+// The banded-kernel variants launched per call: 8 lanes per utterance, G groups per lane -> window 24 / 40 / 64 groups;
+// each exists specialised for C = 66 (the benchmark width, class loop fully unrolled) and for a run-time C.
+constexpr int BAND_NV = 3;
+constexpr int BAND_G[BAND_NV] = {3, 5, 8};
+constexpr int BAND_WARPS = B3_WARPS;
+inline int band_rec_words(int G) { return 4 * G + 1; }
+inline int band_smem_bytes_per_warp(int C, int G) { return (int)band3_smem_per_warp(C, G); }
+
+template <int G>
+cudaError_t band_set_attr(int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(viterbi_band3_kernel<G, 66>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(viterbi_band3_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+template <int G>
+void band_launch(const Band3Args& ba, int grid, size_t smem, cudaStream_t st) {
+    if (ba.C == 66) viterbi_band3_kernel<G, 66><<<grid, BAND_WARPS * 32, smem, st>>>(ba);
+    else viterbi_band3_kernel<G, 0><<<grid, BAND_WARPS * 32, smem, st>>>(ba);
 }
 
 int device_info(DeviceInfo& out) {
@@ -86,9 +94,9 @@ int device_info(DeviceInfo& out) {
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.vg_ctas_per_sm_big, viterbi_generic_kernel<1>, VG_WARPS * 32, smem));
         if (d.vg_ctas_per_sm < 1) d.vg_ctas_per_sm = 1;
         if (d.vg_ctas_per_sm_big < 1) d.vg_ctas_per_sm_big = 1;
-        const int band_smem_max = band_smem_bytes_per_warp(72, 4) * BAND_WARPS;
-        d.band_ok = cudaFuncSetAttribute(viterbi_band_kernel<BAND_LPU, 2, BAND_NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_max) == cudaSuccess &&
-                    cudaFuncSetAttribute(viterbi_band_kernel<BAND_LPU, 4, BAND_NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_max) == cudaSuccess;
+        const int band_smem_max = band_smem_bytes_per_warp(B3_KK, 8) * BAND_WARPS;
+        d.band_ok = band_set_attr<3>(band_smem_max) == cudaSuccess && band_set_attr<5>(band_smem_max) == cudaSuccess &&
+                    band_set_attr<8>(band_smem_max) == cudaSuccess;
         d.ok = true;
     }
     out = d;
@@ -103,9 +111,9 @@ struct Layout {
     int item_cap, gmax, amax, anchor_words, list_ints, max_L, bp_words_per_lane;
     int resident_warps;
     long long slab_words;
-    int band_grid, band_smem_per_warp[2];
-    long long band_slab_words[2];
-    size_t off_tmask, off_tgtok, off_need, off_rowstat, off_items_local, off_items, off_fast[2], off_lists, off_padded, off_anchors, off_counters,
+    int band_grid, band_smem_per_warp[BAND_NV];
+    long long band_slab_words[BAND_NV];
+    size_t off_tmask, off_tgtok, off_need, off_rowstat, off_items_local, off_items, off_fast[BAND_NV], off_lists, off_padded, off_anchors, off_counters,
         off_pathlp, off_bp, total;
 };
 
@@ -132,7 +140,7 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
     L.slab_words = (long long)(s.max_T + 2) * 32 * L.bp_words_per_lane;
     L.band_grid = d.sms;
     size_t band_bytes = 0;
-    for (int v = 0; v < 2; ++v) {
+    for (int v = 0; v < BAND_NV; ++v) {
         const int G = BAND_G[v];
         L.band_smem_per_warp[v] = band_smem_bytes_per_warp(s.C, G);
         L.band_slab_words[v] = (long long)((s.max_T + 31) / 32 + 1) * band_rec_words(G) * 32;
@@ -146,8 +154,7 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
     L.off_rowstat = o; o = align_up(o + (L.want_rowstat ? (size_t)s.total_frames * 8 : 0));
     L.off_items_local = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
     L.off_items = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
-    L.off_fast[0] = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
-    L.off_fast[1] = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
+    for (int v = 0; v < BAND_NV; ++v) { L.off_fast[v] = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item)); }
     L.off_lists = o; o = align_up(o + (size_t)s.B * L.list_ints * 4);
     L.off_padded = o; o = align_up(o + (L.segmenting ? (size_t)s.B * (s.max_T + 16) * 4 : 0));
     L.off_anchors = o; o = align_up(o + (size_t)s.B * L.anchor_words * 4);
@@ -277,8 +284,8 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     pa.item_cap = L.item_cap; pa.gmax = L.gmax; pa.amax = L.amax; pa.anchor_words = L.anchor_words;
     pa.items_local = (Item*)(ws + L.off_items_local); pa.items = (Item*)(ws + L.off_items);
     pa.n_items = counters; pa.lists = (int32_t*)(ws + L.off_lists); pa.list_ints = L.list_ints;
-    const bool fast = (p->reserved & 1) == 0 && C <= 72 && d.band_ok;
-    for (int v = 0; v < 2; ++v) { pa.fast_items[v] = (Item*)(ws + L.off_fast[v]); pa.n_fast[v] = counters + 3 + 2 * v; }
+    const bool fast = (p->reserved & 1) == 0 && C <= B3_KK && d.band_ok;
+    for (int v = 0; v < BAND_NV; ++v) { pa.fast_items[v] = (Item*)(ws + L.off_fast[v]); pa.n_fast[v] = counters + 3 + 2 * v; }
     pa.fast_enable = fast ? 1 : 0; pa.path_lp = path_lp;
     pa.padded = (float*)(ws + L.off_padded); pa.anchors = (uint32_t*)(ws + L.off_anchors);
     plan_kernel<<<(B + 3) / 4, 128, 0, st>>>(pa);
@@ -286,12 +293,12 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
 
     long long max_items = (long long)B * L.item_cap;
     if (fast) {
-        BandArgs ba;
+        Band3Args ba;
         ba.p = *p; ba.C = C; ba.logp = logp; ba.tgt = tgt; ba.tmask = tmask;
         ba.retry_items = pa.items; ba.n_retry = counters;
         ba.frame_ph = frame_ph; ba.frame_idx = frame_idx; ba.dp_final = dp_final; ba.path_lp = path_lp;
-        ba.bp_scratch = (uint32_t*)(ws + L.off_bp); ba.seg_stride = BK_ROWS * C;
-        for (int v = 0; v < 2; ++v) {
+        ba.bp_scratch = (uint32_t*)(ws + L.off_bp); ba.seg_stride = B3_ROWS * C;
+        for (int v = 0; v < BAND_NV; ++v) {
             ba.items = pa.fast_items[v]; ba.n_items = pa.n_fast[v];
             ba.bp_slab_words = L.band_slab_words[v]; ba.smem_per_warp = L.band_smem_per_warp[v];
             const size_t smem = (size_t)ba.smem_per_warp * BAND_WARPS;
@@ -301,8 +308,9 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
                 if (g_prof.on) { e0 = g_prof.get(); e1 = g_prof.get(); }
             }
             if (e0) cudaEventRecord(e0, st);
-            if (v == 0) viterbi_band_kernel<BAND_LPU, 2, BAND_NI><<<L.band_grid, BAND_WARPS * 32, smem, st>>>(ba);
-            else viterbi_band_kernel<BAND_LPU, 4, BAND_NI><<<L.band_grid, BAND_WARPS * 32, smem, st>>>(ba);
+            if (v == 0) band_launch<3>(ba, L.band_grid, smem, st);
+            else if (v == 1) band_launch<5>(ba, L.band_grid, smem, st);
+            else band_launch<8>(ba, L.band_grid, smem, st);
             LAUNCH_CHECK();
             if (e0) {
                 cudaEventRecord(e1, st);

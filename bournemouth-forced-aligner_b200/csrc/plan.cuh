@@ -10,7 +10,7 @@
 // its length stay on the device.
 #pragma once
 #include "bfa_common.cuh"
-#include "viterbi_band.cuh"
+#include "viterbi_band3.cuh"
 
 namespace bfa {
 
@@ -36,8 +36,8 @@ struct PlanArgs {
     Item* items_local;         // [B][item_cap]
     Item* items;               // compacted list for the exact generic kernel
     int* n_items;              // device counter
-    Item* fast_items[2];       // compacted lists for the banded kernel (window 32 / 64 groups)
-    int* n_fast[2];
+    Item* fast_items[3];       // compacted lists for the banded kernel (window 24 / 40 / 64 groups)
+    int* n_fast[3];
     int fast_enable;
     int32_t* lists;            // [B][list_ints]
     int list_ints;
@@ -75,13 +75,15 @@ __device__ __forceinline__ TgtInfo target_info(const int32_t* tgt, long long b, 
     return r;
 }
 
-// Which kernel runs an item: 0 / 1 = banded kernel with a 32 / 64-group window, -1 = exact generic kernel.
+// Which kernel runs an item: 0 / 1 / 2 = banded kernel with a 24 / 40 / 64-group window, -1 = exact generic kernel.
 __device__ __forceinline__ int fast_class(const Item& it, int C, const float* logp, bool tgt_ok, int fast_enable) {
     if (!fast_enable || !tgt_ok) return -1;
-    if (it.stride != 4 || (it.flags & ITEM_ANCHOR) || C > 72 || it.T < 2 || it.L > it.T) return -1;
+    if (it.stride != 4 || (it.flags & ITEM_ANCHOR) || C > B3_KK || it.T < 2 || it.L > it.T) return -1;
     if (((unsigned long long)(logp + it.lp_off) & 15ull) != 0) return -1;   // bulk copies need 16-B aligned rows
-    if (band_window_fits(it.n, it.band, 32)) return 0;
-    if (band_window_fits(it.n, it.band, 64)) return 1;
+    const int need = band3_window_need(it.n, it.T, it.L, it.band);
+    if (need <= 24) return 0;
+    if (need <= 40) return 1;
+    if (need <= 64) return 2;
     return -1;
 }
 
@@ -472,7 +474,7 @@ __global__ void plan_kernel(PlanArgs a) {
         int cl = -2;
         if (i < n_items) cl = fast_class(loc[i], a.C, a.logp, tok, a.fast_enable);
 #pragma unroll
-        for (int c = -1; c <= 1; ++c) {
+        for (int c = -1; c <= 2; ++c) {
             const unsigned m = __ballot_sync(FULL, cl == c);
             if (!m) continue;
             int* cnt = (c < 0) ? a.n_items : a.n_fast[c];

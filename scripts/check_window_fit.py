@@ -1,0 +1,45 @@
+"""Brute-force check of the per-chunk window schedule of the banded kernel (window slides only at 8-frame chunk starts).
+Prints the smallest window W (in groups) that works for each (T, N) and compares with the closed form used on the device."""
+import math, sys
+import numpy as np
+
+def lo_hi(j, pace, band):
+    c = np.float64(j) * pace
+    lo = math.ceil(np.float32(c - band)); hi = math.floor(np.float32(c + band))
+    return lo, hi
+
+def need_W(T, N, rows=8):
+    L = 4 * N + 1
+    band = max(L // 4, 20) if L > 60 else 0
+    if band == 0 or T < 2:
+        return N + 1, band
+    pace = np.float64(L - 1) / np.float64(T - 1)
+    worst = 0
+    for t0 in range(0, T, rows):
+        base_state_grp = 0 if t0 == 0 else max((lo_hi(t0 - 1, pace, band)[0] + 3) >> 2, 0)
+        jmax = min(t0 + rows - 1, T - 1)
+        top = min(lo_hi(jmax, pace, band)[1], L - 1)
+        top_grp = (top + 3) >> 2
+        worst = max(worst, top_grp - base_state_grp + 1)
+    return min(worst, N + 1), band
+
+def closed(T, N, rows=8):
+    L = 4 * N + 1
+    band = max(L // 4, 20) if L > 60 else 0
+    if band == 0 or T < 2: return N + 1
+    # span in states: 2*band + advance of the centre over `rows` frames, +2 for the float roundings, +3 for group alignment
+    adv = ((rows) * (L - 1) + (T - 2)) // (T - 1)     # ceil(rows*pace)
+    return min(N + 1, (2 * band + adv + 2 + 3) // 4 + 1)
+
+bad = 0
+for N in list(range(1, 130)):
+    for T in list(range(max(4 * N + 1, 2), 4 * N + 40)) + [5 * N, 6 * N + 3, 10 * N, 15 * N, 600, 1800, 3600]:
+        if 4 * N + 1 > T: continue
+        w, band = need_W(T, N)
+        c = closed(T, N)
+        if c < w:
+            bad += 1
+            if bad < 20: print("VIOLATION", T, N, band, w, c)
+print("violations", bad)
+for (T, N) in [(600, 40), (3600, 200), (1800, 120), (600, 60), (600, 100), (300, 40), (200, 40), (161, 40)]:
+    print(T, N, need_W(T, N), closed(T, N))
