@@ -5,8 +5,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "lib" / "libbfa_b200.so"
+# BFA_B200_LIB selects another build of the same library (development: e.g. the -DBFA_PHASE_PROF build)
+LIB_PATH = Path(os.environ["BFA_B200_LIB"]) if os.environ.get("BFA_B200_LIB") else HERE / "lib" / "libbfa_b200.so"
 
 BFA_OK, BFA_E_INVALID, BFA_E_UNSUPPORTED, BFA_E_WORKSPACE, BFA_E_CUDA = 0, -1, -2, -3, -4
 ST_OK, ST_EMPTY_TARGET, ST_TOO_SHORT, ST_PROPORTIONAL, ST_SEGMENTED = 0, 1, 2, 3, 4
@@ -54,6 +57,7 @@ _SIGNATURES = {
     "bfa_assort_batch": (C.c_int, [C.POINTER(BfaParams), C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "bfa_align_batch_host": (C.c_int, [C.POINTER(BfaParams), C.POINTER(BfaShape)] + [_P] * 13 + [C.c_int32, C.c_int32]),
     "bfa_host_release": (None, []),
+    "bfa_debug_phases": (C.c_int, [_P, C.c_int]),
     "bfa_profile_enable": (None, [C.c_int]),
     "bfa_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }

@@ -21,18 +21,22 @@ def _stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: Path = None) -> Path:
+    if out is None and not force and not _stale():
         return LIB
+    lib = out or LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
+    cmd = ["nvcc", *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", str(lib), *[str(CSRC / s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--phase-prof" in sys.argv:   # development build with per-phase cycle counters in the banded kernel
+        print(build(force=True, defines=("BFA_PHASE_PROF",), out=HERE / "lib" / "libbfa_b200_prof.so"))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -72,10 +72,14 @@ cudaError_t band_set_attr(int bytes) {
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(viterbi_band3_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
+constexpr int BAND_SMEM_MAX = 227 * 1024;   // dynamic shared memory one CTA may opt in to on sm_100
+inline int band_warps(int smem_per_warp) { return std::max(1, std::min(BAND_WARPS, BAND_SMEM_MAX / smem_per_warp)); }
 template <int G>
-void band_launch(const Band3Args& ba, int grid, size_t smem, cudaStream_t st) {
-    if (ba.C == 66) viterbi_band3_kernel<G, 66><<<grid, BAND_WARPS * 32, smem, st>>>(ba);
-    else viterbi_band3_kernel<G, 0><<<grid, BAND_WARPS * 32, smem, st>>>(ba);
+void band_launch(const Band3Args& ba, int grid, cudaStream_t st) {
+    const int warps = band_warps(ba.smem_per_warp);
+    const size_t smem = (size_t)warps * ba.smem_per_warp;
+    if (ba.C == 66) viterbi_band3_kernel<G, 66><<<grid, warps * 32, smem, st>>>(ba);
+    else viterbi_band3_kernel<G, 0><<<grid, warps * 32, smem, st>>>(ba);
 }
 
 int device_info(DeviceInfo& out) {
@@ -94,9 +98,10 @@ int device_info(DeviceInfo& out) {
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.vg_ctas_per_sm_big, viterbi_generic_kernel<1>, VG_WARPS * 32, smem));
         if (d.vg_ctas_per_sm < 1) d.vg_ctas_per_sm = 1;
         if (d.vg_ctas_per_sm_big < 1) d.vg_ctas_per_sm_big = 1;
-        const int band_smem_max = band_smem_bytes_per_warp(B3_KK, 8) * BAND_WARPS;
+        const int band_smem_max = BAND_SMEM_MAX;
         d.band_ok = band_set_attr<3>(band_smem_max) == cudaSuccess && band_set_attr<5>(band_smem_max) == cudaSuccess &&
                     band_set_attr<8>(band_smem_max) == cudaSuccess;
+        if (!d.band_ok) (void)cudaGetLastError();   // do not leave a sticky error behind: the exact kernel still runs
         d.ok = true;
     }
     out = d;
@@ -265,7 +270,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
 
     uint32_t* tmask = (uint32_t*)(ws + L.off_tmask);
     float2* rowstat = L.want_rowstat ? (float2*)(ws + L.off_rowstat) : nullptr;
-    float* path_lp = (stamps && conf) ? (float*)(ws + L.off_pathlp) : nullptr;
+    float* path_lp = (stamps && conf && !(p->reserved & BFA_FLAG_UNFUSED_CONF)) ? (float*)(ws + L.off_pathlp) : nullptr;
     int* counters = (int*)(ws + L.off_counters);
     CUDA_TRY(cudaMemsetAsync(counters, 0, 64, st));
 
@@ -297,20 +302,19 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         ba.p = *p; ba.C = C; ba.logp = logp; ba.tgt = tgt; ba.tmask = tmask;
         ba.retry_items = pa.items; ba.n_retry = counters;
         ba.frame_ph = frame_ph; ba.frame_idx = frame_idx; ba.dp_final = dp_final; ba.path_lp = path_lp;
-        ba.bp_scratch = (uint32_t*)(ws + L.off_bp); ba.seg_stride = B3_ROWS * C;
+        ba.bp_scratch = (uint32_t*)(ws + L.off_bp);
         for (int v = 0; v < BAND_NV; ++v) {
             ba.items = pa.fast_items[v]; ba.n_items = pa.n_fast[v];
             ba.bp_slab_words = L.band_slab_words[v]; ba.smem_per_warp = L.band_smem_per_warp[v];
-            const size_t smem = (size_t)ba.smem_per_warp * BAND_WARPS;
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (v == 0) {
                 std::lock_guard<std::mutex> lk(g_prof.mu);
                 if (g_prof.on) { e0 = g_prof.get(); e1 = g_prof.get(); }
             }
             if (e0) cudaEventRecord(e0, st);
-            if (v == 0) band_launch<3>(ba, L.band_grid, smem, st);
-            else if (v == 1) band_launch<5>(ba, L.band_grid, smem, st);
-            else band_launch<8>(ba, L.band_grid, smem, st);
+            if (v == 0) band_launch<3>(ba, L.band_grid, st);
+            else if (v == 1) band_launch<5>(ba, L.band_grid, st);
+            else band_launch<8>(ba, L.band_grid, st);
             LAUNCH_CHECK();
             if (e0) {
                 cudaEventRecord(e1, st);
@@ -389,6 +393,18 @@ int bfa_confidence_batch(int32_t B, int32_t C, const float* logp, const int64_t*
     confidence_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(B, C, logp, (const long long*)row_off, T_conf, stamps, n_stamps,
                                                                      max_stamps, conf);
     LAUNCH_CHECK();
+    return BFA_OK;
+}
+
+// Development aid: per-phase warp-clock sums of the banded kernel (all zero unless built with -DBFA_PHASE_PROF).
+int bfa_debug_phases(unsigned long long* out16, int reset) {
+#ifdef BFA_PHASE_PROF
+    if (out16) CUDA_TRY(cudaMemcpyFromSymbol(out16, g_b3_phase, sizeof(unsigned long long) * 16));
+    if (reset) { unsigned long long z[16] = {0}; CUDA_TRY(cudaMemcpyToSymbol(g_b3_phase, z, sizeof(z))); }
+#else
+    if (out16) memset(out16, 0, sizeof(unsigned long long) * 16);
+    (void)reset;
+#endif
     return BFA_OK;
 }
 

@@ -78,7 +78,7 @@ __device__ __forceinline__ TgtInfo target_info(const int32_t* tgt, long long b, 
 // Which kernel runs an item: 0 / 1 / 2 = banded kernel with a 24 / 40 / 64-group window, -1 = exact generic kernel.
 __device__ __forceinline__ int fast_class(const Item& it, int C, const float* logp, bool tgt_ok, int fast_enable) {
     if (!fast_enable || !tgt_ok) return -1;
-    if (it.stride != 4 || (it.flags & ITEM_ANCHOR) || C > B3_KK || it.T < 2 || it.L > it.T) return -1;
+    if (it.stride != 4 || (it.flags & ITEM_ANCHOR) || C > B3_KK || it.T < 2 || it.L > it.T || it.n > B3_NMAX) return -1;
     if (((unsigned long long)(logp + it.lp_off) & 15ull) != 0) return -1;   // bulk copies need 16-B aligned rows
     const int need = band3_window_need(it.n, it.T, it.L, it.band);
     if (need <= 24) return 0;

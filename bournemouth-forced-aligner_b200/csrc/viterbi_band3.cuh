@@ -42,12 +42,14 @@ namespace bfa {
 
 constexpr int B3_LPU = 8;          // lanes per utterance
 constexpr int B3_UPW = 4;          // utterances per warp
-constexpr int B3_NST = 2;          // pipeline stages
+constexpr int B3_NST = 3;          // pipeline stages (chunk c is consumed while c+1 is being reduced and c+2 is in flight)
 constexpr int B3_ROWS = 8;         // rows per stage per utterance (8*C*4 bytes is always a multiple of 16)
 constexpr int B3_WARPS = 8;        // warps per CTA, one CTA per SM
 constexpr int B3_KK = 72;          // floats per utterance in the class-weight table (C <= 72)
 constexpr int B3_STP = 9;          // float2 pitch of the per-utterance (lnS, eb) array (bank spreading)
+constexpr int B3_NMAX = 128;       // phonemes per item on this path (byte-sized class table in shared memory)
 constexpr int B3_MARGIN = 2;       // states of safety margin of the band-legality check
+constexpr int B3_GRING = 16;       // 32-frame blocks of confidence gathers kept in flight during the back-trace
 
 struct Band3Args {
     BfaParams p;
@@ -65,7 +67,6 @@ struct Band3Args {
     float* path_lp;            // [total_frames] raw log-prob of the assigned class per frame (confidence input), or null
     uint32_t* bp_scratch;
     long long bp_slab_words;
-    int seg_stride;            // floats per (stage, utterance) buffer = B3_ROWS * C
     int smem_per_warp;         // bytes
 };
 
@@ -78,22 +79,29 @@ struct Band3Shape {
 };
 
 // Smallest window (in groups) that covers band(t-1) U band(t) for every frame of every 8-frame chunk when the
-// window base is the group of the lower band edge at the frame before the chunk (scripts/check_window_fit.py
-// verifies the closed form by brute force).
+// window base is the group of (a conservative fp32 estimate, at most one state low, of) the lower band edge at
+// the frame before the chunk (scripts/check_window_fit.py verifies the closed form by brute force).
 __host__ __device__ inline int band3_window_need(int N, int T, int L, int band) {
     if (band <= 0 || T < 2 || L < 2) return N + 1;
     const int adv = (int)(((long long)B3_ROWS * (L - 1) + (T - 2)) / (T - 1));   // ceil(8 * pace)
-    const int w = (2 * band + adv + 5) / 4 + 1;
+    const int w = (2 * band + adv + 6) / 4 + 1;
     return w < N + 1 ? w : N + 1;
 }
 
+// The stage ring doubles as the back-trace staging area (cells + visited-cell buffer) once the fill is done.
+__host__ __device__ inline size_t band3_stage_region(int C, int G) {
+    size_t st = (size_t)B3_NST * B3_UPW * B3_ROWS * C * 4;
+    // back-trace: cells [UPW][3*8G] x 8 B, two record buffers [4G+1][32] words, B3_GRING gather blocks [4][32] floats
+    size_t bt = (size_t)B3_UPW * 3 * B3_LPU * G * 8 + (size_t)2 * (4 * G + 1) * 128 + (size_t)B3_GRING * 4 * 128;
+    size_t b = st > bt ? st : bt;
+    return (b + 15) / 16 * 16;
+}
 __host__ __device__ inline size_t band3_smem_per_warp(int C, int G) {
-    size_t b = (size_t)B3_NST * B3_UPW * B3_ROWS * C * 4;   // stage buffers
+    size_t b = band3_stage_region(C, G);
     b += (size_t)B3_UPW * B3_KK * 4;                        // class weights
-    b += (size_t)B3_UPW * B3_STP * 8;                       // (lnS, eb) per staged row
-    b += (size_t)B3_NST * 8;                                // mbarriers
-    b = (b + 15) / 16 * 16;
-    b += (size_t)B3_UPW * 3 * B3_LPU * G * 8;               // back-trace cells
+    b += (size_t)2 * B3_UPW * B3_STP * 8;                   // (lnS, eb) per staged row, double buffered
+    b += (size_t)B3_UPW * B3_NMAX;                          // target classes (bytes)
+    b += (size_t)(B3_NST + 2) * 8;                          // mbarriers: stages + two back-trace record buffers
     return (b + 127) / 128 * 128;
 }
 
@@ -110,16 +118,39 @@ __device__ __forceinline__ float b3_lg2(float x) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// 4-byte asynchronous global->shared copies (LDGSTS): completion is tracked by cp.async groups, not by the register
+// scoreboard, so nothing that follows stalls on them until the matching wait_group
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // push (later > earlier) into acc: the sign bit of (earlier - later) is 1 iff later > earlier (ties -> 0)
 __device__ __forceinline__ void b3_push(uint32_t& acc, float earlier, float later) {
     acc = __funnelshift_l(__float_as_uint(earlier - later), acc, 1);
 }
 
+// Optional phase timers (development only, -DBFA_PHASE_PROF): warp-clock cycles per phase, summed over lane 0 of all warps.
+#ifdef BFA_PHASE_PROF
+__device__ unsigned long long g_b3_phase[16];
+#define PH_DECL long long ph_last = clock64(); long long ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}
+#define PH_T(i) do { const long long ph_now = clock64(); ph_acc[i] += ph_now - ph_last; ph_last = ph_now; } while (0)
+#define PH_FLUSH do { if (lane == 0) for (int i = 0; i < 16; ++i) atomicAdd(&g_b3_phase[i], (unsigned long long)ph_acc[i]); } while (0)
+#else
+#define PH_DECL
+#define PH_T(i)
+#define PH_FLUSH
+#endif
+
 template <int G, int CT>
 __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned char* smem_warp, uint32_t* slab, uint32_t& phase,
                            int lane, uint64_t pol) {
     using S = Band3Shape<G>;
+    PH_DECL;
     constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+    // the log-sum-exp of chunk c+1 is interleaved with the frames of chunk c when the class count is a compile-time even number
+    constexpr bool PIPE = CT != 0 && (CT & 1) == 0 && (CT / 2) >= 8;
+    constexpr int PAIRS = CT / 2, PP = PAIRS / 8, PREM = PAIRS - 8 * PP;   // float2 pairs per frame slot, leftover pairs
     const int seg = lane >> 3, l8 = lane & 7;
     const int C = CT ? CT : a.C;
     const float NEG = a.p.neg_inf;
@@ -129,10 +160,11 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
     float* stage_buf = reinterpret_cast<float*>(smem_warp);
     const int seg_stride = B3_ROWS * C;
     const int stage_floats = B3_UPW * seg_stride;
-    float* kk = stage_buf + B3_NST * stage_floats;                                         // [UPW][B3_KK]
-    float2* stats = reinterpret_cast<float2*>(kk + B3_UPW * B3_KK);                        // [UPW][B3_STP]
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stats + B3_UPW * B3_STP);   // [NST]
-    uint2* bt2 = reinterpret_cast<uint2*>(smem_warp + ((reinterpret_cast<unsigned char*>(bars + B3_NST) - smem_warp + 15) / 16) * 16);   // [UPW][CELLS]
+    float* kk = reinterpret_cast<float*>(smem_warp + band3_stage_region(C, G));             // [UPW][B3_KK]
+    float2* stats = reinterpret_cast<float2*>(kk + B3_UPW * B3_KK);                         // [2][UPW][B3_STP]
+    unsigned char* cls8 = reinterpret_cast<unsigned char*>(stats + 2 * B3_UPW * B3_STP);    // [UPW][B3_NMAX]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(cls8 + B3_UPW * B3_NMAX);   // [NST]
+    uint2* bt2 = reinterpret_cast<uint2*>(smem_warp);                                       // [UPW][CELLS], aliases the stage ring
 
     // ---- per-segment item description (uniform within a segment) ----
     const bool seg_on = seg < n_valid;
@@ -142,8 +174,7 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
     const int trim = it.trim, n_out = it.n_out, idx0 = it.idx0;
     const long long out_off = it.out_off, out_lim = it.out_lim;
     const bool use_band = band > 0 && T > 1 && L > 1;                          // :586
-    const double pace = use_band ? (double)(L - 1) / (double)(T - 1) : 0.0;   // :587
-    const double bandd = (double)band;
+    const float pace_f = use_band ? (float)((double)(L - 1) / (double)(T - 1)) : 0.0f;   // :587
     const bool use_stats = (flags & ITEM_STATS) != 0;
     const bool warp_stats = __any_sync(FULL, use_stats);   // every item of a call shares the mode
     const float min_lp = (flags & ITEM_FLOOR) ? a.p.min_log_prob : -INFINITY;
@@ -156,8 +187,11 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
     for (int d = 8; d < 32; d <<= 1) Tmax = max(Tmax, __shfl_xor_sync(FULL, Tmax, d));
     const int n_chunks = (Tmax + B3_ROWS - 1) / B3_ROWS;
 
-    // ---- class weights of the fused log-sum-exp: exp(x + boost*[c in targets] - boost) = 2^(x*log2e + kk[c]) ----
-    __syncwarp();   // previous task's readers are done with kk / bt2
+    // ---- per-utterance tables: target classes (bytes) and the class weights of the fused log-sum-exp:
+    //      exp(x + boost*[c in targets] - boost) = 2^(x*log2e + kk[c]) ----
+    __syncwarp();   // previous task's readers are done with the tables / the staging area
+    if (seg_on)
+        for (int j = l8; j < N; j += B3_LPU) cls8[seg * B3_NMAX + j] = (unsigned char)seq[j];
     if (warp_stats) {
         for (int c = l8; c < B3_KK; c += B3_LPU) {
             const bool ok = c < C;
@@ -165,19 +199,29 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
             kk[seg * B3_KK + c] = ok ? (tg ? 0.0f : -boostv * LOG2E) : -INFINITY;
         }
     }
+    __syncwarp();
+    const unsigned char* my_cls = cls8 + seg * B3_NMAX;
+    auto group_class = [&](int gi) { return (seg_on && gi >= 1 && gi <= N) ? (int)my_cls[gi - 1] : blank; };
 
     // lanes with l8 == 0 issue their own utterance's copy and arrive once per chunk on the stage barrier (count = UPW)
-    auto issue = [&](int c) {
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t dst0 = smem_u32(stage_buf + seg * seg_stride);
+    const uint32_t full_bytes = (uint32_t)B3_ROWS * C * 4;
+    auto issue = [&](int c, int st) {
         if (l8 == 0) {
-            const int rows = min(B3_ROWS, T - c * B3_ROWS);
-            const uint32_t bar = smem_u32(&bars[c & 1]);
-            if (rows > 0) {
-                float* dst = stage_buf + (c & 1) * stage_floats + seg * seg_stride;
-                const float* s = my_src + (size_t)c * B3_ROWS * C;
+            const int rows = T - c * B3_ROWS;
+            const uint32_t bar = bar0 + 8u * st;
+            const uint32_t dst = dst0 + (uint32_t)st * stage_floats * 4u;
+            const float* s = my_src + (size_t)c * B3_ROWS * C;
+            if (rows >= B3_ROWS) {
+                mbar_expect_tx(bar, full_bytes);
+                bulk_g2s_hint(dst, s, full_bytes, bar, pol);
+            } else if (rows > 0) {
                 const uint32_t bytes = (uint32_t)rows * C * 4, bulk = bytes & ~15u;
-                for (uint32_t w = bulk >> 2; w < (bytes >> 2); ++w) dst[w] = s[w];   // < 4 tail floats of a partial last chunk
+                float* d = stage_buf + st * stage_floats + seg * seg_stride;
+                for (uint32_t w = bulk >> 2; w < (bytes >> 2); ++w) d[w] = s[w];   // < 4 tail floats of a partial last chunk
                 mbar_expect_tx(bar, bulk);
-                if (bulk) bulk_g2s_hint(smem_u32(dst), s, bulk, bar, pol);
+                if (bulk) bulk_g2s_hint(dst, s, bulk, bar, pol);
             } else {
                 mbar_arrive(bar);
             }
@@ -192,7 +236,6 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
     uint32_t slide_acc = 0;
 #pragma unroll
     for (int i = 0; i < S::ACC; ++i) acc[i] = 0;
-    auto group_class = [&](int gi) { return (seg_on && gi >= 1 && gi <= N) ? seq[gi - 1] : blank; };
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         P[g] = M[g] = B3[g] = -INFINITY;
@@ -202,26 +245,68 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
     int next_cls = group_class(S::W);   // class of the group that enters at the next slide (last lane of the segment)
     const bool seg_first = l8 == 0, seg_last = l8 == B3_LPU - 1;
 
-    issue(0);
-
     bool bad = false;                // needs the exact path
     float fin_val = NEG;
     int fin_cell = 0, fin_base = 0;
     float emax = -INFINITY;          // raw mode: emissions must be <= 0 (log-probabilities)
     float lse_chk = 0.f;             // running sum of the rows' log-sum-exp (finite <=> all rows sane)
 
+    // Row statistics of one staged chunk: lane (seg, l8) owns row l8 of its utterance: log-sum-exp of the boosted
+    // row (:51-54) and the blank emission; no cross-lane traffic.  stats_row = all classes at once (prologue, raw
+    // mode, run-time C); the PIPE variant spreads the same sum over the 8 frame slots of the previous chunk.
+    auto stats_finish = [&](const float* rowp, float sum, float rowmax, int t_row, float2* dst) {
+        float lnS = 0.f;
+        if (warp_stats) {
+            lnS = b3_lg2(sum) * LN2;                                // log sum exp(x + b - boost)
+            if (use_stats && t_row < T) lse_chk += lnS;             // any zero / overflowing / NaN sum leaves a non-finite trace
+        } else if (t_row < T) {
+            emax = fmaxf(emax, rowmax);
+        }
+        // blank is never a target: x - lse with lse = lnS + boost; phoneme classes are boosted targets: x - lnS
+        const float eb = rowp[blank] - (warp_stats ? lnS + boostv : 0.f);
+        dst[seg * B3_STP + l8] = make_float2(lnS, eb);
+    };
+    auto stats_row = [&](int st, int t_row, float2* dst) {
+        const float* rowp = stage_buf + st * stage_floats + seg * seg_stride + l8 * C;
+        float sum = 0.f, rowmax = -INFINITY;
+        if (warp_stats) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            const float* kp = kk + seg * B3_KK;
+            int i = 0;
+            for (; i + 4 <= C; i += 4) {
+                s0 += b3_ex2(fmaf(rowp[i], LOG2E, kp[i]));
+                s1 += b3_ex2(fmaf(rowp[i + 1], LOG2E, kp[i + 1]));
+                s2 += b3_ex2(fmaf(rowp[i + 2], LOG2E, kp[i + 2]));
+                s3 += b3_ex2(fmaf(rowp[i + 3], LOG2E, kp[i + 3]));
+            }
+            for (; i < C; ++i) s0 += b3_ex2(fmaf(rowp[i], LOG2E, kp[i]));
+            sum = (s0 + s1) + (s2 + s3);
+        } else {
+            for (int i = 0; i < C; ++i) rowmax = fmaxf(rowmax, rowp[i]);
+        }
+        stats_finish(rowp, sum, rowmax, t_row, dst);
+    };
+
+    // ---- prologue: fill the ring, reduce chunk 0 ----
+#pragma unroll
+    for (int c = 0; c < B3_NST; ++c)
+        if (c < n_chunks) issue(c, c);
+    mbar_wait(bar0, phase & 1u);
+    phase ^= 1u;
+    __syncwarp();                                      // tail floats written by the issuing lane become visible
+    stats_row(0, l8, stats);
+    __syncwarp();
+    PH_T(0);
+
+    int st = 0;                                        // stage of chunk c
+    int nslide_next = 0;
     for (int c = 0; c < n_chunks; ++c) {
         const int t0 = c * B3_ROWS;
-        __syncwarp();                                  // every lane is done with the other stage (chunk c-1)
-        if (c + 1 < n_chunks) issue(c + 1);
+        const int st_n = (st + 1 == B3_NST) ? 0 : st + 1;     // stage of chunk c+1
 
-        // ---- slide the window to the group of the lower band edge at frame t0-1 (exact :651 arithmetic) ----
-        int nslide = 0;
-        if (use_band && c > 0) {
-            const double center = (double)(t0 - 1) * pace;
-            const int s_lo = __float2int_ru((float)(center - bandd));
-            nslide = min(max((s_lo + 3) >> 2, 0), base_max) - base;
-        }
+        // ---- slide the window to the group of the lower band edge at frame t0-1 (fp32 estimate, never above the
+        //      exact :651 value, at most one state below it) ----
+        int nslide = nslide_next;                      // computed during the previous chunk
         slide_acc = (slide_acc << 4) | (uint32_t)nslide;
         while (__any_sync(FULL, nslide > 0)) {
             const float nP = __shfl_down_sync(FULL, P[0], 1), nM = __shfl_down_sync(FULL, M[0], 1);
@@ -239,82 +324,86 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
             }
             --nslide;
         }
-
-        mbar_wait(smem_u32(&bars[c & 1]), (phase >> (c & 1)) & 1u);
-        phase ^= 1u << (c & 1);
-        __syncwarp();                                  // tail floats written by the issuing lane become visible
-
-        const float* seg_rows = stage_buf + (c & 1) * stage_floats + seg * seg_stride;   // the 8 staged rows of this utterance
-
-        // ---- row statistics: lane (seg, l8) owns row l8 of its utterance: log-sum-exp of the boosted row (:51-54)
-        //      and the blank emission; no cross-lane traffic ----
-        {
-            const float* rowp = seg_rows + l8 * C;
-            float lnS = 0.f;
-            if (warp_stats) {
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                const float* kp = kk + seg * B3_KK;
-                if (CT != 0 && (CT & 1) == 0) {
-                    const float2* x2 = reinterpret_cast<const float2*>(rowp);
-                    const float4* k4 = reinterpret_cast<const float4*>(kp);
-#pragma unroll
-                    for (int i = 0; i < CT / 4; ++i) {
-                        const float4 k = k4[i];
-                        const float2 xa = x2[2 * i], xb = x2[2 * i + 1];
-                        s0 += b3_ex2(fmaf(xa.x, LOG2E, k.x));
-                        s1 += b3_ex2(fmaf(xa.y, LOG2E, k.y));
-                        s2 += b3_ex2(fmaf(xb.x, LOG2E, k.z));
-                        s3 += b3_ex2(fmaf(xb.y, LOG2E, k.w));
-                    }
-                    if (CT % 4) {
-                        const float2 xa = x2[CT / 2 - 1];
-                        const float2 k = reinterpret_cast<const float2*>(kp)[CT / 2 - 1];
-                        s0 += b3_ex2(fmaf(xa.x, LOG2E, k.x));
-                        s1 += b3_ex2(fmaf(xa.y, LOG2E, k.y));
-                    }
-                } else {
-                    int i = 0;
-                    for (; i + 4 <= C; i += 4) {
-                        s0 += b3_ex2(fmaf(rowp[i], LOG2E, kp[i]));
-                        s1 += b3_ex2(fmaf(rowp[i + 1], LOG2E, kp[i + 1]));
-                        s2 += b3_ex2(fmaf(rowp[i + 2], LOG2E, kp[i + 2]));
-                        s3 += b3_ex2(fmaf(rowp[i + 3], LOG2E, kp[i + 3]));
-                    }
-                    for (; i < C; ++i) s0 += b3_ex2(fmaf(rowp[i], LOG2E, kp[i]));
-                }
-                lnS = b3_lg2((s0 + s1) + (s2 + s3)) * LN2;   // log sum exp(x + b - boost)
-                if (use_stats && t0 + l8 < T) lse_chk += lnS;   // any zero / overflowing / NaN sum leaves a non-finite trace
-            } else {
-                float m = -INFINITY;
-                for (int i = 0; i < C; ++i) m = fmaxf(m, rowp[i]);
-                if (t0 + l8 < T) emax = fmaxf(emax, m);
-            }
-            // blank is never a target: x - lse with lse = lnS + boost; phoneme classes are boosted targets: x - lnS
-            const float eb = rowp[blank] - (warp_stats ? lnS + boostv : 0.f);
-            stats[seg * B3_STP + l8] = make_float2(lnS, eb);
+        if (use_band) {                                // slide of the next chunk: lower edge at frame t0+7
+            const float lo_est = floorf(fmaf((float)(t0 + B3_ROWS - 1), pace_f, -(float)band - 0.01f));
+            nslide_next = min(max(((int)lo_est + 3) >> 2, 0), base_max) - base;
         }
-        __syncwarp();
+        PH_T(1);
 
+        // ---- chunk c+1 has landed (it was issued two chunks ago) ----
+        const bool has_next = c + 1 < n_chunks;
+        if (has_next) {
+            mbar_wait(bar0 + 8u * st_n, (phase >> st_n) & 1u);
+            phase ^= 1u << st_n;
+        }
+        __syncwarp();                                  // tail floats written by the issuing lane become visible
+        PH_T(2);
+
+        float2* stats_n = stats + ((c + 1) & 1) * B3_UPW * B3_STP;
+        const float* rowp_n = stage_buf + st_n * stage_floats + seg * seg_stride + l8 * C;   // this lane's row of chunk c+1
+        if (!PIPE || !warp_stats) {
+            if (has_next) stats_row(st_n, t0 + B3_ROWS + l8, stats_n);
+        }
+        PH_T(3);
+
+        const float* seg_rows = stage_buf + st * stage_floats + seg * seg_stride;   // the 8 staged rows of this utterance
         const int fin_r = T - 1 - t0;                                      // row of the last frame if it is in this chunk
         const bool fin_here = __any_sync(FULL, fin_r >= 0 && fin_r < B3_ROWS);
         const float* xg[G];                                                // row 0 address of each group's class
 #pragma unroll
         for (int g = 0; g < G; ++g) xg[g] = seg_rows + cls[g];
-        const float2* stp = stats + seg * B3_STP;
+        const float2* stp = stats + (c & 1) * B3_UPW * B3_STP + seg * B3_STP;
         float xp_n[G];                                                     // raw emissions are fetched one frame ahead
 #pragma unroll
         for (int g = 0; g < G; ++g) xp_n[g] = xg[g][0];
-        float2 st_n = stp[0];
+        float2 st_nx = stp[0];
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;                      // partial sums of the next chunk's row
+
+        // one eighth of the next chunk's log-sum-exp (PIPE): pairs r*PP .. r*PP+PP-1, the leftover pairs in slot 7
+        auto stats_part = [&](const int r) {
+            if (PIPE) {
+                const float2* x2 = reinterpret_cast<const float2*>(rowp_n);
+                const float2* k2 = reinterpret_cast<const float2*>(kk + seg * B3_KK);
+#pragma unroll
+                for (int i = 0; i < PP; i += 2) {
+                    if (i + 1 < PP && (PP & 1) == 0) {
+                        const float4 k = *reinterpret_cast<const float4*>(k2 + r * PP + i);
+                        const float2 xa = x2[r * PP + i], xb = x2[r * PP + i + 1];
+                        s0 += b3_ex2(fmaf(xa.x, LOG2E, k.x));
+                        s1 += b3_ex2(fmaf(xa.y, LOG2E, k.y));
+                        s2 += b3_ex2(fmaf(xb.x, LOG2E, k.z));
+                        s3 += b3_ex2(fmaf(xb.y, LOG2E, k.w));
+                    } else {
+                        const float2 k = k2[r * PP + i], xa = x2[r * PP + i];
+                        s0 += b3_ex2(fmaf(xa.x, LOG2E, k.x));
+                        s1 += b3_ex2(fmaf(xa.y, LOG2E, k.y));
+                        if (i + 1 < PP) {
+                            const float2 kb = k2[r * PP + i + 1], xb = x2[r * PP + i + 1];
+                            s2 += b3_ex2(fmaf(xb.x, LOG2E, kb.x));
+                            s3 += b3_ex2(fmaf(xb.y, LOG2E, kb.y));
+                        }
+                    }
+                }
+                if (r == B3_ROWS - 1) {
+#pragma unroll
+                    for (int i = 0; i < PREM; ++i) {
+                        const float2 k = k2[8 * PP + i], xa = x2[8 * PP + i];
+                        s2 += b3_ex2(fmaf(xa.x, LOG2E, k.x));
+                        s3 += b3_ex2(fmaf(xa.y, LOG2E, k.y));
+                    }
+                }
+            }
+        };
 
         auto frame = [&](const int r, auto check_fin) {
             constexpr bool CHECK = decltype(check_fin)::value;
-            const float lnS = st_n.x, eb = st_n.y;
+            const float lnS = st_nx.x, eb = st_nx.y;
             float ep[G];
 #pragma unroll
             for (int g = 0; g < G; ++g) ep[g] = fmaxf(xp_n[g] - lnS, min_lp);
             if (CHECK || r + 1 < B3_ROWS) {
                 const int rn = (r + 1 < B3_ROWS) ? r + 1 : r;
-                st_n = stp[rn];
+                st_nx = stp[rn];
 #pragma unroll
                 for (int g = 0; g < G; ++g) xp_n[g] = xg[g][rn * C];
             }
@@ -394,13 +483,26 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
             }
         };
 
-        if (!fin_here) {
+        auto run_chunk = [&](auto with_stats) {
+            constexpr bool WS = decltype(with_stats)::value;
+            if (!fin_here) {
 #pragma unroll
-            for (int r = 0; r < B3_ROWS; ++r) frame(r, std::false_type{});
-        } else {
+                for (int r = 0; r < B3_ROWS; ++r) {
+                    frame(r, std::false_type{});
+                    if (WS) stats_part(r);
+                }
+            } else {
 #pragma unroll 1
-            for (int r = 0; r < B3_ROWS; ++r) frame(r, std::true_type{});
-        }
+                for (int r = 0; r < B3_ROWS; ++r) {
+                    frame(r, std::true_type{});
+                    if (WS) stats_part(r);
+                }
+            }
+        };
+        if (PIPE && warp_stats) run_chunk(std::true_type{});
+        else run_chunk(std::false_type{});
+        if (PIPE && warp_stats) stats_finish(rowp_n, (s0 + s1) + (s2 + s3), 0.f, has_next ? t0 + B3_ROWS + l8 : T, stats_n);
+        PH_T(4);
         // ---- flush one full 32-frame record (utterances that end inside this chunk flushed at their last frame)
         if ((c & 3) == 3 && T - 1 > t0 + B3_ROWS - 1) {
             uint32_t* rec = slab + (size_t)(c >> 2) * S::REC * 32 + lane;
@@ -408,7 +510,13 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
             for (int i = 0; i < S::ACC; ++i) rec[i * 32] = acc[i];
             rec[S::ACC * 32] = slide_acc;
         }
+        __syncwarp();                                  // every lane is done with stage st; the next chunk's statistics are visible
+        PH_T(11);
+        if (c + B3_NST < n_chunks) issue(c + B3_NST, st);
+        PH_T(12);
+        st = st_n;
     }
+    PH_T(5);
     __syncwarp();
     if (emax > 0.f) bad = true;
     if (use_stats && !(fabsf(lse_chk) < 3.0e38f)) bad = true;
@@ -422,70 +530,128 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
     // bt2[seg][ci] = (first decision word, second decision word or 0), so one 64-bit shared load per frame yields
     // (b0, b1) and every transition is  ci -= b1 ? 2 : b0  (p: from m' = -2 / from b3' = -1, m: from p = -1,
     // b3: from m = -1); a window slide of n groups adds 3n.  cabs = 3*base + ci is slide-invariant.
+    // The walk is branch-free: records of frames past the end of an utterance are zero ("stay"), the cell is kept
+    // as a shared-memory byte address A so the loop-carried chain is LDS -> bit test -> 2 selects, and the visited
+    // cells go through a small shared buffer from which every lane picks the 4 frames it writes out.
     const bool walk = seg_on && !bad && T > 0;
-    int ci = fin_cell;
-    int base3 = 3 * fin_base;
+    const int last_blk = (T - 1) >> 5;
+    const uint32_t cellbase = smem_u32(bt2 + seg * S::CELLS);
+    uint32_t A = cellbase + 8u * (uint32_t)fin_cell;
+    uint32_t K = 24u * (uint32_t)fin_base - cellbase;          // A + K = 8 * cabs
     bool illegal = false;
-    const float pace_f = (float)pace, lim_f = (float)(band - B3_MARGIN);
+    const float lim_f = (float)(band - B3_MARGIN);
     long long pend_o[4] = {-1, -1, -1, -1};   // outputs of the previous 32-frame block, stored one block late
     int pend_cls[4] = {0, 0, 0, 0}, pend_idx[4] = {0, 0, 0, 0};
-    float pend_x[4] = {0.f, 0.f, 0.f, 0.f};
-    bool pend_gather[4] = {false, false, false, false};
     const int nblk = (Tmax + 31) >> 5;
-    for (int b = nblk - 1; b >= 0; --b) {
-        __syncwarp();
-        uint32_t sfw;
-        {
-            const uint32_t* rec = slab + (size_t)b * S::REC * 32 + lane;
-            uint32_t w[S::REC];
-#pragma unroll
-            for (int i = 0; i < S::REC; ++i) w[i] = rec[i * 32];
-            uint2* dst = bt2 + seg * S::CELLS + l8 * G * 3;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                dst[3 * g + 0] = make_uint2(w[4 * g + 0], w[4 * g + 1]);   // p : (A0, A1)
-                dst[3 * g + 1] = make_uint2(w[4 * g + 2], 0u);             // m : (A2, 0)
-                dst[3 * g + 2] = make_uint2(w[4 * g + 3], 0u);             // b3: (A3, 0)
-            }
-            sfw = w[S::ACC];
+    // Shared staging (aliases the stage ring): cells, two record buffers, a ring of gathered log-probs.
+    //  * records (decision words of one 32-frame block) come back from the slab by bulk async copy (TMA) on their own
+    //    mbarriers, one block ahead;
+    //  * the confidence inputs lp[f, phoneme of the stamp] (utils.py:89-103) are gathered with 4-byte cp.async copies that
+    //    nothing waits for inside the loop: up to B3_GRING blocks are in flight, then they are drained and written out.
+    uint32_t* recbuf = reinterpret_cast<uint32_t*>(bt2 + B3_UPW * S::CELLS);                 // [2][REC][32]
+    uint32_t* gbuf = recbuf + 2 * S::REC * 32;                                                 // [B3_GRING][4][32]
+    const uint32_t rec_s = smem_u32(recbuf), g_s = smem_u32(gbuf) + 4u * lane;
+    const uint32_t rbar0 = bar0 + 8u * B3_NST;                                                 // two record barriers follow the stage barriers
+    constexpr uint32_t GNONE = 0x7fffffffu;                                                    // slot not gathered
+    auto issue_rec = [&](int blk) {
+        if (lane == 0) {
+            const uint32_t bar = rbar0 + 8u * (blk & 1);
+            mbar_expect_tx(bar, S::REC * 128u);
+            bulk_g2s(rec_s + (uint32_t)(blk & 1) * S::REC * 128u, slab + (size_t)blk * S::REC * 32, S::REC * 128u, bar);
         }
-        __syncwarp();
-        const uint2* cell = bt2 + seg * S::CELLS;
-        const int qhi = walk ? min(31, T - 1 - b * 32) : -1;   // last frame of this utterance inside the block
-        int keep4[4] = {0, 0, 0, 0};                            // cabs of frames 32b + 8i + l8
+    };
+    auto drain = [&](int b_lo, int b_hi) {      // write out the gathered values of blocks b_lo..b_hi (inclusive)
+        cp_async_wait_all();
+        if (a.path_lp && walk) {
+            for (int bb = b_lo; bb <= b_hi; ++bb) {
 #pragma unroll
-        for (int q = 31; q >= 0; --q) {
-            if (q <= qhi) {
-                if ((q & 7) == l8) keep4[q >> 3] = base3 + ci;
-                if (q > 0 || b > 0) {                      // frame 0 has no predecessor
-                    const uint2 wv = cell[ci];
-                    const uint32_t bit = 1u << (31 - q);
-                    const int d = (wv.y & bit) ? 2 : ((wv.x & bit) ? 1 : 0);
-                    ci -= d;
-                    if ((q & 7) == 0) {                    // the window slid before this chunk's first frame was computed
-                        const int n3 = 3 * (int)((sfw >> (4 * (3 - (q >> 3)))) & 15u);
-                        ci += n3;
-                        base3 -= n3;
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t v = gbuf[(bb % B3_GRING) * 128 + i * 32 + lane];
+                    const int rel = bb * 32 + 8 * i + l8 - trim;
+                    if (v != GNONE) a.path_lp[out_off + rel] = __uint_as_float(v);
                 }
             }
         }
-        // ---- output of the block, software-pipelined by one block: the loads it needs (target ids, gathered
-        //      log-probs for the confidences) are issued now, four independent chains per lane, and consumed
-        //      after the next block's walk, so their latency never stalls the warp ----
+    };
+    asm volatile("fence.proxy.async.global;" ::: "memory");   // the slab was written with ordinary stores, the bulk copies read it through the async proxy
+    __syncwarp();
+    issue_rec(nblk - 1);
+    uint32_t rphase = phase >> B3_NST;         // phase bits of the two record barriers
+    int ring_hi = nblk - 1;                    // highest block whose gathers sit in the ring
+#pragma unroll 1
+    for (int bb = 0; bb < B3_GRING && bb < nblk; ++bb)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gbuf[bb * 128 + i * 32 + lane] = GNONE;
+    PH_T(6);
+    for (int b = nblk - 1; b >= 0; --b) {
+        mbar_wait(rbar0 + 8u * (b & 1), (rphase >> (b & 1)) & 1u);     // record of block b has landed
+        rphase ^= 1u << (b & 1);
+        __syncwarp();                          // all lanes are done with the cells of block b+1
+        uint32_t sfw, sb = 0;
+        {
+            const bool live = walk && b <= last_blk;   // later blocks of a shorter utterance hold stale records
+            const uint32_t* wn = recbuf + (b & 1) * S::REC * 32 + lane;
+            uint2* dst = bt2 + seg * S::CELLS + l8 * G * 3;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                dst[3 * g + 0] = live ? make_uint2(wn[(4 * g + 0) * 32], wn[(4 * g + 1) * 32]) : make_uint2(0u, 0u);   // p : (A0, A1)
+                dst[3 * g + 1] = live ? make_uint2(wn[(4 * g + 2) * 32], 0u) : make_uint2(0u, 0u);                      // m : (A2, 0)
+                dst[3 * g + 2] = live ? make_uint2(wn[(4 * g + 3) * 32], 0u) : make_uint2(0u, 0u);                      // b3: (A3, 0)
+            }
+            sfw = live ? wn[S::ACC * 32] : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)                 // chunks of this block whose first frame follows a window slide
+                if ((sfw >> (4 * (3 - j))) & 15u) sb |= 1u << (31 - 8 * j);
+        }
+        __syncwarp();                          // cells visible; everybody has read its record words
+        PH_T(7);
+        if (b > 0) issue_rec(b - 1);
+
+        // ---- walk the 32 frames of the block, one RUN per iteration (bit 31-f belongs to frame f): the path stays in
+        //      its cell until a decision bit of that cell (or a slide boundary) is set.  The loop-carried chain is
+        //      LDS -> mask -> lowest set bit -> bit tests -> 2 selects; frame numbers are never materialised ----
+        uint32_t keep[4] = {0u, 0u, 0u, 0u};             // 8 * cabs of frames 32b + 8i + l8
+        uint32_t mask = 0xffffffffu;                      // frames not yet walked
+        do {
+            uint32_t w0, w1;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(A) : "memory");
+            const uint32_t stop = (w0 | w1 | sb) & mask;
+            const uint32_t bit = stop & (0u - stop);      // frame whose decision ends the run (0: none left in this block)
+            const uint32_t maskn = bit * 0xfffffffeu;     // frames strictly before it  (= -(2*bit); 0 when bit is 0 or bit 31)
+            const uint32_t run = mask & ~maskn;           // frames of this run
+            const uint32_t AK = A + K;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (run & (0x80000000u >> (8 * i + l8))) keep[i] = AK;
+            const uint32_t A1 = A - 8u, A2 = A - 16u;
+            A = (w0 & bit) ? A1 : A;
+            A = (w1 & bit) ? A2 : A;
+            if (__any_sync(FULL, (sb & bit) != 0u)) {      // the window slid before this chunk's first frame was computed (rare)
+                if (sb & bit) {
+                    const int j = __clz(bit) >> 3;         // chunk of the block: bit 31-8j
+                    const uint32_t n24 = 24u * ((sfw >> (4 * (3 - j))) & 15u);
+                    A += n24;
+                    K -= n24;
+                }
+            }
+            mask = maskn;
+        } while (__any_sync(FULL, mask != 0u));
+        PH_T(8);
+        // ---- store the block decoded in the previous iteration ----
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             if (pend_o[i] >= 0) {
                 a.frame_ph[pend_o[i]] = pend_cls[i];
                 a.frame_idx[pend_o[i]] = pend_idx[i];
-                if (pend_gather[i]) a.path_lp[pend_o[i]] = pend_x[i];
             }
+        // ---- decode this block and issue its gathers ----
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             pend_o[i] = -1;
             const int tf = b * 32 + 8 * i + l8;
             if (walk && tf < T) {
-                const int gi = keep4[i] / 3, k = keep4[i] - 3 * gi;
+                const int cabs = (int)(keep[i] >> 3);
+                const int gi = cabs / 3, k = cabs - 3 * gi;
                 // band legality of the state at frame tf (:650-653), conservative: centre of the (merged) state
                 // must be at least B3_MARGIN states inside the band
                 if (use_band) {
@@ -497,24 +663,31 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
                 if (rel >= 0 && rel < n_out && o < out_lim) {
                     const bool ph = k == 0;
                     pend_o[i] = o;
-                    pend_cls[i] = ph ? seq[gi - 1] : blank;
+                    pend_cls[i] = ph ? (int)my_cls[gi - 1] : blank;
                     pend_idx[i] = ph ? idx0 + gi - 1 : -1;
-                    pend_gather[i] = a.path_lp && (ph || !a.p.ignore_noise);
+                    if (a.path_lp && (ph || !a.p.ignore_noise))
+                        cp_async4(g_s + (uint32_t)(b % B3_GRING) * 512u + 128u * i, my_src + (long long)tf * C + pend_cls[i]);
                 }
             }
         }
-        // confidences (utils.py:89-103) read lp[f, phoneme of the stamp]: gather it here, once per frame
+        if (ring_hi - b + 1 == B3_GRING && b > 0) {     // ring full: drain it, clear it for the next B3_GRING blocks
+            drain(b, ring_hi);
+            ring_hi = b - 1;
+#pragma unroll 1
+            for (int bb = 0; bb < B3_GRING; ++bb)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (pend_o[i] >= 0 && pend_gather[i]) pend_x[i] = __ldg(my_src + (long long)(b * 32 + 8 * i + l8) * C + pend_cls[i]);
+                for (int i = 0; i < 4; ++i) gbuf[bb * 128 + i * 32 + lane] = GNONE;
+        }
+        PH_T(9);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         if (pend_o[i] >= 0) {
             a.frame_ph[pend_o[i]] = pend_cls[i];
             a.frame_idx[pend_o[i]] = pend_idx[i];
-            if (pend_gather[i]) a.path_lp[pend_o[i]] = pend_x[i];
         }
+    drain(0, ring_hi);
+    phase = (phase & ((1u << B3_NST) - 1u)) | (rphase << B3_NST);
     {   // a path that left (or came too close to) the band is not provably the reference's: exact path
         const unsigned m = __ballot_sync(FULL, illegal);
         if ((m >> (seg * B3_LPU)) & 0xffu) bad = true;
@@ -528,6 +701,8 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
         }
     }
     __syncwarp();
+    PH_T(10);
+    PH_FLUSH;
 }
 
 template <int G, int CT>
@@ -537,24 +712,26 @@ __global__ void __launch_bounds__(B3_WARPS * 32, 1) viterbi_band3_kernel(Band3Ar
     unsigned char* smem_warp = smem_raw + (size_t)warp * a.smem_per_warp;
     {
         const int C = CT ? CT : a.C;
-        float* stage_buf = reinterpret_cast<float*>(smem_warp);
-        const int nfl = B3_NST * B3_UPW * B3_ROWS * C + B3_UPW * B3_KK + B3_UPW * B3_STP * 2;
-        for (int i = lane; i < nfl; i += 32) stage_buf[i] = 0.0f;   // never-loaded slots must hold finite values
-        unsigned long long* bars = reinterpret_cast<unsigned long long*>(stage_buf + nfl);
+        uint32_t* w = reinterpret_cast<uint32_t*>(smem_warp);
+        for (int i = lane; i < a.smem_per_warp / 4; i += 32) w[i] = 0u;   // never-loaded slots must hold finite values
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(
+            smem_warp + band3_stage_region(C, G) + B3_UPW * B3_KK * 4 + 2 * B3_UPW * B3_STP * 8 + B3_UPW * B3_NMAX);
+        __syncwarp();
         if (lane == 0)
-            for (int i = 0; i < B3_NST; ++i) mbar_init(smem_u32(&bars[i]), B3_UPW);
+            for (int i = 0; i < B3_NST + 2; ++i) mbar_init(smem_u32(&bars[i]), i < B3_NST ? B3_UPW : 1);
         fence_mbar_init();   // also orders the generic-proxy zero fill before the first async copy
     }
     __syncwarp();
     const uint64_t pol = policy_evict_first();
     uint32_t phase = 0;
-    const int gwarp = blockIdx.x * B3_WARPS + warp;
+    const int nwarps = blockDim.x >> 5;   // <= B3_WARPS, as many as the shared memory of one SM holds
+    const int gwarp = blockIdx.x * nwarps + warp;
     uint32_t* slab = a.bp_scratch + (size_t)gwarp * a.bp_slab_words;
     const int n_items = *a.n_items;
     const int n_tasks = (n_items + B3_UPW - 1) / B3_UPW;
     // static deal: task j -> CTA j % grid, warp (j / grid) % WARPS.  With one CTA per SM this spreads
     // ceil(n_tasks / SMs) tasks evenly over the SMs and over the four schedulers of each SM.
-    for (int j = blockIdx.x + gridDim.x * warp; j < n_tasks; j += gridDim.x * B3_WARPS)
+    for (int j = blockIdx.x + gridDim.x * warp; j < n_tasks; j += gridDim.x * nwarps)
         band3_task<G, CT>(a, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_warp, slab, phase, lane, pol);
 }
 

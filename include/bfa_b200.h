@@ -82,6 +82,8 @@ typedef struct BfaParams {
 #define BFA_HINT_NO_SIL 2     /* caller asserts that no target contains silence_id: skips the row-statistics pass that
                                  only the silence scan needs.  A pure performance hint: if it is wrong the planner
                                  recomputes what it needs (slower), results are unchanged. */
+#define BFA_FLAG_UNFUSED_CONF 4  /* confidences gather lp[f, phoneme] from logp inside the stamp kernel instead of taking the
+                                 * per-frame values the Viterbi back-trace collects (measurement / A-B switch) */
 
 /* framestamp tuple (phoneme_id, start_frame, end_frame_exclusive, target_seq_idx)
  * = the 4-tuples returned by ViterbiDecoder.assort_frames (forced_alignment.py:777-834). */
@@ -196,6 +198,10 @@ int bfa_assort_batch(const BfaParams *p, int32_t B, const int32_t *T, const int6
  * them and returns the summed device time and the number of launches since the previous read. */
 void bfa_profile_enable(int on);
 int bfa_profile_read(float *dominant_ms, int32_t *n_launches);
+
+/* Development aid: sums of warp-clock cycles per phase of the banded Viterbi kernel (16 counters); all zero unless
+ * the library was built with -DBFA_PHASE_PROF (scripts/phase_prof.sh).  reset != 0 clears them after the read. */
+int bfa_debug_phases(unsigned long long *out16, int reset);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 int64_t bfa_launch_count(void);

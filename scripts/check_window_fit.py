@@ -16,7 +16,13 @@ def need_W(T, N, rows=8):
     pace = np.float64(L - 1) / np.float64(T - 1)
     worst = 0
     for t0 in range(0, T, rows):
-        base_state_grp = 0 if t0 == 0 else max((lo_hi(t0 - 1, pace, band)[0] + 3) >> 2, 0)
+        if t0 == 0:
+            base_state_grp = 0
+        else:
+            # device estimate: fp32 fma, floor, 0.01 below -> never above the exact lower edge
+            lo_est = math.floor(np.float32(np.float32(t0 - 1) * np.float32(pace) + np.float32(-band - 0.01)))
+            assert lo_est <= lo_hi(t0 - 1, pace, band)[0], (T, N, t0)
+            base_state_grp = max((lo_est + 3) >> 2, 0)
         jmax = min(t0 + rows - 1, T - 1)
         top = min(lo_hi(jmax, pace, band)[1], L - 1)
         top_grp = (top + 3) >> 2
@@ -29,7 +35,7 @@ def closed(T, N, rows=8):
     if band == 0 or T < 2: return N + 1
     # span in states: 2*band + advance of the centre over `rows` frames, +2 for the float roundings, +3 for group alignment
     adv = ((rows) * (L - 1) + (T - 2)) // (T - 1)     # ceil(rows*pace)
-    return min(N + 1, (2 * band + adv + 2 + 3) // 4 + 1)
+    return min(N + 1, (2 * band + adv + 6) // 4 + 1)
 
 bad = 0
 for N in list(range(1, 130)):

@@ -1,0 +1,24 @@
+"""Development: run the metric batch through the -DBFA_PHASE_PROF build and print warp-clock cycles per phase of the
+banded kernel (BFA_B200_LIB must point at libbfa_b200_prof.so)."""
+import ctypes as C, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bfa_b200
+from bfa_b200 import synth, _cabi
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+CONF = (sys.argv[2] != 'noconf') if len(sys.argv) > 2 else True
+T, N, Cc = 600, 40, 66
+dev = torch.device("cuda:0")
+lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=1, peak=8.0, device=dev)
+au = bfa_b200.AlignmentUtils(blank_id=Cc - 1, silence_id=0, silence_anchors=10, ignore_noise=True, truly_forced=True)
+lens = torch.full((B,), T, dtype=torch.long); nl = torch.full((B,), N, dtype=torch.long)
+for it in range(3):
+    au.decode_alignments(lp, true_seqs=tgt.to(dev), pred_lens=lens, true_seqs_lens=nl, with_confidence=CONF)
+    torch.cuda.synchronize()
+    out = (C.c_ulonglong * 16)()
+    _cabi.lib().bfa_debug_phases(out, 1)
+names = ["setup", "slide", "barrier wait", "row stats (unpiped)", "frames+stats", "loop end", "pre-walk", "stage", "walk", "output", "tail", "flush+sync", "issue"]
+tot = sum(out[:13]); nw = (B + 3) // 4
+print(f"warps {nw}; cycles per warp-task {tot / nw:.0f} = {tot / nw / 1.965e3:.1f} us")
+for n, v in zip(names, out):
+    print(f"{n:14s} {v / nw:10.0f} cyc/task  {100 * v / tot:5.1f}%")
