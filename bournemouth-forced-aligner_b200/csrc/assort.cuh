@@ -54,6 +54,10 @@ __device__ __forceinline__ float stamp_confidence_path(const float* plp, int T, 
     return avg;
 }
 
+constexpr int ASSORT_TS = 1024;    // frames per utterance staged in shared memory (longer utterances read global memory)
+constexpr int ASSORT_WARPS = 4;
+constexpr int ASSORT_SMEM = ASSORT_WARPS * 3 * ASSORT_TS * 4;
+
 struct AssortArgs {
     BfaParams p;
     int B, C, max_stamps;
@@ -81,6 +85,24 @@ __global__ void assort_confidence_kernel(AssortArgs a) {
     const int T = a.T[u];
     const int32_t* ph = a.frame_ph + a.frame_off[u];
     const int32_t* ix = a.frame_idx + a.frame_off[u];
+    const float* plp = a.path_lp ? a.path_lp + a.frame_off[u] : nullptr;
+    // Stage the utterance's per-frame arrays in shared memory with independent coalesced loads (all in flight at
+    // once); the run-length scan and the per-stamp confidence loops below then never wait on global memory.
+    extern __shared__ int32_t assort_smem[];
+    if (T <= ASSORT_TS) {
+        int32_t* ph_s = assort_smem + (threadIdx.x >> 5) * 3 * ASSORT_TS;
+        int32_t* ix_s = ph_s + ASSORT_TS;
+        float* lp_s = reinterpret_cast<float*>(ix_s + ASSORT_TS);
+#pragma unroll 4
+        for (int t = lane; t < T; t += 32) {
+            ph_s[t] = ph[t];
+            ix_s[t] = ix[t];
+            if (plp) lp_s[t] = plp[t];
+        }
+        __syncwarp();
+        ph = ph_s; ix = ix_s;
+        if (plp) plp = lp_s;
+    }
     BfaStamp* out = a.stamps + (size_t)u * a.max_stamps;
     const int blank = a.p.blank_id;
     // Pass 1: every run start emits a provisional stamp (end filled by the next run start).
@@ -149,8 +171,8 @@ __global__ void assort_confidence_kernel(AssortArgs a) {
         const float* lp = a.logp + a.row_off[u];
         for (int i = lane; i < n; i += 32) {
             BfaStamp s = out[i];
-            a.conf[(size_t)u * a.max_stamps + i] = (a.path_lp && s.phoneme < a.C)
-                                                       ? stamp_confidence_path(a.path_lp + a.frame_off[u], T, s.start, s.end)
+            a.conf[(size_t)u * a.max_stamps + i] = (plp && s.phoneme < a.C)
+                                                       ? stamp_confidence_path(plp, T, s.start, s.end)
                                                        : stamp_confidence(lp, T, a.C, s.phoneme, s.start, s.end);
         }
     }

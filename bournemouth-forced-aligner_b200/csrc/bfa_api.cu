@@ -62,7 +62,7 @@ struct DeviceInfo {
 // each exists specialised for C = 66 (the benchmark width, class loop fully unrolled) and for a run-time C.
 constexpr int BAND_NV = 3;
 constexpr int BAND_G[BAND_NV] = {3, 5, 8};
-constexpr int BAND_WARPS = B3_WARPS;
+constexpr int BAND_WARPS = B3_PAIRS;   // (DP, helper) warp pairs per CTA
 inline int band_rec_words(int G) { return 4 * G + 1; }
 inline int band_smem_bytes_per_warp(int C, int G) { return (int)band3_smem_per_warp(C, G); }
 
@@ -76,10 +76,10 @@ constexpr int BAND_SMEM_MAX = 227 * 1024;   // dynamic shared memory one CTA may
 inline int band_warps(int smem_per_warp) { return std::max(1, std::min(BAND_WARPS, BAND_SMEM_MAX / smem_per_warp)); }
 template <int G>
 void band_launch(const Band3Args& ba, int grid, cudaStream_t st) {
-    const int warps = band_warps(ba.smem_per_warp);
-    const size_t smem = (size_t)warps * ba.smem_per_warp;
-    if (ba.C == 66) viterbi_band3_kernel<G, 66><<<grid, warps * 32, smem, st>>>(ba);
-    else viterbi_band3_kernel<G, 0><<<grid, warps * 32, smem, st>>>(ba);
+    const int pairs = band_warps(ba.smem_per_warp);
+    const size_t smem = (size_t)pairs * ba.smem_per_warp;
+    if (ba.C == 66) viterbi_band3_kernel<G, 66><<<grid, pairs * 64, smem, st>>>(ba);
+    else viterbi_band3_kernel<G, 0><<<grid, pairs * 64, smem, st>>>(ba);
 }
 
 int device_info(DeviceInfo& out) {
@@ -293,7 +293,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     for (int v = 0; v < BAND_NV; ++v) { pa.fast_items[v] = (Item*)(ws + L.off_fast[v]); pa.n_fast[v] = counters + 3 + 2 * v; }
     pa.fast_enable = fast ? 1 : 0; pa.path_lp = path_lp;
     pa.padded = (float*)(ws + L.off_padded); pa.anchors = (uint32_t*)(ws + L.off_anchors);
-    plan_kernel<<<(B + 3) / 4, 128, 0, st>>>(pa);
+    plan_kernel<<<(B + 7) / 8, 256, 0, st>>>(pa);
     LAUNCH_CHECK();
 
     long long max_items = (long long)B * L.item_cap;
@@ -340,7 +340,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         aa.T = T; aa.frame_off = (const long long*)frame_off; aa.frame_ph = frame_ph; aa.frame_idx = frame_idx;
         aa.status = status; aa.stamps = stamps; aa.conf = conf; aa.n_stamps = n_stamps; aa.path_lp = path_lp;
         if (shape->max_stamps <= 0) return BFA_E_INVALID;
-        assort_confidence_kernel<<<(B + 3) / 4, 128, 0, st>>>(aa);
+        assort_confidence_kernel<<<(B + ASSORT_WARPS - 1) / ASSORT_WARPS, ASSORT_WARPS * 32, ASSORT_SMEM, st>>>(aa);
         LAUNCH_CHECK();
     }
     return BFA_OK;
@@ -440,7 +440,7 @@ int bfa_assort_batch(const BfaParams* p, int32_t B, const int32_t* T, const int6
     aa.p = *p; aa.B = B; aa.C = 0; aa.max_stamps = max_stamps; aa.logp = nullptr; aa.row_off = nullptr; aa.T = T;
     aa.frame_off = (const long long*)frame_off; aa.frame_ph = frame_ph; aa.frame_idx = frame_idx; aa.status = status;
     aa.stamps = stamps; aa.conf = nullptr; aa.n_stamps = n_stamps; aa.path_lp = nullptr;
-    assort_confidence_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(aa);
+    assort_confidence_kernel<<<(B + ASSORT_WARPS - 1) / ASSORT_WARPS, ASSORT_WARPS * 32, ASSORT_SMEM, (cudaStream_t)stream>>>(aa);
     LAUNCH_CHECK();
     return BFA_OK;
 }

@@ -377,7 +377,10 @@ __device__ int plan_segmented(const UttCtx& c, Item* loc, int32_t* lists, uint32
 
 __global__ void plan_kernel(PlanArgs a) {
     const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (u >= a.B) return;
+    int n_items = 0;
+    Item* loc = nullptr;
+    bool tok = false;
+    if (u < a.B) {
     const BfaParams& p = a.p;
     UttCtx c;
     c.a = &a; c.u = u; c.lane = lane;
@@ -405,8 +408,8 @@ __global__ void plan_kernel(PlanArgs a) {
     }
     const int T = c.T, N = c.N;
     const long long o_base = a.frame_off[u], o_lim = a.frame_off[u + 1];
-    Item* loc = a.items_local + (size_t)u * a.item_cap;
-    int st = BFA_ST_OK, n_items = 0;
+    loc = a.items_local + (size_t)u * a.item_cap;
+    int st = BFA_ST_OK;
     if (lane == 0 && a.dp_final) a.dp_final[u] = 0.0f;
 
     if (N == 0) {                                                                 // :894-897 / :112-118
@@ -467,8 +470,33 @@ __global__ void plan_kernel(PlanArgs a) {
     }
     __syncwarp();
     if (lane == 0) a.status[u] = st;
-    // publish this utterance's items into the compact global lists (banded kernels / exact kernel)
-    const bool tok = ti.all_ok;
+    tok = ti.all_ok;
+    }   // u < B
+
+    // ---- publish the items into the compact global lists (banded kernels / exact kernel).  Counts are aggregated per
+    //      CTA in shared memory first: one global atomic per list per CTA instead of one per utterance ----
+    __shared__ int s_cnt[4], s_base[4];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int my_cnt[4] = {0, 0, 0, 0}, my_off[4] = {0, 0, 0, 0};
+    for (int i0 = 0; i0 < n_items; i0 += 32) {
+        const int i = i0 + lane;
+        int cl = -2;
+        if (i < n_items) cl = fast_class(loc[i], a.C, a.logp, tok, a.fast_enable);
+#pragma unroll
+        for (int c = -1; c <= 2; ++c) my_cnt[c + 1] += __popc(__ballot_sync(FULL, cl == c));
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (lane == 0 && my_cnt[c]) my_off[c] = atomicAdd(&s_cnt[c], my_cnt[c]);
+        my_off[c] = __shfl_sync(FULL, my_off[c], 0);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_cnt[threadIdx.x]) {
+        int* cnt = (threadIdx.x == 0) ? a.n_items : a.n_fast[threadIdx.x - 1];
+        s_base[threadIdx.x] = atomicAdd(cnt, s_cnt[threadIdx.x]);
+    }
+    __syncthreads();
     for (int i0 = 0; i0 < n_items; i0 += 32) {
         const int i = i0 + lane;
         int cl = -2;
@@ -476,13 +504,9 @@ __global__ void plan_kernel(PlanArgs a) {
 #pragma unroll
         for (int c = -1; c <= 2; ++c) {
             const unsigned m = __ballot_sync(FULL, cl == c);
-            if (!m) continue;
-            int* cnt = (c < 0) ? a.n_items : a.n_fast[c];
             Item* dst = (c < 0) ? a.items : a.fast_items[c];
-            int base = 0;
-            if (lane == 0) base = atomicAdd(cnt, __popc(m));
-            base = __shfl_sync(FULL, base, 0);
-            if (cl == c) dst[base + __popc(m & ((1u << lane) - 1u))] = loc[i];
+            if (cl == c) dst[s_base[c + 1] + my_off[c + 1] + __popc(m & ((1u << lane) - 1u))] = loc[i];
+            my_off[c + 1] += __popc(m);
         }
     }
 }

@@ -28,11 +28,15 @@
 //    state is invalid, an emission is > 0, a row's log-sum-exp is not finite) the item is appended to the retry
 //    list and re-run by the exact generic kernel.  No per-frame band bookkeeping is left in the frame loop.
 //
-// 3. Fusion.  Target boost + log_softmax + floor (:121-129) are applied on the fly.  Rows are streamed exactly
-//    once from HBM by 1-D bulk async copies (TMA engine, SASS UBLKCP; 8 rows per utterance per stage, double
-//    buffered, one mbarrier per stage).  At the start of a chunk each lane computes the statistics of ONE staged
-//    row (lane = (utterance, row): 66 exps, no shuffles, no idle lanes; per-utterance class weights come from a
-//    small shared table) and publishes (log-sum-exp, blank emission) for the 8 frames that follow.
+// 3. Fusion and roles.  Target boost + log_softmax + floor (:121-129) are applied on the fly; rows are streamed exactly
+//    once from HBM by 1-D bulk async copies (TMA engine, SASS UBLKCP; 8 rows per utterance per stage, 3 stages).
+//    A task (4 utterances) is run by a PAIR of warps so that twice as many warps hide each other's latencies:
+//      * the helper warp owns the data movement and the transcendental work: it issues the bulk copies, and for every
+//        staged chunk each of its lanes reduces ONE row (lane = (utterance, row): 66 exps, no shuffles, no idle lanes;
+//        per-utterance class weights come from a small shared table) to (log-sum-exp, blank emission);
+//      * the DP warp runs the frame loop (registers only + one shared load per group per frame), flushes the decision
+//        words and, when the fill is done, walks the path back.
+//    They meet on three mbarrier rings: full (TMA -> helper), ready (helper -> DP), free (DP -> helper).
 #pragma once
 #include <type_traits>
 
@@ -44,7 +48,7 @@ constexpr int B3_LPU = 8;          // lanes per utterance
 constexpr int B3_UPW = 4;          // utterances per warp
 constexpr int B3_NST = 3;          // pipeline stages (chunk c is consumed while c+1 is being reduced and c+2 is in flight)
 constexpr int B3_ROWS = 8;         // rows per stage per utterance (8*C*4 bytes is always a multiple of 16)
-constexpr int B3_WARPS = 8;        // warps per CTA, one CTA per SM
+constexpr int B3_PAIRS = 7;        // (DP warp, helper warp) pairs per CTA, one CTA per SM
 constexpr int B3_KK = 72;          // floats per utterance in the class-weight table (C <= 72)
 constexpr int B3_STP = 9;          // float2 pitch of the per-utterance (lnS, eb) array (bank spreading)
 constexpr int B3_NMAX = 128;       // phonemes per item on this path (byte-sized class table in shared memory)
@@ -96,13 +100,16 @@ __host__ __device__ inline size_t band3_stage_region(int C, int G) {
     size_t b = st > bt ? st : bt;
     return (b + 15) / 16 * 16;
 }
-__host__ __device__ inline size_t band3_smem_per_warp(int C, int G) {
-    size_t b = band3_stage_region(C, G);
-    b += (size_t)B3_UPW * B3_KK * 4;                        // class weights
-    b += (size_t)2 * B3_UPW * B3_STP * 8;                   // (lnS, eb) per staged row, double buffered
-    b += (size_t)B3_UPW * B3_NMAX;                          // target classes (bytes)
-    b += (size_t)(B3_NST + 2) * 8;                          // mbarriers: stages + two back-trace record buffers
-    return (b + 127) / 128 * 128;
+// shared memory of one pair: stage ring | class weights | (lnS, eb) per staged row | target classes | helper flags | mbarriers
+enum : int { B3_BAR_FULL = 0, B3_BAR_READY = B3_NST, B3_BAR_FREE = 2 * B3_NST, B3_BAR_REC = 3 * B3_NST, B3_BAR_DONE = 3 * B3_NST + 2,
+             B3_NBARS = 3 * B3_NST + 3 };
+__host__ __device__ inline size_t band3_off_kk(int C, int G) { return band3_stage_region(C, G); }
+__host__ __device__ inline size_t band3_off_stats(int C, int G) { return band3_off_kk(C, G) + (size_t)B3_UPW * B3_KK * 4; }
+__host__ __device__ inline size_t band3_off_cls(int C, int G) { return band3_off_stats(C, G) + (size_t)B3_NST * B3_UPW * B3_STP * 8; }
+__host__ __device__ inline size_t band3_off_flags(int C, int G) { return band3_off_cls(C, G) + (size_t)B3_UPW * B3_NMAX; }
+__host__ __device__ inline size_t band3_off_bars(int C, int G) { return band3_off_flags(C, G) + 16; }
+__host__ __device__ inline size_t band3_smem_per_warp(int C, int G) {   // per PAIR of warps
+    return (band3_off_bars(C, G) + (size_t)B3_NBARS * 8 + 127) / 128 * 128;
 }
 
 __device__ __forceinline__ float b3_ex2(float x) {
@@ -130,7 +137,7 @@ __device__ __forceinline__ void b3_push(uint32_t& acc, float earlier, float late
     acc = __funnelshift_l(__float_as_uint(earlier - later), acc, 1);
 }
 
-// Optional phase timers (development only, -DBFA_PHASE_PROF): warp-clock cycles per phase, summed over lane 0 of all warps.
+// Optional phase timers (development only, -DBFA_PHASE_PROF): warp-clock cycles per phase, summed over lane 0 of the DP warps.
 #ifdef BFA_PHASE_PROF
 __device__ unsigned long long g_b3_phase[16];
 #define PH_DECL long long ph_last = clock64(); long long ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}
@@ -142,83 +149,94 @@ __device__ unsigned long long g_b3_phase[16];
 #define PH_FLUSH
 #endif
 
+// What both warps of a pair derive from the item list (uniform within an 8-lane segment).
 template <int G, int CT>
-__device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned char* smem_warp, uint32_t* slab, uint32_t& phase,
-                           int lane, uint64_t pol) {
-    using S = Band3Shape<G>;
-    PH_DECL;
-    constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-    // the log-sum-exp of chunk c+1 is interleaved with the frames of chunk c when the class count is a compile-time even number
-    constexpr bool PIPE = CT != 0 && (CT & 1) == 0 && (CT / 2) >= 8;
-    constexpr int PAIRS = CT / 2, PP = PAIRS / 8, PREM = PAIRS - 8 * PP;   // float2 pairs per frame slot, leftover pairs
-    const int seg = lane >> 3, l8 = lane & 7;
-    const int C = CT ? CT : a.C;
-    const float NEG = a.p.neg_inf;
-    const int blank = a.p.blank_id;
-
-    // ---- shared memory of this warp ----
-    float* stage_buf = reinterpret_cast<float*>(smem_warp);
-    const int seg_stride = B3_ROWS * C;
-    const int stage_floats = B3_UPW * seg_stride;
-    float* kk = reinterpret_cast<float*>(smem_warp + band3_stage_region(C, G));             // [UPW][B3_KK]
-    float2* stats = reinterpret_cast<float2*>(kk + B3_UPW * B3_KK);                         // [2][UPW][B3_STP]
-    unsigned char* cls8 = reinterpret_cast<unsigned char*>(stats + 2 * B3_UPW * B3_STP);    // [UPW][B3_NMAX]
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(cls8 + B3_UPW * B3_NMAX);   // [NST]
-    uint2* bt2 = reinterpret_cast<uint2*>(smem_warp);                                       // [UPW][CELLS], aliases the stage ring
-
-    // ---- per-segment item description (uniform within a segment) ----
-    const bool seg_on = seg < n_valid;
-    const Item& it = a.items[first + (seg_on ? seg : 0)];
-    const int T = seg_on ? it.T : 0;
-    const int N = it.n, L = it.L, band = it.band, flags = it.flags, utt = it.utt;
-    const int trim = it.trim, n_out = it.n_out, idx0 = it.idx0;
-    const long long out_off = it.out_off, out_lim = it.out_lim;
-    const bool use_band = band > 0 && T > 1 && L > 1;                          // :586
-    const float pace_f = use_band ? (float)((double)(L - 1) / (double)(T - 1)) : 0.0f;   // :587
-    const bool use_stats = (flags & ITEM_STATS) != 0;
-    const bool warp_stats = __any_sync(FULL, use_stats);   // every item of a call shares the mode
-    const float min_lp = (flags & ITEM_FLOOR) ? a.p.min_log_prob : -INFINITY;
-    const int32_t* seq = a.tgt + it.seq_off;
-    const int base_max = max(0, N + 1 - S::W);
-    const float* my_src = a.logp + it.lp_off;
-    const float boostv = a.p.boost_factor;
-    int Tmax = T;
+struct Band3Task {
+    int seg, l8, C;
+    bool seg_on;
+    const Item* it;
+    int T, Tmax, n_chunks, seg_stride, stage_floats;
+    float* stage_buf;
+    float* kk;
+    float2* stats;
+    unsigned char* cls8;
+    int* hflags;
+    uint32_t bar0;
+    const float* my_src;
+    bool use_stats, warp_stats;
+    __device__ __forceinline__ Band3Task(const Band3Args& a, int first, int n_valid, unsigned char* smem_pair, int lane) {
+        seg = lane >> 3; l8 = lane & 7;
+        C = CT ? CT : a.C;
+        seg_on = seg < n_valid;
+        it = &a.items[first + (seg_on ? seg : 0)];
+        T = seg_on ? it->T : 0;
+        Tmax = T;
 #pragma unroll
-    for (int d = 8; d < 32; d <<= 1) Tmax = max(Tmax, __shfl_xor_sync(FULL, Tmax, d));
-    const int n_chunks = (Tmax + B3_ROWS - 1) / B3_ROWS;
+        for (int d = 8; d < 32; d <<= 1) Tmax = max(Tmax, __shfl_xor_sync(FULL, Tmax, d));
+        n_chunks = (Tmax + B3_ROWS - 1) / B3_ROWS;
+        seg_stride = B3_ROWS * C;
+        stage_floats = B3_UPW * seg_stride;
+        stage_buf = reinterpret_cast<float*>(smem_pair);
+        kk = reinterpret_cast<float*>(smem_pair + band3_off_kk(C, G));                   // [UPW][B3_KK]
+        stats = reinterpret_cast<float2*>(smem_pair + band3_off_stats(C, G));            // [NST][UPW][B3_STP]
+        cls8 = smem_pair + band3_off_cls(C, G);                                          // [UPW][B3_NMAX]
+        hflags = reinterpret_cast<int*>(smem_pair + band3_off_flags(C, G));              // [UPW] helper verdict: rows not sane
+        bar0 = smem_u32(smem_pair + band3_off_bars(C, G));
+        my_src = a.logp + it->lp_off;
+        use_stats = (it->flags & ITEM_STATS) != 0;
+        warp_stats = __any_sync(FULL, use_stats);   // every item of a call shares the mode
+    }
+};
 
+// ------------------------------------------------------------------------------------------------------------
+// Helper warp: tables, bulk copies, row statistics.
+// ------------------------------------------------------------------------------------------------------------
+template <int G, int CT>
+__device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigned char* smem_pair, uint32_t& phase, bool not_first,
+                             int lane, uint64_t pol) {
+    constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+    const Band3Task<G, CT> k(a, first, n_valid, smem_pair, lane);
+    const int seg = k.seg, l8 = k.l8, C = k.C, T = k.T;
+    const int blank = a.p.blank_id;
+    const float boostv = a.p.boost_factor;
+    const bool warp_stats = k.warp_stats;
+
+    if (not_first) {   // the DP warp is done with the previous task (tables, staging area)
+        mbar_wait(k.bar0 + 8u * B3_BAR_DONE, (phase >> B3_BAR_DONE) & 1u);
+        phase ^= 1u << B3_BAR_DONE;
+    }
     // ---- per-utterance tables: target classes (bytes) and the class weights of the fused log-sum-exp:
     //      exp(x + boost*[c in targets] - boost) = 2^(x*log2e + kk[c]) ----
-    __syncwarp();   // previous task's readers are done with the tables / the staging area
-    if (seg_on)
-        for (int j = l8; j < N; j += B3_LPU) cls8[seg * B3_NMAX + j] = (unsigned char)seq[j];
+    if (k.seg_on) {
+        const int32_t* seq = a.tgt + k.it->seq_off;
+        const int N = k.it->n;
+        for (int j = l8; j < N; j += B3_LPU) k.cls8[seg * B3_NMAX + j] = (unsigned char)seq[j];
+    }
     if (warp_stats) {
+        const int utt = k.it->utt;
         for (int c = l8; c < B3_KK; c += B3_LPU) {
             const bool ok = c < C;
-            const bool tg = ok && seg_on && ((a.tmask[(size_t)utt * MAX_WORDS + (c >> 5)] >> (c & 31)) & 1u);
-            kk[seg * B3_KK + c] = ok ? (tg ? 0.0f : -boostv * LOG2E) : -INFINITY;
+            const bool tg = ok && k.seg_on && ((a.tmask[(size_t)utt * MAX_WORDS + (c >> 5)] >> (c & 31)) & 1u);
+            k.kk[seg * B3_KK + c] = ok ? (tg ? 0.0f : -boostv * LOG2E) : -INFINITY;
         }
     }
     __syncwarp();
-    const unsigned char* my_cls = cls8 + seg * B3_NMAX;
-    auto group_class = [&](int gi) { return (seg_on && gi >= 1 && gi <= N) ? (int)my_cls[gi - 1] : blank; };
 
-    // lanes with l8 == 0 issue their own utterance's copy and arrive once per chunk on the stage barrier (count = UPW)
-    const uint32_t bar0 = smem_u32(bars);
-    const uint32_t dst0 = smem_u32(stage_buf + seg * seg_stride);
+    // lanes with l8 == 0 issue their own utterance's copy and arrive once per chunk on the stage's full barrier (count = UPW)
+    const uint32_t dst0 = smem_u32(k.stage_buf + seg * k.seg_stride);
     const uint32_t full_bytes = (uint32_t)B3_ROWS * C * 4;
     auto issue = [&](int c, int st) {
         if (l8 == 0) {
             const int rows = T - c * B3_ROWS;
-            const uint32_t bar = bar0 + 8u * st;
-            const uint32_t dst = dst0 + (uint32_t)st * stage_floats * 4u;
-            const float* s = my_src + (size_t)c * B3_ROWS * C;
+            const uint32_t bar = k.bar0 + 8u * (B3_BAR_FULL + st);
+            const uint32_t dst = dst0 + (uint32_t)st * k.stage_floats * 4u;
+            const float* s = k.my_src + (size_t)c * B3_ROWS * C;
             if (rows >= B3_ROWS) {
                 mbar_expect_tx(bar, full_bytes);
                 bulk_g2s_hint(dst, s, full_bytes, bar, pol);
             } else if (rows > 0) {
                 const uint32_t bytes = (uint32_t)rows * C * 4, bulk = bytes & ~15u;
-                float* d = stage_buf + st * stage_floats + seg * seg_stride;
+                float* d = k.stage_buf + st * k.stage_floats + seg * k.seg_stride;
                 for (uint32_t w = bulk >> 2; w < (bytes >> 2); ++w) d[w] = s[w];   // < 4 tail floats of a partial last chunk
                 mbar_expect_tx(bar, bulk);
                 if (bulk) bulk_g2s_hint(dst, s, bulk, bar, pol);
@@ -227,6 +245,115 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
             }
         }
     };
+#pragma unroll
+    for (int c = 0; c < B3_NST; ++c)
+        if (c < k.n_chunks) issue(c, c);
+
+    float emax = -INFINITY;          // raw mode: emissions must be <= 0 (log-probabilities)
+    float lse_chk = 0.f;             // running sum of the rows' log-sum-exp (finite <=> all rows sane)
+    int st = 0;
+    for (int c = 0; c < k.n_chunks; ++c) {
+        mbar_wait(k.bar0 + 8u * (B3_BAR_FULL + st), (phase >> (B3_BAR_FULL + st)) & 1u);
+        phase ^= 1u << (B3_BAR_FULL + st);
+        __syncwarp();                                  // tail floats written by the issuing lane become visible
+
+        // ---- row statistics: lane (seg, l8) owns row l8 of its utterance: log-sum-exp of the boosted row (:51-54)
+        //      and the blank emission; no cross-lane traffic ----
+        {
+            const float* rowp = k.stage_buf + st * k.stage_floats + seg * k.seg_stride + l8 * C;
+            const int t_row = c * B3_ROWS + l8;
+            float lnS = 0.f;
+            if (warp_stats) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                const float* kp = k.kk + seg * B3_KK;
+                if (CT != 0 && (CT & 1) == 0) {
+                    const float2* x2 = reinterpret_cast<const float2*>(rowp);
+                    const float4* k4 = reinterpret_cast<const float4*>(kp);
+#pragma unroll
+                    for (int i = 0; i < CT / 4; ++i) {
+                        const float4 kv = k4[i];
+                        const float2 xa = x2[2 * i], xb = x2[2 * i + 1];
+                        s0 += b3_ex2(fmaf(xa.x, LOG2E, kv.x));
+                        s1 += b3_ex2(fmaf(xa.y, LOG2E, kv.y));
+                        s2 += b3_ex2(fmaf(xb.x, LOG2E, kv.z));
+                        s3 += b3_ex2(fmaf(xb.y, LOG2E, kv.w));
+                    }
+                    if (CT % 4) {
+                        const float2 xa = x2[CT / 2 - 1];
+                        const float2 kv = reinterpret_cast<const float2*>(kp)[CT / 2 - 1];
+                        s0 += b3_ex2(fmaf(xa.x, LOG2E, kv.x));
+                        s1 += b3_ex2(fmaf(xa.y, LOG2E, kv.y));
+                    }
+                } else {
+                    int i = 0;
+                    for (; i + 4 <= C; i += 4) {
+                        s0 += b3_ex2(fmaf(rowp[i], LOG2E, kp[i]));
+                        s1 += b3_ex2(fmaf(rowp[i + 1], LOG2E, kp[i + 1]));
+                        s2 += b3_ex2(fmaf(rowp[i + 2], LOG2E, kp[i + 2]));
+                        s3 += b3_ex2(fmaf(rowp[i + 3], LOG2E, kp[i + 3]));
+                    }
+                    for (; i < C; ++i) s0 += b3_ex2(fmaf(rowp[i], LOG2E, kp[i]));
+                }
+                lnS = b3_lg2((s0 + s1) + (s2 + s3)) * LN2;          // log sum exp(x + b - boost)
+                if (k.use_stats && t_row < T) lse_chk += lnS;       // any zero / overflowing / NaN sum leaves a non-finite trace
+            } else {
+                float m = -INFINITY;
+                for (int i = 0; i < C; ++i) m = fmaxf(m, rowp[i]);
+                if (t_row < T) emax = fmaxf(emax, m);
+            }
+            // blank is never a target: x - lse with lse = lnS + boost; phoneme classes are boosted targets: x - lnS
+            const float eb = rowp[blank] - (warp_stats ? lnS + boostv : 0.f);
+            k.stats[(st * B3_UPW + seg) * B3_STP + l8] = make_float2(lnS, eb);
+        }
+        if (c == k.n_chunks - 1) {                     // verdict on the rows of this task, published with the last chunk
+            const bool badrow = (emax > 0.f) || (k.use_stats && !(fabsf(lse_chk) < 3.0e38f));
+            const unsigned m = __ballot_sync(FULL, badrow);
+            if (l8 == 0) k.hflags[seg] = ((m >> (seg * B3_LPU)) & 0xffu) != 0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(k.bar0 + 8u * (B3_BAR_READY + st));      // release: the DP warp may consume chunk c
+
+        // refill the stage the DP warp has finished with (chunk c-1) with chunk c+2
+        if (c >= 1 && c + 2 < k.n_chunks) {
+            const int st_p = (st == 0) ? B3_NST - 1 : st - 1;
+            mbar_wait(k.bar0 + 8u * (B3_BAR_FREE + st_p), (phase >> (B3_BAR_FREE + st_p)) & 1u);
+            phase ^= 1u << (B3_BAR_FREE + st_p);
+            issue(c + 2, st_p);
+        }
+        st = (st + 1 == B3_NST) ? 0 : st + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// DP warp: frame loop, decision records, back-trace, outputs.
+// ------------------------------------------------------------------------------------------------------------
+template <int G, int CT>
+__device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned char* smem_pair, uint32_t* slab, uint32_t& phase,
+                         int lane) {
+    using S = Band3Shape<G>;
+    PH_DECL;
+    const Band3Task<G, CT> k(a, first, n_valid, smem_pair, lane);
+    const int seg = k.seg, l8 = k.l8, C = k.C, T = k.T, Tmax = k.Tmax, n_chunks = k.n_chunks;
+    const bool seg_on = k.seg_on;
+    const Item& it = *k.it;
+    const float NEG = a.p.neg_inf;
+    const int blank = a.p.blank_id;
+    const uint32_t bar0 = k.bar0;
+    uint2* bt2 = reinterpret_cast<uint2*>(smem_pair);                                       // [UPW][CELLS], aliases the stage ring
+    const int N = it.n, L = it.L, band = it.band, flags = it.flags, utt = it.utt;
+    const int trim = it.trim, n_out = it.n_out, idx0 = it.idx0;
+    const long long out_off = it.out_off, out_lim = it.out_lim;
+    const bool use_band = band > 0 && T > 1 && L > 1;                          // :586
+    const float pace_f = use_band ? (float)((double)(L - 1) / (double)(T - 1)) : 0.0f;   // :587
+    const float min_lp = (flags & ITEM_FLOOR) ? a.p.min_log_prob : -INFINITY;
+    const int base_max = max(0, N + 1 - S::W);
+    const float* my_src = k.my_src;
+    const unsigned char* my_cls = k.cls8 + seg * B3_NMAX;
+    auto group_class = [&](int gi) { return (seg_on && gi >= 1 && gi <= N) ? (int)my_cls[gi - 1] : blank; };
+
+    // chunk 0 is ready: the helper has filled the tables and reduced the first 8 rows
+    mbar_wait(bar0 + 8u * B3_BAR_READY, (phase >> B3_BAR_READY) & 1u);
+    phase ^= 1u << B3_BAR_READY;
 
     // ---- per-lane window state: groups base + l8*G + g, g = 0..G-1; -inf = invalid ----
     int base = 0;
@@ -248,61 +375,12 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
     bool bad = false;                // needs the exact path
     float fin_val = NEG;
     int fin_cell = 0, fin_base = 0;
-    float emax = -INFINITY;          // raw mode: emissions must be <= 0 (log-probabilities)
-    float lse_chk = 0.f;             // running sum of the rows' log-sum-exp (finite <=> all rows sane)
-
-    // Row statistics of one staged chunk: lane (seg, l8) owns row l8 of its utterance: log-sum-exp of the boosted
-    // row (:51-54) and the blank emission; no cross-lane traffic.  stats_row = all classes at once (prologue, raw
-    // mode, run-time C); the PIPE variant spreads the same sum over the 8 frame slots of the previous chunk.
-    auto stats_finish = [&](const float* rowp, float sum, float rowmax, int t_row, float2* dst) {
-        float lnS = 0.f;
-        if (warp_stats) {
-            lnS = b3_lg2(sum) * LN2;                                // log sum exp(x + b - boost)
-            if (use_stats && t_row < T) lse_chk += lnS;             // any zero / overflowing / NaN sum leaves a non-finite trace
-        } else if (t_row < T) {
-            emax = fmaxf(emax, rowmax);
-        }
-        // blank is never a target: x - lse with lse = lnS + boost; phoneme classes are boosted targets: x - lnS
-        const float eb = rowp[blank] - (warp_stats ? lnS + boostv : 0.f);
-        dst[seg * B3_STP + l8] = make_float2(lnS, eb);
-    };
-    auto stats_row = [&](int st, int t_row, float2* dst) {
-        const float* rowp = stage_buf + st * stage_floats + seg * seg_stride + l8 * C;
-        float sum = 0.f, rowmax = -INFINITY;
-        if (warp_stats) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            const float* kp = kk + seg * B3_KK;
-            int i = 0;
-            for (; i + 4 <= C; i += 4) {
-                s0 += b3_ex2(fmaf(rowp[i], LOG2E, kp[i]));
-                s1 += b3_ex2(fmaf(rowp[i + 1], LOG2E, kp[i + 1]));
-                s2 += b3_ex2(fmaf(rowp[i + 2], LOG2E, kp[i + 2]));
-                s3 += b3_ex2(fmaf(rowp[i + 3], LOG2E, kp[i + 3]));
-            }
-            for (; i < C; ++i) s0 += b3_ex2(fmaf(rowp[i], LOG2E, kp[i]));
-            sum = (s0 + s1) + (s2 + s3);
-        } else {
-            for (int i = 0; i < C; ++i) rowmax = fmaxf(rowmax, rowp[i]);
-        }
-        stats_finish(rowp, sum, rowmax, t_row, dst);
-    };
-
-    // ---- prologue: fill the ring, reduce chunk 0 ----
-#pragma unroll
-    for (int c = 0; c < B3_NST; ++c)
-        if (c < n_chunks) issue(c, c);
-    mbar_wait(bar0, phase & 1u);
-    phase ^= 1u;
-    __syncwarp();                                      // tail floats written by the issuing lane become visible
-    stats_row(0, l8, stats);
-    __syncwarp();
     PH_T(0);
 
     int st = 0;                                        // stage of chunk c
     int nslide_next = 0;
     for (int c = 0; c < n_chunks; ++c) {
         const int t0 = c * B3_ROWS;
-        const int st_n = (st + 1 == B3_NST) ? 0 : st + 1;     // stage of chunk c+1
 
         // ---- slide the window to the group of the lower band edge at frame t0-1 (fp32 estimate, never above the
         //      exact :651 value, at most one state below it) ----
@@ -330,70 +408,23 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
         }
         PH_T(1);
 
-        // ---- chunk c+1 has landed (it was issued two chunks ago) ----
-        const bool has_next = c + 1 < n_chunks;
-        if (has_next) {
-            mbar_wait(bar0 + 8u * st_n, (phase >> st_n) & 1u);
-            phase ^= 1u << st_n;
+        if (c > 0) {                                   // the helper has reduced chunk c (which implies that it has landed)
+            mbar_wait(bar0 + 8u * (B3_BAR_READY + st), (phase >> (B3_BAR_READY + st)) & 1u);
+            phase ^= 1u << (B3_BAR_READY + st);
         }
-        __syncwarp();                                  // tail floats written by the issuing lane become visible
         PH_T(2);
 
-        float2* stats_n = stats + ((c + 1) & 1) * B3_UPW * B3_STP;
-        const float* rowp_n = stage_buf + st_n * stage_floats + seg * seg_stride + l8 * C;   // this lane's row of chunk c+1
-        if (!PIPE || !warp_stats) {
-            if (has_next) stats_row(st_n, t0 + B3_ROWS + l8, stats_n);
-        }
-        PH_T(3);
-
-        const float* seg_rows = stage_buf + st * stage_floats + seg * seg_stride;   // the 8 staged rows of this utterance
+        const float* seg_rows = k.stage_buf + st * k.stage_floats + seg * k.seg_stride;   // the 8 staged rows of this utterance
         const int fin_r = T - 1 - t0;                                      // row of the last frame if it is in this chunk
         const bool fin_here = __any_sync(FULL, fin_r >= 0 && fin_r < B3_ROWS);
         const float* xg[G];                                                // row 0 address of each group's class
 #pragma unroll
         for (int g = 0; g < G; ++g) xg[g] = seg_rows + cls[g];
-        const float2* stp = stats + (c & 1) * B3_UPW * B3_STP + seg * B3_STP;
+        const float2* stp = k.stats + (st * B3_UPW + seg) * B3_STP;
         float xp_n[G];                                                     // raw emissions are fetched one frame ahead
 #pragma unroll
         for (int g = 0; g < G; ++g) xp_n[g] = xg[g][0];
         float2 st_nx = stp[0];
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;                      // partial sums of the next chunk's row
-
-        // one eighth of the next chunk's log-sum-exp (PIPE): pairs r*PP .. r*PP+PP-1, the leftover pairs in slot 7
-        auto stats_part = [&](const int r) {
-            if (PIPE) {
-                const float2* x2 = reinterpret_cast<const float2*>(rowp_n);
-                const float2* k2 = reinterpret_cast<const float2*>(kk + seg * B3_KK);
-#pragma unroll
-                for (int i = 0; i < PP; i += 2) {
-                    if (i + 1 < PP && (PP & 1) == 0) {
-                        const float4 k = *reinterpret_cast<const float4*>(k2 + r * PP + i);
-                        const float2 xa = x2[r * PP + i], xb = x2[r * PP + i + 1];
-                        s0 += b3_ex2(fmaf(xa.x, LOG2E, k.x));
-                        s1 += b3_ex2(fmaf(xa.y, LOG2E, k.y));
-                        s2 += b3_ex2(fmaf(xb.x, LOG2E, k.z));
-                        s3 += b3_ex2(fmaf(xb.y, LOG2E, k.w));
-                    } else {
-                        const float2 k = k2[r * PP + i], xa = x2[r * PP + i];
-                        s0 += b3_ex2(fmaf(xa.x, LOG2E, k.x));
-                        s1 += b3_ex2(fmaf(xa.y, LOG2E, k.y));
-                        if (i + 1 < PP) {
-                            const float2 kb = k2[r * PP + i + 1], xb = x2[r * PP + i + 1];
-                            s2 += b3_ex2(fmaf(xb.x, LOG2E, kb.x));
-                            s3 += b3_ex2(fmaf(xb.y, LOG2E, kb.y));
-                        }
-                    }
-                }
-                if (r == B3_ROWS - 1) {
-#pragma unroll
-                    for (int i = 0; i < PREM; ++i) {
-                        const float2 k = k2[8 * PP + i], xa = x2[8 * PP + i];
-                        s2 += b3_ex2(fmaf(xa.x, LOG2E, k.x));
-                        s3 += b3_ex2(fmaf(xa.y, LOG2E, k.y));
-                    }
-                }
-            }
-        };
 
         auto frame = [&](const int r, auto check_fin) {
             constexpr bool CHECK = decltype(check_fin)::value;
@@ -483,25 +514,13 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
             }
         };
 
-        auto run_chunk = [&](auto with_stats) {
-            constexpr bool WS = decltype(with_stats)::value;
-            if (!fin_here) {
+        if (!fin_here) {
 #pragma unroll
-                for (int r = 0; r < B3_ROWS; ++r) {
-                    frame(r, std::false_type{});
-                    if (WS) stats_part(r);
-                }
-            } else {
+            for (int r = 0; r < B3_ROWS; ++r) frame(r, std::false_type{});
+        } else {
 #pragma unroll 1
-                for (int r = 0; r < B3_ROWS; ++r) {
-                    frame(r, std::true_type{});
-                    if (WS) stats_part(r);
-                }
-            }
-        };
-        if (PIPE && warp_stats) run_chunk(std::true_type{});
-        else run_chunk(std::false_type{});
-        if (PIPE && warp_stats) stats_finish(rowp_n, (s0 + s1) + (s2 + s3), 0.f, has_next ? t0 + B3_ROWS + l8 : T, stats_n);
+            for (int r = 0; r < B3_ROWS; ++r) frame(r, std::true_type{});
+        }
         PH_T(4);
         // ---- flush one full 32-frame record (utterances that end inside this chunk flushed at their last frame)
         if ((c & 3) == 3 && T - 1 > t0 + B3_ROWS - 1) {
@@ -510,16 +529,14 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
             for (int i = 0; i < S::ACC; ++i) rec[i * 32] = acc[i];
             rec[S::ACC * 32] = slide_acc;
         }
-        __syncwarp();                                  // every lane is done with stage st; the next chunk's statistics are visible
+        __syncwarp();                                  // every lane is done with stage st
+        if (c + B3_NST < n_chunks && lane == 0) mbar_arrive(bar0 + 8u * (B3_BAR_FREE + st));   // the helper may refill it
         PH_T(11);
-        if (c + B3_NST < n_chunks) issue(c + B3_NST, st);
-        PH_T(12);
-        st = st_n;
+        st = (st + 1 == B3_NST) ? 0 : st + 1;
     }
     PH_T(5);
     __syncwarp();
-    if (emax > 0.f) bad = true;
-    if (use_stats && !(fabsf(lse_chk) < 3.0e38f)) bad = true;
+    if (seg_on && k.hflags[seg]) bad = true;           // helper: an emission > 0 (raw mode) or a non-finite log-sum-exp
     {   // make `bad` uniform per segment
         const unsigned m = __ballot_sync(FULL, bad);
         bad = ((m >> (seg * B3_LPU)) & 0xffu) != 0;
@@ -551,7 +568,7 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
     uint32_t* recbuf = reinterpret_cast<uint32_t*>(bt2 + B3_UPW * S::CELLS);                 // [2][REC][32]
     uint32_t* gbuf = recbuf + 2 * S::REC * 32;                                                 // [B3_GRING][4][32]
     const uint32_t rec_s = smem_u32(recbuf), g_s = smem_u32(gbuf) + 4u * lane;
-    const uint32_t rbar0 = bar0 + 8u * B3_NST;                                                 // two record barriers follow the stage barriers
+    const uint32_t rbar0 = bar0 + 8u * B3_BAR_REC;                                             // the two record barriers
     constexpr uint32_t GNONE = 0x7fffffffu;                                                    // slot not gathered
     auto issue_rec = [&](int blk) {
         if (lane == 0) {
@@ -576,7 +593,7 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
     asm volatile("fence.proxy.async.global;" ::: "memory");   // the slab was written with ordinary stores, the bulk copies read it through the async proxy
     __syncwarp();
     issue_rec(nblk - 1);
-    uint32_t rphase = phase >> B3_NST;         // phase bits of the two record barriers
+    uint32_t rphase = phase >> B3_BAR_REC;     // phase bits of the two record barriers
     int ring_hi = nblk - 1;                    // highest block whose gathers sit in the ring
 #pragma unroll 1
     for (int bb = 0; bb < B3_GRING && bb < nblk; ++bb)
@@ -687,7 +704,7 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
             a.frame_idx[pend_o[i]] = pend_idx[i];
         }
     drain(0, ring_hi);
-    phase = (phase & ((1u << B3_NST) - 1u)) | (rphase << B3_NST);
+    phase = (phase & ~(3u << B3_BAR_REC)) | ((rphase & 3u) << B3_BAR_REC);
     {   // a path that left (or came too close to) the band is not provably the reference's: exact path
         const unsigned m = __ballot_sync(FULL, illegal);
         if ((m >> (seg * B3_LPU)) & 0xffu) bad = true;
@@ -702,37 +719,45 @@ __device__ void band3_task(const Band3Args& a, int first, int n_valid, unsigned 
     }
     __syncwarp();
     PH_T(10);
+    if (lane == 0) mbar_arrive(bar0 + 8u * B3_BAR_DONE);   // the helper may set up the pair's next task
     PH_FLUSH;
 }
 
 template <int G, int CT>
-__global__ void __launch_bounds__(B3_WARPS * 32, 1) viterbi_band3_kernel(Band3Args a) {
+__global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_kernel(Band3Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* smem_warp = smem_raw + (size_t)warp * a.smem_per_warp;
-    {
-        const int C = CT ? CT : a.C;
-        uint32_t* w = reinterpret_cast<uint32_t*>(smem_warp);
-        for (int i = lane; i < a.smem_per_warp / 4; i += 32) w[i] = 0u;   // never-loaded slots must hold finite values
-        unsigned long long* bars = reinterpret_cast<unsigned long long*>(
-            smem_warp + band3_stage_region(C, G) + B3_UPW * B3_KK * 4 + 2 * B3_UPW * B3_STP * 8 + B3_UPW * B3_NMAX);
-        __syncwarp();
-        if (lane == 0)
-            for (int i = 0; i < B3_NST + 2; ++i) mbar_init(smem_u32(&bars[i]), i < B3_NST ? B3_UPW : 1);
-        fence_mbar_init();   // also orders the generic-proxy zero fill before the first async copy
-    }
-    __syncwarp();
-    const uint64_t pol = policy_evict_first();
-    uint32_t phase = 0;
-    const int nwarps = blockDim.x >> 5;   // <= B3_WARPS, as many as the shared memory of one SM holds
-    const int gwarp = blockIdx.x * nwarps + warp;
-    uint32_t* slab = a.bp_scratch + (size_t)gwarp * a.bp_slab_words;
     const int n_items = *a.n_items;
+    if (n_items == 0) return;                 // nothing of this window class in the batch
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int npairs = blockDim.x >> 6;       // <= B3_PAIRS, as many as the shared memory of one SM holds
+    const bool is_dp = warp < npairs;         // warps [0, npairs) run the DP, [npairs, 2 npairs) are their helpers
+    const int pair = is_dp ? warp : warp - npairs;
+    unsigned char* smem_pair = smem_raw + (size_t)pair * a.smem_per_warp;
+    if (is_dp && lane == 0) {
+        // No zero fill: slots that are never loaded (rows past the end of an utterance, unused segments) may hold
+        // anything, NaN included; whatever is computed from them is never looked at.
+        const int C = CT ? CT : a.C;
+        const uint32_t b0 = smem_u32(smem_pair + band3_off_bars(C, G));
+        for (int i = 0; i < B3_NBARS; ++i) mbar_init(b0 + 8u * i, (i >= B3_BAR_FULL && i < B3_BAR_FULL + B3_NST) ? B3_UPW : 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
     const int n_tasks = (n_items + B3_UPW - 1) / B3_UPW;
-    // static deal: task j -> CTA j % grid, warp (j / grid) % WARPS.  With one CTA per SM this spreads
+    // static deal: task j -> CTA j % grid, pair (j / grid) % npairs.  With one CTA per SM this spreads
     // ceil(n_tasks / SMs) tasks evenly over the SMs and over the four schedulers of each SM.
-    for (int j = blockIdx.x + gridDim.x * warp; j < n_tasks; j += gridDim.x * nwarps)
-        band3_task<G, CT>(a, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_warp, slab, phase, lane, pol);
+    if (is_dp) {
+        uint32_t* slab = a.bp_scratch + (size_t)(blockIdx.x * npairs + pair) * a.bp_slab_words;
+        for (int j = blockIdx.x + gridDim.x * pair; j < n_tasks; j += gridDim.x * npairs)
+            band3_dp<G, CT>(a, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, slab, phase, lane);
+    } else {
+        const uint64_t pol = policy_evict_first();
+        bool not_first = false;
+        for (int j = blockIdx.x + gridDim.x * pair; j < n_tasks; j += gridDim.x * npairs) {
+            band3_helper<G, CT>(a, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, phase, not_first, lane, pol);
+            not_first = true;
+        }
+    }
 }
 
 }  // namespace bfa

@@ -382,6 +382,8 @@ template <int KCLASS>
 __global__ void __launch_bounds__(VG_WARPS * 32, KCLASS == 0 ? 2 : 1) viterbi_generic_kernel(VitArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = *a.n_items;
+    if (n_items == 0) return;     // the banded kernel finished everything
     WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
     if (lane == 0) {
         for (int i = 0; i < NSTAGE; ++i) mbar_init(smem_u32(&sm.bar[i]), 1);
@@ -393,7 +395,6 @@ __global__ void __launch_bounds__(VG_WARPS * 32, KCLASS == 0 ? 2 : 1) viterbi_ge
     st.phase = 0;
     const int gwarp = blockIdx.x * VG_WARPS + warp;
     uint32_t* bp = a.bp_scratch + (size_t)gwarp * a.bp_slab_words;
-    const int n_items = *a.n_items;
     for (;;) {
         int i = 0;
         if (lane == 0) i = atomicAdd(a.work_counter + KCLASS, 1);
