@@ -119,7 +119,7 @@ struct Layout {
     int band_grid, band_smem_per_warp[BAND_NV];
     long long band_slab_words[BAND_NV];
     size_t off_tmask, off_tgtok, off_need, off_rowstat, off_items_local, off_items, off_fast[BAND_NV], off_lists, off_padded, off_anchors, off_counters,
-        off_pathlp, off_bp, total;
+        off_pathlp, off_gcls, off_bp, total;
 };
 
 
@@ -165,6 +165,7 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
     L.off_anchors = o; o = align_up(o + (size_t)s.B * L.anchor_words * 4);
     L.off_counters = o; o = align_up(o + 64);
     L.off_pathlp = o; o = align_up(o + (size_t)s.total_frames * 4);
+    L.off_gcls = o; o = align_up(o + (size_t)s.total_frames);
     // the banded and the generic kernels are stream-ordered, so their back-pointer slabs share one region
     L.off_bp = o; o = align_up(o + std::max<size_t>((size_t)L.resident_warps * (size_t)L.slab_words * 4, band_bytes));
     L.total = o;
@@ -302,6 +303,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         ba.p = *p; ba.C = C; ba.logp = logp; ba.tgt = tgt; ba.tmask = tmask;
         ba.retry_items = pa.items; ba.n_retry = counters;
         ba.frame_ph = frame_ph; ba.frame_idx = frame_idx; ba.dp_final = dp_final; ba.path_lp = path_lp;
+        ba.guess_cls = (path_lp && !(p->reserved & BFA_FLAG_NO_SPEC)) ? (unsigned char*)(ws + L.off_gcls) : nullptr;
         ba.bp_scratch = (uint32_t*)(ws + L.off_bp);
         for (int v = 0; v < BAND_NV; ++v) {
             ba.items = pa.fast_items[v]; ba.n_items = pa.n_fast[v];
@@ -397,12 +399,12 @@ int bfa_confidence_batch(int32_t B, int32_t C, const float* logp, const int64_t*
 }
 
 // Development aid: per-phase warp-clock sums of the banded kernel (all zero unless built with -DBFA_PHASE_PROF).
-int bfa_debug_phases(unsigned long long* out16, int reset) {
+int bfa_debug_phases(unsigned long long* out16, int reset) {   // 32 counters: [0,16) DP warps, [16,32) helper warps
 #ifdef BFA_PHASE_PROF
-    if (out16) CUDA_TRY(cudaMemcpyFromSymbol(out16, g_b3_phase, sizeof(unsigned long long) * 16));
-    if (reset) { unsigned long long z[16] = {0}; CUDA_TRY(cudaMemcpyToSymbol(g_b3_phase, z, sizeof(z))); }
+    if (out16) CUDA_TRY(cudaMemcpyFromSymbol(out16, g_b3_phase, sizeof(unsigned long long) * 32));
+    if (reset) { unsigned long long z[32] = {0}; CUDA_TRY(cudaMemcpyToSymbol(g_b3_phase, z, sizeof(z))); }
 #else
-    if (out16) memset(out16, 0, sizeof(unsigned long long) * 16);
+    if (out16) memset(out16, 0, sizeof(unsigned long long) * 32);
     (void)reset;
 #endif
     return BFA_OK;

@@ -16,8 +16,12 @@
 //        alive iff b1 is below the upper edge and b2 above the lower edge.
 //      * p<-{p,b3',m'}, b3<-{b3,m} keep their candidate order, so every arg-max decision that can change the
 //        output is taken on the same fp32 values in the same order as the reference.
-//    A group (p,m,b3) costs 6 FADD + 4 FMNMX and 4 decision bits (FADD sign + funnel shift) per frame instead
-//    of 7 + 6 and 6 bits.
+//      * (1b) b3 <= m at every frame (induction: b3' = max(b3,m)+e = m+e <= max(m,p)+e = m', rounding is monotone), so
+//        b3's arg-max is always "advance from m" unless b3 == m, which holds exactly when m itself stayed one frame
+//        earlier: b3's decision bit at frame t is m's decision bit at frame t-1, and b3's value is m's stay candidate.
+//        b3 therefore costs nothing in the frame loop; its decision word is m's word shifted by one frame, produced
+//        when a record is flushed.  (State 0, the leading blank, lives in m of group 0: same values, same outputs.)
+//    A group (p,m,b3) costs 8 FADD + 3 FMNMX + 3 SHF per frame (3 decision bits) instead of 10 + 6 + 6.
 //
 // 2. Lazy band.  The band mask (:650-653) is not applied state by state.  The window of W = 8*G groups follows
 //    the lower band edge (it slides only at the start of an 8-frame chunk) and always covers the whole band, so
@@ -53,7 +57,8 @@ constexpr int B3_KK = 72;          // floats per utterance in the class-weight t
 constexpr int B3_STP = 9;          // float2 pitch of the per-utterance (lnS, eb) array (bank spreading)
 constexpr int B3_NMAX = 128;       // phonemes per item on this path (byte-sized class table in shared memory)
 constexpr int B3_MARGIN = 2;       // states of safety margin of the band-legality check
-constexpr int B3_GRING = 16;       // 32-frame blocks of confidence gathers kept in flight during the back-trace
+constexpr int B3_NREC = 4;         // decision records of 32-frame blocks in flight from the slab during the back-trace
+constexpr int B3_GRING = 4;        // 32-frame blocks of confidence gathers kept in flight during the back-trace
 
 struct Band3Args {
     BfaParams p;
@@ -69,6 +74,7 @@ struct Band3Args {
     int32_t* frame_idx;
     float* dp_final;
     float* path_lp;            // [total_frames] raw log-prob of the assigned class per frame (confidence input), or null
+    unsigned char* guess_cls;  // [total_frames] class whose raw log-prob the fill left in path_lp (frame-wise best class), or null
     uint32_t* bp_scratch;
     long long bp_slab_words;
     int smem_per_warp;         // bytes
@@ -95,14 +101,18 @@ __host__ __device__ inline int band3_window_need(int N, int T, int L, int band) 
 // The stage ring doubles as the back-trace staging area (cells + visited-cell buffer) once the fill is done.
 __host__ __device__ inline size_t band3_stage_region(int C, int G) {
     size_t st = (size_t)B3_NST * B3_UPW * B3_ROWS * C * 4;
-    // back-trace: cells [UPW][3*8G] x 8 B, two record buffers [4G+1][32] words, B3_GRING gather blocks [4][32] floats
-    size_t bt = (size_t)B3_UPW * 3 * B3_LPU * G * 8 + (size_t)2 * (4 * G + 1) * 128 + (size_t)B3_GRING * 4 * 128;
+    // back-trace: cells [UPW][3*8G] x 8 B, B3_NREC record buffers [4G+1][32] words, two visited-cell buffers [4][32] words,
+    // B3_GRING gather blocks [4][32] floats, per-utterance verdict + final score
+    size_t bt = (size_t)B3_UPW * 3 * B3_LPU * G * 8 + (size_t)B3_NREC * (4 * G + 1) * 128 + (size_t)2 * 4 * 128 + (size_t)B3_GRING * 4 * 128 +
+                (size_t)B3_UPW * 8;
     size_t b = st > bt ? st : bt;
     return (b + 15) / 16 * 16;
 }
+// word offset of the visited-cell buffers inside the back-trace staging area (after the cells and the record buffers)
+__host__ __device__ inline int band3_bt_keep_words(int G) { return B3_UPW * 3 * B3_LPU * G * 2 + B3_NREC * (4 * G + 1) * 32; }
 // shared memory of one pair: stage ring | class weights | (lnS, eb) per staged row | target classes | helper flags | mbarriers
-enum : int { B3_BAR_FULL = 0, B3_BAR_READY = B3_NST, B3_BAR_FREE = 2 * B3_NST, B3_BAR_REC = 3 * B3_NST, B3_BAR_DONE = 3 * B3_NST + 2,
-             B3_NBARS = 3 * B3_NST + 3 };
+enum : int { B3_BAR_FULL = 0, B3_BAR_READY = B3_NST, B3_BAR_FREE = 2 * B3_NST, B3_BAR_REC = 3 * B3_NST, B3_BAR_KREADY = 3 * B3_NST + B3_NREC,
+             B3_BAR_KFREE = 3 * B3_NST + B3_NREC + 2, B3_NBARS = 3 * B3_NST + B3_NREC + 4 };
 __host__ __device__ inline size_t band3_off_kk(int C, int G) { return band3_stage_region(C, G); }
 __host__ __device__ inline size_t band3_off_stats(int C, int G) { return band3_off_kk(C, G) + (size_t)B3_UPW * B3_KK * 4; }
 __host__ __device__ inline size_t band3_off_cls(int C, int G) { return band3_off_stats(C, G) + (size_t)B3_NST * B3_UPW * B3_STP * 8; }
@@ -139,12 +149,16 @@ __device__ __forceinline__ void b3_push(uint32_t& acc, float earlier, float late
 
 // Optional phase timers (development only, -DBFA_PHASE_PROF): warp-clock cycles per phase, summed over lane 0 of the DP warps.
 #ifdef BFA_PHASE_PROF
-__device__ unsigned long long g_b3_phase[16];
-#define PH_DECL long long ph_last = clock64(); long long ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}
+__device__ unsigned long long g_b3_phase[32];
+#define PH_DECL long long ph_last = clock64(); long long ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; const int ph_base = 0
+#define PH_DECL_H long long ph_last = clock64(); long long ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; const int ph_base = 16
+#define PH_RESET ph_last = clock64()
 #define PH_T(i) do { const long long ph_now = clock64(); ph_acc[i] += ph_now - ph_last; ph_last = ph_now; } while (0)
-#define PH_FLUSH do { if (lane == 0) for (int i = 0; i < 16; ++i) atomicAdd(&g_b3_phase[i], (unsigned long long)ph_acc[i]); } while (0)
+#define PH_FLUSH do { if (lane == 0) for (int i = 0; i < 16; ++i) atomicAdd(&g_b3_phase[ph_base + i], (unsigned long long)ph_acc[i]); } while (0)
 #else
 #define PH_DECL
+#define PH_DECL_H
+#define PH_RESET
 #define PH_T(i)
 #define PH_FLUSH
 #endif
@@ -200,12 +214,13 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
     const int blank = a.p.blank_id;
     const float boostv = a.p.boost_factor;
     const bool warp_stats = k.warp_stats;
+    PH_DECL_H;
 
-    if (not_first) {   // the DP warp is done with the previous task (tables, staging area)
-        mbar_wait(k.bar0 + 8u * B3_BAR_DONE, (phase >> B3_BAR_DONE) & 1u);
-        phase ^= 1u << B3_BAR_DONE;
-    }
-    // ---- per-utterance tables: target classes (bytes) and the class weights of the fused log-sum-exp:
+    // This warp finished the previous task last (it wrote that task's outputs), so tables and staging area are free;
+    // the area was last written through the generic proxy and is about to be written by bulk copies.
+    if (not_first) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // ---- per-utterance tables (built before the first bulk copies are issued: behind them these small loads would queue
+    //      for microseconds): target classes (bytes) and the class weights of the fused log-sum-exp:
     //      exp(x + boost*[c in targets] - boost) = 2^(x*log2e + kk[c]) ----
     if (k.seg_on) {
         const int32_t* seq = a.tgt + k.it->seq_off;
@@ -221,7 +236,6 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
         }
     }
     __syncwarp();
-
     // lanes with l8 == 0 issue their own utterance's copy and arrive once per chunk on the stage's full barrier (count = UPW)
     const uint32_t dst0 = smem_u32(k.stage_buf + seg * k.seg_stride);
     const uint32_t full_bytes = (uint32_t)B3_ROWS * C * 4;
@@ -249,6 +263,23 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
     for (int c = 0; c < B3_NST; ++c)
         if (c < k.n_chunks) issue(c, c);
 
+
+    // Speculative confidence inputs: the confidence pass needs lp[f, class of the path at f] (utils.py:89-103), which is
+    // only known after the back-trace, when the row has long left the chip.  While a row is in shared memory this warp
+    // stores the raw log-prob of its frame-wise best (boosted) class together with that class; the back-trace then only
+    // has to fetch the frames where the path disagrees with the guess.
+    const bool spec = warp_stats && a.path_lp != nullptr && a.guess_cls != nullptr;
+    const int o_trim = k.it->trim;
+    const long long o_out = k.it->out_off;
+    int rel_hi = 0;                  // frames [trim, trim + rel_hi) of the item are written out (:447-448, :465-467)
+    if (k.seg_on) {
+        const long long room = k.it->out_lim - o_out;
+        rel_hi = (int)min((long long)k.it->n_out, max(room, 0LL));
+        rel_hi = min(rel_hi, T - o_trim);
+    }
+    float* const plp_row = a.path_lp ? a.path_lp + (o_out - o_trim) : nullptr;           // indexed by the item's frame number
+    unsigned char* const gcl_row = a.guess_cls ? a.guess_cls + (o_out - o_trim) : nullptr;
+
     float emax = -INFINITY;          // raw mode: emissions must be <= 0 (log-probabilities)
     float lse_chk = 0.f;             // running sum of the rows' log-sum-exp (finite <=> all rows sane)
     int st = 0;
@@ -256,6 +287,7 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
         mbar_wait(k.bar0 + 8u * (B3_BAR_FULL + st), (phase >> (B3_BAR_FULL + st)) & 1u);
         phase ^= 1u << (B3_BAR_FULL + st);
         __syncwarp();                                  // tail floats written by the issuing lane become visible
+        PH_T(5);
 
         // ---- row statistics: lane (seg, l8) owns row l8 of its utterance: log-sum-exp of the boosted row (:51-54)
         //      and the blank emission; no cross-lane traffic ----
@@ -265,7 +297,13 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
             float lnS = 0.f;
             if (warp_stats) {
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                float best = -INFINITY;                  // running max of the boosted values, class index in the low 7 mantissa bits
                 const float* kp = k.kk + seg * B3_KK;
+                auto term = [&](float x, float kc, int c, float& acc) {
+                    const float v = fmaf(x, LOG2E, kc);
+                    acc += b3_ex2(v);
+                    best = fmaxf(best, __uint_as_float((__float_as_uint(v) & 0xffffff80u) | (uint32_t)c));
+                };
                 if (CT != 0 && (CT & 1) == 0) {
                     const float2* x2 = reinterpret_cast<const float2*>(rowp);
                     const float4* k4 = reinterpret_cast<const float4*>(kp);
@@ -273,29 +311,37 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
                     for (int i = 0; i < CT / 4; ++i) {
                         const float4 kv = k4[i];
                         const float2 xa = x2[2 * i], xb = x2[2 * i + 1];
-                        s0 += b3_ex2(fmaf(xa.x, LOG2E, kv.x));
-                        s1 += b3_ex2(fmaf(xa.y, LOG2E, kv.y));
-                        s2 += b3_ex2(fmaf(xb.x, LOG2E, kv.z));
-                        s3 += b3_ex2(fmaf(xb.y, LOG2E, kv.w));
+                        term(xa.x, kv.x, 4 * i, s0);
+                        term(xa.y, kv.y, 4 * i + 1, s1);
+                        term(xb.x, kv.z, 4 * i + 2, s2);
+                        term(xb.y, kv.w, 4 * i + 3, s3);
                     }
                     if (CT % 4) {
                         const float2 xa = x2[CT / 2 - 1];
                         const float2 kv = reinterpret_cast<const float2*>(kp)[CT / 2 - 1];
-                        s0 += b3_ex2(fmaf(xa.x, LOG2E, kv.x));
-                        s1 += b3_ex2(fmaf(xa.y, LOG2E, kv.y));
+                        term(xa.x, kv.x, CT - 2, s0);
+                        term(xa.y, kv.y, CT - 1, s1);
                     }
                 } else {
                     int i = 0;
                     for (; i + 4 <= C; i += 4) {
-                        s0 += b3_ex2(fmaf(rowp[i], LOG2E, kp[i]));
-                        s1 += b3_ex2(fmaf(rowp[i + 1], LOG2E, kp[i + 1]));
-                        s2 += b3_ex2(fmaf(rowp[i + 2], LOG2E, kp[i + 2]));
-                        s3 += b3_ex2(fmaf(rowp[i + 3], LOG2E, kp[i + 3]));
+                        term(rowp[i], kp[i], i, s0);
+                        term(rowp[i + 1], kp[i + 1], i + 1, s1);
+                        term(rowp[i + 2], kp[i + 2], i + 2, s2);
+                        term(rowp[i + 3], kp[i + 3], i + 3, s3);
                     }
-                    for (; i < C; ++i) s0 += b3_ex2(fmaf(rowp[i], LOG2E, kp[i]));
+                    for (; i < C; ++i) term(rowp[i], kp[i], i, s0);
                 }
                 lnS = b3_lg2((s0 + s1) + (s2 + s3)) * LN2;          // log sum exp(x + b - boost)
                 if (k.use_stats && t_row < T) lse_chk += lnS;       // any zero / overflowing / NaN sum leaves a non-finite trace
+                if (spec) {
+                    const int cs = min((int)(__float_as_uint(best) & 127u), C - 1);
+                    const int rel = t_row - o_trim;
+                    if (rel >= 0 && rel < rel_hi) {
+                        plp_row[t_row] = rowp[cs];
+                        gcl_row[t_row] = (unsigned char)cs;
+                    }
+                }
             } else {
                 float m = -INFINITY;
                 for (int i = 0; i < C; ++i) m = fmaxf(m, rowp[i]);
@@ -312,6 +358,7 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(k.bar0 + 8u * (B3_BAR_READY + st));      // release: the DP warp may consume chunk c
+        PH_T(6);
 
         // refill the stage the DP warp has finished with (chunk c-1) with chunk c+2
         if (c >= 1 && c + 2 < k.n_chunks) {
@@ -320,7 +367,118 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
             phase ^= 1u << (B3_BAR_FREE + st_p);
             issue(c + 2, st_p);
         }
+        PH_T(7);
         st = (st + 1 == B3_NST) ? 0 : st + 1;
+    }
+
+    // ---- back-trace, output side.  The DP warp walks the path one 32-frame block at a time and hands over the visited
+    //      cells (8 * absolute cell of frames 32b + 8i + l8, lane for lane); this warp turns them into frame_phonemes /
+    //      frame_phonemes_idx (:695-703), checks that the path stayed inside the band, and fetches the confidence inputs
+    //      lp[f, phoneme of the stamp] (utils.py:89-103) the fill did not guess right, with 4-byte cp.async copies, one
+    //      commit group per block, written out B3_GRING-1 blocks later so that no miss latency is ever waited for ----
+    {
+        const Item& it = *k.it;
+        const int L = it.L, band = it.band, idx0 = it.idx0;
+        const bool use_band = band > 0 && T > 1 && L > 1;
+        const float pace_f = use_band ? (float)((double)(L - 1) / (double)(T - 1)) : 0.0f;
+        const float lim_f = use_band ? (float)(band - B3_MARGIN) : INFINITY;
+        const unsigned char* my_cls = k.cls8 + seg * B3_NMAX;
+        const int nblk = (k.Tmax + 31) >> 5;
+        const uint32_t* keepbuf = reinterpret_cast<const uint32_t*>(smem_pair) + band3_bt_keep_words(G);
+        const float* gbuf = reinterpret_cast<const float*>(keepbuf + 2 * 128);
+        const float* finv = gbuf + B3_GRING * 128;                 // [UPW] (verdict, final score) pairs
+        const uint32_t g_s = smem_u32(gbuf) + 4u * lane;
+        // frames [tf_lo, tf_hi) of the item are written; everything is indexed by the item's frame number
+        const int tf_lo = o_trim, tf_hi = o_trim + rel_hi;
+        int32_t* const fph_row = a.frame_ph + (o_out - o_trim);
+        int32_t* const fidx_row = a.frame_idx + (o_out - o_trim);
+        const bool gather_blank = !a.p.ignore_noise;
+        const bool want_lp = a.path_lp != nullptr;
+        PH_RESET;
+        bool walk = false, illegal = false;
+        uint32_t gm = 0;                                           // fetched-slot bits of the last B3_GRING blocks
+        auto write_gathered = [&](int bb, uint32_t bits) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (bits & (1u << i)) plp_row[bb * 32 + 8 * i + l8] = gbuf[(bb % B3_GRING) * 128 + i * 32 + lane];
+        };
+        auto load_guess = [&](int bb, int (&gq)[4]) {              // the fill's guesses for block bb (255: none)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int tf = bb * 32 + 8 * i + l8;
+                gq[i] = (spec && bb >= 0 && tf >= tf_lo && tf < tf_hi) ? (int)__ldcg(gcl_row + tf) : 255;
+            }
+        };
+        int gq[4], gq_next[4];
+        load_guess(nblk - 1, gq);
+        for (int b = nblk - 1; b >= 0; --b) {
+            load_guess(b - 1, gq_next);
+            mbar_wait(k.bar0 + 8u * (B3_BAR_KREADY + (b & 1)), (phase >> (B3_BAR_KREADY + (b & 1))) & 1u);
+            phase ^= 1u << (B3_BAR_KREADY + (b & 1));
+            PH_T(0);
+            if (b == nblk - 1) walk = k.seg_on && T > 0 && __float_as_uint(finv[2 * seg]) == 0u;
+            uint32_t kv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) kv[i] = keepbuf[(b & 1) * 128 + i * 32 + lane];
+            __syncwarp();
+            if (lane == 0 && b >= 2) mbar_arrive(k.bar0 + 8u * (B3_BAR_KFREE + (b & 1)));   // block b-2 may overwrite the buffer
+            uint32_t gbits = 0;
+            int gi[4], pc[4];
+            bool ph[4], on[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {                           // decode: branch-free, the four slots in parallel
+                const int tf = b * 32 + 8 * i + l8;
+                const uint32_t cabs = kv[i] >> 3;
+                gi[i] = (int)((cabs * 43691u) >> 17);               // cabs / 3 (cabs < 2^15)
+                const int kc = (int)cabs - 3 * gi[i];
+                ph[i] = kc == 0;
+                on[i] = walk && tf >= tf_lo && tf < tf_hi;
+                // band legality of the state at frame tf (:650-653), conservative: centre of the (merged) state
+                // must be at least B3_MARGIN states inside the band
+                const float s_c = (float)(4 * gi[i]) - (kc == 0 ? 3.0f : (kc == 1 ? 1.5f : 0.0f));
+                illegal |= walk && tf < T && fabsf(s_c - (float)tf * pace_f) > lim_f;
+                pc[i] = ph[i] ? (int)my_cls[min(max(gi[i] - 1, 0), B3_NMAX - 1)] : blank;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int tf = b * 32 + 8 * i + l8;
+                if (on[i]) {
+                    fph_row[tf] = pc[i];
+                    fidx_row[tf] = ph[i] ? idx0 + gi[i] - 1 : -1;
+                    if (want_lp && (ph[i] || gather_blank) && pc[i] != gq[i]) {
+                        cp_async4(g_s + (uint32_t)(b % B3_GRING) * 512u + 128u * i, k.my_src + (long long)tf * C + pc[i]);
+                        gbits |= 1u << i;
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            PH_T(1);
+            gm = (gm << 4) | gbits;
+            asm volatile("cp.async.wait_group %0;" ::"n"(B3_GRING - 1) : "memory");
+            PH_T(2);
+            if (b + B3_GRING - 1 <= nblk - 1) write_gathered(b + B3_GRING - 1, (gm >> (4 * (B3_GRING - 1))) & 15u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gq[i] = gq_next[i];
+            PH_T(3);
+        }
+        cp_async_wait_all();
+#pragma unroll
+        for (int d = B3_GRING - 2; d >= 0; --d)
+            if (d <= nblk - 1) write_gathered(d, (gm >> (4 * d)) & 15u);
+        // ---- verdict: a path that left (or came too close to) the band is not provably the reference's -> exact kernel ----
+        const unsigned m = __ballot_sync(FULL, illegal);
+        if (k.seg_on && l8 == 0) {
+            const bool bad = __float_as_uint(finv[2 * seg]) != 0u || ((m >> (seg * B3_LPU)) & 0xffu) != 0;
+            if (bad) {
+                const int slot = atomicAdd(a.n_retry, 1);
+                a.retry_items[slot] = it;
+            } else if ((it.flags & ITEM_FINAL) && a.dp_final) {
+                a.dp_final[it.utt] = finv[2 * seg + 1];
+            }
+        }
+        __syncwarp();
+        PH_T(4);
+        PH_FLUSH;
     }
 }
 
@@ -340,9 +498,7 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
     const int blank = a.p.blank_id;
     const uint32_t bar0 = k.bar0;
     uint2* bt2 = reinterpret_cast<uint2*>(smem_pair);                                       // [UPW][CELLS], aliases the stage ring
-    const int N = it.n, L = it.L, band = it.band, flags = it.flags, utt = it.utt;
-    const int trim = it.trim, n_out = it.n_out, idx0 = it.idx0;
-    const long long out_off = it.out_off, out_lim = it.out_lim;
+    const int N = it.n, L = it.L, band = it.band, flags = it.flags;
     const bool use_band = band > 0 && T > 1 && L > 1;                          // :586
     const float pace_f = use_band ? (float)((double)(L - 1) / (double)(T - 1)) : 0.0f;   // :587
     const float min_lp = (flags & ITEM_FLOOR) ? a.p.min_log_prob : -INFINITY;
@@ -359,7 +515,7 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
     int base = 0;
     float P[G], M[G], B3[G];
     int cls[G];
-    uint32_t acc[S::ACC];
+    uint32_t acc[S::ACC];            // per group: decision words of p (2) and m, and m's word of the previous 32-frame block
     uint32_t slide_acc = 0;
 #pragma unroll
     for (int i = 0; i < S::ACC; ++i) acc[i] = 0;
@@ -368,7 +524,7 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
         P[g] = M[g] = B3[g] = -INFINITY;
         cls[g] = group_class(l8 * G + g);
     }
-    if (l8 == 0) B3[0] = 0.0f;        // virtual frame -1: only state 0 is alive, with score 0 (:594-596)
+    if (l8 == 0) M[0] = 0.0f;         // virtual frame -1: only state 0 is alive, with score 0 (:594-596); it lives in m of group 0
     int next_cls = group_class(S::W);   // class of the group that enters at the next slide (last lane of the segment)
     const bool seg_first = l8 == 0, seg_last = l8 == B3_LPU - 1;
 
@@ -390,7 +546,14 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
             const float nP = __shfl_down_sync(FULL, P[0], 1), nM = __shfl_down_sync(FULL, M[0], 1);
             const float n3 = __shfl_down_sync(FULL, B3[0], 1);
             const int nc = __shfl_down_sync(FULL, cls[0], 1);
+            uint32_t nA[4];                            // the decision words of the current block move with their group
+#pragma unroll
+            for (int i = 0; i < 4; ++i) nA[i] = __shfl_down_sync(FULL, acc[i], 1);
             if (nslide > 0) {
+#pragma unroll
+                for (int i = 0; i < S::ACC - 4; ++i) acc[i] = acc[i + 4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[S::ACC - 4 + i] = seg_last ? 0u : nA[i];
 #pragma unroll
                 for (int g = 0; g + 1 < G; ++g) { P[g] = P[g + 1]; M[g] = M[g + 1]; B3[g] = B3[g + 1]; cls[g] = cls[g + 1]; }
                 P[G - 1] = seg_last ? -INFINITY : nP;
@@ -447,7 +610,7 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
                 const float Lm = (g > 0) ? M[(g > 0) ? g - 1 : 0] : lm;
                 const float L3 = (g > 0) ? B3[(g > 0) ? g - 1 : 0] : l3;
                 const float c0 = P[g] + ep[g], c1 = L3 + ep[g], c2 = Lm + ep[g];   // stay / advance from b3' / skip from b2' (= m')
-                const float SP = P[g] + eb, SM = M[g] + eb, S3 = B3[g] + eb;
+                const float SP = P[g] + eb, SM = M[g] + eb;
                 uint32_t* A = &acc[4 * g];
                 // p  : first max of (c0, c1, c2)                      (:645)
                 const float m01 = fmaxf(c0, c1);
@@ -457,9 +620,8 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
                 // m  : (stay SM, from p SP)  -- b1<-{b1,p} / b2<-{b2,b1,p} merged
                 b3_push(A[2], SM, SP);
                 M[g] = fmaxf(SM, SP);
-                // b3 : (stay S3, advance SM)
-                b3_push(A[3], S3, SM);
-                B3[g] = fmaxf(S3, SM);
+                // b3 : max(stay, advance from m) is always the advance (header, point 1b): no compare, no decision bit
+                B3[g] = SM;
             }
 
             if (CHECK) {
@@ -471,7 +633,8 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
                     const int sh = 31 - (t & 31);
                     uint32_t* rec = slab + (size_t)(t >> 5) * S::REC * 32 + lane;
 #pragma unroll
-                    for (int i = 0; i < S::ACC; ++i) rec[i * 32] = acc[i] << sh;
+                    for (int i = 0; i < S::ACC; ++i)
+                        rec[i * 32] = ((i & 3) == 3 ? __funnelshift_r(acc[i - 1], acc[i], 1) : acc[i]) << sh;
                     rec[S::ACC * 32] = slide_acc << (4 * (3 - (c & 3)));
                     // ---- final state (:656-682) from the window at frame T-1; cells are 3*(group - base) + {0:p, 1:m, 2:b3} ----
                     float bv = -INFINITY;
@@ -523,11 +686,15 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
         }
         PH_T(4);
         // ---- flush one full 32-frame record (utterances that end inside this chunk flushed at their last frame)
-        if ((c & 3) == 3 && T - 1 > t0 + B3_ROWS - 1) {
-            uint32_t* rec = slab + (size_t)(c >> 2) * S::REC * 32 + lane;
+        if ((c & 3) == 3) {
+            if (T - 1 > t0 + B3_ROWS - 1) {
+                uint32_t* rec = slab + (size_t)(c >> 2) * S::REC * 32 + lane;
 #pragma unroll
-            for (int i = 0; i < S::ACC; ++i) rec[i * 32] = acc[i];
-            rec[S::ACC * 32] = slide_acc;
+                for (int i = 0; i < S::ACC; ++i) rec[i * 32] = (i & 3) == 3 ? __funnelshift_r(acc[i - 1], acc[i], 1) : acc[i];
+                rec[S::ACC * 32] = slide_acc;
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) acc[4 * g + 3] = acc[4 * g + 2];   // m's word of the block just finished (see b3's word above)
         }
         __syncwarp();                                  // every lane is done with stage st
         if (c + B3_NST < n_chunks && lane == 0) mbar_arrive(bar0 + 8u * (B3_BAR_FREE + st));   // the helper may refill it
@@ -542,72 +709,56 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
         bad = ((m >> (seg * B3_LPU)) & 0xffu) != 0;
     }
 
-    // ---- back-trace (:686-703) ----
+    // ---- back-trace (:686-703), walking side ----
     // A cell is addressed by its window-relative index ci = 3*(group - base) + k.  Staging lays a record out as
-    // bt2[seg][ci] = (first decision word, second decision word or 0), so one 64-bit shared load per frame yields
+    // bt2[seg][ci] = (first decision word, second decision word or 0), so one 64-bit shared load per run yields
     // (b0, b1) and every transition is  ci -= b1 ? 2 : b0  (p: from m' = -2 / from b3' = -1, m: from p = -1,
-    // b3: from m = -1); a window slide of n groups adds 3n.  cabs = 3*base + ci is slide-invariant.
-    // The walk is branch-free: records of frames past the end of an utterance are zero ("stay"), the cell is kept
-    // as a shared-memory byte address A so the loop-carried chain is LDS -> bit test -> 2 selects, and the visited
-    // cells go through a small shared buffer from which every lane picks the 4 frames it writes out.
+    // b3: from m = -1).  The decision words of a block are aligned to the window position at the END of the block (the
+    // fill shifts its accumulators together with the window), so inside a block the walk never sees a slide; between
+    // blocks the cell index moves by 3 * (groups slid during the block).  cabs = 3*base + ci is slide-invariant.
+    // Records of frames past the end of an utterance are zero ("stay"); the cell is kept as a shared-memory byte address
+    // A so the loop-carried chain is LDS -> mask -> lowest set bit -> 2 selects.  The visited cells go to the helper warp
+    // through a double-buffered shared array; it writes the outputs while this warp walks the next block.
     const bool walk = seg_on && !bad && T > 0;
     const int last_blk = (T - 1) >> 5;
     const uint32_t cellbase = smem_u32(bt2 + seg * S::CELLS);
     uint32_t A = cellbase + 8u * (uint32_t)fin_cell;
     uint32_t K = 24u * (uint32_t)fin_base - cellbase;          // A + K = 8 * cabs
-    bool illegal = false;
-    const float lim_f = (float)(band - B3_MARGIN);
-    long long pend_o[4] = {-1, -1, -1, -1};   // outputs of the previous 32-frame block, stored one block late
-    int pend_cls[4] = {0, 0, 0, 0}, pend_idx[4] = {0, 0, 0, 0};
     const int nblk = (Tmax + 31) >> 5;
-    // Shared staging (aliases the stage ring): cells, two record buffers, a ring of gathered log-probs.
+    // Shared staging (aliases the stage ring): cells | two record buffers | two visited-cell buffers | gather ring | verdicts.
     //  * records (decision words of one 32-frame block) come back from the slab by bulk async copy (TMA) on their own
-    //    mbarriers, one block ahead;
-    //  * the confidence inputs lp[f, phoneme of the stamp] (utils.py:89-103) are gathered with 4-byte cp.async copies that
-    //    nothing waits for inside the loop: up to B3_GRING blocks are in flight, then they are drained and written out.
-    uint32_t* recbuf = reinterpret_cast<uint32_t*>(bt2 + B3_UPW * S::CELLS);                 // [2][REC][32]
-    uint32_t* gbuf = recbuf + 2 * S::REC * 32;                                                 // [B3_GRING][4][32]
-    const uint32_t rec_s = smem_u32(recbuf), g_s = smem_u32(gbuf) + 4u * lane;
+    //    mbarriers, one block ahead.
+    uint32_t* recbuf = reinterpret_cast<uint32_t*>(bt2 + B3_UPW * S::CELLS);                 // [B3_NREC][REC][32]
+    uint32_t* keepbuf = reinterpret_cast<uint32_t*>(smem_pair) + band3_bt_keep_words(G);     // [2][4][32]
+    float* finv = reinterpret_cast<float*>(keepbuf + 2 * 128 + B3_GRING * 128);              // [UPW] (verdict, final score)
+    const uint32_t rec_s = smem_u32(recbuf);
     const uint32_t rbar0 = bar0 + 8u * B3_BAR_REC;                                             // the two record barriers
-    constexpr uint32_t GNONE = 0x7fffffffu;                                                    // slot not gathered
     auto issue_rec = [&](int blk) {
         if (lane == 0) {
-            const uint32_t bar = rbar0 + 8u * (blk & 1);
+            const uint32_t bar = rbar0 + 8u * (blk % B3_NREC);
             mbar_expect_tx(bar, S::REC * 128u);
-            bulk_g2s(rec_s + (uint32_t)(blk & 1) * S::REC * 128u, slab + (size_t)blk * S::REC * 32, S::REC * 128u, bar);
-        }
-    };
-    auto drain = [&](int b_lo, int b_hi) {      // write out the gathered values of blocks b_lo..b_hi (inclusive)
-        cp_async_wait_all();
-        if (a.path_lp && walk) {
-            for (int bb = b_lo; bb <= b_hi; ++bb) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t v = gbuf[(bb % B3_GRING) * 128 + i * 32 + lane];
-                    const int rel = bb * 32 + 8 * i + l8 - trim;
-                    if (v != GNONE) a.path_lp[out_off + rel] = __uint_as_float(v);
-                }
-            }
+            bulk_g2s(rec_s + (uint32_t)(blk % B3_NREC) * S::REC * 128u, slab + (size_t)blk * S::REC * 32, S::REC * 128u, bar);
         }
     };
     asm volatile("fence.proxy.async.global;" ::: "memory");   // the slab was written with ordinary stores, the bulk copies read it through the async proxy
     __syncwarp();
-    issue_rec(nblk - 1);
-    uint32_t rphase = phase >> B3_BAR_REC;     // phase bits of the two record barriers
-    int ring_hi = nblk - 1;                    // highest block whose gathers sit in the ring
-#pragma unroll 1
-    for (int bb = 0; bb < B3_GRING && bb < nblk; ++bb)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) gbuf[bb * 128 + i * 32 + lane] = GNONE;
+    for (int d = 1; d <= B3_NREC; ++d)
+        if (nblk - d >= 0) issue_rec(nblk - d);
+    if (l8 == 0) {                             // what the helper needs for the verdict (published by the first KREADY arrive)
+        finv[2 * seg] = __uint_as_float(bad ? 1u : 0u);
+        finv[2 * seg + 1] = fin_val;
+    }
+    uint32_t rphase = phase >> B3_BAR_REC;     // phase bits of the record barriers
     PH_T(6);
     for (int b = nblk - 1; b >= 0; --b) {
-        mbar_wait(rbar0 + 8u * (b & 1), (rphase >> (b & 1)) & 1u);     // record of block b has landed
-        rphase ^= 1u << (b & 1);
+        mbar_wait(rbar0 + 8u * (b % B3_NREC), (rphase >> (b % B3_NREC)) & 1u);     // record of block b has landed
+        rphase ^= 1u << (b % B3_NREC);
         __syncwarp();                          // all lanes are done with the cells of block b+1
-        uint32_t sfw, sb = 0;
+        uint32_t nsl;                          // groups the window slid during this block
         {
             const bool live = walk && b <= last_blk;   // later blocks of a shorter utterance hold stale records
-            const uint32_t* wn = recbuf + (b & 1) * S::REC * 32 + lane;
+            const uint32_t* wn = recbuf + (b % B3_NREC) * S::REC * 32 + lane;
             uint2* dst = bt2 + seg * S::CELLS + l8 * G * 3;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
@@ -615,24 +766,26 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
                 dst[3 * g + 1] = live ? make_uint2(wn[(4 * g + 2) * 32], 0u) : make_uint2(0u, 0u);                      // m : (A2, 0)
                 dst[3 * g + 2] = live ? make_uint2(wn[(4 * g + 3) * 32], 0u) : make_uint2(0u, 0u);                      // b3: (A3, 0)
             }
-            sfw = live ? wn[S::ACC * 32] : 0u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)                 // chunks of this block whose first frame follows a window slide
-                if ((sfw >> (4 * (3 - j))) & 15u) sb |= 1u << (31 - 8 * j);
+            const uint32_t sfw = live ? wn[S::ACC * 32] : 0u;
+            nsl = (sfw & 15u) + ((sfw >> 4) & 15u) + ((sfw >> 8) & 15u) + ((sfw >> 12) & 15u);
         }
         __syncwarp();                          // cells visible; everybody has read its record words
         PH_T(7);
-        if (b > 0) issue_rec(b - 1);
+        if (b >= B3_NREC) issue_rec(b - B3_NREC);   // into the buffer that has just been staged
+        if (b + 2 <= nblk - 1) {               // the helper has read the visited cells of block b+2 out of this buffer
+            mbar_wait(bar0 + 8u * (B3_BAR_KFREE + (b & 1)), (phase >> (B3_BAR_KFREE + (b & 1))) & 1u);
+            phase ^= 1u << (B3_BAR_KFREE + (b & 1));
+        }
+        PH_T(12);
 
         // ---- walk the 32 frames of the block, one RUN per iteration (bit 31-f belongs to frame f): the path stays in
-        //      its cell until a decision bit of that cell (or a slide boundary) is set.  The loop-carried chain is
-        //      LDS -> mask -> lowest set bit -> bit tests -> 2 selects; frame numbers are never materialised ----
+        //      its cell until a decision bit of that cell is set.  Utterances leave the loop on their own ----
         uint32_t keep[4] = {0u, 0u, 0u, 0u};             // 8 * cabs of frames 32b + 8i + l8
         uint32_t mask = 0xffffffffu;                      // frames not yet walked
         do {
             uint32_t w0, w1;
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(A) : "memory");
-            const uint32_t stop = (w0 | w1 | sb) & mask;
+            const uint32_t stop = (w0 | w1) & mask;
             const uint32_t bit = stop & (0u - stop);      // frame whose decision ends the run (0: none left in this block)
             const uint32_t maskn = bit * 0xfffffffeu;     // frames strictly before it  (= -(2*bit); 0 when bit is 0 or bit 31)
             const uint32_t run = mask & ~maskn;           // frames of this run
@@ -643,83 +796,20 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
             const uint32_t A1 = A - 8u, A2 = A - 16u;
             A = (w0 & bit) ? A1 : A;
             A = (w1 & bit) ? A2 : A;
-            if (__any_sync(FULL, (sb & bit) != 0u)) {      // the window slid before this chunk's first frame was computed (rare)
-                if (sb & bit) {
-                    const int j = __clz(bit) >> 3;         // chunk of the block: bit 31-8j
-                    const uint32_t n24 = 24u * ((sfw >> (4 * (3 - j))) & 15u);
-                    A += n24;
-                    K -= n24;
-                }
-            }
             mask = maskn;
-        } while (__any_sync(FULL, mask != 0u));
+        } while (mask != 0u);
+        __syncwarp();
         PH_T(8);
-        // ---- store the block decoded in the previous iteration ----
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (pend_o[i] >= 0) {
-                a.frame_ph[pend_o[i]] = pend_cls[i];
-                a.frame_idx[pend_o[i]] = pend_idx[i];
-            }
-        // ---- decode this block and issue its gathers ----
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            pend_o[i] = -1;
-            const int tf = b * 32 + 8 * i + l8;
-            if (walk && tf < T) {
-                const int cabs = (int)(keep[i] >> 3);
-                const int gi = cabs / 3, k = cabs - 3 * gi;
-                // band legality of the state at frame tf (:650-653), conservative: centre of the (merged) state
-                // must be at least B3_MARGIN states inside the band
-                if (use_band) {
-                    const float s_c = (float)(4 * gi) - (k == 0 ? 3.0f : (k == 1 ? 1.5f : 0.0f));
-                    if (fabsf(s_c - (float)tf * pace_f) > lim_f) illegal = true;
-                }
-                const int rel = tf - trim;
-                const long long o = out_off + rel;
-                if (rel >= 0 && rel < n_out && o < out_lim) {
-                    const bool ph = k == 0;
-                    pend_o[i] = o;
-                    pend_cls[i] = ph ? (int)my_cls[gi - 1] : blank;
-                    pend_idx[i] = ph ? idx0 + gi - 1 : -1;
-                    if (a.path_lp && (ph || !a.p.ignore_noise))
-                        cp_async4(g_s + (uint32_t)(b % B3_GRING) * 512u + 128u * i, my_src + (long long)tf * C + pend_cls[i]);
-                }
-            }
-        }
-        if (ring_hi - b + 1 == B3_GRING && b > 0) {     // ring full: drain it, clear it for the next B3_GRING blocks
-            drain(b, ring_hi);
-            ring_hi = b - 1;
-#pragma unroll 1
-            for (int bb = 0; bb < B3_GRING; ++bb)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) gbuf[bb * 128 + i * 32 + lane] = GNONE;
-        }
+        for (int i = 0; i < 4; ++i) keepbuf[(b & 1) * 128 + i * 32 + lane] = keep[i];
+        A += 24u * nsl;                        // the record of block b-1 is aligned to the window before these slides
+        K -= 24u * nsl;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8u * (B3_BAR_KREADY + (b & 1)));
         PH_T(9);
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (pend_o[i] >= 0) {
-            a.frame_ph[pend_o[i]] = pend_cls[i];
-            a.frame_idx[pend_o[i]] = pend_idx[i];
-        }
-    drain(0, ring_hi);
-    phase = (phase & ~(3u << B3_BAR_REC)) | ((rphase & 3u) << B3_BAR_REC);
-    {   // a path that left (or came too close to) the band is not provably the reference's: exact path
-        const unsigned m = __ballot_sync(FULL, illegal);
-        if ((m >> (seg * B3_LPU)) & 0xffu) bad = true;
-    }
-    if (seg_on && l8 == 0) {
-        if (bad) {
-            const int slot = atomicAdd(a.n_retry, 1);
-            a.retry_items[slot] = it;
-        } else if ((flags & ITEM_FINAL) && a.dp_final) {
-            a.dp_final[utt] = fin_val;
-        }
-    }
-    __syncwarp();
+    phase = (phase & ~(((1u << B3_NREC) - 1u) << B3_BAR_REC)) | ((rphase & ((1u << B3_NREC) - 1u)) << B3_BAR_REC);
     PH_T(10);
-    if (lane == 0) mbar_arrive(bar0 + 8u * B3_BAR_DONE);   // the helper may set up the pair's next task
     PH_FLUSH;
 }
 

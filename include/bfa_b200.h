@@ -84,6 +84,8 @@ typedef struct BfaParams {
                                  recomputes what it needs (slower), results are unchanged. */
 #define BFA_FLAG_UNFUSED_CONF 4  /* confidences gather lp[f, phoneme] from logp inside the stamp kernel instead of taking the
                                  * per-frame values the Viterbi back-trace collects (measurement / A-B switch) */
+#define BFA_FLAG_NO_SPEC 8       /* the banded kernel fetches every confidence input during its back-trace instead of keeping the
+                                 * frame-wise best class's value while the row is on chip (measurement / A-B switch) */
 
 /* framestamp tuple (phoneme_id, start_frame, end_frame_exclusive, target_seq_idx)
  * = the 4-tuples returned by ViterbiDecoder.assort_frames (forced_alignment.py:777-834). */

@@ -1,39 +1,49 @@
-"""Aggregate an `ncu --page source --csv --print-source cuda,sass` export by CUDA source line:
-stall samples and executed instructions per line, top N."""
-import csv, sys, collections
-path = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-rows = list(csv.reader(open(path)))
-# find header row
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Line No")
+"""Aggregate the stall samples of an ncu source-page dump (SASS view, --csv) by CUDA source line.
+The line of every SASS instruction comes from `nvdisasm -g -c` of the cubin inside libbfa_b200.so (same build!).
+usage: ncu_lines.py <source.csv> <mangled kernel substring> [min_pct]"""
+import csv, re, subprocess, sys, tempfile, os, collections
+src_csv = sys.argv[1]; pat = sys.argv[2]; min_pct = float(sys.argv[3]) if len(sys.argv) > 3 else 0.7
+lib = "bournemouth-forced-aligner_b200/lib/libbfa_b200.so"
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
+txt = ""
+for f in os.listdir(tmp):
+    if f.endswith(".cubin"):
+        t = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+        if pat in t: txt = t; break
+assert txt, "kernel not found"
+# locate the function
+i0 = txt.index(".text." + [m for m in re.findall(r"\.text\.(\S+)", txt) if pat in m][0])
+lines = txt[i0:].split("\n")
+sass_line = []   # source line of each instruction in order
+cur = None
+for l in lines[1:]:
+    if l.startswith("\t.section") or l.startswith(".section"): 
+        if sass_line: break
+    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+    if m: cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
+    if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l): sass_line.append(cur)
+rows = list(csv.reader(open(src_csv)))
+hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 h = rows[hi]
-# The export lists source lines first (with aggregated metrics) when print-source is cuda,sass; take rows whose first col is int and Address empty
-col = {n: i for i, n in enumerate(h)}
-samples = collections.Counter(); insts = collections.Counter(); text = {}
-cur_file = ""
-tot_s = tot_i = 0
-for r in rows[hi + 1:]:
-    if len(r) < len(h): 
-        if r and r[0] == "File Path": cur_file = r[1].split("/")[-1]
-        continue
-    try: ln = int(r[0])
-    except: continue
-    addr = r[2]
-    if addr not in ("", "-"): continue   # SASS rows
-    s = int(r[col["# Samples"]] or 0); n = int(r[col["Instructions Executed"]] or 0)
-    key = (cur_file, ln)
-    samples[key] += s; insts[key] += n; text[key] = r[1].strip()[:110]
-    tot_s += s; tot_i += n
-print("total samples", tot_s, "total inst", tot_i)
-print("--- by samples")
-for k, s in samples.most_common(topn):
-    print(f"{k[0]}:{k[1]:4d} samp {s:6d} ({100*s/max(tot_s,1):4.1f}%) inst {insts[k]:9d} ({100*insts[k]/max(tot_i,1):4.1f}%) | {text[k]}")
-if len(sys.argv) > 3:
-    # region summary: "name:lo-hi,name:lo-hi"
-    print("--- regions (viterbi file only)")
-    for spec in sys.argv[3].split(","):
-        name, rng = spec.split(":"); lo, hi = map(int, rng.split("-"))
-        s = sum(v for k, v in samples.items() if k[0].startswith("viterbi") and lo <= k[1] <= hi)
-        n = sum(v for k, v in insts.items() if k[0].startswith("viterbi") and lo <= k[1] <= hi)
-        print(f"{name:12s} samples {100*s/tot_s:5.1f}%  inst {100*n/tot_i:5.1f}%")
-    s = sum(v for k, v in samples.items() if not k[0].startswith("viterbi")); n = sum(v for k, v in insts.items() if not k[0].startswith("viterbi"))
-    print(f"{'other files':12s} samples {100*s/tot_s:5.1f}%  inst {100*n/tot_i:5.1f}%")
+data = [dict(zip(h, r)) for r in rows[hi + 1:] if len(r) == len(h)]
+print("sass in cubin", len(sass_line), "in report", len(data))
+stalls = [c for c in h if c.startswith("stall_") and "Not Issued" not in c]
+agg = collections.defaultdict(lambda: collections.Counter())
+for d, sl in zip(data, sass_line):
+    a = agg[sl]; a["n"] += int(d["# Samples"]); a["ex"] += int(d["Instructions Executed"])
+    for c in stalls: a[c] += int(d[c])
+tot = sum(a["n"] for a in agg.values())
+srcs = {}
+def src(fl):
+    if fl is None: return ""
+    f, n = fl
+    if f not in srcs:
+        p = os.path.join("bournemouth-forced-aligner_b200/csrc", f)
+        srcs[f] = open(p).read().split("\n") if os.path.exists(p) else []
+    return srcs[f][n - 1].strip()[:80] if n - 1 < len(srcs[f]) else ""
+for fl in sorted(agg, key=lambda x: (x is None, x)):
+    a = agg[fl]
+    if a["n"] * 100 >= min_pct * tot:
+        v = sorted(((a[c], c) for c in stalls), reverse=True)[:3]
+        print(f"{str(fl[1]) if fl else '-':>5} {100*a['n']/tot:5.1f}% ex {a['ex']:>9} {src(fl):80s} " + " ".join(f"{c[6:]}:{n}" for n, c in v if n))

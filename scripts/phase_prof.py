@@ -15,10 +15,14 @@ lens = torch.full((B,), T, dtype=torch.long); nl = torch.full((B,), N, dtype=tor
 for it in range(3):
     au.decode_alignments(lp, true_seqs=tgt.to(dev), pred_lens=lens, true_seqs_lens=nl, with_confidence=CONF)
     torch.cuda.synchronize()
-    out = (C.c_ulonglong * 16)()
+    out = (C.c_ulonglong * 32)()
     _cabi.lib().bfa_debug_phases(out, 1)
-names = ["setup", "slide", "barrier wait", "row stats (unpiped)", "frames+stats", "loop end", "pre-walk", "stage", "walk", "output", "tail", "flush+sync", "issue"]
+names = ["setup", "slide", "barrier wait", "-", "frames", "loop end", "pre-walk", "rec wait+stage", "walk", "handoff", "tail", "flush+sync", "keep-free wait"]
 tot = sum(out[:13]); nw = (B + 3) // 4
 print(f"warps {nw}; cycles per warp-task {tot / nw:.0f} = {tot / nw / 1.965e3:.1f} us")
 for n, v in zip(names, out):
     print(f"{n:14s} {v / nw:10.0f} cyc/task  {100 * v / tot:5.1f}%")
+hn = ["kready wait", "decode+stores", "gather wait", "write gathered", "final", "fill: full wait", "fill: row stats", "fill: free wait+issue"]
+print("helper warp:")
+for n, v in zip(hn, out[16:]):
+    print(f"{n:14s} {v / nw:10.0f} cyc/task")
