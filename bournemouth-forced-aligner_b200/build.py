@@ -36,7 +36,10 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: Path = No
 
 
 if __name__ == "__main__":
-    if "--phase-prof" in sys.argv:   # development build with per-phase cycle counters in the banded kernel
+    if "--variant" in sys.argv:      # A/B build: python build.py --variant NAME DEFINE [DEFINE...] -> lib/libbfa_b200_NAME.so
+        i = sys.argv.index("--variant")
+        print(build(force=True, defines=tuple(sys.argv[i + 2:]), out=HERE / "lib" / f"libbfa_b200_{sys.argv[i + 1]}.so"))
+    elif "--phase-prof" in sys.argv:   # development build with per-phase cycle counters in the banded kernel
         print(build(force=True, defines=("BFA_PHASE_PROF",), out=HERE / "lib" / "libbfa_b200_prof.so"))
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -68,18 +68,21 @@ inline int band_smem_bytes_per_warp(int C, int G) { return (int)band3_smem_per_w
 
 template <int G>
 cudaError_t band_set_attr(int bytes) {
-    cudaError_t e = cudaFuncSetAttribute(viterbi_band3_kernel<G, 66>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(viterbi_band3_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(viterbi_band3_kernel<G, 66, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_kernel<G, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_kernel<G, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e;
 }
 constexpr int BAND_SMEM_MAX = 227 * 1024;   // dynamic shared memory one CTA may opt in to on sm_100
 inline int band_warps(int smem_per_warp) { return std::max(1, std::min(BAND_WARPS, BAND_SMEM_MAX / smem_per_warp)); }
+// exact: the items carry the caller's log-probs unchanged (no fused log-softmax), every decision is taken on the sums
 template <int G>
-void band_launch(const Band3Args& ba, int grid, cudaStream_t st) {
+void band_launch(const Band3Args& ba, bool exact, int grid, cudaStream_t st) {
     const int pairs = band_warps(ba.smem_per_warp);
     const size_t smem = (size_t)pairs * ba.smem_per_warp;
-    if (ba.C == 66) viterbi_band3_kernel<G, 66><<<grid, pairs * 64, smem, st>>>(ba);
-    else viterbi_band3_kernel<G, 0><<<grid, pairs * 64, smem, st>>>(ba);
+    if (exact) viterbi_band3_kernel<G, 0, true><<<grid, pairs * 64, smem, st>>>(ba);
+    else if (ba.C == 66) viterbi_band3_kernel<G, 66, false><<<grid, pairs * 64, smem, st>>>(ba);
+    else viterbi_band3_kernel<G, 0, false><<<grid, pairs * 64, smem, st>>>(ba);
 }
 
 int device_info(DeviceInfo& out) {
@@ -314,9 +317,9 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
                 if (g_prof.on) { e0 = g_prof.get(); e1 = g_prof.get(); }
             }
             if (e0) cudaEventRecord(e0, st);
-            if (v == 0) band_launch<3>(ba, L.band_grid, st);
-            else if (v == 1) band_launch<5>(ba, L.band_grid, st);
-            else band_launch<8>(ba, L.band_grid, st);
+            if (v == 0) band_launch<3>(ba, !boost, L.band_grid, st);
+            else if (v == 1) band_launch<5>(ba, !boost, L.band_grid, st);
+            else band_launch<8>(ba, !boost, L.band_grid, st);
             LAUNCH_CHECK();
             if (e0) {
                 cudaEventRecord(e1, st);
@@ -402,7 +405,7 @@ int bfa_confidence_batch(int32_t B, int32_t C, const float* logp, const int64_t*
 int bfa_debug_phases(unsigned long long* out16, int reset) {   // 32 counters: [0,16) DP warps, [16,32) helper warps
 #ifdef BFA_PHASE_PROF
     if (out16) CUDA_TRY(cudaMemcpyFromSymbol(out16, g_b3_phase, sizeof(unsigned long long) * 32));
-    if (reset) { unsigned long long z[32] = {0}; CUDA_TRY(cudaMemcpyToSymbol(g_b3_phase, z, sizeof(z))); }
+    if (reset) { unsigned long long z[32] = {0}; z[15] = z[31] = ~0ull; CUDA_TRY(cudaMemcpyToSymbol(g_b3_phase, z, sizeof(z))); }
 #else
     if (out16) memset(out16, 0, sizeof(unsigned long long) * 32);
     (void)reset;

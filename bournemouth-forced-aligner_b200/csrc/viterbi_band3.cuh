@@ -21,7 +21,14 @@
 //        earlier: b3's decision bit at frame t is m's decision bit at frame t-1, and b3's value is m's stay candidate.
 //        b3 therefore costs nothing in the frame loop; its decision word is m's word shifted by one frame, produced
 //        when a record is flushed.  (State 0, the leading blank, lives in m of group 0: same values, same outputs.)
-//    A group (p,m,b3) costs 8 FADD + 3 FMNMX + 3 SHF per frame (3 decision bits) instead of 10 + 6 + 6.
+//      * (1c) for the same reason the best way into p from the previous group is always worth m' + e; it came "from b3'"
+//        (the reference's first max) exactly when b3' == m'.  One compare decides stay / enter, m's history the rest.
+//    A group then costs 6 FADD + 2 FMNMX + 2 SHF per frame (2 decision bits) instead of 10 + 6 + 6 on the full lattice.
+//    (1b)/(1c) read "b3 == m" off m's decision instead of comparing the sums, so they differ from the reference when
+//    b3 < m but the two sums round to the same float (a half-ulp tie; ~1e-8 per state and frame).  With the fused
+//    log-softmax the emissions already differ from torch's by an ulp now and then, which flips near-ties far more
+//    often; when the kernel consumes the caller's log-probs unchanged (no boost: simple / raw modes) every decision of
+//    the full reduced lattice (p: 2, m, b3) is taken on the sums themselves: template parameter EXACT.
 //
 // 2. Lazy band.  The band mask (:650-653) is not applied state by state.  The window of W = 8*G groups follows
 //    the lower band edge (it slides only at the start of an 8-frame chunk) and always covers the whole band, so
@@ -154,7 +161,8 @@ __device__ unsigned long long g_b3_phase[32];
 #define PH_DECL_H long long ph_last = clock64(); long long ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; const int ph_base = 16
 #define PH_RESET ph_last = clock64()
 #define PH_T(i) do { const long long ph_now = clock64(); ph_acc[i] += ph_now - ph_last; ph_last = ph_now; } while (0)
-#define PH_FLUSH do { if (lane == 0) for (int i = 0; i < 16; ++i) atomicAdd(&g_b3_phase[ph_base + i], (unsigned long long)ph_acc[i]); } while (0)
+#define PH_FLUSH do { if (lane == 0) { long long ph_tot = 0; for (int i = 0; i < 14; ++i) { ph_tot += ph_acc[i]; atomicAdd(&g_b3_phase[ph_base + i], (unsigned long long)ph_acc[i]); } \
+    atomicMax(&g_b3_phase[ph_base + 14], (unsigned long long)ph_tot); atomicMin(&g_b3_phase[ph_base + 15], (unsigned long long)ph_tot); } } while (0)
 #else
 #define PH_DECL
 #define PH_DECL_H
@@ -485,7 +493,7 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
 // ------------------------------------------------------------------------------------------------------------
 // DP warp: frame loop, decision records, back-trace, outputs.
 // ------------------------------------------------------------------------------------------------------------
-template <int G, int CT>
+template <int G, int CT, bool EXACT>
 __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned char* smem_pair, uint32_t* slab, uint32_t& phase,
                          int lane) {
     using S = Band3Shape<G>;
@@ -524,7 +532,10 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
         P[g] = M[g] = B3[g] = -INFINITY;
         cls[g] = group_class(l8 * G + g);
     }
-    if (l8 == 0) M[0] = 0.0f;         // virtual frame -1: only state 0 is alive, with score 0 (:594-596); it lives in m of group 0
+    if (l8 == 0) {                    // virtual frame -1: only state 0 is alive, with score 0 (:594-596)
+        if (EXACT) B3[0] = 0.0f;      // state 0 = b3 of group 0
+        else M[0] = 0.0f;             // reduced form: it lives in m of group 0 (b3 of group 0 follows it one frame later)
+    }
     int next_cls = group_class(S::W);   // class of the group that enters at the next slide (last lane of the segment)
     const bool seg_first = l8 == 0, seg_last = l8 == B3_LPU - 1;
 
@@ -544,11 +555,11 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
         slide_acc = (slide_acc << 4) | (uint32_t)nslide;
         while (__any_sync(FULL, nslide > 0)) {
             const float nP = __shfl_down_sync(FULL, P[0], 1), nM = __shfl_down_sync(FULL, M[0], 1);
-            const float n3 = __shfl_down_sync(FULL, B3[0], 1);
+            const float n3 = EXACT ? __shfl_down_sync(FULL, B3[0], 1) : 0.f;
             const int nc = __shfl_down_sync(FULL, cls[0], 1);
             uint32_t nA[4];                            // the decision words of the current block move with their group
 #pragma unroll
-            for (int i = 0; i < 4; ++i) nA[i] = __shfl_down_sync(FULL, acc[i], 1);
+            for (int i = 0; i < 4; ++i) nA[i] = (EXACT || i != 1) ? __shfl_down_sync(FULL, acc[i], 1) : 0u;   // word 1 is unused in the reduced form
             if (nslide > 0) {
 #pragma unroll
                 for (int i = 0; i < S::ACC - 4; ++i) acc[i] = acc[i + 4];
@@ -589,6 +600,30 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
         for (int g = 0; g < G; ++g) xp_n[g] = xg[g][0];
         float2 st_nx = stp[0];
 
+        // The four decision words per group that go into a record: p's two (from b3' / from m'), m's, b3's.
+        // Reduced form: b3's word is m's one frame later (slot 3 holds m's word of the previous block), and p's single
+        // "entered" word splits by the b3 word of the group to its left (b3' == m' exactly when m' stayed).
+        auto record_words = [&](uint32_t (&w)[S::ACC]) {
+            if (EXACT) {
+#pragma unroll
+                for (int i = 0; i < S::ACC; ++i) w[i] = acc[i];
+            } else {
+                uint32_t w3[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) w3[g] = __funnelshift_r(acc[4 * g + 2], acc[4 * g + 3], 1);
+                uint32_t left = __shfl_up_sync(FULL, w3[G - 1], 1);
+                if (seg_first) left = 0u;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const uint32_t y = g > 0 ? w3[g > 0 ? g - 1 : 0] : left, x = acc[4 * g];
+                    w[4 * g] = x & ~y;
+                    w[4 * g + 1] = x & y;
+                    w[4 * g + 2] = acc[4 * g + 2];
+                    w[4 * g + 3] = w3[g];
+                }
+            }
+        };
+
         auto frame = [&](const int r, auto check_fin) {
             constexpr bool CHECK = decltype(check_fin)::value;
             const float lnS = st_nx.x, eb = st_nx.y;
@@ -603,38 +638,50 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
             }
 
             // ---- DP update, right-most group first so that left neighbours are still frame t-1 ----
-            float lm = __shfl_up_sync(FULL, M[G - 1], 1), l3 = __shfl_up_sync(FULL, B3[G - 1], 1);
+            float lm = __shfl_up_sync(FULL, M[G - 1], 1), l3 = EXACT ? __shfl_up_sync(FULL, B3[G - 1], 1) : 0.f;
             if (seg_first) { lm = -INFINITY; l3 = -INFINITY; }   // nothing (or a dropped group, dead for every legal path) to the left
 #pragma unroll
             for (int g = G - 1; g >= 0; --g) {
                 const float Lm = (g > 0) ? M[(g > 0) ? g - 1 : 0] : lm;
-                const float L3 = (g > 0) ? B3[(g > 0) ? g - 1 : 0] : l3;
-                const float c0 = P[g] + ep[g], c1 = L3 + ep[g], c2 = Lm + ep[g];   // stay / advance from b3' / skip from b2' (= m')
                 const float SP = P[g] + eb, SM = M[g] + eb;
                 uint32_t* A = &acc[4 * g];
-                // p  : first max of (c0, c1, c2)                      (:645)
-                const float m01 = fmaxf(c0, c1);
-                b3_push(A[0], c0, c1);
-                b3_push(A[1], m01, c2);
-                P[g] = fmaxf(m01, c2);
+                if (EXACT) {
+                    const float L3 = (g > 0) ? B3[(g > 0) ? g - 1 : 0] : l3;
+                    const float c0 = P[g] + ep[g], c1 = L3 + ep[g], c2 = Lm + ep[g];   // stay / advance from b3' / skip from b2' (= m')
+                    const float S3 = B3[g] + eb;
+                    // p  : first max of (c0, c1, c2)                      (:645)
+                    const float m01 = fmaxf(c0, c1);
+                    b3_push(A[0], c0, c1);
+                    b3_push(A[1], m01, c2);
+                    P[g] = fmaxf(m01, c2);
+                    // b3 : (stay S3, advance SM)
+                    b3_push(A[3], S3, SM);
+                    B3[g] = fmaxf(S3, SM);
+                } else {
+                    // p  : b3' <= m' (header, 1b), so the best way in is always worth c2 and one decision bit is enough:
+                    //      A[0] = "entered from the previous group"; from b3' or from m' is decided by m's history (flush)
+                    const float c0 = P[g] + ep[g], c2 = Lm + ep[g];
+                    b3_push(A[0], c0, c2);
+                    P[g] = fmaxf(c0, c2);
+                    if (CHECK) B3[g] = SM;     // b3's value is m's stay candidate; only the final-state rule looks at it
+                }
                 // m  : (stay SM, from p SP)  -- b1<-{b1,p} / b2<-{b2,b1,p} merged
                 b3_push(A[2], SM, SP);
                 M[g] = fmaxf(SM, SP);
-                // b3 : max(stay, advance from m) is always the advance (header, point 1b): no compare, no decision bit
-                B3[g] = SM;
             }
 
             if (CHECK) {
                 const bool fin = (r == fin_r);
                 const unsigned fin_mask = __ballot_sync(FULL, fin);
+                uint32_t wrec[S::ACC];
+                if (fin_mask != 0u) record_words(wrec);
                 if (fin) {
                     const int t = t0 + r;
                     // last record of this utterance, left-aligned so that frame 32b+q sits at bit 31-q
                     const int sh = 31 - (t & 31);
                     uint32_t* rec = slab + (size_t)(t >> 5) * S::REC * 32 + lane;
 #pragma unroll
-                    for (int i = 0; i < S::ACC; ++i)
-                        rec[i * 32] = ((i & 3) == 3 ? __funnelshift_r(acc[i - 1], acc[i], 1) : acc[i]) << sh;
+                    for (int i = 0; i < S::ACC; ++i) rec[i * 32] = wrec[i] << sh;
                     rec[S::ACC * 32] = slide_acc << (4 * (3 - (c & 3)));
                     // ---- final state (:656-682) from the window at frame T-1; cells are 3*(group - base) + {0:p, 1:m, 2:b3} ----
                     float bv = -INFINITY;
@@ -687,14 +734,18 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
         PH_T(4);
         // ---- flush one full 32-frame record (utterances that end inside this chunk flushed at their last frame)
         if ((c & 3) == 3) {
+            uint32_t wrec[S::ACC];
+            record_words(wrec);
             if (T - 1 > t0 + B3_ROWS - 1) {
                 uint32_t* rec = slab + (size_t)(c >> 2) * S::REC * 32 + lane;
 #pragma unroll
-                for (int i = 0; i < S::ACC; ++i) rec[i * 32] = (i & 3) == 3 ? __funnelshift_r(acc[i - 1], acc[i], 1) : acc[i];
+                for (int i = 0; i < S::ACC; ++i) rec[i * 32] = wrec[i];
                 rec[S::ACC * 32] = slide_acc;
             }
+            if (!EXACT) {
 #pragma unroll
-            for (int g = 0; g < G; ++g) acc[4 * g + 3] = acc[4 * g + 2];   // m's word of the block just finished (see b3's word above)
+                for (int g = 0; g < G; ++g) acc[4 * g + 3] = acc[4 * g + 2];   // m's word of the block just finished
+            }
         }
         __syncwarp();                                  // every lane is done with stage st
         if (c + B3_NST < n_chunks && lane == 0) mbar_arrive(bar0 + 8u * (B3_BAR_FREE + st));   // the helper may refill it
@@ -813,15 +864,25 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
     PH_FLUSH;
 }
 
-template <int G, int CT>
+template <int G, int CT, bool EXACT>
 __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_kernel(Band3Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int n_items = *a.n_items;
     if (n_items == 0) return;                 // nothing of this window class in the batch
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int npairs = blockDim.x >> 6;       // <= B3_PAIRS, as many as the shared memory of one SM holds
-    const bool is_dp = warp < npairs;         // warps [0, npairs) run the DP, [npairs, 2 npairs) are their helpers
-    const int pair = is_dp ? warp : warp - npairs;
+    // Roles.  A DP warp issues about 1.45x the instructions of a helper warp, and warp w issues on scheduler w % 4.  With 14
+    // warps the schedulers hold 4, 4, 3, 3 of them; giving the two 4-warp schedulers one DP warp + three helpers each and
+    // the 3-warp schedulers 2 + 1 and 3 + 0 keeps the busiest scheduler ~9 % lighter than any contiguous split.
+    bool is_dp = warp < npairs;               // default: warps [0, npairs) run the DP, [npairs, 2 npairs) are their helpers
+    int pair = is_dp ? warp : warp - npairs;
+#ifndef BFA_ROLES_CONTIG
+    if (npairs == 7) {
+        constexpr uint32_t DP_WARPS = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3) | (1u << 6) | (1u << 7) | (1u << 11);
+        is_dp = (DP_WARPS >> warp) & 1u;
+        pair = __popc((is_dp ? DP_WARPS : ~DP_WARPS) & ((1u << warp) - 1u));
+    }
+#endif
     unsigned char* smem_pair = smem_raw + (size_t)pair * a.smem_per_warp;
     if (is_dp && lane == 0) {
         // No zero fill: slots that are never loaded (rows past the end of an utterance, unused segments) may hold
@@ -839,7 +900,7 @@ __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_kernel(Band3Ar
     if (is_dp) {
         uint32_t* slab = a.bp_scratch + (size_t)(blockIdx.x * npairs + pair) * a.bp_slab_words;
         for (int j = blockIdx.x + gridDim.x * pair; j < n_tasks; j += gridDim.x * npairs)
-            band3_dp<G, CT>(a, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, slab, phase, lane);
+            band3_dp<G, CT, EXACT>(a, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, slab, phase, lane);
     } else {
         const uint64_t pol = policy_evict_first();
         bool not_first = false;

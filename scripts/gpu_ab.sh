@@ -1,14 +1,14 @@
 #!/bin/bash
+# A/B: device-timed bench of the default library and of every lib/libbfa_b200_<variant>.so given as argument
 mkdir -p gpurun_out
-
-
-for f in "" "--unfused-conf"; do
-timeout 600 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline $f > gpurun_out/bench_ab.log 2>&1
-python - <<PY
-import json
-l=[x for x in open('gpurun_out/bench_ab.log') if x.startswith('{')]
-if l:
-    d=json.loads(l[-1]); print("$f value %.3e step %.4f ms kernel %.4f ms frac %.3f"%(d['value'],d['ms_per_step'],d['roofline']['kernel_ms'],d['roofline']['frac']))
-else: print(open('gpurun_out/bench_ab.log').read()[-1500:])
-PY
+run() {
+  python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read())
+print('$1: value %.3e ms/step %.4f kernel_ms %.4f frac %.3f' % (d['value'], d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac']))"
+}
+run default
+for v in "$@"; do
+  BFA_B200_LIB=$PWD/bournemouth-forced-aligner_b200/lib/libbfa_b200_$v.so run $v
 done
+run default
