@@ -58,6 +58,7 @@ _SIGNATURES = {
     "bfa_align_batch_host": (C.c_int, [C.POINTER(BfaParams), C.POINTER(BfaShape)] + [_P] * 13 + [C.c_int32, C.c_int32]),
     "bfa_host_release": (None, []),
     "bfa_debug_phases": (C.c_int, [_P, C.c_int]),
+    "bfa_debug_warps": (C.c_int, [_P, C.c_int]),
     "bfa_profile_enable": (None, [C.c_int]),
     "bfa_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }

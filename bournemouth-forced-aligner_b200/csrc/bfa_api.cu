@@ -402,6 +402,17 @@ int bfa_confidence_batch(int32_t B, int32_t C, const float* logp, const int64_t*
 }
 
 // Development aid: per-phase warp-clock sums of the banded kernel (all zero unless built with -DBFA_PHASE_PROF).
+int bfa_debug_warps(unsigned long long* out32, int reset) {   // development: mean task cycles per warp id of the banded kernel
+#ifdef BFA_PHASE_PROF
+    if (out32) CUDA_TRY(cudaMemcpyFromSymbol(out32, g_b3_warp, sizeof(unsigned long long) * 32));
+    if (reset) { unsigned long long z[32] = {0}; CUDA_TRY(cudaMemcpyToSymbol(g_b3_warp, z, sizeof(z))); }
+#else
+    if (out32) memset(out32, 0, sizeof(unsigned long long) * 32);
+    (void)reset;
+#endif
+    return BFA_OK;
+}
+
 int bfa_debug_phases(unsigned long long* out16, int reset) {   // 32 counters: [0,16) DP warps, [16,32) helper warps
 #ifdef BFA_PHASE_PROF
     if (out16) CUDA_TRY(cudaMemcpyFromSymbol(out16, g_b3_phase, sizeof(unsigned long long) * 32));

@@ -139,6 +139,25 @@ __device__ __forceinline__ float b3_lg2(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// packed fp32 pairs (sm_100: FADD2 / FFMA2, one issue slot for two IEEE operations)
+__device__ __forceinline__ unsigned long long b3_pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void b3_unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long b3_add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long b3_fma2(unsigned long long a, float s, unsigned long long c) {   // a * (s, s) + c
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b3_pack2(s, s)), "l"(c));
+    return r;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -157,12 +176,14 @@ __device__ __forceinline__ void b3_push(uint32_t& acc, float earlier, float late
 // Optional phase timers (development only, -DBFA_PHASE_PROF): warp-clock cycles per phase, summed over lane 0 of the DP warps.
 #ifdef BFA_PHASE_PROF
 __device__ unsigned long long g_b3_phase[32];
+__device__ unsigned long long g_b3_warp[32];   // [warp id]: summed task cycles, [16 + warp id]: tasks
 #define PH_DECL long long ph_last = clock64(); long long ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; const int ph_base = 0
 #define PH_DECL_H long long ph_last = clock64(); long long ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; const int ph_base = 16
 #define PH_RESET ph_last = clock64()
 #define PH_T(i) do { const long long ph_now = clock64(); ph_acc[i] += ph_now - ph_last; ph_last = ph_now; } while (0)
 #define PH_FLUSH do { if (lane == 0) { long long ph_tot = 0; for (int i = 0; i < 14; ++i) { ph_tot += ph_acc[i]; atomicAdd(&g_b3_phase[ph_base + i], (unsigned long long)ph_acc[i]); } \
-    atomicMax(&g_b3_phase[ph_base + 14], (unsigned long long)ph_tot); atomicMin(&g_b3_phase[ph_base + 15], (unsigned long long)ph_tot); } } while (0)
+    atomicMax(&g_b3_phase[ph_base + 14], (unsigned long long)ph_tot); atomicMin(&g_b3_phase[ph_base + 15], (unsigned long long)ph_tot); \
+    atomicAdd(&g_b3_warp[threadIdx.x >> 5], (unsigned long long)ph_tot); atomicAdd(&g_b3_warp[16 + (threadIdx.x >> 5)], 1ull); } } while (0)
 #else
 #define PH_DECL
 #define PH_DECL_H
@@ -306,30 +327,38 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
             if (warp_stats) {
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
                 float best = -INFINITY;                  // running max of the boosted values, class index in the low 7 mantissa bits
+                // the mask must live in a register for (v & mask) | class to be ONE three-input logic op (the class is the
+                // immediate); deriving it from a run-time value keeps ptxas from folding it back into a second immediate
+                const uint32_t tagmask = 0xffffff80u | ((uint32_t)a.C >> 16);
+                auto tag = [&](float v, int c) { return __uint_as_float((__float_as_uint(v) & tagmask) | (uint32_t)c); };
                 const float* kp = k.kk + seg * B3_KK;
                 auto term = [&](float x, float kc, int c, float& acc) {
                     const float v = fmaf(x, LOG2E, kc);
                     acc += b3_ex2(v);
-                    best = fmaxf(best, __uint_as_float((__float_as_uint(v) & 0xffffff80u) | (uint32_t)c));
+                    best = fmaxf(best, tag(v, c));
                 };
                 if (CT != 0 && (CT & 1) == 0) {
-                    const float2* x2 = reinterpret_cast<const float2*>(rowp);
-                    const float4* k4 = reinterpret_cast<const float4*>(kp);
+                    // two classes per instruction where the ISA allows it (FFMA2 / FADD2, same IEEE results lane by lane):
+                    // the issue slots, not the FP pipe, are what this warp competes for
+                    const unsigned long long* x64 = reinterpret_cast<const unsigned long long*>(rowp);
+                    const ulonglong2* k128 = reinterpret_cast<const ulonglong2*>(kp);
+                    unsigned long long sA = 0ull, sB = 0ull;          // (s0, s1), (s2, s3)
+                    auto pair_term = [&](unsigned long long x, unsigned long long kc, int c, unsigned long long& acc2) {
+                        const unsigned long long v = b3_fma2(x, LOG2E, kc);
+                        float v0, v1;
+                        b3_unpack2(v, v0, v1);
+                        acc2 = b3_add2(acc2, b3_pack2(b3_ex2(v0), b3_ex2(v1)));
+                        best = fmaxf(best, fmaxf(tag(v0, c), tag(v1, c + 1)));
+                    };
 #pragma unroll
                     for (int i = 0; i < CT / 4; ++i) {
-                        const float4 kv = k4[i];
-                        const float2 xa = x2[2 * i], xb = x2[2 * i + 1];
-                        term(xa.x, kv.x, 4 * i, s0);
-                        term(xa.y, kv.y, 4 * i + 1, s1);
-                        term(xb.x, kv.z, 4 * i + 2, s2);
-                        term(xb.y, kv.w, 4 * i + 3, s3);
+                        const ulonglong2 kv = k128[i];
+                        pair_term(x64[2 * i], kv.x, 4 * i, sA);
+                        pair_term(x64[2 * i + 1], kv.y, 4 * i + 2, sB);
                     }
-                    if (CT % 4) {
-                        const float2 xa = x2[CT / 2 - 1];
-                        const float2 kv = reinterpret_cast<const float2*>(kp)[CT / 2 - 1];
-                        term(xa.x, kv.x, CT - 2, s0);
-                        term(xa.y, kv.y, CT - 1, s1);
-                    }
+                    if (CT % 4) pair_term(x64[CT / 2 - 1], reinterpret_cast<const unsigned long long*>(kp)[CT / 2 - 1], CT - 2, sA);
+                    b3_unpack2(sA, s0, s1);
+                    b3_unpack2(sB, s2, s3);
                 } else {
                     int i = 0;
                     for (; i + 4 <= C; i += 4) {
