@@ -54,13 +54,40 @@ __device__ __forceinline__ float stamp_confidence_path(const float* plp, int T, 
     return avg;
 }
 
-constexpr int ASSORT_TS = 1024;    // frames per utterance staged in shared memory (longer utterances read global memory)
+// Same again on probabilities that are already exponentiated (the staged path below).
+__device__ __forceinline__ float stamp_confidence_prob(const float* pr_s, int T, int start, int end) {
+    int s = max(0, start), e = min(T, end);
+    float avg = pr_s[s];
+    if (s < e) {
+        const float half = avg / 2.0f;
+        int good = 1;
+        float mx = 0.f;
+        for (int f = s + 1; f < e; ++f) {
+            const float pr = pr_s[f];
+            mx = fmaxf(mx, pr);
+            if (pr > half || pr > 0.1f) { avg += pr; ++good; }
+        }
+        if (good > 1) {
+            avg /= (float)good;
+            mx = fmaxf(mx, avg);
+            if (avg < mx / 2.0f) avg = mx;
+        }
+    }
+    return avg;
+}
+
 constexpr int ASSORT_WARPS = 4;
-constexpr int ASSORT_SMEM = ASSORT_WARPS * 3 * ASSORT_TS * 4;
+constexpr int ASSORT_TS_MAX = 2048;   // longest utterance whose per-frame arrays are staged in shared memory
+constexpr int ASSORT_SS_MAX = 512;    // largest stamp pitch assembled in shared memory
+// staged frames / stamps per warp for a batch shape, and the dynamic shared memory of one CTA
+__host__ __device__ inline int assort_ts(int max_T) { return max_T <= ASSORT_TS_MAX ? (max_T + 31) / 32 * 32 : 0; }
+__host__ __device__ inline int assort_ss(int max_stamps) { return max_stamps <= ASSORT_SS_MAX ? max_stamps : 0; }
+__host__ __device__ inline size_t assort_smem(int ts, int ss) { return (size_t)ASSORT_WARPS * ((size_t)8 * ts + (size_t)16 * ss); }
 
 struct AssortArgs {
     BfaParams p;
     int B, C, max_stamps;
+    int ts, ss;        // shared-memory staging per warp: frames (0: read global memory) and stamps (0: assemble in place)
     const float* logp;
     const long long* row_off;
     const int32_t* T;
@@ -74,7 +101,7 @@ struct AssortArgs {
     const float* path_lp;   // per-frame gathered lp (or null: gather from logp)
 };
 
-__global__ void assort_confidence_kernel(AssortArgs a) {
+__global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(AssortArgs a) {
     const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (u >= a.B) return;
     const int st = a.status[u] & 7;
@@ -83,27 +110,48 @@ __global__ void assort_confidence_kernel(AssortArgs a) {
         return;
     }
     const int T = a.T[u];
-    const int32_t* ph = a.frame_ph + a.frame_off[u];
-    const int32_t* ix = a.frame_idx + a.frame_off[u];
-    const float* plp = a.path_lp ? a.path_lp + a.frame_off[u] : nullptr;
+    const long long fo = a.frame_off[u];
+    const int32_t* ph = a.frame_ph + fo;
+    const int32_t* ix = a.frame_idx + fo;
+    const float* plp = a.path_lp ? a.path_lp + fo : nullptr;
     // Stage the utterance's per-frame arrays in shared memory with independent coalesced loads (all in flight at
-    // once); the run-length scan and the per-stamp confidence loops below then never wait on global memory.
-    extern __shared__ int32_t assort_smem[];
-    if (T <= ASSORT_TS) {
-        int32_t* ph_s = assort_smem + (threadIdx.x >> 5) * 3 * ASSORT_TS;
-        int32_t* ix_s = ph_s + ASSORT_TS;
-        float* lp_s = reinterpret_cast<float*>(ix_s + ASSORT_TS);
-#pragma unroll 4
-        for (int t = lane; t < T; t += 32) {
-            ph_s[t] = ph[t];
-            ix_s[t] = ix[t];
-            if (plp) lp_s[t] = plp[t];
+    // once), exponentiating the confidence inputs on the way in (one frame per lane instead of one stamp per lane);
+    // the run-length scan and the per-stamp confidence loops below then never wait on global memory.
+    extern __shared__ __align__(16) int32_t assort_smem_raw[];
+    int32_t* wsm = assort_smem_raw + (size_t)(threadIdx.x >> 5) * (2 * a.ts + 4 * a.ss);
+    const float* pr_s = nullptr;                    // exp(plp[t]) when staged
+    const int32_t* pk_s = nullptr;                  // (idx << 16) | phoneme when staged (C <= 256, idx < 32768)
+    if (T <= a.ts) {
+        int32_t* pk = wsm;
+        float* lp_s = reinterpret_cast<float*>(pk + a.ts);
+        constexpr int UNR = 10;                     // 3 x 10 independent loads per lane before the first use
+        for (int t0 = lane; t0 < T; t0 += 32 * UNR) {
+            int32_t v_ph[UNR], v_ix[UNR];
+            float v_lp[UNR];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int t = t0 + 32 * j;
+                if (t < T) {
+                    v_ph[j] = ph[t];
+                    v_ix[j] = ix[t];
+                    if (plp) v_lp[j] = plp[t];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int t = t0 + 32 * j;
+                if (t < T) {
+                    pk[t] = (v_ix[j] << 16) | (v_ph[j] & 0xffff);
+                    if (plp) lp_s[t] = expf(v_lp[j]);
+                }
+            }
         }
         __syncwarp();
-        ph = ph_s; ix = ix_s;
-        if (plp) plp = lp_s;
+        pk_s = pk;
+        if (plp) pr_s = lp_s;
     }
-    BfaStamp* out = a.stamps + (size_t)u * a.max_stamps;
+    BfaStamp* gout = a.stamps + (size_t)u * a.max_stamps;
+    BfaStamp* out = a.ss ? reinterpret_cast<BfaStamp*>(wsm + 2 * a.ts) : gout;   // stamps are assembled here
     const int blank = a.p.blank_id;
     // Pass 1: every run start emits a provisional stamp (end filled by the next run start).
     // A run is emitted if non-blank (:830-831), or blank, !ignore_noise and longer than max_blanks
@@ -115,8 +163,14 @@ __global__ void assort_confidence_kernel(AssortArgs a) {
         bool startf = false, cand = false;
         int p_t = blank, i_t = -1;
         if (t < T) {
-            p_t = ph[t]; i_t = ix[t];
-            startf = (t == 0) || p_t != ph[t - 1] || i_t != ix[t - 1];          // :798-801
+            if (pk_s) {
+                const int32_t w = pk_s[t];
+                p_t = w & 0xffff; i_t = w >> 16;
+                startf = (t == 0) || w != pk_s[t - 1];                              // :798-801
+            } else {
+                p_t = ph[t]; i_t = ix[t];
+                startf = (t == 0) || p_t != ph[t - 1] || i_t != ix[t - 1];
+            }
             cand = startf && (p_t != blank || !a.p.ignore_noise);
         }
         uint32_t sbits = __ballot_sync(FULL, startf), cbits = __ballot_sync(FULL, cand);
@@ -129,10 +183,12 @@ __global__ void assort_confidence_kernel(AssortArgs a) {
             int slot = n + __popc(cbits & ((1u << lane) - 1u));
             if (slot < a.max_stamps) {
                 uint32_t later = sbits & ~((2u << lane) - 1u);       // run starts after this lane
-                out[slot].phoneme = p_t;
-                out[slot].start = t;
-                out[slot].target_idx = i_t;   // runs are constant in idx, the :812-816 search is a no-op
-                out[slot].end = later ? base + __ffs(later) - 1 : -1;
+                BfaStamp sv;
+                sv.phoneme = p_t;
+                sv.start = t;
+                sv.end = later ? base + __ffs(later) - 1 : -1;
+                sv.target_idx = i_t;   // runs are constant in idx, the :812-816 search is a no-op
+                out[slot] = sv;
             }
         }
         if (cbits) {
@@ -142,6 +198,7 @@ __global__ void assort_confidence_kernel(AssortArgs a) {
             if (!later) open = min(n + cnt - 1, a.max_stamps - 1);
             n += cnt;
         }
+        __syncwarp();
     }
     if (n > a.max_stamps) {   // caller's stamp pitch too small: flag it, keep the first max_stamps
         if (lane == 0) atomicOr(&a.status[u], BFA_ST_STAMP_OVERFLOW);
@@ -167,13 +224,16 @@ __global__ void assort_confidence_kernel(AssortArgs a) {
         n = m;
     }
     if (lane == 0) a.n_stamps[u] = n;
-    if (a.conf) {
-        const float* lp = a.logp + a.row_off[u];
-        for (int i = lane; i < n; i += 32) {
-            BfaStamp s = out[i];
-            a.conf[(size_t)u * a.max_stamps + i] = (plp && s.phoneme < a.C)
-                                                       ? stamp_confidence_path(plp, T, s.start, s.end)
-                                                       : stamp_confidence(lp, T, a.C, s.phoneme, s.start, s.end);
+    const float* lp = a.logp ? a.logp + a.row_off[u] : nullptr;
+    for (int i = lane; i < n; i += 32) {
+        const BfaStamp s = out[i];
+        if (a.ss) gout[i] = s;                       // one 16-byte store per stamp
+        if (a.conf) {
+            float cf;
+            if (pr_s && s.phoneme < a.C) cf = stamp_confidence_prob(pr_s, T, s.start, s.end);
+            else if (plp && s.phoneme < a.C) cf = stamp_confidence_path(plp, T, s.start, s.end);
+            else cf = stamp_confidence(lp, T, a.C, s.phoneme, s.start, s.end);
+            a.conf[(size_t)u * a.max_stamps + i] = cf;
         }
     }
 }

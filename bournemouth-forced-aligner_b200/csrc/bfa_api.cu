@@ -101,6 +101,8 @@ int device_info(DeviceInfo& out) {
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.vg_ctas_per_sm_big, viterbi_generic_kernel<1>, VG_WARPS * 32, smem));
         if (d.vg_ctas_per_sm < 1) d.vg_ctas_per_sm = 1;
         if (d.vg_ctas_per_sm_big < 1) d.vg_ctas_per_sm_big = 1;
+        CUDA_TRY(cudaFuncSetAttribute(assort_confidence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)assort_smem(ASSORT_TS_MAX, ASSORT_SS_MAX)));
         const int band_smem_max = BAND_SMEM_MAX;
         d.band_ok = band_set_attr<3>(band_smem_max) == cudaSuccess && band_set_attr<5>(band_smem_max) == cudaSuccess &&
                     band_set_attr<8>(band_smem_max) == cudaSuccess;
@@ -345,7 +347,9 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         aa.T = T; aa.frame_off = (const long long*)frame_off; aa.frame_ph = frame_ph; aa.frame_idx = frame_idx;
         aa.status = status; aa.stamps = stamps; aa.conf = conf; aa.n_stamps = n_stamps; aa.path_lp = path_lp;
         if (shape->max_stamps <= 0) return BFA_E_INVALID;
-        assort_confidence_kernel<<<(B + ASSORT_WARPS - 1) / ASSORT_WARPS, ASSORT_WARPS * 32, ASSORT_SMEM, st>>>(aa);
+        aa.ts = shape->max_N < 32768 ? assort_ts(shape->max_T) : 0;   // staged frames pack (idx, phoneme) into 16 + 16 bits
+        aa.ss = assort_ss(shape->max_stamps);
+        assort_confidence_kernel<<<(B + ASSORT_WARPS - 1) / ASSORT_WARPS, ASSORT_WARPS * 32, assort_smem(aa.ts, aa.ss), st>>>(aa);
         LAUNCH_CHECK();
     }
     return BFA_OK;
@@ -456,7 +460,8 @@ int bfa_assort_batch(const BfaParams* p, int32_t B, const int32_t* T, const int6
     aa.p = *p; aa.B = B; aa.C = 0; aa.max_stamps = max_stamps; aa.logp = nullptr; aa.row_off = nullptr; aa.T = T;
     aa.frame_off = (const long long*)frame_off; aa.frame_ph = frame_ph; aa.frame_idx = frame_idx; aa.status = status;
     aa.stamps = stamps; aa.conf = nullptr; aa.n_stamps = n_stamps; aa.path_lp = nullptr;
-    assort_confidence_kernel<<<(B + ASSORT_WARPS - 1) / ASSORT_WARPS, ASSORT_WARPS * 32, ASSORT_SMEM, (cudaStream_t)stream>>>(aa);
+    aa.ts = 0; aa.ss = assort_ss(max_stamps);     // utterance lengths are only known on the device here: frames are read in place
+    assort_confidence_kernel<<<(B + ASSORT_WARPS - 1) / ASSORT_WARPS, ASSORT_WARPS * 32, assort_smem(aa.ts, aa.ss), (cudaStream_t)stream>>>(aa);
     LAUNCH_CHECK();
     return BFA_OK;
 }

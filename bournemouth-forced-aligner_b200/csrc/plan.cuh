@@ -68,8 +68,7 @@ __device__ __forceinline__ TgtInfo target_info(const int32_t* tgt, long long b, 
             if ((c >> 5) == i) r.w[i] |= 1u << (c & 31);
     }
 #pragma unroll
-    for (int i = 0; i < MAX_WORDS; ++i)
-        for (int d = 16; d >= 1; d >>= 1) r.w[i] |= __shfl_xor_sync(FULL, r.w[i], d);
+    for (int i = 0; i < MAX_WORDS; ++i) r.w[i] = __reduce_or_sync(FULL, r.w[i]);
     r.all_ok = __all_sync(FULL, all_ok);
     r.has_sil = __any_sync(FULL, has_sil);
     return r;
@@ -375,10 +374,12 @@ __device__ int plan_segmented(const UttCtx& c, Item* loc, int32_t* lists, uint32
     return n_items;
 }
 
-__global__ void plan_kernel(PlanArgs a) {
+__global__ void __launch_bounds__(256, 4) plan_kernel(PlanArgs a) {
     const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     int n_items = 0;
     Item* loc = nullptr;
+    Item single;                 // the common case, one item = the whole utterance, never leaves lane 0's registers
+    bool have_single = false;
     bool tok = false;
     if (u < a.B) {
     const BfaParams& p = a.p;
@@ -417,7 +418,8 @@ __global__ void plan_kernel(PlanArgs a) {
         st = BFA_ST_EMPTY_TARGET;
     } else {
         bool done = false;
-        if (p.mode == BFA_MODE_FULL && p.silence_anchors > 0 && p.silence_id >= 0 && T > 0) {   // :133
+        // :133; without a SIL in the target _find_target_sil_groups is empty and the attempt returns [] at once (:293-295)
+        if (p.mode == BFA_MODE_FULL && p.silence_anchors > 0 && p.silence_id >= 0 && T > 0 && ti.has_sil) {
             int r = plan_segmented(c, loc, a.lists + (size_t)u * a.list_ints, a.anchors + (size_t)u * a.anchor_words);
             if (r >= 0) { n_items = r; st = BFA_ST_SEGMENTED; done = true; }
         }
@@ -462,8 +464,9 @@ __global__ void plan_kernel(PlanArgs a) {
                     if (p.mode == BFA_MODE_FULL)
                         it.flags |= (p.boost_targets ? ITEM_STATS : 0) | (p.enforce_minimum ? ITEM_FLOOR : 0);
                     it.pad = 0;
-                    loc[0] = it;
+                    single = it;
                 }
+                have_single = true;
                 n_items = 1;
             }
         }
@@ -479,10 +482,12 @@ __global__ void plan_kernel(PlanArgs a) {
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     int my_cnt[4] = {0, 0, 0, 0}, my_off[4] = {0, 0, 0, 0};
+    int cl0 = -2;                // class of item `lane` (the first, usually the only, pass over the items)
     for (int i0 = 0; i0 < n_items; i0 += 32) {
         const int i = i0 + lane;
         int cl = -2;
-        if (i < n_items) cl = fast_class(loc[i], a.C, a.logp, tok, a.fast_enable);
+        if (i < n_items) cl = have_single ? fast_class(single, a.C, a.logp, tok, a.fast_enable) : fast_class(loc[i], a.C, a.logp, tok, a.fast_enable);
+        if (i0 == 0) cl0 = cl;
 #pragma unroll
         for (int c = -1; c <= 2; ++c) my_cnt[c + 1] += __popc(__ballot_sync(FULL, cl == c));
     }
@@ -500,12 +505,17 @@ __global__ void plan_kernel(PlanArgs a) {
     for (int i0 = 0; i0 < n_items; i0 += 32) {
         const int i = i0 + lane;
         int cl = -2;
-        if (i < n_items) cl = fast_class(loc[i], a.C, a.logp, tok, a.fast_enable);
+        if (i0 == 0) cl = cl0;
+        else if (i < n_items) cl = fast_class(loc[i], a.C, a.logp, tok, a.fast_enable);
 #pragma unroll
         for (int c = -1; c <= 2; ++c) {
             const unsigned m = __ballot_sync(FULL, cl == c);
             Item* dst = (c < 0) ? a.items : a.fast_items[c];
-            if (cl == c) dst[s_base[c + 1] + my_off[c + 1] + __popc(m & ((1u << lane) - 1u))] = loc[i];
+            if (cl == c) {
+                Item* d = dst + (s_base[c + 1] + my_off[c + 1] + __popc(m & ((1u << lane) - 1u)));
+                if (have_single) *d = single;
+                else *d = loc[i];
+            }
             my_off[c + 1] += __popc(m);
         }
     }

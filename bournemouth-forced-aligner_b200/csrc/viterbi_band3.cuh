@@ -100,7 +100,9 @@ struct Band3Shape {
 // the frame before the chunk (scripts/check_window_fit.py verifies the closed form by brute force).
 __host__ __device__ inline int band3_window_need(int N, int T, int L, int band) {
     if (band <= 0 || T < 2 || L < 2) return N + 1;
-    const int adv = (int)(((long long)B3_ROWS * (L - 1) + (T - 2)) / (T - 1));   // ceil(8 * pace)
+    const int adv = (L - 1 < (1 << 27))                                           // ceil(8 * pace), 32-bit whenever it fits
+                        ? (int)(((unsigned)B3_ROWS * (unsigned)(L - 1) + (unsigned)(T - 2)) / (unsigned)(T - 1))
+                        : (int)(((long long)B3_ROWS * (L - 1) + (T - 2)) / (T - 1));
     const int w = (2 * band + adv + 6) / 4 + 1;
     return w < N + 1 ? w : N + 1;
 }
