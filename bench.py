@@ -257,7 +257,7 @@ def main():
     dom_avg_ms = dom_ms.value / max(dom_n.value, 1)
     achieved = alg / (dom_avg_ms / 1e3) / 1e9 if dom_avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "viterbi_band_kernel<3,9>", "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_avg_ms / (ms / a.steps),
+                "kernel": "viterbi_band3_kernel<3,66,false> (fill + back-trace)", "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_avg_ms / (ms / a.steps),
                 "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}
     tf = ROOT / "profiles" / "traffic_latest.json"
     if tf.exists():
