@@ -862,12 +862,19 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
 
         // ---- walk the 32 frames of the block, one RUN per iteration (bit 31-f belongs to frame f): the path stays in
         //      its cell until a decision bit of that cell is set.  Utterances leave the loop on their own ----
+        //      The decision words of the two cells the path can move to are fetched one iteration ahead, so the shared-memory
+        //      latency is off the loop-carried chain (mask -> lowest set bit -> selects).
         uint32_t keep[4] = {0u, 0u, 0u, 0u};             // 8 * cabs of frames 32b + 8i + l8
         uint32_t mask = 0xffffffffu;                      // frames not yet walked
+        uint32_t c0, c1, p0, p1, q0, q1;                  // words of the cells A, A - 1 cell, A - 2 cells
+        auto lds2 = [](uint32_t addr, uint32_t& x, uint32_t& y) {
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(addr) : "memory");
+        };
+        lds2(A, c0, c1);
+        lds2(A - 8u, p0, p1);
+        lds2(A - 16u, q0, q1);
         do {
-            uint32_t w0, w1;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(A) : "memory");
-            const uint32_t stop = (w0 | w1) & mask;
+            const uint32_t stop = (c0 | c1) & mask;
             const uint32_t bit = stop & (0u - stop);      // frame whose decision ends the run (0: none left in this block)
             const uint32_t maskn = bit * 0xfffffffeu;     // frames strictly before it  (= -(2*bit); 0 when bit is 0 or bit 31)
             const uint32_t run = mask & ~maskn;           // frames of this run
@@ -875,10 +882,13 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (run & (0x80000000u >> (8 * i + l8))) keep[i] = AK;
-            const uint32_t A1 = A - 8u, A2 = A - 16u;
-            A = (w0 & bit) ? A1 : A;
-            A = (w1 & bit) ? A2 : A;
+            const bool m1 = (c0 & bit) != 0u, m2 = (c1 & bit) != 0u;   // from b3' / from m' (m' wins)
+            A = m2 ? A - 16u : (m1 ? A - 8u : A);
+            c0 = m2 ? q0 : (m1 ? p0 : c0);
+            c1 = m2 ? q1 : (m1 ? p1 : c1);
             mask = maskn;
+            lds2(A - 8u, p0, p1);
+            lds2(A - 16u, q0, q1);
         } while (mask != 0u);
         __syncwarp();
         PH_T(8);
