@@ -21,6 +21,7 @@ using namespace bfa;
 namespace {
 
 std::atomic<long long> g_launches{0};
+int* g_last_counters = nullptr;   // development aid, see bfa_debug_item_counts
 thread_local char g_cuda_err[256] = "";
 
 #define CUDA_TRY(expr)                                                                              \
@@ -279,6 +280,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     float* path_lp = (stamps && conf && !(p->reserved & BFA_FLAG_UNFUSED_CONF)) ? (float*)(ws + L.off_pathlp) : nullptr;
     int* counters = (int*)(ws + L.off_counters);
     CUDA_TRY(cudaMemsetAsync(counters, 0, 64, st));
+    g_last_counters = counters;
 
     // Row statistics are only materialised for the planner's silence scan (utterances whose target holds
     // SIL); the Viterbi kernels fuse boost + log_softmax + floor into their row loads.
@@ -406,6 +408,17 @@ int bfa_confidence_batch(int32_t B, int32_t C, const float* logp, const int64_t*
 }
 
 // Development aid: per-phase warp-clock sums of the banded kernel (all zero unless built with -DBFA_PHASE_PROF).
+// Development aid: the item counters of the most recent bfa_align_batch on this thread's device (blocks on the device):
+// out[0] = items the exact kernel ran (ineligible + retried), out[1..3] = items of the banded kernels (24/40/64-group window).
+int bfa_debug_item_counts(int32_t* out4) {
+    if (!out4 || !g_last_counters) return BFA_E_INVALID;
+    int h[16];
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(h, g_last_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    out4[0] = h[0]; out4[1] = h[3]; out4[2] = h[5]; out4[3] = h[7];
+    return BFA_OK;
+}
+
 int bfa_debug_warps(unsigned long long* out32, int reset) {   // development: mean task cycles per warp id of the banded kernel
 #ifdef BFA_PHASE_PROF
     if (out32) CUDA_TRY(cudaMemcpyFromSymbol(out32, g_b3_warp, sizeof(unsigned long long) * 32));

@@ -205,6 +205,7 @@ int bfa_profile_read(float *dominant_ms, int32_t *n_launches);
  * the library was built with -DBFA_PHASE_PROF (scripts/phase_prof.sh).  reset != 0 clears them after the read. */
 int bfa_debug_phases(unsigned long long *out32, int reset);
 int bfa_debug_warps(unsigned long long *out32, int reset);
+int bfa_debug_item_counts(int32_t *out4);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 int64_t bfa_launch_count(void);
