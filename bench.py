@@ -208,11 +208,9 @@ def main():
         result[0] = r
         if world > 1:  # final gather of the timestamp arrays (the path's only exchange)
             nonlocal gather_bufs
-            if gather_bufs is None:
-                gather_bufs = [torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)
-                               for x in (r.stamps, r.conf, r.n_stamps)]
-            for g, x in zip(gather_bufs, (r.stamps, r.conf, r.n_stamps)):
-                dist.all_gather_into_tensor(g, x)
+            if gather_bufs is None:   # stamps | conf | n_stamps | status | dp_final are one allocation: one collective
+                gather_bufs = torch.empty(world * r.arena.numel(), dtype=r.arena.dtype, device=dev)
+            dist.all_gather_into_tensor(gather_bufs, r.arena)
         return r
 
     for _ in range(max(a.warmup, 3)):

@@ -49,6 +49,22 @@ class _Workspace:
         return b
 
 
+def result_arena_words(B: int, ms: int, want_stamps=True, want_conf=True) -> dict:
+    """Word offsets of the per-utterance result arrays inside one int32 allocation (sections 16-byte aligned)."""
+    off, o = {}, 0
+    def sec(name, n):
+        nonlocal o
+        off[name] = o
+        o += (n + 3) // 4 * 4
+    sec("stamps", B * ms * 4 if want_stamps else 0)
+    sec("conf", B * ms if (want_stamps and want_conf) else 0)
+    sec("n_stamps", B if want_stamps else 0)
+    sec("status", B)
+    sec("dp_final", B)
+    off["total"] = max(o, 4)
+    return off
+
+
 class BatchResult:
     """Device-resident result arrays of one batched alignment call (C-ABI layout)."""
 
@@ -57,6 +73,7 @@ class BatchResult:
         self.dp_final, self.status = dp_final, status
         self.stamps, self.conf, self.n_stamps = stamps, conf, n_stamps
         self.T, self.max_stamps = T, max_stamps
+        self.arena = None   # the single allocation behind stamps/conf/n_stamps/status/dp_final (align_batch), or None
 
     def stamp_lists(self, with_conf: bool = False) -> List[List[tuple]]:
         """list[B] of list[(phoneme, start, end_exclusive, target_idx[, conf])] -- forced_alignment.py:871-872."""
@@ -147,15 +164,21 @@ class ViterbiDecoder:
         if out is None:
             frame_ph = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
             frame_idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-            dp_final = torch.empty(max(B, 1), dtype=torch.float32, device=dev)
-            status = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
+            # the per-utterance results live in ONE allocation (stamps | conf | n_stamps | status | dp_final, 4-byte words),
+            # so that the multi-GPU gather of the timestamp arrays is a single collective (sharding.gather_packed)
+            Bp = max(B, 1)
+            words = result_arena_words(Bp, ms, want_stamps, want_conf)
+            arena = torch.empty(words["total"], dtype=torch.int32, device=dev)
+            dp_final = arena[words["dp_final"]:words["dp_final"] + Bp].view(torch.float32)
+            status = arena[words["status"]:words["status"] + Bp]
             stamps = conf = n_stamps = None
             if want_stamps:
-                stamps = torch.empty((max(B, 1), ms, 4), dtype=torch.int32, device=dev)
-                n_stamps = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
+                stamps = arena[words["stamps"]:words["stamps"] + Bp * ms * 4].view(Bp, ms, 4)
+                n_stamps = arena[words["n_stamps"]:words["n_stamps"] + Bp]
                 if want_conf:
-                    conf = torch.empty((max(B, 1), ms), dtype=torch.float32, device=dev)
+                    conf = arena[words["conf"]:words["conf"] + Bp * ms].view(torch.float32).view(Bp, ms)
             out = BatchResult(frame_ph, frame_idx, plan.frame_off, dp_final, status, stamps, conf, n_stamps, plan.T_np, ms)
+            out.arena = arena
         l = _cabi.lib()
         with torch.cuda.device(dev):
             if plan.ws_bytes is None:

@@ -61,3 +61,32 @@ def gather_results(stamps: torch.Tensor, conf: torch.Tensor, n_stamps: torch.Ten
         buf = buf.view((world, bmax) + tuple(x.shape[1:]))
         outs.append(torch.cat([buf[r, : counts[r]] for r in range(world)], dim=0))
     return tuple(outs)
+
+
+def gather_packed(result, counts: Sequence[int], group=None):
+    """The same gather as gather_results in ONE collective: `result` is a BatchResult whose per-utterance arrays are
+    views of a single allocation (`result.arena`, see aligner.result_arena_words).  Returns
+    (stamps [sum B_r, P, 4] i32, conf [sum B_r, P] f32 or None, n_stamps, status, dp_final) over all utterances."""
+    from .aligner import result_arena_words
+    world = dist.get_world_size(group)
+    ms = result.max_stamps
+    want_conf = result.conf is not None
+    sizes = [result_arena_words(max(int(c), 1), ms, True, want_conf) for c in counts]
+    wmax = max(sz["total"] for sz in sizes)
+    arena = result.arena
+    if arena.numel() < wmax:
+        arena = torch.cat([arena, arena.new_zeros(wmax - arena.numel())])
+    buf = arena.new_empty(world * wmax)
+    dist.all_gather_into_tensor(buf, arena[:wmax].contiguous(), group=group)
+    buf = buf.view(world, wmax)
+    st, cf, ns, ss, dp = [], [], [], [], []
+    for r in range(world):
+        b, sz = int(counts[r]), sizes[r]
+        bp = max(b, 1)
+        st.append(buf[r, sz["stamps"]:sz["stamps"] + bp * ms * 4].view(bp, ms, 4)[:b])
+        if want_conf:
+            cf.append(buf[r, sz["conf"]:sz["conf"] + bp * ms].view(torch.float32).view(bp, ms)[:b])
+        ns.append(buf[r, sz["n_stamps"]:sz["n_stamps"] + bp][:b])
+        ss.append(buf[r, sz["status"]:sz["status"] + bp][:b])
+        dp.append(buf[r, sz["dp_final"]:sz["dp_final"] + bp].view(torch.float32)[:b])
+    return (torch.cat(st), torch.cat(cf) if want_conf else None, torch.cat(ns), torch.cat(ss), torch.cat(dp))

@@ -45,6 +45,21 @@ def _worker(rank, world, port, q):
     g = gather_results(stamps, conf, n_st, st, counts)
     ok = (g[0].shape == (11, P, 4) and bool((g[0][:, 0, 0] == torch.arange(11)).all()) and bool((g[1][:, 3] == torch.arange(11) + 0.5).all())
           and bool((g[2] == torch.arange(11)).all()) and g[3].tolist() == sum([[r] * counts[r] for r in range(world)], []))
+    # the same through the single-collective path: the result arrays are views of one allocation
+    from bfa_b200.sharding import gather_packed
+    from bfa_b200.aligner import BatchResult, result_arena_words
+    bp = max(counts[rank], 1)
+    w = result_arena_words(bp, P, True, True)
+    arena = torch.zeros(w["total"], dtype=torch.int32)
+    a_st = arena[w["stamps"]:w["stamps"] + bp * P * 4].view(bp, P, 4); a_st[:counts[rank]] = stamps
+    a_cf = arena[w["conf"]:w["conf"] + bp * P].view(torch.float32).view(bp, P); a_cf[:counts[rank]] = conf
+    a_ns = arena[w["n_stamps"]:w["n_stamps"] + bp]; a_ns[:counts[rank]] = n_st
+    a_ss = arena[w["status"]:w["status"] + bp]; a_ss[:counts[rank]] = st
+    a_dp = arena[w["dp_final"]:w["dp_final"] + bp].view(torch.float32); a_dp[:counts[rank]] = -n_st.float()
+    res = BatchResult(None, None, None, a_dp, a_ss, a_st, a_cf, a_ns, None, P)
+    res.arena = arena
+    h = gather_packed(res, counts)
+    ok = ok and all(bool((x == y).all()) for x, y in zip(h[:4], g)) and bool((h[4] == -torch.arange(11).float()).all())
     q.put((rank, ok))
     dist.destroy_process_group()
 
