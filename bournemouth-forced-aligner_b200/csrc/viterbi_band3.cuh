@@ -410,6 +410,7 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
         st = (st + 1 == B3_NST) ? 0 : st + 1;
     }
 
+    if (a.p.reserved & BFA_FLAG_FILL_ONLY) return;   // measurement switch, see bfa_b200.h
     // ---- back-trace, output side.  The DP warp walks the path one 32-frame block at a time and hands over the visited
     //      cells (8 * absolute cell of frames 32b + 8i + l8, lane for lane); this warp turns them into frame_phonemes /
     //      frame_phonemes_idx (:695-703), checks that the path stayed inside the band, and fetches the confidence inputs
@@ -791,6 +792,10 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
         bad = ((m >> (seg * B3_LPU)) & 0xffu) != 0;
     }
 
+    if (a.p.reserved & BFA_FLAG_FILL_ONLY) {   // measurement switch: time the fill by itself (no outputs)
+        PH_FLUSH;
+        return;
+    }
     // ---- back-trace (:686-703), walking side ----
     // A cell is addressed by its window-relative index ci = 3*(group - base) + k.  Staging lays a record out as
     // bt2[seg][ci] = (first decision word, second decision word or 0), so one 64-bit shared load per run yields

@@ -84,6 +84,9 @@ typedef struct BfaParams {
                                  recomputes what it needs (slower), results are unchanged. */
 #define BFA_FLAG_UNFUSED_CONF 4  /* confidences gather lp[f, phoneme] from logp inside the stamp kernel instead of taking the
                                  * per-frame values the Viterbi back-trace collects (measurement / A-B switch) */
+#define BFA_FLAG_FILL_ONLY 16     /* MEASUREMENT ONLY: the banded kernel stops after the DP fill (rows streamed, log-sum-exp, forward
+                                 * recursion, decision records written) and skips the back-trace: outputs are NOT produced.  bench.py
+                                 * uses it to time the fill phase by itself; never set it in production. */
 #define BFA_FLAG_NO_SPEC 8       /* the banded kernel fetches every confidence input during its back-trace instead of keeping the
                                  * frame-wise best class's value while the row is on chip (measurement / A-B switch) */
 
