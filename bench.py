@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--unfused-conf", action="store_true", help="A/B switch: gather the confidence inputs in the stamp kernel (BFA_FLAG_UNFUSED_CONF)")
+    ap.add_argument("--one-stream", action="store_true", help="A/B switch: keep every kernel on one stream (BFA_FLAG_ONE_STREAM)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU baseline sample (0 = auto)")
     return ap.parse_args()
 
@@ -196,6 +197,8 @@ def main():
         params.reserved |= _cabi.HINT_NO_SIL   # host-side knowledge of the targets (they come from the phonemizer on the host)
     if a.unfused_conf:
         params.reserved |= 4
+    if a.one_stream:
+        params.reserved |= 32
     row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T * Cc)
     tgt32 = tgt.to(torch.int32).reshape(-1).contiguous()
     Ts, Ns = [T] * B, [N] * B

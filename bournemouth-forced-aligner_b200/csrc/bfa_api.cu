@@ -86,6 +86,32 @@ void band_launch(const Band3Args& ba, bool exact, int grid, cudaStream_t st) {
     else viterbi_band3_kernel<G, 0, false><<<grid, pairs * 64, smem, st>>>(ba);
 }
 
+// Internal fork/join streams: after the planner the three banded variants work on disjoint item lists, so they run side by
+// side (a kernel without work leaves its SMs at once); the caller's stream joins them before the exact kernel.  Created once per device, never destroyed; capture-safe (events only).
+struct Fork {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    bool ok = false, tried = false;
+};
+Fork* fork_streams() {
+    static std::mutex mu;
+    static Fork cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    Fork& f = cache[dev & 63];
+    if (!f.tried) {
+        f.tried = true;
+        bool ok = cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 2 && ok; ++i)
+            ok = cudaStreamCreateWithFlags(&f.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&f.join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) (void)cudaGetLastError();
+        f.ok = ok;
+    }
+    return f.ok ? &f : nullptr;
+}
+
 int device_info(DeviceInfo& out) {
     static std::mutex mu;
     static DeviceInfo cache[64];
@@ -125,7 +151,7 @@ struct Layout {
     int band_grid, band_smem_per_warp[BAND_NV];
     long long band_slab_words[BAND_NV];
     size_t off_tmask, off_tgtok, off_need, off_rowstat, off_items_local, off_items, off_fast[BAND_NV], off_lists, off_padded, off_anchors, off_counters,
-        off_pathlp, off_gcls, off_bp, total;
+        off_pathlp, off_gcls, off_bp, off_bp_band[BAND_NV], total;
 };
 
 
@@ -150,12 +176,10 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
     L.resident_warps = d.sms * d.vg_ctas_per_sm * VG_WARPS;
     L.slab_words = (long long)(s.max_T + 2) * 32 * L.bp_words_per_lane;
     L.band_grid = d.sms;
-    size_t band_bytes = 0;
     for (int v = 0; v < BAND_NV; ++v) {
         const int G = BAND_G[v];
         L.band_smem_per_warp[v] = band_smem_bytes_per_warp(s.C, G);
         L.band_slab_words[v] = (long long)((s.max_T + 31) / 32 + 1) * band_rec_words(G) * 32;
-        band_bytes = std::max<size_t>(band_bytes, (size_t)L.band_grid * BAND_WARPS * (size_t)L.band_slab_words[v] * 4);
     }
     size_t o = 0;
     L.off_tmask = o; o = align_up(o + (size_t)s.B * MAX_WORDS * 4);
@@ -172,8 +196,12 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
     L.off_counters = o; o = align_up(o + 64);
     L.off_pathlp = o; o = align_up(o + (size_t)s.total_frames * 4);
     L.off_gcls = o; o = align_up(o + (size_t)s.total_frames);
-    // the banded and the generic kernels are stream-ordered, so their back-pointer slabs share one region
-    L.off_bp = o; o = align_up(o + std::max<size_t>((size_t)L.resident_warps * (size_t)L.slab_words * 4, band_bytes));
+    // the banded variants and the exact kernel run concurrently (internal streams): every kernel owns its slabs
+    L.off_bp = o; o = align_up(o + (size_t)L.resident_warps * (size_t)L.slab_words * 4);
+    for (int v = 0; v < BAND_NV; ++v) {
+        L.off_bp_band[v] = o;
+        o = align_up(o + (size_t)L.band_grid * BAND_WARPS * (size_t)L.band_slab_words[v] * 4);
+    }
     L.total = o;
     return BFA_OK;
 }
@@ -285,7 +313,9 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     // Row statistics are only materialised for the planner's silence scan (utterances whose target holds
     // SIL); the Viterbi kernels fuse boost + log_softmax + floor into their row loads.
     if (rowstat && shape->max_T > 0) {
-        rowstat_kernel<<<B, 256, 0, st>>>(C, p->blank_id, p->silence_id, p->boost_factor, logp, (const long long*)row_off, T, tgt,
+        // ~64 rows per warp: one CTA of 8 warps per 512 rows of the longest utterance
+        const int ysplit = std::max(1, std::min(64, (shape->max_T + 511) / 512));
+        rowstat_kernel<<<dim3(B, ysplit), 256, 0, st>>>(C, p->blank_id, p->silence_id, p->boost_factor, logp, (const long long*)row_off, T, tgt,
                                           (const long long*)tgt_off, (const long long*)frame_off, rowstat);
         LAUNCH_CHECK();
     }
@@ -305,34 +335,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     LAUNCH_CHECK();
 
     long long max_items = (long long)B * L.item_cap;
-    if (fast) {
-        Band3Args ba;
-        ba.p = *p; ba.C = C; ba.logp = logp; ba.tgt = tgt; ba.tmask = tmask;
-        ba.retry_items = pa.items; ba.n_retry = counters;
-        ba.frame_ph = frame_ph; ba.frame_idx = frame_idx; ba.dp_final = dp_final; ba.path_lp = path_lp;
-        ba.guess_cls = (path_lp && !(p->reserved & BFA_FLAG_NO_SPEC)) ? (unsigned char*)(ws + L.off_gcls) : nullptr;
-        ba.bp_scratch = (uint32_t*)(ws + L.off_bp);
-        for (int v = 0; v < BAND_NV; ++v) {
-            ba.items = pa.fast_items[v]; ba.n_items = pa.n_fast[v];
-            ba.bp_slab_words = L.band_slab_words[v]; ba.smem_per_warp = L.band_smem_per_warp[v];
-            cudaEvent_t e0 = nullptr, e1 = nullptr;
-            if (v == 0) {
-                std::lock_guard<std::mutex> lk(g_prof.mu);
-                if (g_prof.on) { e0 = g_prof.get(); e1 = g_prof.get(); }
-            }
-            if (e0) cudaEventRecord(e0, st);
-            if (v == 0) band_launch<3>(ba, !boost, L.band_grid, st);
-            else if (v == 1) band_launch<5>(ba, !boost, L.band_grid, st);
-            else band_launch<8>(ba, !boost, L.band_grid, st);
-            LAUNCH_CHECK();
-            if (e0) {
-                cudaEventRecord(e1, st);
-                std::lock_guard<std::mutex> lk(g_prof.mu);
-                g_prof.pending.emplace_back(e0, e1);
-            }
-        }
-    }
-
+    const int max_items_i = (int)(max_items > (1 << 30) ? (1 << 30) : max_items);
     VitArgs va;
     va.p = *p; va.C = C; va.logp = logp; va.tmask = tmask; va.tgt = tgt;
     va.path = nullptr; va.true_idx = nullptr; va.anchors = pa.anchors; va.items = pa.items;
@@ -340,8 +343,50 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     va.frame_ph = frame_ph; va.frame_idx = frame_idx; va.dp_final = dp_final; va.status = status; va.final_state = nullptr;
     va.path_lp = path_lp;
     va.bp_scratch = (uint32_t*)(ws + L.off_bp); va.bp_slab_words = L.slab_words;
-    rc = launch_viterbi(va, (int)(max_items > (1 << 30) ? (1 << 30) : max_items), L.max_L, d, st, !fast);
-    if (rc) return rc;
+    if (fast) {
+        Band3Args ba;
+        ba.p = *p; ba.C = C; ba.logp = logp; ba.tgt = tgt; ba.tmask = tmask;
+        ba.retry_items = pa.items; ba.n_retry = counters;
+        ba.frame_ph = frame_ph; ba.frame_idx = frame_idx; ba.dp_final = dp_final; ba.path_lp = path_lp;
+        ba.guess_cls = (path_lp && !(p->reserved & BFA_FLAG_NO_SPEC)) ? (unsigned char*)(ws + L.off_gcls) : nullptr;
+        Fork* fk = (p->reserved & BFA_FLAG_ONE_STREAM) ? nullptr : fork_streams();
+        if (fk) {
+            CUDA_TRY(cudaEventRecord(fk->fork, st));
+            for (int i = 0; i < BAND_NV - 1; ++i) CUDA_TRY(cudaStreamWaitEvent(fk->s[i], fk->fork, 0));
+        }
+        // Launch order when forked: the wide-window variants first.  On the usual batch their lists are empty and they leave
+        // the SMs within microseconds, side by side, before the 24-group variant (which fills every SM) starts.
+        for (int vi = 0; vi < BAND_NV; ++vi) {
+            const int v = fk ? (vi + 1) % BAND_NV : vi;            // forked: 1, 2, 0
+            cudaStream_t sv = (fk && v > 0) ? fk->s[v - 1] : st;
+            ba.items = pa.fast_items[v]; ba.n_items = pa.n_fast[v];
+            ba.bp_scratch = (uint32_t*)(ws + L.off_bp_band[v]);
+            ba.bp_slab_words = L.band_slab_words[v]; ba.smem_per_warp = L.band_smem_per_warp[v];
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (v == 0) {
+                std::lock_guard<std::mutex> lk(g_prof.mu);
+                if (g_prof.on) { e0 = g_prof.get(); e1 = g_prof.get(); }
+            }
+            if (e0) cudaEventRecord(e0, sv);
+            if (v == 0) band_launch<3>(ba, !boost, L.band_grid, sv);
+            else if (v == 1) band_launch<5>(ba, !boost, L.band_grid, sv);
+            else band_launch<8>(ba, !boost, L.band_grid, sv);
+            LAUNCH_CHECK();
+            if (e0) {
+                cudaEventRecord(e1, sv);
+                std::lock_guard<std::mutex> lk(g_prof.mu);
+                g_prof.pending.emplace_back(e0, e1);
+            }
+            if (fk && v > 0) CUDA_TRY(cudaEventRecord(fk->join[v - 1], sv));
+        }
+        if (fk) for (int i = 0; i < BAND_NV - 1; ++i) CUDA_TRY(cudaStreamWaitEvent(st, fk->join[i], 0));
+        // the exact kernel: what the planner gave it plus what the banded kernels sent back
+        rc = launch_viterbi(va, max_items_i, L.max_L, d, st, false);
+        if (rc) return rc;
+    } else {
+        rc = launch_viterbi(va, max_items_i, L.max_L, d, st, true);
+        if (rc) return rc;
+    }
 
     if (stamps) {
         AssortArgs aa;

@@ -19,7 +19,8 @@ struct __align__(16) Item {
     long long seq_off;   // structured: offset into tgt of the first phoneme; explicit: offset into path[]
     int T, L, band, stride;  // stride 0 => explicit path/true_idx arrays
     int n, idx0, trim, n_out;
-    int utt, anchor_off, flags, pad;
+    int utt, anchor_off, flags;
+    int lead;            // floats between the previous 16-byte boundary and the item's first row (0..3): the banded kernel's bulk copies start there
 };
 enum : int { ITEM_FINAL = 1, ITEM_STATS = 2, ITEM_FLOOR = 4, ITEM_ANCHOR = 8 };
 

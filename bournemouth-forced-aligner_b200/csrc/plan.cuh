@@ -78,7 +78,10 @@ __device__ __forceinline__ TgtInfo target_info(const int32_t* tgt, long long b, 
 __device__ __forceinline__ int fast_class(const Item& it, int C, const float* logp, bool tgt_ok, int fast_enable) {
     if (!fast_enable || !tgt_ok) return -1;
     if (it.stride != 4 || (it.flags & ITEM_ANCHOR) || C > B3_KK || it.T < 2 || it.L > it.T || it.n > B3_NMAX) return -1;
-    if (((unsigned long long)(logp + it.lp_off) & 15ull) != 0) return -1;   // bulk copies need 16-B aligned rows
+    // Bulk copies need 16-byte aligned sources: a misaligned item (e.g. a segment that starts on an odd row of a C=66 matrix)
+    // is copied from the boundary before it, `lead` floats early.  Those floats must exist inside the caller's buffer, and the
+    // C=66 instantiation reads the staged rows as 8-byte pairs.
+    if (it.lead != 0 && (it.lp_off < it.lead || (C == 66 && (it.lead & 1)))) return -1;
     const int need = band3_window_need(it.n, it.T, it.L, it.band);
     if (need <= 24) return 0;
     if (need <= 40) return 1;
@@ -100,7 +103,9 @@ __global__ void rowstat_kernel(int C, int blank_id, int silence_id, float boost,
     uint32_t tbits = 0;
 #pragma unroll
     for (int i = 0; i < MAX_WORDS; ++i) tbits |= ((ti.w[i] >> lane) & 1u) << i;
-    for (int t = warp; t < Tu; t += (blockDim.x >> 5)) {
+    // gridDim.y CTAs share an utterance's rows: enough rows in flight to pull them at HBM speed
+    const int nw = (blockDim.x >> 5) * gridDim.y;
+    for (int t = warp + (blockDim.x >> 5) * blockIdx.y; t < Tu; t += nw) {
         const float* row = logp + row_off[u] + (long long)t * C;
         float2 st = row_stats_warp([&](int c) { return row[c]; }, C, lane, tbits, boost);
         if (lane == 0) rowstat[frame_off[u] + t] = st;
@@ -360,7 +365,7 @@ __device__ int plan_segmented(const UttCtx& c, Item* loc, int32_t* lists, uint32
             it.utt = c.u;
             it.anchor_off = (int)((size_t)c.u * a.anchor_words) + anc_used;
             it.flags = (p.boost_targets ? ITEM_STATS : 0) | (p.enforce_minimum ? ITEM_FLOOR : 0) | flags_anchor;
-            it.pad = 0;
+            it.lead = (int)(((unsigned long long)(a.logp + it.lp_off) & 15ull) >> 2);
             loc[n_items] = it;
         }
         if (flags_anchor) anc_used += words;
@@ -463,7 +468,7 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(PlanArgs a) {
                     it.flags = ITEM_FINAL;
                     if (p.mode == BFA_MODE_FULL)
                         it.flags |= (p.boost_targets ? ITEM_STATS : 0) | (p.enforce_minimum ? ITEM_FLOOR : 0);
-                    it.pad = 0;
+                    it.lead = (int)(((unsigned long long)(a.logp + it.lp_off) & 15ull) >> 2);
                     single = it;
                 }
                 have_single = true;
@@ -532,7 +537,7 @@ __global__ void items_from_arrays_kernel(int n, int C, const long long* row_off,
     it.lp_off = row_off[i]; it.stat_off = 0; it.out_off = frame_off[i]; it.out_lim = frame_off[i] + T[i];
     it.seq_off = path_off[i];
     it.T = T[i]; it.L = L[i]; it.band = band[i]; it.stride = 0; it.n = 0; it.idx0 = 0; it.trim = 0; it.n_out = T[i];
-    it.utt = i; it.anchor_off = 0; it.flags = ITEM_FINAL; it.pad = 0;
+    it.utt = i; it.anchor_off = 0; it.flags = ITEM_FINAL; it.lead = 0;
     items[i] = it;
 }
 

@@ -62,6 +62,7 @@ constexpr int B3_ROWS = 8;         // rows per stage per utterance (8*C*4 bytes 
 constexpr int B3_PAIRS = 7;        // (DP warp, helper warp) pairs per CTA, one CTA per SM
 constexpr int B3_KK = 72;          // floats per utterance in the class-weight table (C <= 72)
 constexpr int B3_STP = 9;          // float2 pitch of the per-utterance (lnS, eb) array (bank spreading)
+constexpr int B3_SLOT_PAD = 4;      // floats of slack per staged (utterance, chunk) slot: room for an item's lead-in (Item::lead)
 constexpr int B3_NMAX = 128;       // phonemes per item on this path (byte-sized class table in shared memory)
 constexpr int B3_MARGIN = 2;       // states of safety margin of the band-legality check
 constexpr int B3_NREC = 4;         // decision records of 32-frame blocks in flight from the slab during the back-trace
@@ -109,7 +110,7 @@ __host__ __device__ inline int band3_window_need(int N, int T, int L, int band) 
 
 // The stage ring doubles as the back-trace staging area (cells + visited-cell buffer) once the fill is done.
 __host__ __device__ inline size_t band3_stage_region(int C, int G) {
-    size_t st = (size_t)B3_NST * B3_UPW * B3_ROWS * C * 4;
+    size_t st = (size_t)B3_NST * B3_UPW * (B3_ROWS * C + B3_SLOT_PAD) * 4;
     // back-trace: cells [UPW][3*8G] x 8 B, B3_NREC record buffers [4G+1][32] words, two visited-cell buffers [4][32] words,
     // B3_GRING gather blocks [4][32] floats, per-utterance verdict + final score
     size_t bt = (size_t)B3_UPW * 3 * B3_LPU * G * 8 + (size_t)B3_NREC * (4 * G + 1) * 128 + (size_t)2 * 4 * 128 + (size_t)B3_GRING * 4 * 128 +
@@ -200,7 +201,7 @@ struct Band3Task {
     int seg, l8, C;
     bool seg_on;
     const Item* it;
-    int T, Tmax, n_chunks, seg_stride, stage_floats;
+    int T, Tmax, n_chunks, seg_stride, stage_floats, lead;
     float* stage_buf;
     float* kk;
     float2* stats;
@@ -219,7 +220,8 @@ struct Band3Task {
 #pragma unroll
         for (int d = 8; d < 32; d <<= 1) Tmax = max(Tmax, __shfl_xor_sync(FULL, Tmax, d));
         n_chunks = (Tmax + B3_ROWS - 1) / B3_ROWS;
-        seg_stride = B3_ROWS * C;
+        seg_stride = B3_ROWS * C + B3_SLOT_PAD;
+        lead = seg_on ? it->lead : 0;
         stage_floats = B3_UPW * seg_stride;
         stage_buf = reinterpret_cast<float*>(smem_pair);
         kk = reinterpret_cast<float*>(smem_pair + band3_off_kk(C, G));                   // [UPW][B3_KK]
@@ -270,19 +272,21 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
     // lanes with l8 == 0 issue their own utterance's copy and arrive once per chunk on the stage's full barrier (count = UPW)
     const uint32_t dst0 = smem_u32(k.stage_buf + seg * k.seg_stride);
     const uint32_t full_bytes = (uint32_t)B3_ROWS * C * 4;
+    const uint32_t lead_b = 4u * (uint32_t)k.lead;      // the copy starts this many bytes before the chunk (16-byte aligned source)
     auto issue = [&](int c, int st) {
         if (l8 == 0) {
             const int rows = T - c * B3_ROWS;
             const uint32_t bar = k.bar0 + 8u * (B3_BAR_FULL + st);
             const uint32_t dst = dst0 + (uint32_t)st * k.stage_floats * 4u;
-            const float* s = k.my_src + (size_t)c * B3_ROWS * C;
-            if (rows >= B3_ROWS) {
-                mbar_expect_tx(bar, full_bytes);
-                bulk_g2s_hint(dst, s, full_bytes, bar, pol);
-            } else if (rows > 0) {
-                const uint32_t bytes = (uint32_t)rows * C * 4, bulk = bytes & ~15u;
+            const float* s = k.my_src + (size_t)c * B3_ROWS * C - k.lead;
+            if (rows > B3_ROWS || (rows == B3_ROWS && lead_b == 0)) {
+                const uint32_t nb = (full_bytes + lead_b + 15u) & ~15u;   // may take in the first floats of the next chunk
+                mbar_expect_tx(bar, nb);
+                bulk_g2s_hint(dst, s, nb, bar, pol);
+            } else if (rows > 0) {                                        // last chunk: never read past the item's last row
+                const uint32_t bytes = (uint32_t)rows * C * 4 + lead_b, bulk = bytes & ~15u;
                 float* d = k.stage_buf + st * k.stage_floats + seg * k.seg_stride;
-                for (uint32_t w = bulk >> 2; w < (bytes >> 2); ++w) d[w] = s[w];   // < 4 tail floats of a partial last chunk
+                for (uint32_t w = bulk >> 2; w < (bytes >> 2); ++w) d[w] = s[w];   // < 4 tail floats
                 mbar_expect_tx(bar, bulk);
                 if (bulk) bulk_g2s_hint(dst, s, bulk, bar, pol);
             } else {
@@ -323,7 +327,7 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
         // ---- row statistics: lane (seg, l8) owns row l8 of its utterance: log-sum-exp of the boosted row (:51-54)
         //      and the blank emission; no cross-lane traffic ----
         {
-            const float* rowp = k.stage_buf + st * k.stage_floats + seg * k.seg_stride + l8 * C;
+            const float* rowp = k.stage_buf + st * k.stage_floats + seg * k.seg_stride + k.lead + l8 * C;
             const int t_row = c * B3_ROWS + l8;
             float lnS = 0.f;
             if (warp_stats) {
@@ -620,7 +624,7 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
         }
         PH_T(2);
 
-        const float* seg_rows = k.stage_buf + st * k.stage_floats + seg * k.seg_stride;   // the 8 staged rows of this utterance
+        const float* seg_rows = k.stage_buf + st * k.stage_floats + seg * k.seg_stride + k.lead;   // the 8 staged rows of this utterance
         const int fin_r = T - 1 - t0;                                      // row of the last frame if it is in this chunk
         const bool fin_here = __any_sync(FULL, fin_r >= 0 && fin_r < B3_ROWS);
         const float* xg[G];                                                // row 0 address of each group's class
