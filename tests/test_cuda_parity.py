@@ -332,3 +332,77 @@ def test_exact_only_flag_matches_fast_path(bfa, dev):
     np.testing.assert_array_equal(res[0].frame_idx.cpu().numpy(), res[1].frame_idx.cpu().numpy())
     np.testing.assert_allclose(res[0].dp_final.cpu().numpy(), res[1].dp_final.cpu().numpy(), rtol=RTOL)
     np.testing.assert_allclose(res[0].conf.cpu().numpy()[:, :N], res[1].conf.cpu().numpy()[:, :N], rtol=1e-5)
+
+
+# ---- packed corpora, arbitrary row alignment, every mode -------------------------------------------
+def _packed_vs_oracle(bfa, orc, dev, utts, Cc, *, gap_floats, boost=True, floor=True, mode=0, anchors=10, base_shift=0):
+    """Rows packed back to back with `gap_floats` floats between utterances (so that row starts land on every
+    residue of the 16-byte grid the bulk copies need) -> bfa_align_batch vs the oracle, utterance by utterance."""
+    from bfa_b200 import _cabi
+    import ctypes as C
+    B = len(utts)
+    Ts = [int(l.shape[0]) for l, _ in utts]; Ns = [int(t.shape[0]) for _, t in utts]
+    offs, cur = [], base_shift
+    for t, g in zip(Ts, gap_floats):
+        offs.append(cur); cur += t * Cc + g
+    flat = torch.zeros(cur + 8, dtype=torch.float32)
+    for (l, _), o, t in zip(utts, offs, Ts):
+        flat[o:o + t * Cc] = l.reshape(-1)
+    au = bfa.AlignmentUtils(Cc - 1, 0, silence_anchors=anchors)
+    dec = au.viterbi_decoder
+    p = dec._params(boost, floor, anchors > 0, mode=mode)
+    tg = torch.cat([t for _, t in utts]).to(torch.int32).contiguous()
+    r = dec.align_batch(flat.to(dev), torch.tensor(offs, dtype=torch.int64, device=dev), Ts, Cc, tg.to(dev), Ns, params=p)
+    torch.cuda.synchronize()
+    ic = (C.c_int32 * 4)(); _cabi.lib().bfa_debug_item_counts(ic)
+    po = orc.params(Cc - 1, 0, anchors, True, True, boost, floor, mode)
+    fo = np.zeros(B + 1, np.int64); np.cumsum(np.asarray(Ts, np.int64), out=fo[1:])
+    fph, fix, st = r.frame_ph.cpu().numpy(), r.frame_idx.cpu().numpy(), r.status.cpu().numpy()
+    nst, stamps, conf = r.n_stamps.cpu().numpy(), r.stamps.cpu().numpy(), r.conf.cpu().numpy()
+    for u, (l, t) in enumerate(utts):
+        T, N = Ts[u], Ns[u]
+        o = orc.align_batch(po, l.numpy().reshape(1, T, Cc), np.zeros(1, np.int64), np.asarray([T], np.int32), Cc,
+                            t.numpy().astype(np.int32), np.asarray([0, N], np.int64), max_stamps=r.max_stamps, n_threads=1)
+        assert (int(o["status"][0]) & 15) == (int(st[u]) & 15), f"utterance {u}: status"
+        np.testing.assert_array_equal(fph[fo[u]:fo[u + 1]], o["frame_ph"], err_msg=f"utterance {u} (T={T}, N={N})")
+        np.testing.assert_array_equal(fix[fo[u]:fo[u + 1]], o["frame_idx"], err_msg=f"utterance {u} (T={T}, N={N})")
+        n = int(o["n_stamps"][0])
+        assert n == int(nst[u])
+        if n:
+            want = np.stack([o["stamps"][0][f][:n] for f in ("phoneme", "start", "end", "target_idx")], 1)
+            np.testing.assert_array_equal(stamps[u, :n], want)
+            np.testing.assert_allclose(conf[u, :n], o["conf"][0, :n], rtol=RTOL, atol=1e-6)
+    return [int(x) for x in ic]
+
+
+@pytest.mark.parametrize("Cc", [66, 67, 30])
+def test_packed_rows_on_every_alignment_vs_oracle(bfa, orc, dev, Cc):
+    """Row starts on all four residues of the 16-byte grid (Item::lead 0..3): the banded kernel keeps its bulk copies by
+    starting them at the boundary before the item; what it cannot take (odd lead at C=66) runs in the exact kernel."""
+    from bfa_b200 import synth
+    rng = np.random.default_rng(17 + Cc)
+    utts = synth.ragged_batch(48, C=Cc, t_range=(60, 500), n_range=(4, 40), seed=400 + Cc)
+    gaps = rng.integers(0, 4, len(utts)).tolist()
+    counts = _packed_vs_oracle(bfa, orc, dev, utts, Cc, gap_floats=gaps, base_shift=int(rng.integers(0, 4)))
+    assert sum(counts[1:]) > len(utts) // 3, f"the banded kernels were hardly used: {counts}"
+
+
+@pytest.mark.parametrize("boost,floor,mode", [(False, True, 0), (False, False, 0), (True, False, 0), (True, True, 1)])
+def test_packed_rows_all_modes_vs_oracle(bfa, orc, dev, boost, floor, mode):
+    """boost off / floor off / decode_alignments_simple (mode 1): without boost the banded kernel runs its EXACT instantiation."""
+    from bfa_b200 import synth
+    utts = synth.ragged_batch(40, C=66, t_range=(80, 700), n_range=(4, 60), seed=500 + 2 * int(boost) + int(floor) + 10 * mode)
+    gaps = [0, 2] * (len(utts) // 2)
+    counts = _packed_vs_oracle(bfa, orc, dev, utts, 66, gap_floats=gaps, boost=boost, floor=floor, mode=mode, anchors=10 if mode == 0 else 0)
+    assert sum(counts[1:]) > 0
+
+
+def test_segmented_packed_misaligned_vs_oracle(bfa, orc, dev):
+    """Silence-anchored segments of utterances that themselves start off the 16-byte grid."""
+    from bfa_b200 import synth
+    utts = []
+    for u in range(12):
+        lp, tgt, _ = synth.planted_batch(1, 900 + 37 * u, 60, 66, seed=600 + u, peak=10.0, sil_every=12, sil_frames=20)
+        utts.append((lp[0], tgt[0]))
+    counts = _packed_vs_oracle(bfa, orc, dev, utts, 66, gap_floats=[2, 0, 6, 2] * 3, base_shift=2)
+    assert sum(counts[1:]) > 12
