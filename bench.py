@@ -342,7 +342,7 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import oracle as orc
         n = a.cpu_sample or B
-        cpu_baseline, _ = cpu_arm(a, n, 3, 1)
+        cpu_baseline, _ = cpu_arm(a, n, 8, 1)    # ~1 s wall on 16 threads = ~17 core-seconds of CPU work
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
