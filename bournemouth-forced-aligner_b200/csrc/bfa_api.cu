@@ -43,7 +43,9 @@ thread_local char g_cuda_err[256] = "";
 struct Prof {
     std::mutex mu;
     bool on = false;
+    int mode = 0;     // 2: also time the planner and the stamp kernel (development)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> tagged;   // mode 2: (0 planner, 1 stamps) kernels too
     std::vector<cudaEvent_t> pool;
     cudaEvent_t get() {
         if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
@@ -331,8 +333,19 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     for (int v = 0; v < BAND_NV; ++v) { pa.fast_items[v] = (Item*)(ws + L.off_fast[v]); pa.n_fast[v] = counters + 3 + 2 * v; }
     pa.fast_enable = fast ? 1 : 0; pa.path_lp = path_lp;
     pa.padded = (float*)(ws + L.off_padded); pa.anchors = (uint32_t*)(ws + L.off_anchors);
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_prof.mu);
+        if (g_prof.on && g_prof.mode == 2) { pe0 = g_prof.get(); pe1 = g_prof.get(); }
+    }
+    if (pe0) cudaEventRecord(pe0, st);
     plan_kernel<<<(B + 7) / 8, 256, 0, st>>>(pa);
     LAUNCH_CHECK();
+    if (pe0) {
+        cudaEventRecord(pe1, st);
+        std::lock_guard<std::mutex> lk(g_prof.mu);
+        g_prof.tagged.push_back({0, {pe0, pe1}});
+    }
 
     long long max_items = (long long)B * L.item_cap;
     const int max_items_i = (int)(max_items > (1 << 30) ? (1 << 30) : max_items);
@@ -396,8 +409,19 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         if (shape->max_stamps <= 0) return BFA_E_INVALID;
         aa.ts = shape->max_N < 32768 ? assort_ts(shape->max_T) : 0;   // staged frames pack (idx, phoneme) into 16 + 16 bits
         aa.ss = assort_ss(shape->max_stamps);
+        cudaEvent_t ae0 = nullptr, ae1 = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_prof.mu);
+            if (g_prof.on && g_prof.mode == 2) { ae0 = g_prof.get(); ae1 = g_prof.get(); }
+        }
+        if (ae0) cudaEventRecord(ae0, st);
         assort_confidence_kernel<<<(B + ASSORT_WARPS - 1) / ASSORT_WARPS, ASSORT_WARPS * 32, assort_smem(aa.ts, aa.ss), st>>>(aa);
         LAUNCH_CHECK();
+        if (ae0) {
+            cudaEventRecord(ae1, st);
+            std::lock_guard<std::mutex> lk(g_prof.mu);
+            g_prof.tagged.push_back({1, {ae0, ae1}});
+        }
     }
     return BFA_OK;
 }
@@ -486,9 +510,27 @@ int bfa_debug_phases(unsigned long long* out16, int reset) {   // 32 counters: [
     return BFA_OK;
 }
 
-void bfa_profile_enable(int on) {
+void bfa_profile_enable(int on) {   // 1: the dominant kernel; 2 (development): the planner and the stamp kernel as well
     std::lock_guard<std::mutex> lk(g_prof.mu);
     g_prof.on = on != 0;
+    g_prof.mode = on;
+}
+
+// Development aid (mode 2): mean device time in ms of the planner (out2[0]) and of the stamp kernel (out2[1]) since the last read.
+int bfa_profile_read_aux(float* out2) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    float sum[2] = {0.f, 0.f};
+    int n[2] = {0, 0};
+    for (auto& t : g_prof.tagged) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventSynchronize(t.second.second));
+        CUDA_TRY(cudaEventElapsedTime(&ms, t.second.first, t.second.second));
+        sum[t.first] += ms; ++n[t.first];
+        g_prof.pool.push_back(t.second.first); g_prof.pool.push_back(t.second.second);
+    }
+    g_prof.tagged.clear();
+    if (out2) { out2[0] = n[0] ? sum[0] / n[0] : 0.f; out2[1] = n[1] ? sum[1] / n[1] : 0.f; }
+    return BFA_OK;
 }
 
 // Sum of the device time of the dominant kernel launches recorded since the last read; blocks on them.

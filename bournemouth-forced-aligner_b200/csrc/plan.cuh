@@ -59,16 +59,18 @@ __device__ __forceinline__ TgtInfo target_info(const int32_t* tgt, long long b, 
 #pragma unroll
     for (int i = 0; i < MAX_WORDS; ++i) r.w[i] = 0;
     bool all_ok = true, has_sil = false;
+    const int nw = (C + 31) >> 5;              // mask words in use
     for (long long j = b + lane; j < e; j += 32) {
         const int c = tgt[j];
         has_sil |= (c == silence_id);
         if (c == blank_id || c == -100 || c < 0 || c >= C) { all_ok = false; continue; }
 #pragma unroll
         for (int i = 0; i < MAX_WORDS; ++i)
-            if ((c >> 5) == i) r.w[i] |= 1u << (c & 31);
+            if (i < nw && (c >> 5) == i) r.w[i] |= 1u << (c & 31);
     }
 #pragma unroll
-    for (int i = 0; i < MAX_WORDS; ++i) r.w[i] = __reduce_or_sync(FULL, r.w[i]);
+    for (int i = 0; i < MAX_WORDS; ++i)
+        if (i < nw) r.w[i] = __reduce_or_sync(FULL, r.w[i]);      // nw is warp-uniform
     r.all_ok = __all_sync(FULL, all_ok);
     r.has_sil = __any_sync(FULL, has_sil);
     return r;
@@ -379,7 +381,7 @@ __device__ int plan_segmented(const UttCtx& c, Item* loc, int32_t* lists, uint32
     return n_items;
 }
 
-__global__ void __launch_bounds__(256, 4) plan_kernel(PlanArgs a) {
+__global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ PlanArgs a) {
     const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     int n_items = 0;
     Item* loc = nullptr;

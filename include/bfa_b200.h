@@ -205,6 +205,7 @@ int bfa_assort_batch(const BfaParams *p, int32_t B, const int32_t *T, const int6
  * them and returns the summed device time and the number of launches since the previous read. */
 void bfa_profile_enable(int on);
 int bfa_profile_read(float *dominant_ms, int32_t *n_launches);
+int bfa_profile_read_aux(float *out2);   /* development: planner / stamp kernel means after bfa_profile_enable(2) */
 
 /* Development aid: sums of warp-clock cycles per phase of the banded Viterbi kernel (16 counters); all zero unless
  * the library was built with -DBFA_PHASE_PROF (scripts/phase_prof.sh).  reset != 0 clears them after the read. */
