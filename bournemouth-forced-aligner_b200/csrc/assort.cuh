@@ -158,19 +158,83 @@ __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(As
     // (:819-827) -- the length test needs the end, so blank candidates are compacted in pass 2.
     int n = 0;            // provisional stamps so far (uniform)
     int open = -1;        // index of the provisional stamp whose end is still unknown
+    if (pk_s) {
+        // Staged utterances (T <= 2048 = 64 blocks of 32 frames).  (A) one sweep turns the packed (idx, phoneme) words into
+        // run-start / candidate bit masks, block j kept by lane j % 32; (B) every lane emits the stamps that start in its own
+        // blocks: slots from a prefix count over the blocks, ends from the next run start (same mask, or the first later
+        // non-empty block, found with one ballot and one indexed shuffle).
+        uint32_t sb[2] = {0u, 0u}, cb[2] = {0u, 0u};
+        const int nb = (T + 31) >> 5;
+        int32_t carry = 0;
+        for (int b = 0; b < nb; ++b) {
+            const int t = b * 32 + lane;
+            const int32_t w = t < T ? pk_s[t] : 0;
+            int32_t wp = __shfl_up_sync(FULL, w, 1);
+            if (lane == 0) wp = carry;
+            carry = __shfl_sync(FULL, w, 31);
+            const bool startf = t < T && (t == 0 || w != wp);                                  // :798-801
+            const bool cand = startf && ((w & 0xffff) != blank || !a.p.ignore_noise);
+            const uint32_t sbits = __ballot_sync(FULL, startf), cbits = __ballot_sync(FULL, cand);
+            if (lane == (b & 31)) {
+                if (b < 32) { sb[0] = sbits; cb[0] = cbits; }
+                else { sb[1] = sbits; cb[1] = cbits; }
+            }
+        }
+        // exclusive prefix of the candidate counts over the blocks (two rounds of 32 blocks)
+        int ex[2], tot = 0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int c = __popc(cb[r]);
+            int inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d) inc += o;
+            }
+            ex[r] = tot + inc - c;
+            tot += __shfl_sync(FULL, inc, 31);
+        }
+        n = tot;
+        // first run start after each block: position inside the nearest later block that holds one (T if none)
+        const uint32_t nz0 = __ballot_sync(FULL, sb[0] != 0u), nz1 = __ballot_sync(FULL, sb[1] != 0u);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t later_same = (r == 0 ? nz0 : nz1) & ~((2u << lane) - 1u);   // blocks after mine in my round
+            const uint32_t other = r == 0 ? nz1 : 0u;                                    // the round after mine
+            const int src = later_same ? __ffs(later_same) - 1 : (other ? __ffs(other) - 1 : 0);
+            const uint32_t m0 = __shfl_sync(FULL, sb[0], src), m1 = __shfl_sync(FULL, sb[1], src);
+            int next_start = T;
+            if (later_same) next_start = (r * 32 + src) * 32 + __ffs(r == 0 ? m0 : m1) - 1;
+            else if (other) next_start = (32 + src) * 32 + __ffs(m1) - 1;
+            uint32_t cbl = cb[r];
+            int slot = ex[r];
+            const int blk = r * 32 + lane;
+            while (cbl) {
+                const int pos = __ffs(cbl) - 1;
+                cbl &= cbl - 1u;
+                if (slot < a.max_stamps) {
+                    const int t = blk * 32 + pos;
+                    const int32_t w = pk_s[t];
+                    const uint32_t later = sb[r] & ~((2u << pos) - 1u);     // run starts after this one in the same block
+                    BfaStamp sv;
+                    sv.phoneme = w & 0xffff;
+                    sv.start = t;
+                    sv.end = later ? blk * 32 + __ffs(later) - 1 : next_start;
+                    sv.target_idx = w >> 16;   // runs are constant in idx, the :812-816 search is a no-op
+                    out[slot] = sv;
+                }
+                ++slot;
+            }
+        }
+        __syncwarp();
+    } else
     for (int base = 0; base < T; base += 32) {
         int t = base + lane;
         bool startf = false, cand = false;
         int p_t = blank, i_t = -1;
         if (t < T) {
-            if (pk_s) {
-                const int32_t w = pk_s[t];
-                p_t = w & 0xffff; i_t = w >> 16;
-                startf = (t == 0) || w != pk_s[t - 1];                              // :798-801
-            } else {
-                p_t = ph[t]; i_t = ix[t];
-                startf = (t == 0) || p_t != ph[t - 1] || i_t != ix[t - 1];
-            }
+            p_t = ph[t]; i_t = ix[t];
+            startf = (t == 0) || p_t != ph[t - 1] || i_t != ix[t - 1];          // :798-801
             cand = startf && (p_t != blank || !a.p.ignore_noise);
         }
         uint32_t sbits = __ballot_sync(FULL, startf), cbits = __ballot_sync(FULL, cand);
