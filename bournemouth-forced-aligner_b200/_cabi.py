@@ -61,6 +61,7 @@ _SIGNATURES = {
     "bfa_debug_warps": (C.c_int, [_P, C.c_int]),
     "bfa_profile_read_aux": (C.c_int, [_P]),
     "bfa_debug_item_counts": (C.c_int, [_P]),
+    "bfa_debug_ctas": (C.c_int, [_P, C.c_int]),
     "bfa_profile_enable": (None, [C.c_int]),
     "bfa_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }

@@ -66,7 +66,7 @@ struct DeviceInfo {
 constexpr int BAND_NV = 3;
 constexpr int BAND_G[BAND_NV] = {3, 5, 8};
 constexpr int BAND_WARPS = B3_PAIRS;   // (DP, helper) warp pairs per CTA
-inline int band_rec_words(int G) { return 4 * G + 1; }
+inline int band_rec_words(int G) { return 6 * G + 1; }   // per lane: its 3G cells as (w0, w1) pairs + the slide word
 inline int band_smem_bytes_per_warp(int C, int G) { return (int)band3_smem_per_warp(C, G); }
 
 template <int G>
@@ -485,6 +485,17 @@ int bfa_debug_item_counts(int32_t* out4) {
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(h, g_last_counters, sizeof(h), cudaMemcpyDeviceToHost));
     out4[0] = h[0]; out4[1] = h[3]; out4[2] = h[5]; out4[3] = h[7];
+    return BFA_OK;
+}
+
+int bfa_debug_ctas(unsigned long long* out320, int reset) {   // development: per-CTA max DP task cycles + SM id of the banded kernel
+#ifdef BFA_PHASE_PROF
+    if (out320) CUDA_TRY(cudaMemcpyFromSymbol(out320, g_b3_cta, sizeof(unsigned long long) * 320));
+    if (reset) { static unsigned long long z[320]; CUDA_TRY(cudaMemcpyToSymbol(g_b3_cta, z, sizeof(z))); }
+#else
+    if (out320) memset(out320, 0, sizeof(unsigned long long) * 320);
+    (void)reset;
+#endif
     return BFA_OK;
 }
 

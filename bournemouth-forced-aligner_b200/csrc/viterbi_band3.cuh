@@ -92,7 +92,7 @@ template <int G>
 struct Band3Shape {
     static constexpr int W = B3_LPU * G;    // groups in the window
     static constexpr int ACC = 4 * G;       // decision accumulators per lane
-    static constexpr int REC = ACC + 1;     // + window-slide word
+    static constexpr int REC = 6 * G + 1;   // words per lane of a record: its 3G cells as (w0, w1) pairs + the window-slide word
     static constexpr int CELLS = 3 * W;     // back-trace cells per utterance
 };
 
@@ -111,15 +111,14 @@ __host__ __device__ inline int band3_window_need(int N, int T, int L, int band) 
 // The stage ring doubles as the back-trace staging area (cells + visited-cell buffer) once the fill is done.
 __host__ __device__ inline size_t band3_stage_region(int C, int G) {
     size_t st = (size_t)B3_NST * B3_UPW * (B3_ROWS * C + B3_SLOT_PAD) * 4;
-    // back-trace: cells [UPW][3*8G] x 8 B, B3_NREC record buffers [4G+1][32] words, two visited-cell buffers [4][32] words,
-    // B3_GRING gather blocks [4][32] floats, per-utterance verdict + final score
-    size_t bt = (size_t)B3_UPW * 3 * B3_LPU * G * 8 + (size_t)B3_NREC * (4 * G + 1) * 128 + (size_t)2 * 4 * 128 + (size_t)B3_GRING * 4 * 128 +
-                (size_t)B3_UPW * 8;
+    // back-trace: B3_NREC record buffers (a record IS the cell array of its block: [UPW][3*8G] x 8 B, + 32 slide words), two
+    // visited-cell buffers [4][32] words, B3_GRING gather blocks [4][32] floats, per-utterance verdict + final score
+    size_t bt = (size_t)B3_NREC * (6 * G + 1) * 128 + (size_t)2 * 4 * 128 + (size_t)B3_GRING * 4 * 128 + (size_t)B3_UPW * 8;
     size_t b = st > bt ? st : bt;
     return (b + 15) / 16 * 16;
 }
-// word offset of the visited-cell buffers inside the back-trace staging area (after the cells and the record buffers)
-__host__ __device__ inline int band3_bt_keep_words(int G) { return B3_UPW * 3 * B3_LPU * G * 2 + B3_NREC * (4 * G + 1) * 32; }
+// word offset of the visited-cell buffers inside the back-trace staging area (after the record buffers)
+__host__ __device__ inline int band3_bt_keep_words(int G) { return B3_NREC * (6 * G + 1) * 32; }
 // shared memory of one pair: stage ring | class weights | (lnS, eb) per staged row | target classes | helper flags | mbarriers
 enum : int { B3_BAR_FULL = 0, B3_BAR_READY = B3_NST, B3_BAR_FREE = 2 * B3_NST, B3_BAR_REC = 3 * B3_NST, B3_BAR_KREADY = 3 * B3_NST + B3_NREC,
              B3_BAR_KFREE = 3 * B3_NST + B3_NREC + 2, B3_NBARS = 3 * B3_NST + B3_NREC + 4 };
@@ -179,14 +178,16 @@ __device__ __forceinline__ void b3_push(uint32_t& acc, float earlier, float late
 // Optional phase timers (development only, -DBFA_PHASE_PROF): warp-clock cycles per phase, summed over lane 0 of the DP warps.
 #ifdef BFA_PHASE_PROF
 __device__ unsigned long long g_b3_phase[32];
-__device__ unsigned long long g_b3_warp[32];   // [warp id]: summed task cycles, [16 + warp id]: tasks
+__device__ unsigned long long g_b3_warp[32];
+__device__ unsigned long long g_b3_cta[160 * 2];   // [cta]: max DP task cycles, [160 + cta]: physical SM id   // [warp id]: summed task cycles, [16 + warp id]: tasks
 #define PH_DECL long long ph_last = clock64(); long long ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; const int ph_base = 0
 #define PH_DECL_H long long ph_last = clock64(); long long ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; const int ph_base = 16
 #define PH_RESET ph_last = clock64()
 #define PH_T(i) do { const long long ph_now = clock64(); ph_acc[i] += ph_now - ph_last; ph_last = ph_now; } while (0)
 #define PH_FLUSH do { if (lane == 0) { long long ph_tot = 0; for (int i = 0; i < 14; ++i) { ph_tot += ph_acc[i]; atomicAdd(&g_b3_phase[ph_base + i], (unsigned long long)ph_acc[i]); } \
     atomicMax(&g_b3_phase[ph_base + 14], (unsigned long long)ph_tot); atomicMin(&g_b3_phase[ph_base + 15], (unsigned long long)ph_tot); \
-    atomicAdd(&g_b3_warp[threadIdx.x >> 5], (unsigned long long)ph_tot); atomicAdd(&g_b3_warp[16 + (threadIdx.x >> 5)], 1ull); } } while (0)
+    atomicAdd(&g_b3_warp[threadIdx.x >> 5], (unsigned long long)ph_tot); atomicAdd(&g_b3_warp[16 + (threadIdx.x >> 5)], 1ull); \
+    if (ph_base == 0 && blockIdx.x < 160) { unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); atomicMax(&g_b3_cta[blockIdx.x], (unsigned long long)ph_tot); g_b3_cta[160 + blockIdx.x] = smid; } } } while (0)
 #else
 #define PH_DECL
 #define PH_DECL_H
@@ -660,6 +661,19 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
             }
         };
 
+        // A record is stored as the back-trace reads it: per cell one (w0, w1) pair -- p: (from b3', from m'), m: (from p, 0),
+        // b3: (from m, 0) -- in cell order, so the bulk copy that brings it back IS the staging; then one slide word per lane.
+        auto write_record = [&](uint32_t* rec, const uint32_t (&w)[S::ACC], int sh, uint32_t slide_word) {
+            uint2* cells = reinterpret_cast<uint2*>(rec) + seg * S::CELLS + l8 * G * 3;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                cells[3 * g + 0] = make_uint2(w[4 * g] << sh, w[4 * g + 1] << sh);
+                cells[3 * g + 1] = make_uint2(w[4 * g + 2] << sh, 0u);
+                cells[3 * g + 2] = make_uint2(w[4 * g + 3] << sh, 0u);
+            }
+            rec[B3_UPW * S::CELLS * 2 + lane] = slide_word;
+        };
+
         auto frame = [&](const int r, auto check_fin) {
             constexpr bool CHECK = decltype(check_fin)::value;
             const float lnS = st_nx.x, eb = st_nx.y;
@@ -715,10 +729,7 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
                     const int t = t0 + r;
                     // last record of this utterance, left-aligned so that frame 32b+q sits at bit 31-q
                     const int sh = 31 - (t & 31);
-                    uint32_t* rec = slab + (size_t)(t >> 5) * S::REC * 32 + lane;
-#pragma unroll
-                    for (int i = 0; i < S::ACC; ++i) rec[i * 32] = wrec[i] << sh;
-                    rec[S::ACC * 32] = slide_acc << (4 * (3 - (c & 3)));
+                    write_record(slab + (size_t)(t >> 5) * S::REC * 32, wrec, sh, slide_acc << (4 * (3 - (c & 3))));
                     // ---- final state (:656-682) from the window at frame T-1; cells are 3*(group - base) + {0:p, 1:m, 2:b3} ----
                     float bv = -INFINITY;
                     int bs = -1;
@@ -773,10 +784,7 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
             uint32_t wrec[S::ACC];
             record_words(wrec);
             if (T - 1 > t0 + B3_ROWS - 1) {
-                uint32_t* rec = slab + (size_t)(c >> 2) * S::REC * 32 + lane;
-#pragma unroll
-                for (int i = 0; i < S::ACC; ++i) rec[i * 32] = wrec[i];
-                rec[S::ACC * 32] = slide_acc;
+                write_record(slab + (size_t)(c >> 2) * S::REC * 32, wrec, 0, slide_acc);
             }
             if (!EXACT) {
 #pragma unroll
@@ -812,23 +820,24 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
     // through a double-buffered shared array; it writes the outputs while this warp walks the next block.
     const bool walk = seg_on && !bad && T > 0;
     const int last_blk = (T - 1) >> 5;
-    const uint32_t cellbase = smem_u32(bt2 + seg * S::CELLS);
-    uint32_t A = cellbase + 8u * (uint32_t)fin_cell;
-    uint32_t K = 24u * (uint32_t)fin_base - cellbase;          // A + K = 8 * cabs
-    const int nblk = (Tmax + 31) >> 5;
-    // Shared staging (aliases the stage ring): cells | two record buffers | two visited-cell buffers | gather ring | verdicts.
-    //  * records (decision words of one 32-frame block) come back from the slab by bulk async copy (TMA) on their own
-    //    mbarriers, one block ahead.
-    uint32_t* recbuf = reinterpret_cast<uint32_t*>(bt2 + B3_UPW * S::CELLS);                 // [B3_NREC][REC][32]
+    // Shared staging (aliases the stage ring): B3_NREC record buffers | two visited-cell buffers | fetch ring | verdicts.
+    // A record comes back from the slab by bulk async copy (TMA) on its own mbarrier, B3_NREC blocks ahead, and is already
+    // laid out as the cells of its block (see write_record): nothing to stage.
+    uint32_t* recbuf = reinterpret_cast<uint32_t*>(smem_pair);                                // [B3_NREC][REC][32]
     uint32_t* keepbuf = reinterpret_cast<uint32_t*>(smem_pair) + band3_bt_keep_words(G);     // [2][4][32]
     float* finv = reinterpret_cast<float*>(keepbuf + 2 * 128 + B3_GRING * 128);              // [UPW] (verdict, final score)
+    constexpr uint32_t RECB = (uint32_t)S::REC * 128u;                                         // bytes of one record
     const uint32_t rec_s = smem_u32(recbuf);
-    const uint32_t rbar0 = bar0 + 8u * B3_BAR_REC;                                             // the two record barriers
+    const uint32_t cellbase = rec_s + (uint32_t)seg * S::CELLS * 8u;                           // this utterance's cells in record buffer 0
+    uint32_t A = cellbase + 8u * (uint32_t)fin_cell;                                           // cell address, kept relative to buffer 0
+    uint32_t K = 24u * (uint32_t)fin_base - cellbase;                                          // A + K = 8 * cabs
+    const int nblk = (Tmax + 31) >> 5;
+    const uint32_t rbar0 = bar0 + 8u * B3_BAR_REC;                                             // the record barriers
     auto issue_rec = [&](int blk) {
         if (lane == 0) {
             const uint32_t bar = rbar0 + 8u * (blk % B3_NREC);
-            mbar_expect_tx(bar, S::REC * 128u);
-            bulk_g2s(rec_s + (uint32_t)(blk % B3_NREC) * S::REC * 128u, slab + (size_t)blk * S::REC * 32, S::REC * 128u, bar);
+            mbar_expect_tx(bar, RECB);
+            bulk_g2s(rec_s + (uint32_t)(blk % B3_NREC) * RECB, slab + (size_t)blk * S::REC * 32, RECB, bar);
         }
     };
     asm volatile("fence.proxy.async.global;" ::: "memory");   // the slab was written with ordinary stores, the bulk copies read it through the async proxy
@@ -845,36 +854,25 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
     for (int b = nblk - 1; b >= 0; --b) {
         mbar_wait(rbar0 + 8u * (b % B3_NREC), (rphase >> (b % B3_NREC)) & 1u);     // record of block b has landed
         rphase ^= 1u << (b % B3_NREC);
-        __syncwarp();                          // all lanes are done with the cells of block b+1
-        uint32_t nsl;                          // groups the window slid during this block
-        {
-            const bool live = walk && b <= last_blk;   // later blocks of a shorter utterance hold stale records
-            const uint32_t* wn = recbuf + (b % B3_NREC) * S::REC * 32 + lane;
-            uint2* dst = bt2 + seg * S::CELLS + l8 * G * 3;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                dst[3 * g + 0] = live ? make_uint2(wn[(4 * g + 0) * 32], wn[(4 * g + 1) * 32]) : make_uint2(0u, 0u);   // p : (A0, A1)
-                dst[3 * g + 1] = live ? make_uint2(wn[(4 * g + 2) * 32], 0u) : make_uint2(0u, 0u);                      // m : (A2, 0)
-                dst[3 * g + 2] = live ? make_uint2(wn[(4 * g + 3) * 32], 0u) : make_uint2(0u, 0u);                      // b3: (A3, 0)
-            }
-            const uint32_t sfw = live ? wn[S::ACC * 32] : 0u;
-            nsl = (sfw & 15u) + ((sfw >> 4) & 15u) + ((sfw >> 8) & 15u) + ((sfw >> 12) & 15u);
-        }
-        __syncwarp();                          // cells visible; everybody has read its record words
+        const bool live = walk && b <= last_blk;   // later blocks of a shorter utterance hold stale records: not walked
+        const uint32_t boff = (uint32_t)(b % B3_NREC) * RECB;
+        const uint32_t sfw = live ? recbuf[(b % B3_NREC) * S::REC * 32 + B3_UPW * S::CELLS * 2 + lane] : 0u;
+        const uint32_t nsl = (sfw & 15u) + ((sfw >> 4) & 15u) + ((sfw >> 8) & 15u) + ((sfw >> 12) & 15u);   // groups slid during the block
         PH_T(7);
-        if (b >= B3_NREC) issue_rec(b - B3_NREC);   // into the buffer that has just been staged
         if (b + 2 <= nblk - 1) {               // the helper has read the visited cells of block b+2 out of this buffer
             mbar_wait(bar0 + 8u * (B3_BAR_KFREE + (b & 1)), (phase >> (B3_BAR_KFREE + (b & 1))) & 1u);
             phase ^= 1u << (B3_BAR_KFREE + (b & 1));
         }
         PH_T(12);
+        A += boff;                             // same cell in the buffer this block's record landed in
+        K -= boff;
 
         // ---- walk the 32 frames of the block, one RUN per iteration (bit 31-f belongs to frame f): the path stays in
         //      its cell until a decision bit of that cell is set.  Utterances leave the loop on their own ----
         //      The decision words of the two cells the path can move to are fetched one iteration ahead, so the shared-memory
         //      latency is off the loop-carried chain (mask -> lowest set bit -> selects).
         uint32_t keep[4] = {0u, 0u, 0u, 0u};             // 8 * cabs of frames 32b + 8i + l8
-        uint32_t mask = 0xffffffffu;                      // frames not yet walked
+        uint32_t mask = live ? 0xffffffffu : 0u;          // frames not yet walked (none for an utterance that is not walked)
         uint32_t c0, c1, p0, p1, q0, q1;                  // words of the cells A, A - 1 cell, A - 2 cells
         auto lds2 = [](uint32_t addr, uint32_t& x, uint32_t& y) {
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(addr) : "memory");
@@ -899,12 +897,13 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
             lds2(A - 8u, p0, p1);
             lds2(A - 16u, q0, q1);
         } while (mask != 0u);
-        __syncwarp();
+        __syncwarp();                          // every lane is done with this record buffer
+        if (b >= B3_NREC) issue_rec(b - B3_NREC);
         PH_T(8);
 #pragma unroll
         for (int i = 0; i < 4; ++i) keepbuf[(b & 1) * 128 + i * 32 + lane] = keep[i];
-        A += 24u * nsl;                        // the record of block b-1 is aligned to the window before these slides
-        K -= 24u * nsl;
+        A += 24u * nsl - boff;                 // the record of block b-1 is aligned to the window before these slides
+        K -= 24u * nsl - boff;
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + 8u * (B3_BAR_KREADY + (b & 1)));
         PH_T(9);

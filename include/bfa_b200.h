@@ -212,6 +212,7 @@ int bfa_profile_read_aux(float *out2);   /* development: planner / stamp kernel 
 int bfa_debug_phases(unsigned long long *out32, int reset);
 int bfa_debug_warps(unsigned long long *out32, int reset);
 int bfa_debug_item_counts(int32_t *out4);
+int bfa_debug_ctas(unsigned long long *out320, int reset);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 int64_t bfa_launch_count(void);

@@ -19,6 +19,8 @@ for it in range(3):
     _cabi.lib().bfa_debug_phases(out, 1)
     wout = (C.c_ulonglong * 32)()
     _cabi.lib().bfa_debug_warps(wout, 1)
+    cout = (C.c_ulonglong * 320)()
+    _cabi.lib().bfa_debug_ctas(cout, 1)
 names = ["setup", "slide", "barrier wait", "-", "frames", "loop end", "pre-walk", "rec wait+stage", "walk", "handoff", "tail", "flush+sync", "keep-free wait"]
 tot = sum(out[:14]); nw = (B + 3) // 4
 print(f"warps {nw}; cycles per warp-task {tot / nw:.0f} = {tot / nw / 1.965e3:.1f} us")
@@ -30,3 +32,10 @@ for n, v in zip(hn, out[16:30]):
     print(f"{n:14s} {v / nw:10.0f} cyc/task")
 print(f"DP task cycles: max {out[14]} min {out[15]}  ({out[14]/1.965e3:.1f} / {out[15]/1.965e3:.1f} us);  helper: max {out[30]} min {out[31]} ({out[30]/1.965e3:.1f} / {out[31]/1.965e3:.1f} us)")
 print("mean task us by warp id (scheduler = id % 4):", " ".join(f"w{i}:{wout[i] / max(wout[16 + i], 1) / 1.965e3:.0f}" for i in range(14)))
+ct = sorted((cout[i] / 1.965e3, int(cout[160 + i]), i) for i in range(148))
+print("slowest CTAs (us, smid, cta):", [(round(a), b, c) for a, b, c in ct[-12:]])
+print("fastest CTAs (us, smid, cta):", [(round(a), b, c) for a, b, c in ct[:12]])
+import collections
+gp = collections.defaultdict(list)
+for a, b, c in ct: gp[b // 2 // 10].append(a)   # rough grouping by smid / 20
+print("mean of per-CTA max by smid//20:", {k: round(sum(v) / len(v), 1) for k, v in sorted(gp.items())})
