@@ -69,49 +69,22 @@ constexpr int BAND_WARPS = B3_PAIRS;   // (DP, helper) warp pairs per CTA
 inline int band_rec_words(int G) { return 6 * G + 1; }   // per lane: its 3G cells as (w0, w1) pairs + the slide word
 inline int band_smem_bytes_per_warp(int C, int G) { return (int)band3_smem_per_warp(C, G); }
 
-template <int G>
 cudaError_t band_set_attr(int bytes) {
-    cudaError_t e = cudaFuncSetAttribute(viterbi_band3_kernel<G, 66, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_kernel<G, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_kernel<G, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(viterbi_band3_kernel<66, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     return e;
 }
 constexpr int BAND_SMEM_MAX = 227 * 1024;   // dynamic shared memory one CTA may opt in to on sm_100
 inline int band_warps(int smem_per_warp) { return std::max(1, std::min(BAND_WARPS, BAND_SMEM_MAX / smem_per_warp)); }
-// exact: the items carry the caller's log-probs unchanged (no fused log-softmax), every decision is taken on the sums
-template <int G>
+// One launch for the three window classes.  exact: the items carry the caller's log-probs unchanged (no fused log-softmax),
+// every decision is taken on the sums.
 void band_launch(const Band3Args& ba, bool exact, int grid, cudaStream_t st) {
-    const int pairs = band_warps(ba.smem_per_warp);
-    const size_t smem = (size_t)pairs * ba.smem_per_warp;
-    if (exact) viterbi_band3_kernel<G, 0, true><<<grid, pairs * 64, smem, st>>>(ba);
-    else if (ba.C == 66) viterbi_band3_kernel<G, 66, false><<<grid, pairs * 64, smem, st>>>(ba);
-    else viterbi_band3_kernel<G, 0, false><<<grid, pairs * 64, smem, st>>>(ba);
-}
-
-// Internal fork/join streams: after the planner the three banded variants work on disjoint item lists, so they run side by
-// side (a kernel without work leaves its SMs at once); the caller's stream joins them before the exact kernel.  Created once per device, never destroyed; capture-safe (events only).
-struct Fork {
-    cudaStream_t s[2] = {nullptr, nullptr};
-    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
-    bool ok = false, tried = false;
-};
-Fork* fork_streams() {
-    static std::mutex mu;
-    static Fork cache[64];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    std::lock_guard<std::mutex> lk(mu);
-    Fork& f = cache[dev & 63];
-    if (!f.tried) {
-        f.tried = true;
-        bool ok = cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) == cudaSuccess;
-        for (int i = 0; i < 2 && ok; ++i)
-            ok = cudaStreamCreateWithFlags(&f.s[i], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&f.join[i], cudaEventDisableTiming) == cudaSuccess;
-        if (!ok) (void)cudaGetLastError();
-        f.ok = ok;
-    }
-    return f.ok ? &f : nullptr;
+    size_t smem = 0;
+    for (int v = 0; v < BAND_NV; ++v) smem = std::max(smem, (size_t)ba.cls[v].npairs * ba.cls[v].smem_per_warp);
+    if (exact) viterbi_band3_kernel<0, true><<<grid, BAND_WARPS * 64, smem, st>>>(ba);
+    else if (ba.C == 66) viterbi_band3_kernel<66, false><<<grid, BAND_WARPS * 64, smem, st>>>(ba);
+    else viterbi_band3_kernel<0, false><<<grid, BAND_WARPS * 64, smem, st>>>(ba);
 }
 
 int device_info(DeviceInfo& out) {
@@ -133,8 +106,7 @@ int device_info(DeviceInfo& out) {
         CUDA_TRY(cudaFuncSetAttribute(assort_confidence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)assort_smem(ASSORT_TS_MAX, ASSORT_SS_MAX)));
         const int band_smem_max = BAND_SMEM_MAX;
-        d.band_ok = band_set_attr<3>(band_smem_max) == cudaSuccess && band_set_attr<5>(band_smem_max) == cudaSuccess &&
-                    band_set_attr<8>(band_smem_max) == cudaSuccess;
+        d.band_ok = band_set_attr(band_smem_max) == cudaSuccess;
         if (!d.band_ok) (void)cudaGetLastError();   // do not leave a sticky error behind: the exact kernel still runs
         d.ok = true;
     }
@@ -362,37 +334,26 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         ba.retry_items = pa.items; ba.n_retry = counters;
         ba.frame_ph = frame_ph; ba.frame_idx = frame_idx; ba.dp_final = dp_final; ba.path_lp = path_lp;
         ba.guess_cls = (path_lp && !(p->reserved & BFA_FLAG_NO_SPEC)) ? (unsigned char*)(ws + L.off_gcls) : nullptr;
-        Fork* fk = (p->reserved & BFA_FLAG_ONE_STREAM) ? nullptr : fork_streams();
-        if (fk) {
-            CUDA_TRY(cudaEventRecord(fk->fork, st));
-            for (int i = 0; i < BAND_NV - 1; ++i) CUDA_TRY(cudaStreamWaitEvent(fk->s[i], fk->fork, 0));
+        for (int v = 0; v < BAND_NV; ++v) {
+            ba.cls[v].items = pa.fast_items[v]; ba.cls[v].n_items = pa.n_fast[v];
+            ba.cls[v].bp_scratch = (uint32_t*)(ws + L.off_bp_band[v]);
+            ba.cls[v].bp_slab_words = L.band_slab_words[v];
+            ba.cls[v].smem_per_warp = L.band_smem_per_warp[v];
+            ba.cls[v].npairs = band_warps(L.band_smem_per_warp[v]);
         }
-        // Launch order when forked: the wide-window variants first.  On the usual batch their lists are empty and they leave
-        // the SMs within microseconds, side by side, before the 24-group variant (which fills every SM) starts.
-        for (int vi = 0; vi < BAND_NV; ++vi) {
-            const int v = fk ? (vi + 1) % BAND_NV : vi;            // forked: 1, 2, 0
-            cudaStream_t sv = (fk && v > 0) ? fk->s[v - 1] : st;
-            ba.items = pa.fast_items[v]; ba.n_items = pa.n_fast[v];
-            ba.bp_scratch = (uint32_t*)(ws + L.off_bp_band[v]);
-            ba.bp_slab_words = L.band_slab_words[v]; ba.smem_per_warp = L.band_smem_per_warp[v];
-            cudaEvent_t e0 = nullptr, e1 = nullptr;
-            if (v == 0) {
-                std::lock_guard<std::mutex> lk(g_prof.mu);
-                if (g_prof.on) { e0 = g_prof.get(); e1 = g_prof.get(); }
-            }
-            if (e0) cudaEventRecord(e0, sv);
-            if (v == 0) band_launch<3>(ba, !boost, L.band_grid, sv);
-            else if (v == 1) band_launch<5>(ba, !boost, L.band_grid, sv);
-            else band_launch<8>(ba, !boost, L.band_grid, sv);
-            LAUNCH_CHECK();
-            if (e0) {
-                cudaEventRecord(e1, sv);
-                std::lock_guard<std::mutex> lk(g_prof.mu);
-                g_prof.pending.emplace_back(e0, e1);
-            }
-            if (fk && v > 0) CUDA_TRY(cudaEventRecord(fk->join[v - 1], sv));
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_prof.mu);
+            if (g_prof.on) { e0 = g_prof.get(); e1 = g_prof.get(); }
         }
-        if (fk) for (int i = 0; i < BAND_NV - 1; ++i) CUDA_TRY(cudaStreamWaitEvent(st, fk->join[i], 0));
+        if (e0) cudaEventRecord(e0, st);
+        band_launch(ba, !boost, L.band_grid, st);     // all three window classes in one launch
+        LAUNCH_CHECK();
+        if (e0) {
+            cudaEventRecord(e1, st);
+            std::lock_guard<std::mutex> lk(g_prof.mu);
+            g_prof.pending.emplace_back(e0, e1);
+        }
         // the exact kernel: what the planner gave it plus what the banded kernels sent back
         rc = launch_viterbi(va, max_items_i, L.max_L, d, st, false);
         if (rc) return rc;

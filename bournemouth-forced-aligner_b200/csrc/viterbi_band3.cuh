@@ -74,8 +74,6 @@ struct Band3Args {
     const float* logp;
     const int32_t* tgt;
     const uint32_t* tmask;     // [B][MAX_WORDS]
-    const Item* items;         // fast list
-    const int* n_items;
     Item* retry_items;         // generic list: items this kernel could not finish are appended
     int* n_retry;
     int32_t* frame_ph;
@@ -83,9 +81,14 @@ struct Band3Args {
     float* dp_final;
     float* path_lp;            // [total_frames] raw log-prob of the assigned class per frame (confidence input), or null
     unsigned char* guess_cls;  // [total_frames] class whose raw log-prob the fill left in path_lp (frame-wise best class), or null
-    uint32_t* bp_scratch;
-    long long bp_slab_words;
-    int smem_per_warp;         // bytes
+    struct Class {             // one per window class (24 / 40 / 64 groups)
+        const Item* items;
+        const int* n_items;
+        uint32_t* bp_scratch;  // decision-record slabs, one per resident pair
+        long long bp_slab_words;
+        int smem_per_warp;     // bytes of shared memory per (DP, helper) pair
+        int npairs;            // pairs per CTA that fit
+    } cls[3];
 };
 
 template <int G>
@@ -211,11 +214,11 @@ struct Band3Task {
     uint32_t bar0;
     const float* my_src;
     bool use_stats, warp_stats;
-    __device__ __forceinline__ Band3Task(const Band3Args& a, int first, int n_valid, unsigned char* smem_pair, int lane) {
+    __device__ __forceinline__ Band3Task(const Band3Args& a, const Item* items, int first, int n_valid, unsigned char* smem_pair, int lane) {
         seg = lane >> 3; l8 = lane & 7;
         C = CT ? CT : a.C;
         seg_on = seg < n_valid;
-        it = &a.items[first + (seg_on ? seg : 0)];
+        it = &items[first + (seg_on ? seg : 0)];
         T = seg_on ? it->T : 0;
         Tmax = T;
 #pragma unroll
@@ -240,10 +243,10 @@ struct Band3Task {
 // Helper warp: tables, bulk copies, row statistics.
 // ------------------------------------------------------------------------------------------------------------
 template <int G, int CT>
-__device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigned char* smem_pair, uint32_t& phase, bool not_first,
+__device__ void band3_helper(const Band3Args& a, const Item* items, int first, int n_valid, unsigned char* smem_pair, uint32_t& phase, bool not_first,
                              int lane, uint64_t pol) {
     constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-    const Band3Task<G, CT> k(a, first, n_valid, smem_pair, lane);
+    const Band3Task<G, CT> k(a, items, first, n_valid, smem_pair, lane);
     const int seg = k.seg, l8 = k.l8, C = k.C, T = k.T;
     const int blank = a.p.blank_id;
     const float boostv = a.p.boost_factor;
@@ -531,11 +534,11 @@ __device__ void band3_helper(const Band3Args& a, int first, int n_valid, unsigne
 // DP warp: frame loop, decision records, back-trace, outputs.
 // ------------------------------------------------------------------------------------------------------------
 template <int G, int CT, bool EXACT>
-__device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned char* smem_pair, uint32_t* slab, uint32_t& phase,
+__device__ void band3_dp(const Band3Args& a, const Item* items, int first, int n_valid, unsigned char* smem_pair, uint32_t* slab, uint32_t& phase,
                          int lane) {
     using S = Band3Shape<G>;
     PH_DECL;
-    const Band3Task<G, CT> k(a, first, n_valid, smem_pair, lane);
+    const Band3Task<G, CT> k(a, items, first, n_valid, smem_pair, lane);
     const int seg = k.seg, l8 = k.l8, C = k.C, T = k.T, Tmax = k.Tmax, n_chunks = k.n_chunks;
     const bool seg_on = k.seg_on;
     const Item& it = *k.it;
@@ -913,27 +916,31 @@ __device__ void band3_dp(const Band3Args& a, int first, int n_valid, unsigned ch
     PH_FLUSH;
 }
 
+// One window class of one launch: every CTA works through the tasks dealt to it, then moves on to the next class without
+// waiting for anybody else (the item lists are disjoint).
 template <int G, int CT, bool EXACT>
-__global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_kernel(Band3Args a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int n_items = *a.n_items;
-    if (n_items == 0) return;                 // nothing of this window class in the batch
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int npairs = blockDim.x >> 6;       // <= B3_PAIRS, as many as the shared memory of one SM holds
+__device__ void band3_run(const Band3Args& a, const Band3Args::Class& k, unsigned char* smem_raw, int warp, int lane) {
+    const int n_items = *k.n_items;
+    if (n_items == 0) return;                 // nothing of this window class in the batch (uniform over the CTA)
+    const int npairs = min((int)(blockDim.x >> 6), k.npairs);   // as many pairs as the shared memory of one SM holds
     // Roles.  A DP warp issues about 1.45x the instructions of a helper warp, and warp w issues on scheduler w % 4.  With 14
     // warps the schedulers hold 4, 4, 3, 3 of them; giving the two 4-warp schedulers one DP warp + three helpers each and
     // the 3-warp schedulers 2 + 1 and 3 + 0 keeps the busiest scheduler ~9 % lighter than any contiguous split.
     bool is_dp = warp < npairs;               // default: warps [0, npairs) run the DP, [npairs, 2 npairs) are their helpers
     int pair = is_dp ? warp : warp - npairs;
+    bool idle = warp >= 2 * npairs;
 #ifndef BFA_ROLES_CONTIG
     if (npairs == 7) {
         constexpr uint32_t DP_WARPS = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3) | (1u << 6) | (1u << 7) | (1u << 11);
         is_dp = (DP_WARPS >> warp) & 1u;
         pair = __popc((is_dp ? DP_WARPS : ~DP_WARPS) & ((1u << warp) - 1u));
+        idle = warp >= 14;
     }
 #endif
-    unsigned char* smem_pair = smem_raw + (size_t)pair * a.smem_per_warp;
-    if (is_dp && lane == 0) {
+    unsigned char* smem_pair = smem_raw + (size_t)pair * k.smem_per_warp;
+    __syncthreads();                          // the previous class is done with the shared memory
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // its generic-proxy writes are ordered before this class's bulk copies
+    if (!idle && is_dp && lane == 0) {
         // No zero fill: slots that are never loaded (rows past the end of an utterance, unused segments) may hold
         // anything, NaN included; whatever is computed from them is never looked at.
         const int C = CT ? CT : a.C;
@@ -946,18 +953,35 @@ __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_kernel(Band3Ar
     const int n_tasks = (n_items + B3_UPW - 1) / B3_UPW;
     // static deal: task j -> CTA j % grid, pair (j / grid) % npairs.  With one CTA per SM this spreads
     // ceil(n_tasks / SMs) tasks evenly over the SMs and over the four schedulers of each SM.
-    if (is_dp) {
-        uint32_t* slab = a.bp_scratch + (size_t)(blockIdx.x * npairs + pair) * a.bp_slab_words;
+    if (idle) {
+    } else if (is_dp) {
+        uint32_t* slab = k.bp_scratch + (size_t)(blockIdx.x * npairs + pair) * k.bp_slab_words;
         for (int j = blockIdx.x + gridDim.x * pair; j < n_tasks; j += gridDim.x * npairs)
-            band3_dp<G, CT, EXACT>(a, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, slab, phase, lane);
+            band3_dp<G, CT, EXACT>(a, k.items, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, slab, phase, lane);
     } else {
         const uint64_t pol = policy_evict_first();
         bool not_first = false;
         for (int j = blockIdx.x + gridDim.x * pair; j < n_tasks; j += gridDim.x * npairs) {
-            band3_helper<G, CT>(a, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, phase, not_first, lane, pol);
+            band3_helper<G, CT>(a, k.items, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, phase, not_first, lane, pol);
             not_first = true;
         }
     }
+    __syncthreads();                          // every pair of this CTA is done with this class
+    if (!idle && is_dp && lane == 0) {        // the barrier words are about to become ordinary shared memory again
+        const int C = CT ? CT : a.C;
+        const uint32_t b0 = smem_u32(smem_pair + band3_off_bars(C, G));
+        for (int i = 0; i < B3_NBARS; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(b0 + 8u * i) : "memory");
+    }
+}
+
+// The launch: all three window classes (24 / 40 / 64 groups per window), one after the other inside every CTA.
+template <int CT, bool EXACT>
+__global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_kernel(Band3Args a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    band3_run<3, CT, EXACT>(a, a.cls[0], smem_raw, warp, lane);
+    band3_run<5, CT, EXACT>(a, a.cls[1], smem_raw, warp, lane);
+    band3_run<8, CT, EXACT>(a, a.cls[2], smem_raw, warp, lane);
 }
 
 }  // namespace bfa

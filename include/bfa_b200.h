@@ -87,8 +87,6 @@ typedef struct BfaParams {
 #define BFA_FLAG_FILL_ONLY 16     /* MEASUREMENT ONLY: the banded kernel stops after the DP fill (rows streamed, log-sum-exp, forward
                                  * recursion, decision records written) and skips the back-trace: outputs are NOT produced.  bench.py
                                  * uses it to time the fill phase by itself; never set it in production. */
-#define BFA_FLAG_ONE_STREAM 32    /* keep every kernel on the caller's stream (by default the banded variants, which work on disjoint
-                                 * item lists, run on internal streams forked from / joined to it) */
 #define BFA_FLAG_NO_SPEC 8       /* the banded kernel fetches every confidence input during its back-trace instead of keeping the
                                  * frame-wise best class's value while the row is on chip (measurement / A-B switch) */
 

@@ -13,6 +13,6 @@ import csv
 rows=[r for r in csv.reader(open('gpurun_out/launches.csv')) if len(r)>10 and r[0].isdigit()]
 for r in rows[-8:]: print(r[4][:60], r[7], r[8], r[-1])
 PY
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:band3_kernel<.int.3, .int.66" -s 3 -c 1 -f -o gpurun_out/prof_band \
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:band3_kernel<.int.66" -s 3 -c 1 -f -o gpurun_out/prof_band \
    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_run.log 2>&1
 ls -la gpurun_out/*.ncu-rep

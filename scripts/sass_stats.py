@@ -2,7 +2,7 @@
 (the unrolled 8-frame body of the banded Viterbi kernel is the longest one)."""
 import re, subprocess, sys, collections
 lib = "bournemouth-forced-aligner_b200/lib/libbfa_b200.so"
-pat = sys.argv[1] if len(sys.argv) > 1 else "viterbi_band3_kernelILi3ELi66"
+pat = sys.argv[1] if len(sys.argv) > 1 else "viterbi_band3_kernelILi66ELb0"
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", out)
 body = [f for f in funcs if f.startswith("_Z") and pat in f.split("\n")[0]]
