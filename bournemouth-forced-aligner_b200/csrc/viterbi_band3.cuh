@@ -64,7 +64,7 @@ constexpr int B3_KK = 72;          // floats per utterance in the class-weight t
 constexpr int B3_STP = 9;          // float2 pitch of the per-utterance (lnS, eb) array (bank spreading)
 constexpr int B3_SLOT_PAD = 4;      // floats of slack per staged (utterance, chunk) slot: room for an item's lead-in (Item::lead)
 constexpr int B3_NMAX = 128;       // phonemes per item on this path (byte-sized class table in shared memory)
-constexpr int B3_MARGIN = 2;       // states of safety margin of the band-legality check
+constexpr int B3_MARGIN = 3;       // states of safety margin of the band-legality check (a frame spent in m may be reported as b3: 2 states)
 constexpr int B3_NREC = 4;         // decision records of 32-frame blocks in flight from the slab during the back-trace
 constexpr int B3_GRING = 4;        // 32-frame blocks of confidence gathers kept in flight during the back-trace
 
@@ -672,7 +672,11 @@ __device__ void band3_dp(const Band3Args& a, const Item* items, int first, int n
             for (int g = 0; g < G; ++g) {
                 cells[3 * g + 0] = make_uint2(w[4 * g] << sh, w[4 * g + 1] << sh);
                 cells[3 * g + 1] = make_uint2(w[4 * g + 2] << sh, 0u);
-                cells[3 * g + 2] = make_uint2(w[4 * g + 3] << sh, 0u);
+                // b3 advanced from m at frame t exactly when m came from p at t-1 (reduced form), and m and b3 produce the same
+                // output (blank, -1): attribute frame t-1 to b3 as well and hop straight to p -- one walk iteration per
+                // phoneme less.  (First frame of a block: the ordinary one-cell hop, the bit cannot move into the previous record.)
+                const uint32_t w3 = w[4 * g + 3] << sh;
+                cells[3 * g + 2] = EXACT ? make_uint2(w3, 0u) : make_uint2(w3 & 0x80000000u, w3 << 1);
             }
             rec[B3_UPW * S::CELLS * 2 + lane] = slide_word;
         };
