@@ -308,7 +308,7 @@ def main():
     if not a.no_e2e:
         lp_h = torch.empty((B, T, Cc), dtype=torch.float32, pin_memory=True); lp_h.copy_(lp)
         tgt_h = torch.empty(B * N, dtype=torch.int32, pin_memory=True); tgt_h.copy_(tgt32)
-        ms_stamps = 2 * N + 8
+        ms_stamps = N + 8
         out = {k: torch.empty(s, dtype=d, pin_memory=True).numpy() for k, s, d in (
             ("frame_ph", (B * T,), torch.int32), ("frame_idx", (B * T,), torch.int32), ("dp_final", (B,), torch.float32),
             ("status", (B,), torch.int32), ("stamps", (B, ms_stamps, 4), torch.int32), ("n_stamps", (B,), torch.int32),

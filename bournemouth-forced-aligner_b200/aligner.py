@@ -103,7 +103,10 @@ class BatchPlan:
         max_T = int(self.T_np.max()) if B else 0
         max_N = int(N_np.max()) if B else 0
         if max_stamps is None:
-            max_stamps = (2 * max_N + 8) if params.ignore_noise else max(max_T, 1)
+            # with ignore_noise every target index owns one run of frames on a monotone path: N stamps.  Degenerate paths
+            # (scores below the -1000 sentinel) can produce more; the library flags that (ST_STAMP_OVERFLOW) and the
+            # reference-API entry points below then repeat the call with the pitch nothing can exceed (max_T).
+            max_stamps = (max_N + 8) if params.ignore_noise else max(max_T, 1)
         self.max_stamps = int(max_stamps)
         self.shape = BfaShape(B, C_, max_T, max_N, self.total, self.max_stamps, 0)
         meta = torch.from_numpy(np.concatenate([frame_off_np, tgt_off_np])).to(dev)
@@ -335,8 +338,13 @@ class AlignmentUtils:
         tgt = seqs[mask].to(torch.int32).contiguous()
         row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T_max * C_)
         r = self.viterbi_decoder.align_batch(lp, row_off, T, C_, tgt, N, params=params, want_stamps=True, want_conf=want_conf)
+        st = r.status[:B].cpu().numpy()
+        if (st & _cabi.ST_STAMP_OVERFLOW).any():   # more runs than the default stamp pitch (degenerate paths): use the safe pitch
+            r = self.viterbi_decoder.align_batch(lp, row_off, T, C_, tgt, N, params=params, want_stamps=True, want_conf=want_conf,
+                                                 max_stamps=max(T_max, 1))
+            st = r.status[:B].cpu().numpy()
         self.last_result = r
-        self.viterbi_decoder._raise_if_too_short(r.status[:B].cpu().numpy(), T, N)
+        self.viterbi_decoder._raise_if_too_short(st, T, N)
         return r
 
     def decode_alignments(self, log_probs, true_seqs=None, pred_lens=None, true_seqs_lens=None, forced_alignment=True,
@@ -408,7 +416,7 @@ def align_host(params: BfaParams, log_probs: np.ndarray, row_off: np.ndarray, T:
     N = np.diff(tgt_off)
     max_T, max_N = (int(T.max()), int(N.max())) if B else (0, 0)
     if max_stamps is None:
-        max_stamps = (2 * max_N + 8) if params.ignore_noise else max(max_T, 1)
+        max_stamps = (max_N + 8) if params.ignore_noise else max(max_T, 1)   # see BatchPlan; check status & ST_STAMP_OVERFLOW
     shape = BfaShape(B, C_, max_T, max_N, total, int(max_stamps), 0)
     o = out if out is not None else {}
 

@@ -150,7 +150,7 @@ def _compare_with_oracle(bfa, orc, dev, lp, tgt, T, N, Cc, blank, **kw):
     Nd = torch.tensor(N, device=dev)
     mask = torch.arange(tgt.shape[1], device=dev)[None, :] < Nd[:, None]
     r = au.viterbi_decoder.align_batch(lp_d, torch.arange(B, dtype=torch.int64, device=dev) * Tm * Cc, T, Cc,
-                                       seqs[mask].to(torch.int32).contiguous(), N, params=dparams)
+                                       seqs[mask].to(torch.int32).contiguous(), N, params=dparams, max_stamps=2 * int(max(N)) + 8)
     o = _oracle_batch(orc, p, lp.numpy(), tgt.numpy(), T, N, Cc)
     st = r.status[:B].cpu().numpy()
     np.testing.assert_array_equal(st & 15, o["status"] & 15)
@@ -406,3 +406,29 @@ def test_segmented_packed_misaligned_vs_oracle(bfa, orc, dev):
         utts.append((lp[0], tgt[0]))
     counts = _packed_vs_oracle(bfa, orc, dev, utts, 66, gap_floats=[2, 0, 6, 2] * 3, base_shift=2)
     assert sum(counts[1:]) > 12
+
+
+def test_stamp_overflow_is_flagged_and_the_reference_api_recovers(bfa, orc, dev):
+    """Degenerate posteriors produce more runs than targets: the low-level call flags ST_STAMP_OVERFLOW at the default stamp
+    pitch (N + 8); decode_alignments repeats the call with the safe pitch and returns what the oracle returns."""
+    from bfa_b200 import _cabi
+    g = torch.Generator().manual_seed(12)
+    B, T, N, Cc = 8, 600, 40, 66
+    lp = torch.log_softmax(torch.randn(B, T, Cc, generator=g) * 3.0, -1)
+    tgt = torch.randint(1, Cc - 1, (B, N), generator=g)
+    au = bfa.AlignmentUtils(Cc - 1, 0, silence_anchors=0)
+    dec = au.viterbi_decoder
+    p = dec._params(True, True, False)
+    r = dec.align_batch(lp.to(dev), torch.arange(B, dtype=torch.int64, device=dev) * T * Cc, [T] * B, Cc,
+                        tgt.to(torch.int32).reshape(-1).to(dev), [N] * B, params=p)
+    o = _oracle_batch(orc, orc.params(Cc - 1, 0, 0), lp.numpy(), tgt.numpy(), [T] * B, [N] * B, Cc)
+    big = o["n_stamps"] > r.max_stamps
+    st = r.status[:B].cpu().numpy()
+    np.testing.assert_array_equal((st & _cabi.ST_STAMP_OVERFLOW) != 0, big)
+    got = au.decode_alignments(lp.to(dev), true_seqs=tgt, pred_lens=torch.full((B,), T), true_seqs_lens=torch.full((B,), N))
+    o2 = orc.align_batch(orc.params(Cc - 1, 0, 0), lp.numpy(), np.arange(B, dtype=np.int64) * T * Cc, np.full(B, T, np.int32), Cc,
+                         tgt.numpy().astype(np.int32).reshape(-1), np.arange(B + 1, dtype=np.int64) * N, max_stamps=T, n_threads=4)
+    for b in range(B):
+        n = int(o2["n_stamps"][b])
+        want = [tuple(int(o2["stamps"][b][f][i]) for f in ("phoneme", "start", "end", "target_idx")) for i in range(n)]
+        assert got[b] == want
