@@ -45,9 +45,19 @@
 //      * the helper warp owns the data movement and the transcendental work: it issues the bulk copies, and for every
 //        staged chunk each of its lanes reduces ONE row (lane = (utterance, row): 66 exps, no shuffles, no idle lanes;
 //        per-utterance class weights come from a small shared table) to (log-sum-exp, blank emission);
-//      * the DP warp runs the frame loop (registers only + one shared load per group per frame), flushes the decision
-//        words and, when the fill is done, walks the path back.
+//        while a row is on chip it also keeps the raw log-prob of the frame-wise best class, the confidence pass's input
+//        wherever the path agrees with that guess (path_lp / guess_cls);
+//      * the DP warp runs the frame loop (registers only + one shared load per group per frame) and flushes one decision
+//        record per 32 frames, stored as the cell image the back-trace walks.
 //    They meet on three mbarrier rings: full (TMA -> helper), ready (helper -> DP), free (DP -> helper).
+//
+// 4. Back-trace, again split over the pair.  Records come back by bulk copy straight into place (4 deep); the DP warp walks one
+//    RUN of the path per iteration and hands the visited cells of a 32-frame block to the helper warp (kready / kfree
+//    barriers, two buffers), which writes frame_phonemes / frame_phonemes_idx, checks that the path kept B3_MARGIN states
+//    away from the band edges and fetches the confidence inputs the fill guessed wrong.
+//
+// 5. One launch serves the three window classes (G = 3, 5, 8 groups per lane = 24, 40, 64 groups per window): every CTA works
+//    through the classes in turn (band3_run), re-initialising its barriers in between.
 #pragma once
 #include <type_traits>
 
@@ -545,7 +555,6 @@ __device__ void band3_dp(const Band3Args& a, const Item* items, int first, int n
     const float NEG = a.p.neg_inf;
     const int blank = a.p.blank_id;
     const uint32_t bar0 = k.bar0;
-    uint2* bt2 = reinterpret_cast<uint2*>(smem_pair);                                       // [UPW][CELLS], aliases the stage ring
     const int N = it.n, L = it.L, band = it.band, flags = it.flags;
     const bool use_band = band > 0 && T > 1 && L > 1;                          // :586
     const float pace_f = use_band ? (float)((double)(L - 1) / (double)(T - 1)) : 0.0f;   // :587
