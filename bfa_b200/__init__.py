@@ -9,5 +9,7 @@ from ._cabi import BfaError, BfaParams, BfaShape, default_params  # noqa: E402,F
 from .aligner import (AlignmentUtils, BatchResult, ViterbiDecoder, _calculate_confidences,  # noqa: E402,F401
                       align_host)
 
-__all__ = ["AlignmentUtils", "ViterbiDecoder", "_calculate_confidences", "align_host", "BatchResult",
+from .postprocess import convert_to_ms, stamps_to_ms  # noqa: E402,F401
+
+__all__ = ["AlignmentUtils", "ViterbiDecoder", "_calculate_confidences", "align_host", "BatchResult", "convert_to_ms", "stamps_to_ms",
            "BfaError", "BfaParams", "BfaShape", "default_params"]

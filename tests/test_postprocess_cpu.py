@@ -1,0 +1,28 @@
+"""CPU: the host epilogue (frames -> milliseconds) against fixtures from the unmodified reference's utils.convert_to_ms."""
+from pathlib import Path
+
+import numpy as np
+
+
+def test_convert_to_ms_bit_identical_to_reference():
+    from bfa_b200.postprocess import convert_to_ms, stamps_to_ms
+    g = np.load(Path(__file__).parent / "golden" / "post.npz")
+    cases = sorted({k.split("/")[0] for k in g.files})
+    assert len(cases) == 12
+    for c in cases:
+        T, off, wav_len, sr, tl = g[f"{c}/args"]
+        raw = g[f"{c}/stamps"]
+        stamps = [tuple([int(r[0]), int(r[1]), int(r[2]), int(r[3]), bool(r[4]), float(r[5])][:int(tl)]) for r in raw]
+        got = convert_to_ms(stamps, int(T), float(off), int(wav_len), int(sr))
+        want = g[f"{c}/full"]
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert len(a) == 8
+            assert [float(x) for x in a] == list(b)          # exact, including the defaults of short tuples
+        if len(stamps):                                      # batch form on the BfaStamp layout
+            arr = np.zeros((1, len(stamps) + 2, 4), np.int32)
+            arr[0, :len(stamps), 0] = raw[:, 0]; arr[0, :len(stamps), 1] = raw[:, 1]; arr[0, :len(stamps), 2] = raw[:, 2]
+            s_ms, e_ms = stamps_to_ms(arr, np.array([len(stamps)]), [T], [off], [wav_len], sr)
+            np.testing.assert_array_equal(s_ms[0, :len(stamps)], g[f"{c}/ms"][:, 0])
+            np.testing.assert_array_equal(e_ms[0, :len(stamps)], g[f"{c}/ms"][:, 1])
+            assert (s_ms[0, len(stamps):] == 0).all()
