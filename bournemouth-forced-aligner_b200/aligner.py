@@ -90,6 +90,22 @@ class BatchResult:
         return out
 
 
+def exact_items_hint(T, N, params) -> int:
+    """How many utterances will (probably) need the exact kernel instead of the banded stride-4 one: the stride rule picks
+    3/2/1 (forced_alignment.py:153-157, :963-968), more than 128 phonemes, or a band wider than the 64-group window.
+    Only a scheduling hint (BfaShape.reserved): with silence-anchored segmentation the planner may decide otherwise."""
+    T = np.asarray(T, np.int64); N = np.asarray(N, np.int64)
+    if T.size == 0:
+        return 0
+    L = 4 * N + 1
+    dense = (L > 0.9 * T) if params.mode == _cabi.MODE_SIMPLE else (L > T)
+    band = np.where(L > 60, np.maximum(L // 4, 20), 0)
+    adv = (8 * (L - 1) + np.maximum(T - 2, 0)) // np.maximum(T - 1, 1)
+    need = np.where(band > 0, np.minimum((2 * band + adv + 6) // 4 + 1, N + 1), N + 1)
+    exact = (N > 0) & (T >= N) & (dense | (N > 128) | (need > 64))
+    return int(exact.sum())
+
+
 class BatchPlan:
     """Device-resident shape metadata of one ragged batch (frame / target offsets, lengths, BfaShape)."""
 
@@ -108,7 +124,7 @@ class BatchPlan:
             # reference-API entry points below then repeat the call with the pitch nothing can exceed (max_T).
             max_stamps = (max_N + 8) if params.ignore_noise else max(max_T, 1)
         self.max_stamps = int(max_stamps)
-        self.shape = BfaShape(B, C_, max_T, max_N, self.total, self.max_stamps, 0)
+        self.shape = BfaShape(B, C_, max_T, max_N, self.total, self.max_stamps, exact_items_hint(self.T_np, N_np, params))
         meta = torch.from_numpy(np.concatenate([frame_off_np, tgt_off_np])).to(dev)
         self.frame_off, self.tgt_off = meta[: B + 1], meta[B + 1:]
         self.T_dev = torch.from_numpy(self.T_np).to(dev)

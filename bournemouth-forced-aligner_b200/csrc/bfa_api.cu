@@ -87,6 +87,31 @@ void band_launch(const Band3Args& ba, bool exact, int grid, cudaStream_t st) {
     else viterbi_band3_kernel<0, false><<<grid, BAND_WARPS * 64, smem, st>>>(ba);
 }
 
+// One internal side stream per device: when the caller expects items for the exact kernel (BfaShape.reserved), its first pass
+// runs there, next to the banded kernel, on SMs the banded kernel leaves free.  Created once, never destroyed; events only,
+// so the fork and the join can be captured into a CUDA graph.
+struct Fork {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok = false, tried = false;
+};
+Fork* fork_stream() {
+    static std::mutex mu;
+    static Fork cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    Fork& f = cache[dev & 63];
+    if (!f.tried) {
+        f.tried = true;
+        f.ok = cudaStreamCreateWithFlags(&f.s, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) == cudaSuccess;
+        if (!f.ok) (void)cudaGetLastError();
+    }
+    return f.ok ? &f : nullptr;
+}
+
 int device_info(DeviceInfo& out) {
     static std::mutex mu;
     static DeviceInfo cache[64];
@@ -182,9 +207,10 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
 
 // max_L: upper bound of the path length of any item; the long-path kernel is only launched when
 // an item can need it.  Both classes use the same per-warp slabs (kernels are stream-ordered).
-int launch_viterbi(VitArgs& va, int max_items, int max_L, const DeviceInfo& d, cudaStream_t st, bool profile = true) {
+int launch_viterbi(VitArgs& va, int max_items, int max_L, const DeviceInfo& d, cudaStream_t st, bool profile = true, int max_ctas = 1 << 30) {
     int want = (max_items + VG_WARPS - 1) / VG_WARPS;
     if (want < 1) want = 1;
+    if (want > max_ctas) want = max_ctas;
     int ctas = want < d.sms * d.vg_ctas_per_sm ? want : d.sms * d.vg_ctas_per_sm;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     {
@@ -324,7 +350,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     VitArgs va;
     va.p = *p; va.C = C; va.logp = logp; va.tmask = tmask; va.tgt = tgt;
     va.path = nullptr; va.true_idx = nullptr; va.anchors = pa.anchors; va.items = pa.items;
-    va.n_items = counters; va.work_counter = counters + 1;
+    va.n_items = counters; va.work_counter = counters + 1; va.first = nullptr;
     va.frame_ph = frame_ph; va.frame_idx = frame_idx; va.dp_final = dp_final; va.status = status; va.final_state = nullptr;
     va.path_lp = path_lp;
     va.bp_scratch = (uint32_t*)(ws + L.off_bp); va.bp_slab_words = L.slab_words;
@@ -341,20 +367,39 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
             ba.cls[v].smem_per_warp = L.band_smem_per_warp[v];
             ba.cls[v].npairs = band_warps(L.band_smem_per_warp[v]);
         }
+        // The caller expects `hint` items for the exact kernel (utterances too dense for stride 4, ...): its first pass, over the
+        // planner's list, runs on a side stream on a few SMs of its own while the banded kernel takes the rest; what the banded
+        // kernel sends back is done afterwards.  One CTA of the exact kernel (8 items at a time) per reserved SM.
+        const int hint = shape->reserved > 0 ? shape->reserved : 0;
+        Fork* fk = hint > 0 ? fork_stream() : nullptr;
+        int band_grid = L.band_grid;
+        if (fk) {
+            const int reserve = std::max(1, std::min(d.sms / 4, (hint + VG_WARPS - 1) / VG_WARPS));
+            band_grid = d.sms - reserve;
+            CUDA_TRY(cudaMemcpyAsync(counters + 10, counters, sizeof(int), cudaMemcpyDeviceToDevice, st));   // the planner's count
+            CUDA_TRY(cudaEventRecord(fk->fork, st));
+            CUDA_TRY(cudaStreamWaitEvent(fk->s, fk->fork, 0));
+            va.n_items = counters + 10;
+            rc = launch_viterbi(va, max_items_i, L.max_L, d, fk->s, false, reserve);
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(fk->join, fk->s));
+            va.n_items = counters; va.first = counters + 10; va.work_counter = counters + 11;   // second pass: the retries
+        }
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         {
             std::lock_guard<std::mutex> lk(g_prof.mu);
             if (g_prof.on) { e0 = g_prof.get(); e1 = g_prof.get(); }
         }
         if (e0) cudaEventRecord(e0, st);
-        band_launch(ba, !boost, L.band_grid, st);     // all three window classes in one launch
+        band_launch(ba, !boost, band_grid, st);       // all three window classes in one launch
         LAUNCH_CHECK();
         if (e0) {
             cudaEventRecord(e1, st);
             std::lock_guard<std::mutex> lk(g_prof.mu);
             g_prof.pending.emplace_back(e0, e1);
         }
-        // the exact kernel: what the planner gave it plus what the banded kernels sent back
+        if (fk) CUDA_TRY(cudaStreamWaitEvent(st, fk->join, 0));
+        // the exact kernel: what the planner gave it (unless that ran on the side stream) plus what the banded kernel sent back
         rc = launch_viterbi(va, max_items_i, L.max_L, d, st, false);
         if (rc) return rc;
     } else {
@@ -420,7 +465,7 @@ int bfa_viterbi_paths(const BfaParams* p, int32_t n_items, int32_t C, int32_t ma
     VitArgs va;
     va.p = *p; va.C = C; va.logp = logp; va.tmask = nullptr; va.tgt = nullptr;
     va.path = path; va.true_idx = true_idx; va.anchors = nullptr; va.items = items;
-    va.n_items = counters; va.work_counter = counters + 1;
+    va.n_items = counters; va.work_counter = counters + 1; va.first = nullptr;
     va.frame_ph = frame_ph; va.frame_idx = frame_idx; va.dp_final = dp_final; va.status = nullptr; va.final_state = final_state;
     va.path_lp = nullptr;
     va.bp_scratch = bp; va.bp_slab_words = (long long)(max_T + 2) * 32 * (max_L > 512 ? 2 : 1);

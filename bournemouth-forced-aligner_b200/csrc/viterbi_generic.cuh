@@ -32,6 +32,7 @@ struct VitArgs {
     const Item* items;
     const int* n_items;         // device scalar
     int* work_counter;          // device scalar, zeroed before launch
+    const int* first;           // device scalar: index of the first item of this launch (null: 0)
     int32_t* frame_ph;
     int32_t* frame_idx;
     float* path_lp;             // [total_frames] raw log-prob of the assigned class per frame, or null
@@ -382,8 +383,9 @@ template <int KCLASS>
 __global__ void __launch_bounds__(VG_WARPS * 32, KCLASS == 0 ? 2 : 1) viterbi_generic_kernel(VitArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = *a.n_items;
-    if (n_items == 0) return;     // the banded kernel finished everything
+    const int first = a.first ? *a.first : 0;
+    const int n_items = *a.n_items - first;
+    if (n_items <= 0) return;     // nothing (left) for the exact kernel
     WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
     if (lane == 0) {
         for (int i = 0; i < NSTAGE; ++i) mbar_init(smem_u32(&sm.bar[i]), 1);
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(VG_WARPS * 32, KCLASS == 0 ? 2 : 1) viterbi_ge
         if (lane == 0) i = atomicAdd(a.work_counter + KCLASS, 1);
         i = __shfl_sync(FULL, i, 0);
         if (i >= n_items) break;
-        const Item& it = a.items[i];
+        const Item& it = a.items[first + i];
         const int J = (it.L + 31) / 32;
         if (KCLASS == 0) {
             if (J > 8) continue;

@@ -107,7 +107,9 @@ typedef struct BfaShape {
     int32_t max_N;        /* max target length of any utterance */
     int64_t total_frames; /* sum of T_u */
     int32_t max_stamps;   /* row pitch of stamps/conf (>= max_N, or >= max_T if !ignore_noise) */
-    int32_t reserved;
+    int32_t reserved;     /* hint, 0 = none: how many utterances the caller expects to need the exact kernel (too dense for the
+                             stride-4 path, more than 128 phonemes, ...).  When > 0 the exact kernel's first pass runs next to
+                             the banded kernel on a few SMs of its own.  Results never depend on it. */
 } BfaShape;
 
 int bfa_version(void);
