@@ -91,8 +91,8 @@ void band_launch(const Band3Args& ba, bool exact, int grid, cudaStream_t st) {
 // runs there, next to the banded kernel, on SMs the banded kernel leaves free.  Created once, never destroyed; events only,
 // so the fork and the join can be captured into a CUDA graph.
 struct Fork {
-    cudaStream_t s = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaStream_t s = nullptr, s2 = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr;
     bool ok = false, tried = false;
 };
 Fork* fork_stream() {
@@ -105,6 +105,8 @@ Fork* fork_stream() {
     if (!f.tried) {
         f.tried = true;
         f.ok = cudaStreamCreateWithFlags(&f.s, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaStreamCreateWithFlags(&f.s2, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&f.join2, cudaEventDisableTiming) == cudaSuccess &&
                cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) == cudaSuccess &&
                cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) == cudaSuccess;
         if (!f.ok) (void)cudaGetLastError();
@@ -207,7 +209,8 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
 
 // max_L: upper bound of the path length of any item; the long-path kernel is only launched when
 // an item can need it.  Both classes use the same per-warp slabs (kernels are stream-ordered).
-int launch_viterbi(VitArgs& va, int max_items, int max_L, const DeviceInfo& d, cudaStream_t st, bool profile = true, int max_ctas = 1 << 30) {
+int launch_viterbi(VitArgs& va, int max_items, int max_L, const DeviceInfo& d, cudaStream_t st, bool profile = true, int max_ctas = 1 << 30,
+                   cudaStream_t st_long = nullptr) {   // st_long: the long-path class runs there, side by side with the short-path class
     int want = (max_items + VG_WARPS - 1) / VG_WARPS;
     if (want < 1) want = 1;
     if (want > max_ctas) want = max_ctas;
@@ -226,8 +229,11 @@ int launch_viterbi(VitArgs& va, int max_items, int max_L, const DeviceInfo& d, c
         g_prof.pending.emplace_back(e0, e1);
     }
     if (max_L > 256) {
+        const int ctas0 = ctas;
         ctas = want < d.sms * d.vg_ctas_per_sm_big ? want : d.sms * d.vg_ctas_per_sm_big;
-        viterbi_generic_kernel<1><<<ctas, VG_WARPS * 32, sizeof(WarpSmem) * VG_WARPS, st>>>(va);
+        VitArgs vb = va;
+        if (st_long) vb.warp_base = va.warp_base + ctas0 * VG_WARPS;   // its own slabs
+        viterbi_generic_kernel<1><<<ctas, VG_WARPS * 32, sizeof(WarpSmem) * VG_WARPS, st_long ? st_long : st>>>(vb);
         LAUNCH_CHECK();
     }
     return BFA_OK;
@@ -350,7 +356,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     VitArgs va;
     va.p = *p; va.C = C; va.logp = logp; va.tmask = tmask; va.tgt = tgt;
     va.path = nullptr; va.true_idx = nullptr; va.anchors = pa.anchors; va.items = pa.items;
-    va.n_items = counters; va.work_counter = counters + 1; va.first = nullptr;
+    va.n_items = counters; va.work_counter = counters + 1; va.first = nullptr; va.warp_base = 0;
     va.frame_ph = frame_ph; va.frame_idx = frame_idx; va.dp_final = dp_final; va.status = status; va.final_state = nullptr;
     va.path_lp = path_lp;
     va.bp_scratch = (uint32_t*)(ws + L.off_bp); va.bp_slab_words = L.slab_words;
@@ -374,15 +380,18 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         Fork* fk = hint > 0 ? fork_stream() : nullptr;
         int band_grid = L.band_grid;
         if (fk) {
-            const int reserve = std::max(1, std::min(d.sms / 4, (hint + VG_WARPS - 1) / VG_WARPS));
-            band_grid = d.sms - reserve;
+            const bool two = L.max_L > 256;      // short-path and long-path classes of the exact kernel side by side
+            const int reserve = std::max(1, std::min(d.sms / (two ? 8 : 4), (hint + VG_WARPS - 1) / VG_WARPS));
+            band_grid = d.sms - (two ? 2 : 1) * reserve;
             CUDA_TRY(cudaMemcpyAsync(counters + 10, counters, sizeof(int), cudaMemcpyDeviceToDevice, st));   // the planner's count
             CUDA_TRY(cudaEventRecord(fk->fork, st));
             CUDA_TRY(cudaStreamWaitEvent(fk->s, fk->fork, 0));
+            if (two) CUDA_TRY(cudaStreamWaitEvent(fk->s2, fk->fork, 0));
             va.n_items = counters + 10;
-            rc = launch_viterbi(va, max_items_i, L.max_L, d, fk->s, false, reserve);
+            rc = launch_viterbi(va, max_items_i, L.max_L, d, fk->s, false, reserve, two ? fk->s2 : nullptr);
             if (rc) return rc;
             CUDA_TRY(cudaEventRecord(fk->join, fk->s));
+            if (two) CUDA_TRY(cudaEventRecord(fk->join2, fk->s2));
             va.n_items = counters; va.first = counters + 10; va.work_counter = counters + 11;   // second pass: the retries
         }
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -398,7 +407,10 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
             std::lock_guard<std::mutex> lk(g_prof.mu);
             g_prof.pending.emplace_back(e0, e1);
         }
-        if (fk) CUDA_TRY(cudaStreamWaitEvent(st, fk->join, 0));
+        if (fk) {
+            CUDA_TRY(cudaStreamWaitEvent(st, fk->join, 0));
+            if (L.max_L > 256) CUDA_TRY(cudaStreamWaitEvent(st, fk->join2, 0));
+        }
         // the exact kernel: what the planner gave it (unless that ran on the side stream) plus what the banded kernel sent back
         rc = launch_viterbi(va, max_items_i, L.max_L, d, st, false);
         if (rc) return rc;
@@ -465,7 +477,7 @@ int bfa_viterbi_paths(const BfaParams* p, int32_t n_items, int32_t C, int32_t ma
     VitArgs va;
     va.p = *p; va.C = C; va.logp = logp; va.tmask = nullptr; va.tgt = nullptr;
     va.path = path; va.true_idx = true_idx; va.anchors = nullptr; va.items = items;
-    va.n_items = counters; va.work_counter = counters + 1; va.first = nullptr;
+    va.n_items = counters; va.work_counter = counters + 1; va.first = nullptr; va.warp_base = 0;
     va.frame_ph = frame_ph; va.frame_idx = frame_idx; va.dp_final = dp_final; va.status = nullptr; va.final_state = final_state;
     va.path_lp = nullptr;
     va.bp_scratch = bp; va.bp_slab_words = (long long)(max_T + 2) * 32 * (max_L > 512 ? 2 : 1);

@@ -964,17 +964,23 @@ __device__ void band3_run(const Band3Args& a, const Band3Args::Class& k, unsigne
     __syncthreads();
     uint32_t phase = 0;
     const int n_tasks = (n_items + B3_UPW - 1) / B3_UPW;
-    // static deal: task j -> CTA j % grid, pair (j / grid) % npairs.  With one CTA per SM this spreads
-    // ceil(n_tasks / SMs) tasks evenly over the SMs and over the four schedulers of each SM.
+    // static deal: slot q -> CTA q % grid, pair (q / grid) % npairs.  With one CTA per SM this spreads ceil(n_tasks / SMs)
+    // tasks evenly over the SMs and over the four schedulers of each SM.  The widest window class hands its list out front to
+    // back, the other two back to front: when the caller orders the utterances by length (a length-bucketing loader), the pair
+    // that gets the longest task of one class gets the shortest of the others.
+    constexpr bool REV = G != 8;
     if (idle) {
     } else if (is_dp) {
         uint32_t* slab = k.bp_scratch + (size_t)(blockIdx.x * npairs + pair) * k.bp_slab_words;
-        for (int j = blockIdx.x + gridDim.x * pair; j < n_tasks; j += gridDim.x * npairs)
+        for (int q = blockIdx.x + gridDim.x * pair; q < n_tasks; q += gridDim.x * npairs) {
+            const int j = REV ? n_tasks - 1 - q : q;
             band3_dp<G, CT, EXACT>(a, k.items, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, slab, phase, lane);
+        }
     } else {
         const uint64_t pol = policy_evict_first();
         bool not_first = false;
-        for (int j = blockIdx.x + gridDim.x * pair; j < n_tasks; j += gridDim.x * npairs) {
+        for (int q = blockIdx.x + gridDim.x * pair; q < n_tasks; q += gridDim.x * npairs) {
+            const int j = REV ? n_tasks - 1 - q : q;
             band3_helper<G, CT>(a, k.items, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, phase, not_first, lane, pol);
             not_first = true;
         }

@@ -33,6 +33,7 @@ struct VitArgs {
     const int* n_items;         // device scalar
     int* work_counter;          // device scalar, zeroed before launch
     const int* first;           // device scalar: index of the first item of this launch (null: 0)
+    int warp_base;              // first slab of this launch (launches that run side by side own disjoint slab ranges)
     int32_t* frame_ph;
     int32_t* frame_idx;
     float* path_lp;             // [total_frames] raw log-prob of the assigned class per frame, or null
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(VG_WARPS * 32, KCLASS == 0 ? 2 : 1) viterbi_ge
     const uint64_t pol = policy_evict_first();
     Stream st;
     st.phase = 0;
-    const int gwarp = blockIdx.x * VG_WARPS + warp;
+    const int gwarp = a.warp_base + blockIdx.x * VG_WARPS + warp;
     uint32_t* bp = a.bp_scratch + (size_t)gwarp * a.bp_slab_words;
     for (;;) {
         int i = 0;

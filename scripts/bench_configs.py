@@ -84,6 +84,8 @@ del lp
 B = int(os.environ.get("RAGGED_B", "8192"))
 t0 = time.time()
 utts = synth.ragged_batch(B, C=Cc, seed=23, device=dev)
+if os.environ.get("RAGGED_SORT", "1") == "1":      # what a length-bucketing loader does: the four utterances of a task are alike
+    utts.sort(key=lambda u: -int(u[0].shape[0]))
 Ts = [int(l.shape[0]) for l, _ in utts]; Ns = [int(t.shape[0]) for _, t in utts]
 # rows packed back to back; every utterance starts on a 16-byte boundary (T*C*4 is a multiple of 8 at C=66: pad odd T by one row)
 offs, cur = [], 0
@@ -95,5 +97,5 @@ for (l, _), o, t in zip(utts, offs, Ts):
 tg = torch.cat([t for _, t in utts]).to(torch.int32).contiguous()
 row_off = torch.tensor(offs, dtype=torch.int64, device=dev)
 print(f"# ragged corpus built in {time.time() - t0:.1f} s: {sum(Ts)} frames, {cur * 4 / 1e9:.2f} GB", flush=True)
-run(f"4: ragged B={B} T in [60,1800] N in [4,120] packed", flat, row_off, Ts, tg, Ns, list(range(0, B, max(1, B // 24))),
+run(f"4: ragged B={B} T in [60,1800] N in [4,120] packed" + (", utterances ordered by length" if os.environ.get("RAGGED_SORT", "1") == "1" else ""), flat, row_off, Ts, tg, Ns, list(range(0, B, max(1, B // 24))),
     lambda u: utts[u][0], lambda u: utts[u][1])
