@@ -205,23 +205,44 @@ def main():
     pending = [None, None]
     nstep = [0]
 
+    # ---- the gather of the packed result arrays (the path's only exchange).  Preferred: every rank PUSHES its arena into the
+    #      peers' receive buffers with copy-engine peer-to-peer writes over NVLink (torch symmetric memory), on a side stream:
+    #      no SM is taken from the banded kernel, which needs all of them.  Fallback: one NCCL all_gather per batch.
+    pusher = None                 # sharding.PushGather once the arena size is known; False: NCCL fallback
+    use_push = world > 1 and os.environ.get("BFA_GATHER", "p2p") == "p2p"
+
     def step():
+        nonlocal gather_bufs, pusher, use_push
         i = nstep[0] & 1
         nstep[0] += 1
+        if pusher is not None:
+            pusher.wait(i)
         if pending[i] is not None:     # the gather that still reads this result set
             pending[i].wait()
             pending[i] = None
         r = dec.align_batch(lp, row_off, Ts, Cc, tgt32, Ns, params=params, want_stamps=True, want_conf=True, plan=bplan, out=result[i])
         result[i] = r
-        if world > 1:  # final gather of the timestamp arrays (the path's only exchange)
-            nonlocal gather_bufs
-            if gather_bufs is None:   # stamps | conf | n_stamps | status | dp_final are one allocation: one collective
-                gather_bufs = [torch.empty(world * r.arena.numel(), dtype=r.arena.dtype, device=dev) for _ in range(2)]
-            pending[i] = dist.all_gather_into_tensor(gather_bufs[i], r.arena, async_op=True)
+        if world > 1:
+            if use_push and pusher is None:   # first batch: the arena size is known now (collective call)
+                try:
+                    from bfa_b200.sharding import PushGather
+                    pusher = PushGather(r.arena.numel(), dev)
+                except Exception as e:   # noqa: BLE001
+                    use_push = False
+                    if rank == 0:
+                        print(f"# symmetric memory unavailable ({e}); using NCCL all_gather", file=sys.stderr)
+            if pusher is not None:
+                pusher.push(i, r.arena)
+            else:
+                if gather_bufs is None:   # stamps | conf | n_stamps | status | dp_final are one allocation: one collective
+                    gather_bufs = [torch.empty(world * r.arena.numel(), dtype=r.arena.dtype, device=dev) for _ in range(2)]
+                pending[i] = dist.all_gather_into_tensor(gather_bufs[i], r.arena, async_op=True)
         return r
 
     def drain():
         for i in range(2):
+            if pusher is not None:
+                pusher.wait(i)
             if pending[i] is not None:
                 pending[i].wait()
                 pending[i] = None
@@ -230,6 +251,16 @@ def main():
         r = step()
     drain()
     torch.cuda.synchronize()
+    if world > 1 and pusher is not None:
+        # untimed check of the push gather: what landed in my receive buffer is what the peers computed
+        dist.barrier()
+        torch.cuda.synchronize()
+        i_last = (nstep[0] - 1) & 1
+        mine = result[i_last].arena.to(torch.int64).sum().reshape(1)
+        sums = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sums, mine)
+        got = pusher.recv[i_last].view(world, -1).to(torch.int64).sum(1)
+        assert bool((got == sums).all()), "push gather: receive buffer does not match the peers' results"
     assert int((r.status[:B] & 7 != 0).sum()) == 0, "unexpected non-OK status on the synthetic workload"
 
     def barrier():
@@ -345,8 +376,9 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "impl": "b200",
-               "config": workload_config(a, {"sharding": f"{world} rank(s) x {B} utterances, no data-path collective; "
-                                                         f"one all_gather of the packed result arrays per step when n_gpus>1 (overlapping the next step's kernels)"}),
+               "config": workload_config(a, {"gather": ("none (1 GPU)" if world == 1 else "copy-engine P2P pushes over NVLink (sharding.PushGather)"
+                                                        if pusher is not None else "NCCL all_gather_into_tensor"), "sharding": f"{world} rank(s) x {B} utterances, no data-path collective; "
+                                                         f"when n_gpus>1 every rank pushes its packed result arrays to all peers each step (copy-engine P2P writes over NVLink on a side stream; NCCL all_gather as fallback), completed inside the timed region"}),
                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(out))
     if world > 1:

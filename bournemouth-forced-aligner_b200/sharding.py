@@ -90,3 +90,48 @@ def gather_packed(result, counts: Sequence[int], group=None):
         ss.append(buf[r, sz["status"]:sz["status"] + bp][:b])
         dp.append(buf[r, sz["dp_final"]:sz["dp_final"] + bp].view(torch.float32)[:b])
     return (torch.cat(st), torch.cat(cf) if want_conf else None, torch.cat(ns), torch.cat(ss), torch.cat(dp))
+
+
+class PushGather:
+    """The same gather without taking SMs from the aligner: every rank PUSHES its packed result arena into all peers'
+    receive buffers with copy-engine peer-to-peer writes over NVLink (torch symmetric memory), on a side stream.
+    The banded kernel needs every SM of the GPU for one task per warp pair; a collective kernel that grabs a few SMs
+    delays it by the collective's whole duration, the copy engines do not.
+
+        pg = PushGather(result.arena.numel(), device)          # collective: every rank of the group calls it
+        pg.wait(i); r = align_batch(..., out=results[i]); pg.push(i, r.arena)      # i = batch & 1 (two receive buffers)
+        pg.wait(i) ... then a barrier of the group: pg.recv[i].view(world, -1)[q] is rank q's arena of that batch
+
+    `wait(i)` makes the CURRENT stream wait until this rank's pushes of buffer i have left (the arena may be overwritten);
+    that the PEERS' pushes have landed is known after a barrier of the group (or any later collective).
+    Raises if symmetric memory is not available (callers fall back to gather_packed / all_gather_into_tensor)."""
+
+    def __init__(self, n_words: int, device, group=None, buffers: int = 2):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.n = dist.get_world_size(group), dist.get_rank(group), int(n_words)
+        self.stream = torch.cuda.Stream(device=device)
+        self.recv, self._peers, self._done = [], [], []
+        for _ in range(buffers):
+            buf = symm.empty(self.world * self.n, dtype=torch.int32, device=device)
+            hdl = symm.rendezvous(buf, group)
+            self.recv.append(buf)
+            self._peers.append([hdl.get_buffer(q, (self.world * self.n,), torch.int32) for q in range(self.world)])
+            self._done.append(None)
+
+    def push(self, i: int, arena: torch.Tensor) -> None:
+        ready = torch.cuda.Event()
+        ready.record()                                        # the batch's kernels on the current stream
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            for k in range(self.world):                       # start with the next rank: spreads the load over the links
+                q = (self.rank + k) % self.world
+                self._peers[i][q][self.rank * self.n:(self.rank + 1) * self.n].copy_(arena, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        self._done[i] = done
+
+    def wait(self, i: int) -> None:
+        if self._done[i] is not None:
+            torch.cuda.current_stream().wait_event(self._done[i])
+            self._done[i] = None
