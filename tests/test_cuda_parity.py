@@ -432,3 +432,21 @@ def test_stamp_overflow_is_flagged_and_the_reference_api_recovers(bfa, orc, dev)
         n = int(o2["n_stamps"][b])
         want = [tuple(int(o2["stamps"][b][f][i]) for f in ("phoneme", "start", "end", "target_idx")) for i in range(n)]
         assert got[b] == want
+
+
+@pytest.mark.parametrize("seed", list(range(1, 13)))
+def test_random_configurations_vs_oracle(bfa, orc, dev, seed):
+    """Seeded sweep over class counts, length ranges (partial chunks, T < 8, N = 1, paths at the window-class boundaries),
+    decoder switches and row alignment: every utterance must match the oracle."""
+    from bfa_b200 import synth
+    rng = np.random.default_rng(9000 + seed)
+    Cc = int(rng.choice([9, 17, 33, 48, 66, 67, 72]))
+    t_hi = int(rng.choice([40, 200, 700, 1300]))
+    n_hi = int(rng.choice([3, 20, 60, 130]))
+    utts = synth.ragged_batch(36, C=Cc, t_range=(max(2, t_hi // 12), t_hi), n_range=(1, max(1, min(n_hi, Cc * 4))), seed=7000 + seed,
+                              peak=float(rng.choice([7.0, 10.0, 13.0])))
+    gaps = rng.integers(0, 4, len(utts)).tolist()
+    boost, floor = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+    mode = int(rng.integers(0, 2))
+    _packed_vs_oracle(bfa, orc, dev, utts, Cc, gap_floats=gaps, boost=boost, floor=floor, mode=mode,
+                      anchors=int(rng.choice([0, 3, 10])) if mode == 0 else 0, base_shift=int(rng.integers(0, 4)))
