@@ -59,6 +59,7 @@ _SIGNATURES = {
     "bfa_host_release": (None, []),
     "bfa_debug_phases": (C.c_int, [_P, C.c_int]),
     "bfa_debug_warps": (C.c_int, [_P, C.c_int]),
+    "bfa_soft_boundaries_batch": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
     "bfa_profile_read_aux": (C.c_int, [_P]),
     "bfa_debug_item_counts": (C.c_int, [_P]),
     "bfa_debug_ctas": (C.c_int, [_P, C.c_int]),

@@ -419,6 +419,33 @@ def _calculate_confidences(log_probs: torch.Tensor, framestamps):
     return [(f[0], max(0, int(f[1])), min(T, int(f[2])), f[3], f[4], c[i]) for i, f in enumerate(framestamps)]
 
 
+def extend_soft_boundaries_func(log_probs: torch.Tensor, framestamps, boundary_softness=3, debug=False):
+    """PhonemeTimestampAligner.extend_soft_boundaries_func (core.py:682-809) as a free function: log_probs [B, T, C] (CUDA),
+    framestamps list[B] of lists of 5-tuples (phoneme, start, end, target_idx, is_estimated) -> the same structure with the
+    stretched boundaries.  One kernel over the whole batch (bfa_soft_boundaries_batch)."""
+    _require_cuda(log_probs, "log_probs")
+    lp = log_probs if (log_probs.dtype == torch.float32 and log_probs.is_contiguous()) else log_probs.contiguous().float()
+    B, T, C_ = lp.shape
+    if len(framestamps) != B:
+        raise ValueError("framestamps must hold one list per batch item")
+    dev = lp.device
+    ms = max(1, max((len(f) for f in framestamps), default=1))
+    st = np.zeros((B, ms, 4), np.int32)
+    for b, fs in enumerate(framestamps):
+        for i, f in enumerate(fs):
+            st[b, i] = (int(f[0]), int(f[1]), int(f[2]), int(f[3]))
+    st_d = torch.from_numpy(st).to(dev)
+    n_d = torch.tensor([len(f) for f in framestamps], dtype=torch.int32, device=dev)
+    T_d = torch.full((B,), T, dtype=torch.int32, device=dev)
+    row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T * C_)
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().bfa_soft_boundaries_batch(B, C_, _ptr(lp), _ptr(row_off), _ptr(T_d), _ptr(st_d), _ptr(n_d), ms,
+                                                   int(boundary_softness), _stream(dev))
+    _cabi.check(rc)
+    out = st_d.cpu().numpy()
+    return [[(f[0], int(out[b, i, 1]), int(out[b, i, 2]), f[3], f[4]) for i, f in enumerate(fs)] for b, fs in enumerate(framestamps)]
+
+
 def align_host(params: BfaParams, log_probs: np.ndarray, row_off: np.ndarray, T: np.ndarray, C_: int, tgt: np.ndarray,
                tgt_off: np.ndarray, *, max_stamps: Optional[int] = None, want_conf=True, device=0, chunk_utts=0, out=None):
     """bfa_align_batch_host: every buffer is a HOST numpy array (pin them for full PCIe speed).

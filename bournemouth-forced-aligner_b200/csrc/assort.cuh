@@ -315,4 +315,74 @@ __global__ void confidence_kernel(int B, int C, const float* logp, const long lo
     }
 }
 
+// PhonemeTimestampAligner.extend_soft_boundaries_func (core.py:682-809), the step between decode_alignments and
+// _calculate_confidences in the reference pipeline (core.py:925-937): four passes that stretch each stamp's start / end
+// over neighbouring frames while exp(lp[f, phoneme]) stays above a threshold.  Within a pass a stamp only reads what
+// EARLIER passes wrote to its neighbours, so every pass is data-parallel over the stamps: one warp per utterance, the
+// stamps dealt to the lanes, __syncwarp between passes.  Thresholds are doubles like the reference's Python floats.
+constexpr int SOFT_WARPS = 4;
+__global__ void __launch_bounds__(SOFT_WARPS * 32) soft_boundaries_kernel(int B, int C, const float* __restrict__ logp,
+                                                                          const long long* row_off, const int32_t* T, BfaStamp* stamps,
+                                                                          const int32_t* n_stamps, int max_stamps, double t1, double t2) {
+    extern __shared__ double soft_thr[];                         // [SOFT_WARPS][max_stamps]: min(mean * t1, t1) per stamp
+    const int u = blockIdx.x * SOFT_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (u >= B) return;
+    const float* lp = logp + row_off[u];
+    const int Tu = T[u], n = min(n_stamps[u], max_stamps);
+    BfaStamp* st = stamps + (size_t)u * max_stamps;
+    double* thr = soft_thr + (size_t)(threadIdx.x >> 5) * max_stamps;
+    auto prob = [&](int f, int ph) { return (double)expf(lp[(size_t)f * C + ph]); };
+    for (int i = lane; i < n; i += 32) {                         // mean probability over the ORIGINAL stamp (:710-716)
+        const BfaStamp s = st[i];
+        double m = 0.001;
+        if (s.start < Tu && s.phoneme < C && s.start < s.end) {
+            const int e = min(s.end, Tu);
+            double acc = 0.0;
+            for (int f = s.start; f < e; ++f) acc += prob(f, s.phoneme);
+            m = (double)(float)(acc / (double)(e - s.start));
+        }
+        thr[i] = fmin(m * t1, t1);
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {                         // pass 1: starts, strict (:719-737)
+        const BfaStamp s = st[i];
+        if (s.start >= Tu || s.phoneme >= C) continue;
+        int lo = max(0, (int)((double)s.start - (double)(s.end - s.start) * 10.0));
+        if (i > 0) lo = max(lo, min(st[i - 1].end + 10, s.start));
+        int ns = s.start;
+        for (int f = s.start - 1; f >= lo; --f) { if (prob(f, s.phoneme) >= thr[i]) ns = f; else break; }
+        st[i].start = ns;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {                         // pass 2: ends, strict (:740-757)
+        const BfaStamp s = st[i];
+        if (s.start >= Tu || s.phoneme >= C) continue;
+        int hi = min(Tu, (int)((double)s.end + (double)(s.end - s.start) * 10.0));
+        if (i + 1 < n) hi = min(hi, min(s.end, st[i + 1].start - 10));     // :749 as written
+        int ne = s.end;
+        for (int f = s.end; f < hi; ++f) { if (prob(f, s.phoneme) >= thr[i]) ne = f + 1; else break; }
+        st[i].end = ne;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {                         // pass 3: starts, lenient, up to the previous end (:760-780)
+        const BfaStamp s = st[i];
+        if (s.start >= Tu || s.phoneme >= C) continue;
+        const int lo = i > 0 ? st[i - 1].end : 0;
+        if (s.start <= lo) continue;
+        int ns = s.start;
+        for (int f = s.start - 1; f >= lo; --f) { if (prob(f, s.phoneme) >= t2) ns = f; else break; }
+        st[i].start = ns;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {                         // pass 4: ends, lenient, up to the next start (:784-805)
+        const BfaStamp s = st[i];
+        if (s.start >= Tu || s.phoneme >= C) continue;
+        int hi = min(Tu, (int)((double)s.end + (double)(s.end - s.start) * 10.0));
+        if (i + 1 < n) hi = min(hi, st[i + 1].start);
+        int ne = s.end;
+        for (int f = s.end; f < hi; ++f) { if (prob(f, s.phoneme) >= t2) ne = f + 1; else break; }
+        st[i].end = ne;
+    }
+}
+
 }  // namespace bfa

@@ -494,6 +494,21 @@ int bfa_confidence_batch(int32_t B, int32_t C, const float* logp, const int64_t*
     return BFA_OK;
 }
 
+int bfa_soft_boundaries_batch(int32_t B, int32_t C, const float* logp, const int64_t* row_off, const int32_t* T, BfaStamp* stamps,
+                              const int32_t* n_stamps, int32_t max_stamps, int32_t boundary_softness, void* stream) {
+    if (!logp || !row_off || !T || !stamps || !n_stamps || C <= 0 || max_stamps <= 0) return BFA_E_INVALID;
+    if (B <= 0) return B == 0 ? BFA_OK : BFA_E_INVALID;
+    const size_t smem = (size_t)SOFT_WARPS * max_stamps * sizeof(double);
+    if (smem > 200 * 1024) return BFA_E_UNSUPPORTED;
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(soft_boundaries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    const double t1 = pow(10.0, -1.0 * 3.0), t2 = pow(10.0, -1.0 * (double)boundary_softness);   // core.py:699-701
+    soft_boundaries_kernel<<<(B + SOFT_WARPS - 1) / SOFT_WARPS, SOFT_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        B, C, logp, (const long long*)row_off, T, stamps, n_stamps, max_stamps, t1, t2);
+    LAUNCH_CHECK();
+    return BFA_OK;
+}
+
 // Development aid: per-phase warp-clock sums of the banded kernel (all zero unless built with -DBFA_PHASE_PROF).
 // Development aid: the item counters of the most recent bfa_align_batch on this thread's device (blocks on the device):
 // out[0] = items the exact kernel ran (ineligible + retried), out[1..3] = items of the banded kernels (24/40/64-group window).

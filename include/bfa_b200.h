@@ -200,6 +200,14 @@ int bfa_assort_batch(const BfaParams *p, int32_t B, const int32_t *T, const int6
                      const int32_t *frame_ph, const int32_t *frame_idx, int32_t *status,
                      BfaStamp *stamps, int32_t *n_stamps, int32_t max_stamps, void *stream);
 
+/* == PhonemeTimestampAligner.extend_soft_boundaries_func (core.py:682-809), the step the reference runs between
+ * decode_alignments and _calculate_confidences (core.py:925-937): stretches the start / end of every stamp in place over
+ * neighbouring frames whose probability of the stamp's phoneme stays above the reference's thresholds (10^-3 scaled by the
+ * stamp's mean probability, then 10^-boundary_softness).  stamps [B, max_stamps] with n_stamps[u] valid rows each (the
+ * output layout of bfa_align_batch), T[u] frames per utterance.  max_stamps <= 6400. */
+int bfa_soft_boundaries_batch(int32_t B, int32_t C, const float *logp, const int64_t *row_off, const int32_t *T, BfaStamp *stamps,
+                              const int32_t *n_stamps, int32_t max_stamps, int32_t boundary_softness, void *stream);
+
 /* Measurement hook: when enabled, bfa_align_batch / bfa_viterbi_paths bracket the dominant kernel
  * (the Viterbi fill+back-trace) with CUDA events on the launch stream; bfa_profile_read waits for
  * them and returns the summed device time and the number of launches since the previous read. */

@@ -497,6 +497,77 @@ void orc_confidence(const float *lp, int T, int C, const OrcStamp *st, int n, fl
 /* Batch driver == AlignmentUtils.decode_alignments (:856-910) + confidences   */
 /* (core.py:935-937 minus coverage repair / boundary extension), threaded over */
 /* utterances for the CPU baseline.                                            */
+/* ------------------------------------------------------------------------------------------
+ * PhonemeTimestampAligner.extend_soft_boundaries_func (core.py:682-809): four passes that stretch each stamp's start /
+ * end over neighbouring frames while exp(lp[f, phoneme]) stays above a threshold.  Within a pass every stamp reads only
+ * what earlier passes wrote (pass 1: previous ORIGINAL end, pass 2: next start after pass 1, pass 3: previous end after
+ * pass 2, pass 4: next start after pass 3), so the passes are data-parallel over the stamps.
+ * Thresholds are Python doubles (core.py:700-703); probabilities are float32 exp compared after promotion to double
+ * (.item()).  mean_probs (:712-716) is a float32 tensor mean in the reference; it is restated as a double sum rounded to
+ * float (within an ulp or two of torch's vectorised sum; it only scales a threshold). */
+void orc_soft_boundaries(const float *lp, int T, int C, OrcStamp *st, int n, int boundary_softness)
+{
+    const double max_ext = 10.0;                                            /* :698 */
+    const double t1 = pow(10.0, -1.0 * 3.0);                                /* :699-700: max(2, 7 - 4) = 3 */
+    const double t2 = pow(10.0, -1.0 * (double)boundary_softness);          /* :701 */
+    if (n <= 0) return;
+    double *mean = (double *)malloc(sizeof(double) * (size_t)n);
+    for (int i = 0; i < n; ++i) {                                           /* :710-716 */
+        const int ph = st[i].phoneme, s = st[i].start, e = st[i].end;
+        if (s < T && ph < C && s < e) {
+            const int ee = e < T ? e : T;
+            double acc = 0.0;
+            for (int f = s; f < ee; ++f) acc += (double)expf(lp[(size_t)f * C + ph]);
+            mean[i] = (double)(float)(acc / (double)(ee - s));
+        } else mean[i] = 0.001;
+    }
+    for (int i = 0; i < n; ++i) {                                           /* pass 1, :719-737 */
+        const int ph = st[i].phoneme, s = st[i].start, e = st[i].end;
+        if (s >= T || ph >= C) continue;
+        const int dur = e - s;
+        int lo = (int)((double)s - (double)dur * max_ext);
+        if (lo < 0) lo = 0;
+        if (i > 0) { int b = st[i - 1].end + 10; if (b > s) b = s; if (b > lo) lo = b; }
+        const double thr = mean[i] * t1 < t1 ? mean[i] * t1 : t1;
+        int ns = s;
+        for (int f = s - 1; f >= lo; --f) { if ((double)expf(lp[(size_t)f * C + ph]) >= thr) ns = f; else break; }
+        st[i].start = ns;
+    }
+    for (int i = 0; i < n; ++i) {                                           /* pass 2, :740-757 */
+        const int ph = st[i].phoneme, s = st[i].start, e = st[i].end;
+        if (s >= T || ph >= C) continue;
+        const int dur = e - s;
+        int hi = (int)((double)e + (double)dur * max_ext);
+        if (hi > T) hi = T;
+        if (i + 1 < n) { int b = st[i + 1].start - 10; if (b > e) b = e; if (b < hi) hi = b; }   /* :749: min(end, next - 10) */
+        const double thr = mean[i] * t1 < t1 ? mean[i] * t1 : t1;
+        int ne = e;
+        for (int f = e; f < hi; ++f) { if ((double)expf(lp[(size_t)f * C + ph]) >= thr) ne = f + 1; else break; }
+        st[i].end = ne;
+    }
+    for (int i = 0; i < n; ++i) {                                           /* pass 3, :760-780 */
+        const int ph = st[i].phoneme, s = st[i].start;
+        if (s >= T || ph >= C) continue;
+        const int lo = i > 0 ? st[i - 1].end : 0;
+        if (s <= lo) continue;
+        int ns = s;
+        for (int f = s - 1; f >= lo; --f) { if ((double)expf(lp[(size_t)f * C + ph]) >= t2) ns = f; else break; }
+        st[i].start = ns;
+    }
+    for (int i = 0; i < n; ++i) {                                           /* pass 4, :784-805 */
+        const int ph = st[i].phoneme, s = st[i].start, e = st[i].end;
+        if (s >= T || ph >= C) continue;
+        const int dur = e - s;
+        int hi = (int)((double)e + (double)dur * max_ext);
+        if (hi > T) hi = T;
+        if (i + 1 < n && st[i + 1].start < hi) hi = st[i + 1].start;
+        int ne = e;
+        for (int f = e; f < hi; ++f) { if ((double)expf(lp[(size_t)f * C + ph]) >= t2) ne = f + 1; else break; }
+        st[i].end = ne;
+    }
+    free(mean);
+}
+
 typedef struct {
     const float *lp; const int64_t *row_off; const int32_t *T; int C;
     const int32_t *tgt; const int64_t *tgt_off; const OrcParams *P;

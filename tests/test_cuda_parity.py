@@ -450,3 +450,47 @@ def test_random_configurations_vs_oracle(bfa, orc, dev, seed):
     mode = int(rng.integers(0, 2))
     _packed_vs_oracle(bfa, orc, dev, utts, Cc, gap_floats=gaps, boost=boost, floor=floor, mode=mode,
                       anchors=int(rng.choice([0, 3, 10])) if mode == 0 else 0, base_shift=int(rng.integers(0, 4)))
+
+
+def test_soft_boundaries_golden_and_oracle(golden, bfa, orc, dev):
+    """extend_soft_boundaries_func (core.py:682-809): the batch kernel against fixtures from the unmodified method, one
+    ragged batch per class count (utterances padded to the longest, shorter ones exercise T[u] < T_max via the C ABI)."""
+    import ctypes as C
+    from pathlib import Path
+    from bfa_b200 import _cabi
+    g = np.load(Path(__file__).parent / "golden" / "soft.npz")
+    cases = sorted({k.split("/")[0] for k in g.files}, key=lambda c: int(c[1:]))
+    # (a) reference-style call, one utterance at a time
+    for c in cases:
+        lp = torch.from_numpy(g[f"{c}/lp"]).to(dev)[None]
+        fs = [[(int(r[0]), int(r[1]), int(r[2]), int(r[3]), bool(r[4])) for r in g[f"{c}/in"]]]
+        got = bfa.extend_soft_boundaries_func(lp, fs, boundary_softness=int(g[f"{c}/soft"][0]))
+        want = [(int(r[0]), int(r[1]), int(r[2]), int(r[3]), bool(r[4])) for r in g[f"{c}/out"]]
+        assert got[0] == want, c
+    # (b) one launch over utterances of different length and stamp count that share C and the softness (C ABI, packed rows)
+    groups = {}
+    for c in cases:
+        groups.setdefault((g[f"{c}/lp"].shape[1], int(g[f"{c}/soft"][0])), []).append(c)
+    for (Cc, soft), cs in groups.items():
+        lps = [g[f"{c}/lp"] for c in cs]
+        Ts = [l.shape[0] for l in lps]
+        offs = np.concatenate([[0], np.cumsum([l.size for l in lps])]).astype(np.int64)
+        flat = torch.from_numpy(np.concatenate([l.reshape(-1) for l in lps])).to(dev)
+        ms = max(len(g[f"{c}/in"]) for c in cs)
+        st = np.zeros((len(cs), ms, 4), np.int32)
+        for b, c in enumerate(cs):
+            st[b, :len(g[f"{c}/in"])] = g[f"{c}/in"][:, :4]
+        st_d = torch.from_numpy(st).to(dev)
+        n_d = torch.tensor([len(g[f"{c}/in"]) for c in cs], dtype=torch.int32, device=dev)
+        off_d = torch.from_numpy(offs[:-1].copy()).to(dev)          # keep the device arrays alive across the call
+        T_d = torch.tensor(Ts, dtype=torch.int32, device=dev)
+        rc = _cabi.lib().bfa_soft_boundaries_batch(len(cs), Cc, C.c_void_p(flat.data_ptr()), C.c_void_p(off_d.data_ptr()),
+                                                   C.c_void_p(T_d.data_ptr()), C.c_void_p(st_d.data_ptr()),
+                                                   C.c_void_p(n_d.data_ptr()), ms, soft, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert rc == 0
+        out = st_d.cpu().numpy()
+        for b, c in enumerate(cs):
+            np.testing.assert_array_equal(out[b, :len(g[f"{c}/out"])], g[f"{c}/out"][:, :4], err_msg=c)
+            o = orc.soft_boundaries(g[f"{c}/lp"], [tuple(r) for r in g[f"{c}/in"]], soft)
+            np.testing.assert_array_equal(out[b, :len(o)], np.array(o, np.int32).reshape(-1, 4))

@@ -113,3 +113,20 @@ def test_silence_scan(golden):
         np.testing.assert_array_equal(np.array(segs, np.int32).reshape(-1, 2), g[f"silscan/segs{j}"])
         nonempty += len(segs) > 0
     assert nonempty >= 3
+
+
+def test_soft_boundaries_oracle_vs_reference():
+    """extend_soft_boundaries_func (core.py:682-809): the C restatement against fixtures from the unmodified method."""
+    import numpy as np
+    from pathlib import Path
+    from oracle import oracle as orc
+    g = np.load(Path(__file__).parent / "golden" / "soft.npz")
+    cases = sorted({k.split("/")[0] for k in g.files}, key=lambda c: int(c[1:]))
+    assert len(cases) == 15
+    changed = 0
+    for c in cases:
+        st_in, st_out = g[f"{c}/in"], g[f"{c}/out"]
+        got = orc.soft_boundaries(g[f"{c}/lp"], [tuple(r) for r in st_in], int(g[f"{c}/soft"][0]))
+        np.testing.assert_array_equal(np.array(got, np.int32).reshape(-1, 4), st_out[:, :4], err_msg=c)
+        changed += int((st_in[:, 1:3] != st_out[:, 1:3]).any(1).sum())
+    assert changed > 200
