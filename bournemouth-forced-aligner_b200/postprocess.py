@@ -44,3 +44,150 @@ def stamps_to_ms(stamps: np.ndarray, n_stamps: np.ndarray, spectral_lengths, sta
     s_ms = (off + stamps[:, :, 1].astype(np.float64) * spf) * 1000.0
     e_ms = (off + stamps[:, :, 2].astype(np.float64) * spf) * 1000.0
     return np.where(live, s_ms, 0.0), np.where(live, e_ms, 0.0)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Coverage repair: PhonemeTimestampAligner.ensure_target_coverage, core.py:462-679.
+# Host-side list surgery between decode_alignments and the boundary extension / confidence pass (core.py:925-937): every target
+# phoneme ends up with exactly one stamp -- stamps with indices outside the target are dropped, repeated indices are merged or
+# reduced to their longest piece, missing indices get estimated one-frame-or-more stamps placed between their aligned
+# neighbours.  Returns 5-tuples (phoneme, start, end, target_idx, is_estimated).
+# ------------------------------------------------------------------------------------------------------------------------
+class CoverageError(Exception):
+    """The reference raises a bare Exception when the repaired list does not cover the target exactly (core.py:676-677)."""
+
+
+def _dedupe(stamps, repeated):
+    """Stamps whose target index occurs more than once: pieces that touch or overlap are fused, then the longest piece
+    (the earliest among equals) stands for the index (core.py:514-537).  Other stamps keep their order and come first."""
+    single = [s for s in stamps if int(s[3]) not in repeated]
+    pieces = {}
+    for s in stamps:
+        if int(s[3]) in repeated:
+            pieces.setdefault(int(s[3]), []).append(s)
+    for idx in sorted(pieces):
+        fused = []
+        for s in sorted(pieces[idx], key=lambda x: x[1]):
+            if fused and s[1] <= fused[-1][2]:
+                p = fused[-1]
+                fused[-1] = (p[0], p[1], max(p[2], s[2]), p[3])
+            else:
+                fused.append((s[0], s[1], s[2], s[3]))
+        single.append(max(fused, key=lambda x: x[2] - x[1]))
+    return single
+
+
+def _make_room_at_the_end(stamps, need, silence_class):
+    """Trailing targets without an aligned successor (core.py:590-626): free `need` frames at the end of the utterance by
+    shortening stamps from the back -- silence stamps first, then any stamp longer than one frame -- and pulling everything
+    behind a shortened stamp forward by the same amount."""
+    seq = sorted(stamps, key=lambda x: x[1])
+    freed = 0
+    for only_silence in (True, False):
+        for k in range(len(seq) - 1, -1, -1):
+            if freed >= need:
+                break
+            s = seq[k]
+            span = s[2] - s[1]
+            if span > 1 and (s[0] == silence_class or not only_silence):
+                give = min(span - 1, need - freed)
+                seq[k] = (*s[:2], s[2] - give, *s[3:])
+                for j in range(k + 1, len(seq)):
+                    t = seq[j]
+                    seq[j] = (t[0], t[1] - give, t[2] - give, *t[3:])
+                freed += give
+        if freed >= need:
+            break
+    return seq
+
+
+def ensure_target_coverage(phoneme_sequences, aligned_frames, seq_lens=None, _silence_class=0, debug=False, ensure_completeness=True,
+                           stats=None):
+    """core.py:462-679 with the same arguments (the reference reads `ensure_completeness` from the aligner object; `stats`, if a
+    dict, receives the counters it keeps there).  `aligned_frames` is updated in place and returned, like the reference does."""
+    for b in range(len(aligned_frames)):
+        stamps = aligned_frames[b]
+        frames_end = max((s[2] for s in stamps), default=0)                                   # "ctc_len", :479
+        seq = phoneme_sequences[b]
+        seq = seq.tolist() if hasattr(seq, "tolist") else list(seq)
+        targets = seq[: (int(seq_lens[b]) if seq_lens is not None else len(seq))]
+        n_t = len(targets)
+        seen = [0] * n_t
+        outside = set()
+        for s in stamps:                                                                     # :487-493 (a -1 never counts)
+            i = int(s[3])
+            if i < n_t and i != -1:
+                seen[i] += 1
+            else:
+                outside.add(i)
+        repeated = {i for i, c in enumerate(seen) if c > 1}
+        missing = [i for i, c in enumerate(seen) if c == 0]
+        if stats is not None:
+            stats["aligned"] = stats.get("aligned", 0) + len(stamps)
+            stats["target"] = stats.get("target", 0) + n_t
+            stats["extra"] = stats.get("extra", 0) + sum(seen[i] - 1 for i in repeated)
+            stats["missed"] = stats.get("missed", 0) + len(missing)
+        if outside:                                                                          # :509-513
+            stamps = [s for s in stamps if int(s[3]) not in outside]
+        if repeated and ensure_completeness:
+            stamps = _dedupe(stamps, repeated)
+        skipped_silence = set()
+        if missing and ensure_completeness:                                                  # :540-651
+            by_idx = {int(s[3]): s for s in stamps}
+            runs = [[missing[0]]]
+            for i in missing[1:]:
+                if i == runs[-1][-1] + 1:
+                    runs[-1].append(i)
+                else:
+                    runs.append([i])
+            for run in runs:
+                before = next((by_idx[i] for i in range(run[0] - 1, -1, -1) if i in by_idx), None)
+                after = next((by_idx[i] for i in range(run[-1] + 1, n_t) if i in by_idx), None)
+                if before and not after:          # the tail of the target: silence needs no stamp, the rest gets one frame each
+                    wanted = [i for i in run if targets[i] != _silence_class]
+                    skipped_silence.update(i for i in run if targets[i] == _silence_class)
+                    if not wanted:
+                        continue
+                    stamps = _make_room_at_the_end(stamps, len(wanted), _silence_class)
+                    by_idx = {int(s[3]): s for s in stamps}
+                    tail = max(s[2] for s in stamps)
+                    for k, i in enumerate(wanted):
+                        a = min(tail + k, frames_end - 1)
+                        new = (targets[i], a, min(a + 1, frames_end), i, True)
+                        stamps.append(new)
+                        by_idx[i] = new
+                    continue
+                if before and after:
+                    lo, hi = before[2], after[1]
+                elif after:
+                    hi = after[1]
+                    lo = max(0, hi - len(run))
+                else:
+                    lo, hi = 0, len(run)
+                step = max(hi - lo, len(run)) / len(run)                                     # :640-641, Python float
+                for k, i in enumerate(run):
+                    a = min(int(lo + k * step), frames_end - 1)
+                    z = min(max(int(lo + (k + 1) * step), a + 1), frames_end)
+                    new = (targets[i], a, z, i, True)
+                    stamps.append(new)
+                    by_idx[i] = new
+        stamps.sort(key=lambda x: x[1])                                                      # :654 (stable)
+        easy = 0
+        for k, s in enumerate(stamps):
+            if len(s) == 4:
+                stamps[k] = (*s, False)
+                easy += 1
+        if stats is not None:
+            stats["aligned_easily"] = stats.get("aligned_easily", 0) + easy
+        aligned_frames[b] = stamps
+        if ensure_completeness:                                                              # :663-677
+            want = n_t - len(skipped_silence)
+            cover = [0] * n_t
+            for s in stamps:
+                i = int(s[3])
+                if i < n_t and i != -1:
+                    cover[i] += 1
+            if sum(cover) != want or len(stamps) != want:
+                raise CoverageError(f"Post-processing error: target coverage mismatch for segment {b}. Expected {want}, got {sum(cover)} "
+                                    f"covered, {len(stamps)} aligned. Skipped SIL: {skipped_silence}")
+    return aligned_frames

@@ -26,3 +26,27 @@ def test_convert_to_ms_bit_identical_to_reference():
             np.testing.assert_array_equal(s_ms[0, :len(stamps)], g[f"{c}/ms"][:, 0])
             np.testing.assert_array_equal(e_ms[0, :len(stamps)], g[f"{c}/ms"][:, 1])
             assert (s_ms[0, len(stamps):] == 0).all()
+
+
+def test_ensure_target_coverage_identical_to_reference():
+    """core.py:462-679 on 160 seeded, damaged stamp lists (missing runs at the head / middle / tail, trailing silence, repeated
+    and out-of-range target indices, completeness off): every repaired list equals the reference's."""
+    from bfa_b200.postprocess import ensure_target_coverage
+    g = np.load(Path(__file__).parent / "golden" / "coverage.npz")
+    cases = sorted({k.split("/")[0] for k in g.files}, key=lambda c: int(c[1:]))
+    assert len(cases) == 160
+    inserted = 0
+    for c in cases:
+        tgt = [int(x) for x in g[f"{c}/tgt"]]
+        inp = [tuple(int(x) for x in r) for r in g[f"{c}/in"]]
+        raised, complete = (int(x) for x in g[f"{c}/meta"])
+        try:
+            got = ensure_target_coverage([tgt], [list(inp)], seq_lens=[len(tgt)], _silence_class=0, ensure_completeness=bool(complete))[0]
+            assert not raised, c
+        except Exception:
+            assert raised, c
+            continue
+        want = [(int(r[0]), int(r[1]), int(r[2]), int(r[3]), bool(r[4])) for r in g[f"{c}/out"]]
+        assert got == want, c
+        inserted += sum(1 for s in got if s[4])
+    assert inserted > 400
