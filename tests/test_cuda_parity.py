@@ -494,3 +494,29 @@ def test_soft_boundaries_golden_and_oracle(golden, bfa, orc, dev):
             np.testing.assert_array_equal(out[b, :len(g[f"{c}/out"])], g[f"{c}/out"][:, :4], err_msg=c)
             o = orc.soft_boundaries(g[f"{c}/lp"], [tuple(r) for r in g[f"{c}/in"]], soft)
             np.testing.assert_array_equal(out[b, :len(o)], np.array(o, np.int32).reshape(-1, 4))
+
+
+def test_post_acoustic_pipeline_vs_reference(bfa, dev):
+    """decode_alignments -> ensure_target_coverage -> extend_soft_boundaries_func -> _calculate_confidences -> convert_to_ms
+    (core.py:902-937, :960-975) on this library against the same chain of the unmodified reference (tests/golden/make_golden_pipeline.py):
+    phonemes, frames, target indices, flags and milliseconds identical, confidences within 1e-4."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "pipeline.npz")
+    utts = sorted({k.split("/")[0] for k in g.files}, key=lambda c: int(c[1:]))
+    assert len(utts) == 11
+    for u in utts:
+        T, N, Cc, b = (int(x) for x in g[f"{u}/meta"])
+        lp = torch.from_numpy(g[f"{u}/lp"]).to(dev)[None]
+        tgt = torch.from_numpy(g[f"{u}/tgt"]).long()[None]
+        au = bfa.AlignmentUtils(blank_id=Cc - 1, silence_id=0, silence_anchors=10, ignore_noise=True, truly_forced=True)
+        frames = au.decode_alignments(lp, true_seqs=tgt, pred_lens=torch.tensor([T]), true_seqs_lens=torch.tensor([N]))
+        frames = bfa.ensure_target_coverage(tgt, frames, seq_lens=torch.tensor([N]), _silence_class=0)
+        frames = bfa.extend_soft_boundaries_func(lp, frames, boundary_softness=3)
+        fs = bfa._calculate_confidences(lp[0], frames[0])
+        fs = bfa.convert_to_ms(fs, T, 1.5 * b, T * 320, 16000)
+        want = g[f"{u}/out"]
+        assert len(fs) == len(want), u
+        got = np.array([[float(x) for x in f] for f in fs], np.float64).reshape(-1, 8)
+        np.testing.assert_array_equal(got[:, :5], want[:, :5], err_msg=u)
+        np.testing.assert_allclose(got[:, 5], want[:, 5], rtol=RTOL, atol=1e-7, err_msg=u)
+        np.testing.assert_array_equal(got[:, 6:], want[:, 6:], err_msg=u)
