@@ -419,6 +419,39 @@ def _calculate_confidences(log_probs: torch.Tensor, framestamps):
     return [(f[0], max(0, int(f[1])), min(T, int(f[2])), f[3], f[4], c[i]) for i, f in enumerate(framestamps)]
 
 
+def _calculate_confidences_batch(log_probs: torch.Tensor, framestamps, pred_lens=None):
+    """utils._calculate_confidences (utils.py:70-113) for a whole batch in ONE launch: log_probs [B, T, C] (CUDA), framestamps
+    list[B] of lists of 5-tuples -> list[B] of lists of 6-tuples.  The reference loops over the batch (core.py:936-937);
+    `pred_lens[b]` plays the role of `log_probs[b].shape[0]` when the batch is padded."""
+    _require_cuda(log_probs, "log_probs")
+    lp = log_probs if (log_probs.dtype == torch.float32 and log_probs.is_contiguous()) else log_probs.contiguous().float()
+    B, T_max, C_ = lp.shape
+    T = [T_max] * B if pred_lens is None else [int(v) for v in (pred_lens.tolist() if hasattr(pred_lens, "tolist") else pred_lens)]
+    dev = lp.device
+    for b, fs in enumerate(framestamps):
+        for (ph, s, e, _i, est) in fs:
+            s2, e2 = max(0, int(s)), min(T[b], int(e))
+            if est and not (s2 < T[b] and e2 <= T[b]):  # utils.py:88-91
+                raise ValueError(f"Invalid frame range for estimated timestamp: start_frame={s2}, end_frame={e2}, "
+                                 f"log_probs shape={(T[b], C_)}, is_estimated={est}, phoneme_id={ph}")
+    ms = max(1, max((len(f) for f in framestamps), default=1))
+    st = np.zeros((B, ms, 4), np.int32)
+    for b, fs in enumerate(framestamps):
+        for i, f in enumerate(fs):
+            st[b, i] = (int(f[0]), int(f[1]), int(f[2]), int(f[3]))
+    st_d = torch.from_numpy(st).to(dev)
+    n_d = torch.tensor([len(f) for f in framestamps], dtype=torch.int32, device=dev)
+    T_d = torch.tensor(T, dtype=torch.int32, device=dev)
+    row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T_max * C_)
+    conf = torch.zeros((B, ms), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().bfa_confidence_batch(B, C_, _ptr(lp), _ptr(row_off), _ptr(T_d), _ptr(st_d), _ptr(n_d), ms, _ptr(conf), _stream(dev))
+    _cabi.check(rc)
+    c = conf.cpu().numpy()
+    return [[(f[0], max(0, int(f[1])), min(T[b], int(f[2])), f[3], f[4], float(c[b, i])) for i, f in enumerate(fs)]
+            for b, fs in enumerate(framestamps)]
+
+
 def extend_soft_boundaries_func(log_probs: torch.Tensor, framestamps, boundary_softness=3, debug=False):
     """PhonemeTimestampAligner.extend_soft_boundaries_func (core.py:682-809) as a free function: log_probs [B, T, C] (CUDA),
     framestamps list[B] of lists of 5-tuples (phoneme, start, end, target_idx, is_estimated) -> the same structure with the

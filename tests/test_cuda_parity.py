@@ -520,3 +520,19 @@ def test_post_acoustic_pipeline_vs_reference(bfa, dev):
         np.testing.assert_array_equal(got[:, :5], want[:, :5], err_msg=u)
         np.testing.assert_allclose(got[:, 5], want[:, 5], rtol=RTOL, atol=1e-7, err_msg=u)
         np.testing.assert_array_equal(got[:, 6:], want[:, 6:], err_msg=u)
+
+
+def test_confidences_batch_equals_per_utterance(bfa, dev):
+    """One launch over the batch (bfa_confidence_batch) == the reference-style per-utterance calls, padded lengths included."""
+    from bfa_b200 import synth
+    B, T, N, Cc = 6, 220, 18, 67
+    lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=31, peak=5.0)
+    lens = torch.tensor([220, 200, 180, 220, 150, 199])
+    au = bfa.AlignmentUtils(Cc - 1, 0)
+    frames = au.decode_alignments(lp.to(dev), true_seqs=tgt, pred_lens=lens, true_seqs_lens=torch.full((B,), N))
+    frames = bfa.ensure_target_coverage(tgt, frames, seq_lens=torch.full((B,), N))
+    one = bfa._calculate_confidences_batch(lp.to(dev), frames, pred_lens=lens)
+    for b in range(B):
+        ref = bfa._calculate_confidences(lp[b, :int(lens[b])].to(dev), frames[b])
+        assert [f[:5] for f in one[b]] == [f[:5] for f in ref]
+        np.testing.assert_array_equal([f[5] for f in one[b]], [f[5] for f in ref])
