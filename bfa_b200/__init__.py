@@ -9,7 +9,8 @@ from ._cabi import BfaError, BfaParams, BfaShape, default_params  # noqa: E402,F
 from .aligner import (AlignmentUtils, BatchResult, ViterbiDecoder, _calculate_confidences,  # noqa: E402,F401
                       align_host, extend_soft_boundaries_func, _calculate_confidences_batch)
 
-from .postprocess import CoverageError, convert_to_ms, ensure_target_coverage, stamps_to_ms  # noqa: E402,F401
+from .postprocess import (CoverageError, align_words, analyze_alignment_coverage, convert_to_ms,  # noqa: E402,F401
+                          ensure_target_coverage, post_process_segment, stamps_to_ms)
 
-__all__ = ["AlignmentUtils", "ViterbiDecoder", "_calculate_confidences", "align_host", "BatchResult", "convert_to_ms", "stamps_to_ms", "extend_soft_boundaries_func", "_calculate_confidences_batch", "ensure_target_coverage", "CoverageError",
+__all__ = ["AlignmentUtils", "ViterbiDecoder", "_calculate_confidences", "align_host", "BatchResult", "convert_to_ms", "stamps_to_ms", "extend_soft_boundaries_func", "_calculate_confidences_batch", "ensure_target_coverage", "CoverageError", "align_words", "analyze_alignment_coverage", "post_process_segment",
            "BfaError", "BfaParams", "BfaShape", "default_params"]

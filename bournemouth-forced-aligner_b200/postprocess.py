@@ -191,3 +191,73 @@ def ensure_target_coverage(phoneme_sequences, aligned_frames, seq_lens=None, _si
                 raise CoverageError(f"Post-processing error: target coverage mismatch for segment {b}. Expected {want}, got {sum(cover)} "
                                     f"covered, {len(stamps)} aligned. Skipped SIL: {skipped_silence}")
     return aligned_frames
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Word timestamps: PhonemeTimestampAligner._align_words, core.py:1062-1120.
+# ------------------------------------------------------------------------------------------------------------------------
+def align_words(phoneme_ts, word_num, words_list):
+    """Groups consecutive phoneme timestamps (dicts with phoneme_id, ipa_label, start_ms, end_ms, confidence) by their word
+    index into word entries {word, start_ms, end_ms, confidence, ph66, ipa}.  Same walk as the reference, including what it
+    does at the last position: the phoneme at index len(word_num) - 1 closes the current word (joining it only if it carries
+    the same word index), and nothing is emitted after it."""
+    if not phoneme_ts or not word_num:
+        return []
+    n = min(len(word_num), len(phoneme_ts))
+    last = len(word_num) - 1
+    out = []
+    cur, start, members = word_num[0], phoneme_ts[0]["start_ms"], []
+    for i in range(n):
+        ph = phoneme_ts[i]
+        if word_num[i] == cur and i != last:
+            members.append(ph)
+            continue
+        if i == last and word_num[i] == cur:
+            members.append(ph)
+        out.append({"word": words_list[cur] if cur < len(words_list) else f"UNK_WORD_{cur}",
+                    "start_ms": start, "end_ms": members[-1]["end_ms"],
+                    "confidence": sum(m["confidence"] for m in members) / len(members),
+                    "ph66": [m["phoneme_id"] for m in members], "ipa": [m["ipa_label"] for m in members]})
+        if i < last:
+            cur, start, members = word_num[i], ph["start_ms"], [ph]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# The per-segment output record (SURVEY.md section 8f, row 2): analyze_alignment_coverage (core.py:1701-1732) and
+# post_process_segment (core.py:1140-1210) -- the dict that becomes the `.vs.json` file.  The label tables come from the
+# phonemizer in the reference (index_to_plabel / index_to_glabel); here they are arguments.
+# ------------------------------------------------------------------------------------------------------------------------
+def analyze_alignment_coverage(target_sequence, aligned_timestamps, index_to_label):
+    wanted = set(target_sequence.tolist() if hasattr(target_sequence, "tolist") else target_sequence)
+    found = set([t[0] for t in aligned_timestamps])
+    missing, extra = wanted - found, found - wanted
+    ratio = len(wanted - missing) / len(wanted) if wanted else 1.0
+    return {"target_count": len(wanted), "aligned_count": len(found), "missing_count": len(missing), "extra_count": len(extra),
+            "coverage_ratio": ratio,
+            "missing_phonemes": [index_to_label.get(p, f"UNK_{p}") for p in missing],
+            "extra_phonemes": [index_to_label.get(p, f"UNK_{p}") for p in extra],
+            "bad_alignment": ratio < 0.8}
+
+
+def post_process_segment(segment, ts, phoneme_sequence, phoneme_timestamps, group_timestamps=None, *, index_to_plabel, index_to_glabel=None):
+    """segment: the caller's dict (copied); ts: the phonemizer's record (eipa / word_num / words); phoneme_timestamps /
+    group_timestamps: 8-tuples (id, start_frame, end_frame, target_idx, is_estimated, confidence, start_ms, end_ms) as produced by
+    convert_to_ms.  Returns the reference's output dict: coverage_analysis, ipa, word_num, words, phoneme_ts[, group_ts], words_ts."""
+    out = segment.copy()
+    out["coverage_analysis"] = analyze_alignment_coverage(phoneme_sequence, phoneme_timestamps, index_to_plabel)
+    out["ipa"] = ts.get("eipa", "")
+    out["word_num"] = ts.get("word_num", "")
+    out["words"] = ts.get("words", "")
+    ipa = out["ipa"]
+    out["phoneme_ts"] = [{"phoneme_id": int(p[0]), "phoneme_label": index_to_plabel.get(p[0], f"UNK_{p[0]}"),
+                          "ipa_label": ipa[p[3]] if 0 <= p[3] < len(ipa) else "overflow",
+                          "start_ms": float(p[6]), "end_ms": float(p[7]), "confidence": float(p[5]), "is_estimated": bool(p[4]),
+                          "target_seq_idx": int(p[3]), "index": k} for k, p in enumerate(phoneme_timestamps)]
+    if group_timestamps is not None:
+        labels = index_to_glabel if index_to_glabel is not None else {}
+        out["group_ts"] = [{"group_id": int(q[0]), "group_label": labels.get(q[0], f"UNK_{q[0]}"), "start_ms": float(q[6]),
+                            "end_ms": float(q[7]), "confidence": float(q[5]), "is_estimated": bool(q[4]), "target_seq_idx": int(q[3]),
+                            "index": k} for k, q in enumerate(group_timestamps)]
+    out["words_ts"] = align_words(out["phoneme_ts"], ts.get("word_num", []), ts.get("words", []))
+    return out

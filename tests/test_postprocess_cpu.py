@@ -50,3 +50,34 @@ def test_ensure_target_coverage_identical_to_reference():
         assert got == want, c
         inserted += sum(1 for s in got if s[4])
     assert inserted > 400
+
+
+def test_align_words_identical_to_reference():
+    """core.py:1062-1120 on 60 seeded lists (unsorted word indices, word_num shorter / longer than the timestamps, indices
+    beyond the word list)."""
+    import json
+    from bfa_b200.postprocess import align_words
+    cases = json.loads((Path(__file__).parent / "golden" / "words.json").read_text())
+    assert len(cases) == 60
+    for k, c in enumerate(cases):
+        if c["err"]:
+            try:
+                align_words(c["phoneme_ts"], c["word_num"], c["words"])
+                assert False, k
+            except Exception:
+                continue
+        assert align_words(c["phoneme_ts"], c["word_num"], c["words"]) == c["out"], k
+
+
+def test_post_process_segment_identical_to_reference():
+    """core.py:1140-1210 (+ :1701-1732, :1062-1120): the per-segment output dict, compared as JSON with the reference's."""
+    import json
+    from bfa_b200.postprocess import post_process_segment
+    cases = json.loads((Path(__file__).parent / "golden" / "segment.json").read_text())
+    assert len(cases) == 40
+    plabel = {i: f"ph{i}" for i in range(0, 60)}
+    glabel = {i: f"g{i}" for i in range(0, 14)}
+    for k, c in enumerate(cases):
+        got = post_process_segment(dict(c["segment"]), c["ts"], list(c["seq"]), [tuple(p) for p in c["pts"]],
+                                   None if c["gts"] is None else [tuple(g) for g in c["gts"]], index_to_plabel=plabel, index_to_glabel=glabel)
+        assert json.loads(json.dumps(got)) == c["out"], k
