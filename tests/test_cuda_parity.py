@@ -536,3 +536,39 @@ def test_confidences_batch_equals_per_utterance(bfa, dev):
         ref = bfa._calculate_confidences(lp[b, :int(lens[b])].to(dev), frames[b])
         assert [f[:5] for f in one[b]] == [f[:5] for f in ref]
         np.testing.assert_array_equal([f[5] for f in one[b]], [f[5] for f in ref])
+
+
+def test_shim_aligner_from_posteriors_vs_reference(bfa, dev):
+    """PhonemeTimestampAligner.timestamps_from_posteriors (the post-acoustic half of core.py:896-957, whole batch at once) against
+    the chain of the unmodified reference pieces; the group head runs through the same code at C = 17."""
+    from pathlib import Path
+    from bfa_b200 import synth
+    g = np.load(Path(__file__).parent / "golden" / "pipeline.npz")
+    utts = sorted({k.split("/")[0] for k in g.files}, key=lambda c: int(c[1:]))
+    al = bfa.PhonemeTimestampAligner(blank_class=66, silence_class=0)
+    batches = {}
+    for u in utts:                                   # utterances of one golden batch share (N, C) and the padded length
+        T, N, Cc, b = (int(x) for x in g[f"{u}/meta"])
+        batches.setdefault((g[f"{u}/lp"].shape[0], N, Cc), []).append((u, T, b))
+    for (Tm, N, Cc), items in batches.items():
+        lp = torch.from_numpy(np.stack([g[f"{u}/lp"] for u, _, _ in items])).to(dev)
+        tgt = torch.from_numpy(np.stack([g[f"{u}/tgt"] for u, _, _ in items])).long()
+        lens = torch.tensor([T for _, T, _ in items])
+        offs = [1.5 * b for _, _, b in items]
+        res = al.timestamps_from_posteriors(lp, tgt, torch.full((len(items),), N), lens, [int(T) * 320 for _, T, _ in items], offs)
+        for (u, _, _), r in zip(items, res):
+            want = g[f"{u}/out"]
+            got = np.array([[float(x) for x in f] for f in r["phoneme_timestamps"]], np.float64).reshape(-1, 8)
+            np.testing.assert_array_equal(got[:, :5], want[:, :5], err_msg=u)
+            np.testing.assert_allclose(got[:, 5], want[:, 5], rtol=RTOL, atol=1e-7, err_msg=u)
+            np.testing.assert_array_equal(got[:, 6:], want[:, 6:], err_msg=u)
+            assert r["group_timestamps"] is None
+    # both heads
+    B, T, N = 3, 200, 16
+    lp_p, tgt_p, _ = synth.planted_batch(B, T, N, 67, seed=41, peak=6.0)
+    lp_g, tgt_g, _ = synth.planted_batch(B, T, N, 17, seed=42, peak=6.0)
+    res = al.timestamps_from_posteriors(lp_p.to(dev), tgt_p, torch.full((B,), N), torch.full((B,), T), [T * 320] * B, 0.0,
+                                        log_probs_g=lp_g.to(dev), grp_seqs=tgt_g)
+    for r in res:
+        assert [f[3] for f in r["phoneme_timestamps"]] == list(range(N)) and [f[3] for f in r["group_timestamps"]] == list(range(N))
+        assert all(len(f) == 8 and f[7] >= f[6] for f in r["group_timestamps"])
