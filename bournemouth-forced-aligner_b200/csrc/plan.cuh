@@ -53,24 +53,23 @@ struct TgtInfo {
     uint32_t w[MAX_WORDS];
     bool all_ok, has_sil;
 };
+// `sw` = MAX_WORDS words of shared memory owned by the calling warp: the lanes OR their targets' bits into it (one
+// shared atomic per target instead of a MAX_WORDS-way select on register words), then every lane reads the mask back.
 __device__ __forceinline__ TgtInfo target_info(const int32_t* tgt, long long b, long long e, int C, int blank_id, int silence_id,
-                                               int lane) {
+                                               int lane, uint32_t* sw) {
     TgtInfo r;
-#pragma unroll
-    for (int i = 0; i < MAX_WORDS; ++i) r.w[i] = 0;
+    if (lane < MAX_WORDS) sw[lane] = 0;
+    __syncwarp();
     bool all_ok = true, has_sil = false;
-    const int nw = (C + 31) >> 5;              // mask words in use
     for (long long j = b + lane; j < e; j += 32) {
         const int c = tgt[j];
         has_sil |= (c == silence_id);
         if (c == blank_id || c == -100 || c < 0 || c >= C) { all_ok = false; continue; }
-#pragma unroll
-        for (int i = 0; i < MAX_WORDS; ++i)
-            if (i < nw && (c >> 5) == i) r.w[i] |= 1u << (c & 31);
+        atomicOr(&sw[c >> 5], 1u << (c & 31));
     }
+    __syncwarp();
 #pragma unroll
-    for (int i = 0; i < MAX_WORDS; ++i)
-        if (i < nw) r.w[i] = __reduce_or_sync(FULL, r.w[i]);      // nw is warp-uniform
+    for (int i = 0; i < MAX_WORDS; ++i) r.w[i] = sw[i];
     r.all_ok = __all_sync(FULL, all_ok);
     r.has_sil = __any_sync(FULL, has_sil);
     return r;
@@ -99,7 +98,8 @@ __global__ void rowstat_kernel(int C, int blank_id, int silence_id, float boost,
                                const long long* row_off, const int32_t* T, const int32_t* tgt, const long long* tgt_off,
                                const long long* frame_off, float2* rowstat) {
     const int u = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const TgtInfo ti = target_info(tgt, tgt_off[u], tgt_off[u + 1], C, blank_id, silence_id, lane);
+    __shared__ uint32_t s_mask[32][MAX_WORDS];
+    const TgtInfo ti = target_info(tgt, tgt_off[u], tgt_off[u + 1], C, blank_id, silence_id, lane, s_mask[warp]);
     if (!ti.has_sil) return;
     const int Tu = T[u];
     uint32_t tbits = 0;
@@ -388,6 +388,7 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
     Item single;                 // the common case, one item = the whole utterance, never leaves lane 0's registers
     bool have_single = false;
     bool tok = false;
+    __shared__ uint32_t s_mask[8][MAX_WORDS];
     if (u < a.B) {
     const BfaParams& p = a.p;
     UttCtx c;
@@ -398,22 +399,13 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
     c.seq = a.tgt + a.tgt_off[u];
     c.stat = a.rowstat ? a.rowstat + a.frame_off[u] : nullptr;
     c.padded = a.padded + (size_t)u * (a.max_T + 16);
-    const TgtInfo ti = target_info(a.tgt, a.tgt_off[u], a.tgt_off[u + 1], a.C, p.blank_id, p.silence_id, lane);
-    if (lane < MAX_WORDS) {
-        uint32_t wv = 0;
-#pragma unroll
-        for (int i = 0; i < MAX_WORDS; ++i)
-            if (i == lane) wv = ti.w[i];
-        a.tmask[(size_t)u * MAX_WORDS + lane] = wv;      // consumed by the Viterbi kernels
-    }
+    uint32_t* sw = s_mask[threadIdx.x >> 5];
+    const TgtInfo ti = target_info(a.tgt, a.tgt_off[u], a.tgt_off[u + 1], a.C, p.blank_id, p.silence_id, lane, sw);
+    if (lane < MAX_WORDS) a.tmask[(size_t)u * MAX_WORDS + lane] = sw[lane];      // consumed by the Viterbi kernels
 #pragma unroll
     for (int i = 0; i < MAX_WORDS; ++i) c.tw[i] = ti.w[i];
     c.sil_is_target = false;
-    if (p.silence_id >= 0 && p.silence_id < a.C) {
-#pragma unroll
-        for (int i = 0; i < MAX_WORDS; ++i)
-            if (i == (p.silence_id >> 5)) c.sil_is_target = (ti.w[i] >> (p.silence_id & 31)) & 1u;
-    }
+    if (p.silence_id >= 0 && p.silence_id < a.C) c.sil_is_target = (sw[p.silence_id >> 5] >> (p.silence_id & 31)) & 1u;
     const int T = c.T, N = c.N;
     const long long o_base = a.frame_off[u], o_lim = a.frame_off[u + 1];
     loc = a.items_local + (size_t)u * a.item_cap;
