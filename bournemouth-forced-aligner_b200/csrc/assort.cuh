@@ -103,6 +103,7 @@ struct AssortArgs {
 
 __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(AssortArgs a) {
     const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    pdl_wait();                   // the frame labels of the Viterbi kernels
     if (u >= a.B) return;
     const int st = a.status[u] & 7;
     if (st == BFA_ST_EMPTY_TARGET || st == BFA_ST_TOO_SHORT) {   // :894-897 -> [] ; ValueError

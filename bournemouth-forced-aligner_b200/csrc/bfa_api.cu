@@ -77,14 +77,27 @@ cudaError_t band_set_attr(int bytes) {
 }
 constexpr int BAND_SMEM_MAX = 227 * 1024;   // dynamic shared memory one CTA may opt in to on sm_100
 inline int band_warps(int smem_per_warp) { return std::max(1, std::min(BAND_WARPS, BAND_SMEM_MAX / smem_per_warp)); }
+// Launch with programmatic stream serialization: the grid may become resident while the kernel before it in the stream
+// drains; the kernel itself waits (pdl_wait) before it touches anything that kernel wrote.  After anything but a kernel
+// (a copy, an event wait) this is an ordinary launch.
+template <typename A>
+cudaError_t launch_pdl(void (*k)(A), int grid, int block, size_t smem, cudaStream_t st, const A& arg) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, arg);
+}
 // One launch for the three window classes.  exact: the items carry the caller's log-probs unchanged (no fused log-softmax),
 // every decision is taken on the sums.
 void band_launch(const Band3Args& ba, bool exact, int grid, cudaStream_t st) {
     size_t smem = 0;
     for (int v = 0; v < BAND_NV; ++v) smem = std::max(smem, (size_t)ba.cls[v].npairs * ba.cls[v].smem_per_warp);
-    if (exact) viterbi_band3_kernel<0, true><<<grid, BAND_WARPS * 64, smem, st>>>(ba);
-    else if (ba.C == 66) viterbi_band3_kernel<66, false><<<grid, BAND_WARPS * 64, smem, st>>>(ba);
-    else viterbi_band3_kernel<0, false><<<grid, BAND_WARPS * 64, smem, st>>>(ba);
+    if (exact) launch_pdl(viterbi_band3_kernel<0, true>, grid, BAND_WARPS * 64, smem, st, ba);
+    else if (ba.C == 66) launch_pdl(viterbi_band3_kernel<66, false>, grid, BAND_WARPS * 64, smem, st, ba);
+    else launch_pdl(viterbi_band3_kernel<0, false>, grid, BAND_WARPS * 64, smem, st, ba);
 }
 
 // One internal side stream per device: when the caller expects items for the exact kernel (BfaShape.reserved), its first pass
@@ -221,7 +234,7 @@ int launch_viterbi(VitArgs& va, int max_items, int max_L, const DeviceInfo& d, c
         if (g_prof.on && profile) { e0 = g_prof.get(); e1 = g_prof.get(); }
     }
     if (e0) cudaEventRecord(e0, st);
-    viterbi_generic_kernel<0><<<ctas, VG_WARPS * 32, sizeof(WarpSmem) * VG_WARPS, st>>>(va);
+    launch_pdl(viterbi_generic_kernel<0>, ctas, VG_WARPS * 32, sizeof(WarpSmem) * VG_WARPS, st, va);
     LAUNCH_CHECK();
     if (e0) {
         cudaEventRecord(e1, st);
@@ -433,7 +446,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
             if (g_prof.on && g_prof.mode == 2) { ae0 = g_prof.get(); ae1 = g_prof.get(); }
         }
         if (ae0) cudaEventRecord(ae0, st);
-        assort_confidence_kernel<<<(B + ASSORT_WARPS - 1) / ASSORT_WARPS, ASSORT_WARPS * 32, assort_smem(aa.ts, aa.ss), st>>>(aa);
+        launch_pdl(assort_confidence_kernel, (B + ASSORT_WARPS - 1) / ASSORT_WARPS, ASSORT_WARPS * 32, assort_smem(aa.ts, aa.ss), st, aa);
         LAUNCH_CHECK();
         if (ae0) {
             cudaEventRecord(ae1, st);

@@ -119,4 +119,10 @@ __device__ __forceinline__ float mod_value(float x, bool is_target, bool use_sta
     return x;
 }
 
+// Programmatic dependent launch: a kernel launched with the stream-serialization attribute may become resident while the
+// kernel before it in the stream is still draining; pdl_wait() blocks until that kernel has completed and its writes are
+// visible (a no-op for an ordinary launch), pdl_release() lets the next kernel's CTAs take SM slots as this grid frees them.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace bfa

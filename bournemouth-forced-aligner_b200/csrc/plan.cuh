@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
     bool have_single = false;
     bool tok = false;
     __shared__ uint32_t s_mask[8][MAX_WORDS];
+    pdl_release();               // the banded kernel's CTAs may take their SMs while this grid drains
     if (u < a.B) {
     const BfaParams& p = a.p;
     UttCtx c;

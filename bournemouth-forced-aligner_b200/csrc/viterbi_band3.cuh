@@ -998,6 +998,8 @@ template <int CT, bool EXACT>
 __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_kernel(Band3Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_release();
+    pdl_wait();                               // the planner's item lists
     band3_run<3, CT, EXACT>(a, a.cls[0], smem_raw, warp, lane);
     band3_run<5, CT, EXACT>(a, a.cls[1], smem_raw, warp, lane);
     band3_run<8, CT, EXACT>(a, a.cls[2], smem_raw, warp, lane);

@@ -384,6 +384,8 @@ template <int KCLASS>
 __global__ void __launch_bounds__(VG_WARPS * 32, KCLASS == 0 ? 2 : 1) viterbi_generic_kernel(VitArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_release();
+    pdl_wait();                   // the item list of the planner / the banded kernel's retries
     const int first = a.first ? *a.first : 0;
     const int n_items = *a.n_items - first;
     if (n_items <= 0) return;     // nothing (left) for the exact kernel
