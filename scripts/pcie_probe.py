@@ -1,6 +1,6 @@
 """What bounds the host-buffer entry (bfa_align_batch_host): pinned host->device copy rate of the headline batch, next to the
 e2e step time at several chunk sizes.  Prints one JSON line.  The posteriors here are plain noise, the worst case for the
-aligner (no utterance passes the banded kernel's legality check, all are redone by the exact kernel), so the e2e times are an
+aligner (with no peak to follow, paths leave the band and utterances are redone by the exact kernel), so the e2e times are an
 upper bound; bench.py's e2e leg uses the headline's planted-peaky batch.  Measured (B200 box, PCIe Gen5 x16): 49.8-50.1 GB/s
 pinned H2D => the headline batch (650 MB) cannot arrive in less than 13.0 ms; bench.py's e2e step is 12.85-12.98 ms."""
 import json, sys, time
