@@ -16,6 +16,10 @@
  *    reference clones before mutating, forced_alignment.py:121).
  *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no
  *    hidden synchronisation and allocates nothing, except the *_host convenience entry.
+ *    The device entries can therefore be captured into a CUDA graph (stream capture) and replayed on
+ *    new data in the same buffers: the internal side streams fork and join with events only, and the
+ *    kernels that use programmatic dependent launch are captured as such
+ *    (tests/test_cuda_parity.py::test_align_batch_replays_from_a_cuda_graph).
  *  - return value: 0 on success, negative BFA_E_* on argument/launch errors.  Data conditions
  *    are reported per utterance in status[] (BFA_ST_*), mirroring the reference's exceptions
  *    (ValueError "Audio too short to align", forced_alignment.py:161-165).

@@ -572,3 +572,55 @@ def test_shim_aligner_from_posteriors_vs_reference(bfa, dev):
     for r in res:
         assert [f[3] for f in r["phoneme_timestamps"]] == list(range(N)) and [f[3] for f in r["group_timestamps"]] == list(range(N))
         assert all(len(f) == 8 and f[7] >= f[6] for f in r["group_timestamps"])
+
+
+def test_align_batch_replays_from_a_cuda_graph(bfa, dev):
+    """The whole launch sequence of bfa_align_batch (planner, banded kernel with its dependent launches, the exact kernel's
+    pass on the forked side streams, stamps + confidences) is capturable: a CUDA graph captured on one batch and replayed on
+    new posteriors in the same buffers gives exactly what a direct call gives."""
+    from bfa_b200 import synth
+    Cc = 66
+    Ts = [600] * 24 + [90] * 4 + [300] * 4          # 90 frames for 40 phonemes: stride 2 -> the exact kernel (hint > 0)
+    Ns = [40] * 32
+    B = len(Ts)
+    dec = bfa.AlignmentUtils(Cc - 1, 0).viterbi_decoder
+    params = dec._params(True, True, True)
+
+    def batch(seed):
+        rows, tg = [], []
+        for b in range(B):
+            lp, tgt, _ = synth.planted_batch(1, Ts[b], Ns[b], Cc, seed=seed + b, peak=9.0)
+            rows.append(lp.reshape(-1)); tg.append(tgt.reshape(-1))
+        return torch.cat(rows).to(dev), torch.cat(tg).to(torch.int32).to(dev)
+
+    lp0, tg0 = batch(1000)
+    lp1, tg1 = batch(2000)
+    row_off = torch.tensor(np.concatenate([[0], np.cumsum(np.asarray(Ts[:-1], np.int64) * Cc)]), dtype=torch.int64, device=dev)
+    plan = dec.plan_batch(Ts, Ns, Cc, params=params, device=dev)
+    assert plan.shape.reserved > 0                   # the side-stream pass is part of what gets captured
+    lp_buf, tg_buf = lp0.clone(), tg0.clone()
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(s):
+        res = dec.align_batch(lp_buf, row_off, Ts, Cc, tg_buf, Ns, params=params, plan=plan)        # warm-up: allocates everything
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            dec.align_batch(lp_buf, row_off, Ts, Cc, tg_buf, Ns, params=params, plan=plan, out=res)
+    torch.cuda.current_stream(dev).wait_stream(s)
+    lp_buf.copy_(lp1); tg_buf.copy_(tg1)
+    res.arena.zero_(); res.frame_ph.fill_(-7); res.frame_idx.fill_(-7)
+    g.replay()
+    torch.cuda.synchronize()
+    got = [t.cpu().numpy().copy() for t in (res.frame_ph, res.frame_idx, res.status, res.n_stamps, res.stamps, res.conf, res.dp_final)]
+    ref = dec.align_batch(lp1, row_off, Ts, Cc, tg1, Ns, params=params, plan=plan)
+    torch.cuda.synchronize()
+    want = [t.cpu().numpy() for t in (ref.frame_ph, ref.frame_idx, ref.status, ref.n_stamps, ref.stamps, ref.conf, ref.dp_final)]
+    assert (want[2] & 7 == 0).all()
+    for a_, b_ in zip(got[:4], want[:4]):
+        np.testing.assert_array_equal(a_, b_)
+    for b in range(B):
+        n = want[3][b]
+        np.testing.assert_array_equal(got[4][b, :n], want[4][b, :n])
+        np.testing.assert_array_equal(got[5][b, :n], want[5][b, :n])
+    np.testing.assert_array_equal(got[6], want[6])
