@@ -44,6 +44,8 @@ struct Prof {
     std::mutex mu;
     bool on = false;
     int mode = 0;     // 2: also time the planner and the stamp kernel (development)
+    int every = 1;    // bracket the banded kernel of every `every`-th bfa_align_batch call only (the events cost device time)
+    unsigned calls = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> tagged;   // mode 2: (0 planner, 1 stamps) kernels too
     std::vector<cudaEvent_t> pool;
@@ -410,7 +412,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         {
             std::lock_guard<std::mutex> lk(g_prof.mu);
-            if (g_prof.on) { e0 = g_prof.get(); e1 = g_prof.get(); }
+            if (g_prof.on && (g_prof.calls++ % (unsigned)g_prof.every) == 0) { e0 = g_prof.get(); e1 = g_prof.get(); }
         }
         if (e0) cudaEventRecord(e0, st);
         band_launch(ba, !boost, band_grid, st);       // all three window classes in one launch
@@ -567,10 +569,14 @@ int bfa_debug_phases(unsigned long long* out16, int reset) {   // 32 counters: [
     return BFA_OK;
 }
 
-void bfa_profile_enable(int on) {   // 1: the dominant kernel; 2 (development): the planner and the stamp kernel as well
+// low byte 1: the dominant kernel; 2 (development): the planner and the stamp kernel as well.  Bits 8-15, when non-zero:
+// sample the banded kernel of every n-th bfa_align_batch call only, starting with the next call.
+void bfa_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(g_prof.mu);
-    g_prof.on = on != 0;
-    g_prof.mode = on;
+    g_prof.on = (on & 0xff) != 0;
+    g_prof.mode = on & 0xff;
+    g_prof.every = ((on >> 8) & 0xff) ? ((on >> 8) & 0xff) : 1;
+    g_prof.calls = 0;
 }
 
 // Development aid (mode 2): mean device time in ms of the planner (out2[0]) and of the stamp kernel (out2[1]) since the last read.

@@ -214,7 +214,10 @@ int bfa_soft_boundaries_batch(int32_t B, int32_t C, const float *logp, const int
 
 /* Measurement hook: when enabled, bfa_align_batch / bfa_viterbi_paths bracket the dominant kernel
  * (the Viterbi fill+back-trace) with CUDA events on the launch stream; bfa_profile_read waits for
- * them and returns the summed device time and the number of launches since the previous read. */
+ * them and returns the summed device time and the number of launches since the previous read.
+ * on: 0 off, 1 on; (n << 8) | 1 brackets only every n-th bfa_align_batch call (n <= 255), starting
+ * with the next one: the event records cost device time and stand between kernels that otherwise use
+ * programmatic dependent launch, so a sampled measurement disturbs the timed loop less. */
 void bfa_profile_enable(int on);
 int bfa_profile_read(float *dominant_ms, int32_t *n_launches);
 int bfa_profile_read_aux(float *out2);   /* development: planner / stamp kernel means after bfa_profile_enable(2) */
