@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--unfused-conf", action="store_true", help="A/B switch: gather the confidence inputs in the stamp kernel (BFA_FLAG_UNFUSED_CONF)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--chain", action="store_true", help="A/B: always launch the full planner chain (no BFA_FLAG_DIRECT_ONLY)")
+    ap.add_argument("--no-pipeline", action="store_true", help="A/B: no BFA_FLAG_PIPELINED (launches do not overlap)")
     return ap.parse_args()
 
 
@@ -109,6 +111,15 @@ class ClockSampler:
 def algorithmic_bytes(B, T, N, C):
     """per frame 4*C read + 8 written; per utterance 24*N (targets + stamp records)."""
     return B * (T * (4 * C + 8) + 24 * N)
+
+
+def csrc_hash():
+    """sha256 (16 hex digits) over the kernel sources: ties an ncu capture to the build it was taken on."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "bournemouth-forced-aligner_b200" / "csrc").glob("*.cu*")):
+        h.update(f.name.encode()); h.update(f.read_bytes())
+    return h.hexdigest()[:16]
 
 
 def measured_peak():
@@ -193,7 +204,15 @@ def main():
     dec = au.viterbi_decoder
     params = dec._params(True, True, True)
     if not bool((tgt == 0).any()):
-        params.reserved |= _cabi.HINT_NO_SIL   # host-side knowledge of the targets (they come from the phonemizer on the host)
+        # host-side knowledge of the targets (they come from the phonemizer on the host): no silence_id anywhere, every utterance
+        # is one plain stride-4 problem -> the library launches ONE kernel per batch (BFA_FLAG_DIRECT_ONLY; utterances it could not
+        # finish would be flagged BFA_ST_DEFERRED, checked below), and because the posteriors are resident before the loop starts
+        # the launches may overlap their ramp-up / tail (BFA_FLAG_PIPELINED)
+        params.reserved |= _cabi.HINT_NO_SIL
+        if not a.chain:
+            params.reserved |= _cabi.FLAG_DIRECT_ONLY
+            if not a.no_pipeline:
+                params.reserved |= _cabi.FLAG_PIPELINED
     if a.unfused_conf:
         params.reserved |= 4
     row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T * Cc)
@@ -268,11 +287,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    l0 = lib.bfa_launch_count()
+    step(); drain(); torch.cuda.synchronize()
+    one_kernel = (lib.bfa_launch_count() - l0) == 1     # the whole step is ONE kernel: the region's events are that kernel's events
     launches0 = lib.bfa_launch_count()
-    # N=1: the banded kernel of every step is bracketed by CUDA events.  N>1: every 4th step only (first timed step included) -
-    # there the event records cost more (they also serialise against the side-stream pushes), and the roofline is an N=1 matter
+    # More than one kernel per step: the dominant kernel is bracketed by CUDA events of its own (N=1: every step, N>1: every 4th
+    # step - there the event records also serialise against the side-stream pushes).  One kernel per step: no events inside the
+    # region, the kernel's average duration is the region's time / K.
     PROFILE_EVERY = 1 if world == 1 else 4
-    lib.bfa_profile_enable(1 | (PROFILE_EVERY << 8))
+    lib.bfa_profile_enable(0 if one_kernel else (1 | (PROFILE_EVERY << 8)))
     lib.bfa_profile_read(None, None)
     sampler = ClockSampler(local)
     sampler.start()
@@ -318,14 +341,34 @@ def main():
              "how": "same K steps, bfa_profile_enable(0): no per-kernel events inside any step"}
 
     # ---- roofline of the dominant kernel (Viterbi fill + back-trace), timed by CUDA events on its stream
+    assert int((r.status[:B] & 7 != 0).sum()) == 0, "an utterance of the timed region was not finished (deferred / non-OK status)"
     peak, peak_src = measured_peak()
     alg = algorithmic_bytes(B, T, N, Cc)
-    dom_avg_ms = dom_ms.value / max(dom_n.value, 1)
+    ctag = f"<{Cc},false>" if Cc == 66 else "<0,false> (run-time class count)"
+    if one_kernel:
+        dom_avg_ms = ms / a.steps
+        kname = f"viterbi_band3_direct_kernel{ctag} (the whole step: in-kernel planning, fill, back-trace, frame labels, stamps, confidences)"
+        how = (f"one kernel per step: CUDA events on the launch stream around the {a.steps} back-to-back launches of the timed region / {a.steps}"
+               + ("; consecutive launches overlap ramp-up and tail SM by SM (programmatic dependent launch), see isolated_launch_ms" if params.reserved & _cabi.FLAG_PIPELINED else ""))
+    else:
+        dom_avg_ms = dom_ms.value / max(dom_n.value, 1)
+        kname = f"viterbi_band3_direct_kernel{ctag} (first kernel of the chain: planning, fill, back-trace, stamps, confidences of every plain utterance)"
+        how = f"CUDA events on the launch stream around {'every' if PROFILE_EVERY == 1 else f'every {PROFILE_EVERY}th'} launch inside the timed region, {dom_n.value} launches averaged"
     achieved = alg / (dom_avg_ms / 1e3) / 1e9 if dom_avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "viterbi_band3_kernel<66,false> (fill + back-trace; one launch for the three window classes)", "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_avg_ms / (ms / a.steps),
-                "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                "kernel_ms_how": f"CUDA events on the launch stream around {'every' if PROFILE_EVERY == 1 else f'every {PROFILE_EVERY}th'} launch inside the timed region, {dom_n.value} launches averaged"}
+                "kernel": kname, "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_avg_ms / (ms / a.steps),
+                "algorithmic_bytes_per_launch": alg, "peak_source": peak_src, "kernel_ms_how": how}
+    # ---- the same kernel launched ALONE (events around every launch: nothing overlaps), and the full chain for comparison
+    if rank == 0 or world > 1:
+        lib.bfa_profile_enable(1); lib.bfa_profile_read(None, None)
+        for _ in range(10):
+            step()
+        drain(); torch.cuda.synchronize()
+        i_ms, i_n = C.c_float(), C.c_int32()
+        lib.bfa_profile_read(C.byref(i_ms), C.byref(i_n)); lib.bfa_profile_enable(0)
+        iso = i_ms.value / max(i_n.value, 1)
+        roofline["isolated_launch_ms"] = iso
+        roofline["isolated_launch_frac"] = (alg / (iso / 1e3) / 1e9 / peak) if iso > 0 else 0.0
     # ---- the fill phase by itself (north_star: ">= 70 % of the HBM roofline on the batched Viterbi fill"): the same kernel with
     #      the measurement switch BFA_FLAG_FILL_ONLY (rows streamed once, log-sum-exp, forward recursion, decision records
     #      written; no back-trace, no outputs), a few extra launches outside the timed region above
@@ -350,10 +393,15 @@ def main():
                                   "frac": (fill_bytes / (fill_ms / 1e3) / 1e9 / peak) if fill_ms > 0 else 0.0, "bytes": fill_bytes,
                                   "how": "same kernel, BFA_FLAG_FILL_ONLY (no back-trace, no outputs), 10 launches, CUDA events"}
         del scratch
+    # DRAM traffic per launch comes from an ncu capture (it cannot be measured in an unprofiled run); it is only quoted when the
+    # capture was taken on the kernel sources of THIS build (hash of csrc/), otherwise null
     tf = ROOT / "profiles" / "traffic_latest.json"
     if tf.exists():
         try:
-            roofline["traffic"] = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+            tj = json.loads(tf.read_text())
+            if tj.get("csrc_sha16") == csrc_hash():
+                roofline["traffic"] = tj.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = tj.get("source")
         except Exception:
             pass
 

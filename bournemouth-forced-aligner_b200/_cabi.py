@@ -13,9 +13,12 @@ LIB_PATH = Path(os.environ["BFA_B200_LIB"]) if os.environ.get("BFA_B200_LIB") el
 
 BFA_OK, BFA_E_INVALID, BFA_E_UNSUPPORTED, BFA_E_WORKSPACE, BFA_E_CUDA = 0, -1, -2, -3, -4
 ST_OK, ST_EMPTY_TARGET, ST_TOO_SHORT, ST_PROPORTIONAL, ST_SEGMENTED = 0, 1, 2, 3, 4
+ST_DEFERRED = 5
 ST_DEGENERATE, ST_STAMP_OVERFLOW = 8, 16
 MODE_FULL, MODE_SIMPLE = 0, 1
 FLAG_EXACT_ONLY, HINT_NO_SIL = 1, 2
+FLAG_UNFUSED_CONF, FLAG_NO_SPEC, FLAG_FILL_ONLY = 4, 8, 16
+FLAG_NO_DIRECT, FLAG_DIRECT_ONLY, FLAG_PIPELINED = 32, 64, 128
 MAX_C, MAX_L = 256, 1024
 
 
@@ -63,6 +66,7 @@ _SIGNATURES = {
     "bfa_profile_read_aux": (C.c_int, [_P]),
     "bfa_debug_item_counts": (C.c_int, [_P]),
     "bfa_debug_ctas": (C.c_int, [_P, C.c_int]),
+    "bfa_debug_fin": (C.c_int, [_P, C.c_int]),
     "bfa_profile_enable": (None, [C.c_int]),
     "bfa_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }

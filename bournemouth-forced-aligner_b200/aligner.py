@@ -98,12 +98,28 @@ def exact_items_hint(T, N, params) -> int:
     if T.size == 0:
         return 0
     L = 4 * N + 1
-    dense = (L > 0.9 * T) if params.mode == _cabi.MODE_SIMPLE else (L > T)
+    dense = (L > 0.8 * T) if params.mode == _cabi.MODE_SIMPLE else (L > T)
     band = np.where(L > 60, np.maximum(L // 4, 20), 0)
     adv = (8 * (L - 1) + np.maximum(T - 2, 0)) // np.maximum(T - 1, 1)
     need = np.where(band > 0, np.minimum((2 * band + adv + 6) // 4 + 1, N + 1), N + 1)
     exact = (N > 0) & (T >= N) & (dense | (N > 128) | (need > 64))
     return int(exact.sum())
+
+
+def direct_only_worthwhile(T, N, params) -> bool:
+    """True when (nearly) every utterance of the batch is a plain stride-4 DP problem (forced_alignment.py:153: 4N+1 <= T), i.e.
+    when launching only the direct kernel (BFA_FLAG_DIRECT_ONLY) will finish the batch.  The caller has already established that no
+    target holds silence_id (or anchoring is off).  A wrong guess costs one extra launch of the full chain, never a wrong result."""
+    T = np.asarray(T, np.int64); N = np.asarray(N, np.int64)
+    if T.size == 0 or not params.ignore_noise:
+        return False
+    L = 4 * N + 1
+    ok = (N >= 1) & (N <= 128) & (T >= 2) & ((L <= 0.8 * T) if params.mode == _cabi.MODE_SIMPLE else (L <= T))
+    band = np.where(L > 60, np.maximum(L // 4, 20), 0)
+    adv = (8 * (L - 1) + np.maximum(T - 2, 0)) // np.maximum(T - 1, 1)
+    need = np.where(band > 0, np.minimum((2 * band + adv + 6) // 4 + 1, N + 1), N + 1)
+    ok &= need <= 24
+    return bool(ok.all())
 
 
 class BatchPlan:
@@ -341,13 +357,20 @@ class AlignmentUtils:
         T = self._lens(pred_lens, B, T_max)
         S = int(true_seqs.shape[1]) if true_seqs.dim() == 2 else 0
         N = self._lens(true_seqs_lens, B, S)
-        if not true_seqs.is_cuda and params.silence_id >= 0 and S > 0:
+        # can any utterance take the silence-anchored segmentation attempt (forced_alignment.py:133)?
+        may_segment = params.mode == _cabi.MODE_FULL and params.silence_anchors > 0 and params.silence_id >= 0
+        if may_segment and not true_seqs.is_cuda and S > 0:
             # targets still live on the host (core.py builds them there): a free check lets the library skip the
             # row-statistics pass that only the silence scan needs (BFA_HINT_NO_SIL; purely a performance hint)
             lens = torch.as_tensor(N)[:, None]
             has_sil = bool(((true_seqs == params.silence_id) & (torch.arange(S)[None, :] < lens)).any())
             if not has_sil:
                 params.reserved |= _cabi.HINT_NO_SIL
+                may_segment = False
+        # Without segmentation every utterance that is a plain stride-4 problem is finished by ONE kernel (in-kernel planning,
+        # Viterbi, stamps, confidences): launch only that kernel; whatever it flags as deferred is run again below
+        if not may_segment and S > 0 and direct_only_worthwhile(T, N, params):
+            params.reserved |= _cabi.FLAG_DIRECT_ONLY
         seqs = true_seqs.to(dev)
         N_dev = torch.tensor(N, dtype=torch.int64, device=dev)
         mask = torch.arange(S, device=dev)[None, :] < N_dev[:, None]
@@ -355,6 +378,10 @@ class AlignmentUtils:
         row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T_max * C_)
         r = self.viterbi_decoder.align_batch(lp, row_off, T, C_, tgt, N, params=params, want_stamps=True, want_conf=want_conf)
         st = r.status[:B].cpu().numpy()
+        if ((st & 7) == _cabi.ST_DEFERRED).any():  # the one-kernel path handed utterances back: the full chain takes the batch
+            params.reserved &= ~(_cabi.FLAG_DIRECT_ONLY | _cabi.FLAG_PIPELINED)
+            r = self.viterbi_decoder.align_batch(lp, row_off, T, C_, tgt, N, params=params, want_stamps=True, want_conf=want_conf)
+            st = r.status[:B].cpu().numpy()
         if (st & _cabi.ST_STAMP_OVERFLOW).any():   # more runs than the default stamp pitch (degenerate paths): use the safe pitch
             r = self.viterbi_decoder.align_batch(lp, row_off, T, C_, tgt, N, params=params, want_stamps=True, want_conf=want_conf,
                                                  max_stamps=max(T_max, 1))

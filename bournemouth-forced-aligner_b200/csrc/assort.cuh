@@ -99,12 +99,14 @@ struct AssortArgs {
     float* conf;       // may be null
     int32_t* n_stamps;
     const float* path_lp;   // per-frame gathered lp (or null: gather from logp)
+    const int32_t* uflag;   // when non-null: utterances with uflag[u] != 0 were finished (stamps included) by the direct kernel
 };
 
 __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(AssortArgs a) {
     const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     pdl_wait();                   // the frame labels of the Viterbi kernels
     if (u >= a.B) return;
+    if (a.uflag && a.uflag[u]) return;
     const int st = a.status[u] & 7;
     if (st == BFA_ST_EMPTY_TARGET || st == BFA_ST_TOO_SHORT) {   // :894-897 -> [] ; ValueError
         if (lane == 0) a.n_stamps[u] = 0;

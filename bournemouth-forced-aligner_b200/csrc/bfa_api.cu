@@ -22,6 +22,7 @@ namespace {
 
 std::atomic<long long> g_launches{0};
 int* g_last_counters = nullptr;   // development aid, see bfa_debug_item_counts
+int g_last_direct_B = 0;          // utterances offered to the direct kernel by that call (0: not used)
 thread_local char g_cuda_err[256] = "";
 
 #define CUDA_TRY(expr)                                                                              \
@@ -60,8 +61,14 @@ struct DeviceInfo {
     int vg_ctas_per_sm = 0;      // short-path class (L <= 256)
     int vg_ctas_per_sm_big = 0;  // long-path class
     bool band_ok = false;        // banded kernel usable (dynamic smem attribute set)
+    int nsmid = 0;               // %nsmid: exclusive upper bound of %smid (the direct kernel's per-SM scratch slots)
     bool ok = false;
 };
+__global__ void nsmid_kernel(int* out) {
+    unsigned n;
+    asm("mov.u32 %0, %%nsmid;" : "=r"(n));
+    *out = (int)n;
+}
 
 // The banded-kernel variants launched per call: 8 lanes per utterance, G groups per lane -> window 24 / 40 / 64 groups;
 // each exists specialised for C = 66 (the benchmark width, class loop fully unrolled) and for a run-time C.
@@ -75,6 +82,9 @@ cudaError_t band_set_attr(int bytes) {
     cudaError_t e = cudaFuncSetAttribute(viterbi_band3_kernel<66, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<66, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     return e;
 }
 constexpr int BAND_SMEM_MAX = 227 * 1024;   // dynamic shared memory one CTA may opt in to on sm_100
@@ -91,6 +101,21 @@ cudaError_t launch_pdl(void (*k)(A), int grid, int block, size_t smem, cudaStrea
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, k, arg);
+}
+template <typename A>
+cudaError_t launch_maybe_pdl(void (*k)(A), int grid, int block, size_t smem, cudaStream_t st, const A& arg, bool pdl) {
+    if (pdl) return launch_pdl(k, grid, block, smem, st, arg);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    return cudaLaunchKernelEx(&cfg, k, arg);
+}
+// The direct kernel (one launch per batch on the common path).  At least half of an SM's shared memory is requested so that two
+// CTAs of it can never share an SM: its scratch is indexed by the physical SM.
+void direct_launch(const Band3Args& ba, bool exact, int grid, cudaStream_t st, bool pdl) {
+    const size_t smem = std::max((size_t)ba.cls[0].npairs * ba.cls[0].smem_per_warp, (size_t)116 * 1024);
+    if (exact) launch_maybe_pdl(viterbi_band3_direct_kernel<0, true>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
+    else if (ba.C == 66) launch_maybe_pdl(viterbi_band3_direct_kernel<66, false>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
+    else launch_maybe_pdl(viterbi_band3_direct_kernel<0, false>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
 }
 // One launch for the three window classes.  exact: the items carry the caller's log-probs unchanged (no fused log-softmax),
 // every decision is taken on the sums.
@@ -150,6 +175,17 @@ int device_info(DeviceInfo& out) {
         const int band_smem_max = BAND_SMEM_MAX;
         d.band_ok = band_set_attr(band_smem_max) == cudaSuccess;
         if (!d.band_ok) (void)cudaGetLastError();   // do not leave a sticky error behind: the exact kernel still runs
+        {   // one-time query of %nsmid (first call on this device only; never inside a stream capture: bfa_workspace_bytes comes first)
+            int* dn = nullptr;
+            int hn = 0;
+            if (cudaMalloc(&dn, sizeof(int)) == cudaSuccess) {
+                nsmid_kernel<<<1, 1>>>(dn);
+                if (cudaMemcpy(&hn, dn, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) hn = 0;
+                cudaFree(dn);
+            }
+            (void)cudaGetLastError();
+            d.nsmid = hn >= d.sms ? hn : 0;     // 0: direct kernel unavailable
+        }
         d.ok = true;
     }
     out = d;
@@ -168,6 +204,11 @@ struct Layout {
     long long band_slab_words[BAND_NV];
     size_t off_tmask, off_tgtok, off_need, off_rowstat, off_items_local, off_items, off_fast[BAND_NV], off_lists, off_padded, off_anchors, off_counters,
         off_pathlp, off_gcls, off_bp, off_bp_band[BAND_NV], total;
+    // direct kernel
+    bool direct;                 // usable for this shape / parameter set
+    int d_tpitch, d_ncap, d_region, d_smem_per_pair, d_npairs;
+    long long d_slab_words;
+    size_t off_deferred, off_uflag, off_dslab, off_pscr_lp, off_pscr_gs;
 };
 
 
@@ -218,6 +259,24 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
         L.off_bp_band[v] = o;
         o = align_up(o + (size_t)L.band_grid * BAND_WARPS * (size_t)L.band_slab_words[v] * 4);
     }
+    // ---- direct kernel: in-kernel planning + stamps; needs ignore_noise (stamps = phoneme runs) and a shape whose back-trace
+    //      staging fits at least 4 pairs per SM.  Scratch is per physical SM (d.nsmid slots).
+    L.direct = false;
+    L.d_tpitch = (std::max(s.max_T, 1) + 15) & ~15;
+    L.d_ncap = std::max(1, std::min(s.max_N, B3_NMAX));
+    L.d_region = (int)band3_direct_region(s.C, L.d_tpitch, L.d_ncap);
+    L.d_smem_per_pair = (int)band3_smem_per_pair((size_t)L.d_region);
+    L.d_npairs = std::min(BAND_WARPS, BAND_SMEM_MAX / L.d_smem_per_pair);
+    L.d_slab_words = (long long)((s.max_T + 31) / 32 + 1) * band_rec_words(3) * 32;
+    if (d.band_ok && d.nsmid > 0 && s.C <= B3_KK && p.ignore_noise && !(p.reserved & (BFA_FLAG_EXACT_ONLY | BFA_FLAG_NO_DIRECT)) &&
+        (p.mode == BFA_MODE_FULL || p.mode == BFA_MODE_SIMPLE) && L.d_npairs >= 4 && s.max_T < (1 << 22) && s.B > 0)
+        L.direct = true;
+    L.off_deferred = o; o = align_up(o + (L.direct ? (size_t)s.B * 4 : 0));
+    L.off_uflag = o; o = align_up(o + (L.direct ? (size_t)s.B * 4 : 0));
+    const size_t dslots = L.direct ? (size_t)d.nsmid * L.d_npairs : 0;
+    L.off_dslab = o; o = align_up(o + dslots * (size_t)L.d_slab_words * 4);
+    L.off_pscr_lp = o; o = align_up(o + dslots * B3_UPW * (size_t)L.d_tpitch * 4);
+    L.off_pscr_gs = o; o = align_up(o + dslots * B3_UPW * (size_t)L.d_tpitch);
     L.total = o;
     return BFA_OK;
 }
@@ -324,12 +383,59 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     const int B = shape->B, C = shape->C;
     const bool boost = p->boost_targets && p->mode == BFA_MODE_FULL;
 
+    if (stamps && shape->max_stamps <= 0) return BFA_E_INVALID;
     uint32_t* tmask = (uint32_t*)(ws + L.off_tmask);
     float2* rowstat = L.want_rowstat ? (float2*)(ws + L.off_rowstat) : nullptr;
     float* path_lp = (stamps && conf && !(p->reserved & BFA_FLAG_UNFUSED_CONF)) ? (float*)(ws + L.off_pathlp) : nullptr;
+    // counter slots: 0 items of the exact kernel (planner + retries), 1-2 its work counters (short / long class), 3 5 7 items of
+    // the banded window classes, 10 the planner's exact-item count (side-stream pass), 11-12 work counters of the second exact
+    // pass, 13 utterances the direct kernel handed back
     int* counters = (int*)(ws + L.off_counters);
-    CUDA_TRY(cudaMemsetAsync(counters, 0, 64, st));
     g_last_counters = counters;
+    g_last_direct_B = 0;
+    const bool fast = (p->reserved & 1) == 0 && C <= B3_KK && d.band_ok;
+    // The direct kernel takes every utterance that is one plain stride-4 DP problem and finishes it (frame labels, timestamps,
+    // confidences); the planner chain below then only sees what it handed back (device-side list).  With BFA_FLAG_DIRECT_ONLY the
+    // chain is not launched at all and such utterances are flagged instead.
+    const bool use_direct = L.direct && fast;
+    const bool direct_only = use_direct && (p->reserved & BFA_FLAG_DIRECT_ONLY) != 0;
+    int* deferred = use_direct && !direct_only ? (int*)(ws + L.off_deferred) : nullptr;
+    int32_t* uflag = use_direct && !direct_only ? (int32_t*)(ws + L.off_uflag) : nullptr;
+    if (!direct_only) CUDA_TRY(cudaMemsetAsync(counters, 0, 64, st));
+    if (use_direct) {
+        g_last_direct_B = direct_only ? 0 : B;
+        Band3Args da;
+        memset(&da, 0, sizeof(da));
+        da.p = *p; da.C = C; da.logp = logp; da.tgt = tgt;
+        da.frame_ph = frame_ph; da.frame_idx = frame_idx; da.dp_final = dp_final;
+        da.cls[0].bp_scratch = (uint32_t*)(ws + L.off_dslab);
+        da.cls[0].bp_slab_words = L.d_slab_words;
+        da.cls[0].smem_per_warp = L.d_smem_per_pair;
+        da.cls[0].npairs = L.d_npairs;
+        da.cls[0].region = L.d_region;
+        da.B = B; da.row_off = (const long long*)row_off; da.T = T; da.tgt_off = (const long long*)tgt_off;
+        da.frame_off = (const long long*)frame_off; da.status = status; da.stamps = stamps; da.conf = stamps ? conf : nullptr;
+        da.n_stamps = n_stamps; da.max_stamps = shape->max_stamps;
+        da.uflag = uflag; da.deferred = deferred; da.n_deferred = counters + 13;
+        const bool spec = path_lp != nullptr && !(p->reserved & BFA_FLAG_NO_SPEC);
+        da.pscr_lp = spec ? (float*)(ws + L.off_pscr_lp) : nullptr;
+        da.pscr_gs = spec ? (unsigned char*)(ws + L.off_pscr_gs) : nullptr;
+        da.tpitch = L.d_tpitch; da.ncap = L.d_ncap; da.nslots = d.nsmid; da.direct_only = direct_only ? 1 : 0;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_prof.mu);
+            if (g_prof.on && (g_prof.calls++ % (unsigned)g_prof.every) == 0) { e0 = g_prof.get(); e1 = g_prof.get(); }
+        }
+        if (e0) cudaEventRecord(e0, st);
+        direct_launch(da, !boost, d.sms, st, direct_only && (p->reserved & BFA_FLAG_PIPELINED) != 0);
+        LAUNCH_CHECK();
+        if (e0) {
+            cudaEventRecord(e1, st);
+            std::lock_guard<std::mutex> lk(g_prof.mu);
+            g_prof.pending.emplace_back(e0, e1);
+        }
+        if (direct_only) return BFA_OK;
+    }
 
     // Row statistics are only materialised for the planner's silence scan (utterances whose target holds
     // SIL); the Viterbi kernels fuse boost + log_softmax + floor into their row loads.
@@ -348,7 +454,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     pa.item_cap = L.item_cap; pa.gmax = L.gmax; pa.amax = L.amax; pa.anchor_words = L.anchor_words;
     pa.items_local = (Item*)(ws + L.off_items_local); pa.items = (Item*)(ws + L.off_items);
     pa.n_items = counters; pa.lists = (int32_t*)(ws + L.off_lists); pa.list_ints = L.list_ints;
-    const bool fast = (p->reserved & 1) == 0 && C <= B3_KK && d.band_ok;
+    pa.deferred = deferred; pa.n_deferred = counters + 13;
     for (int v = 0; v < BAND_NV; ++v) { pa.fast_items[v] = (Item*)(ws + L.off_fast[v]); pa.n_fast[v] = counters + 3 + 2 * v; }
     pa.fast_enable = fast ? 1 : 0; pa.path_lp = path_lp;
     pa.padded = (float*)(ws + L.off_padded); pa.anchors = (uint32_t*)(ws + L.off_anchors);
@@ -387,6 +493,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
             ba.cls[v].bp_slab_words = L.band_slab_words[v];
             ba.cls[v].smem_per_warp = L.band_smem_per_warp[v];
             ba.cls[v].npairs = band_warps(L.band_smem_per_warp[v]);
+            ba.cls[v].region = (int)band3_stage_region(C, BAND_G[v]);
         }
         // The caller expects `hint` items for the exact kernel (utterances too dense for stride 4, ...): its first pass, over the
         // planner's list, runs on a side stream on a few SMs of its own while the banded kernel takes the rest; what the banded
@@ -412,7 +519,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         {
             std::lock_guard<std::mutex> lk(g_prof.mu);
-            if (g_prof.on && (g_prof.calls++ % (unsigned)g_prof.every) == 0) { e0 = g_prof.get(); e1 = g_prof.get(); }
+            if (!use_direct && g_prof.on && (g_prof.calls++ % (unsigned)g_prof.every) == 0) { e0 = g_prof.get(); e1 = g_prof.get(); }
         }
         if (e0) cudaEventRecord(e0, st);
         band_launch(ba, !boost, band_grid, st);       // all three window classes in one launch
@@ -439,7 +546,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         aa.p = *p; aa.B = B; aa.C = C; aa.max_stamps = shape->max_stamps; aa.logp = logp; aa.row_off = (const long long*)row_off;
         aa.T = T; aa.frame_off = (const long long*)frame_off; aa.frame_ph = frame_ph; aa.frame_idx = frame_idx;
         aa.status = status; aa.stamps = stamps; aa.conf = conf; aa.n_stamps = n_stamps; aa.path_lp = path_lp;
-        if (shape->max_stamps <= 0) return BFA_E_INVALID;
+        aa.uflag = uflag;
         aa.ts = shape->max_N < 32768 ? assort_ts(shape->max_T) : 0;   // staged frames pack (idx, phoneme) into 16 + 16 bits
         aa.ss = assort_ss(shape->max_stamps);
         cudaEvent_t ae0 = nullptr, ae1 = nullptr;
@@ -533,6 +640,7 @@ int bfa_debug_item_counts(int32_t* out4) {
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(h, g_last_counters, sizeof(h), cudaMemcpyDeviceToHost));
     out4[0] = h[0]; out4[1] = h[3]; out4[2] = h[5]; out4[3] = h[7];
+    if (g_last_direct_B > 0) out4[1] += g_last_direct_B - h[13];   // finished by the direct kernel (24-group window as well)
     return BFA_OK;
 }
 
@@ -551,6 +659,17 @@ int bfa_debug_warps(unsigned long long* out32, int reset) {   // development: me
 #ifdef BFA_PHASE_PROF
     if (out32) CUDA_TRY(cudaMemcpyFromSymbol(out32, g_b3_warp, sizeof(unsigned long long) * 32));
     if (reset) { unsigned long long z[32] = {0}; CUDA_TRY(cudaMemcpyToSymbol(g_b3_warp, z, sizeof(z))); }
+#else
+    if (out32) memset(out32, 0, sizeof(unsigned long long) * 32);
+    (void)reset;
+#endif
+    return BFA_OK;
+}
+
+int bfa_debug_fin(unsigned long long* out32, int reset) {   // development: sub-phases of the direct kernel's finishing pass, [which * 16 + i]
+#ifdef BFA_PHASE_PROF
+    if (out32) CUDA_TRY(cudaMemcpyFromSymbol(out32, g_b3_fin, sizeof(unsigned long long) * 32));
+    if (reset) { unsigned long long z[32] = {0}; CUDA_TRY(cudaMemcpyToSymbol(g_b3_fin, z, sizeof(z))); }
 #else
     if (out32) memset(out32, 0, sizeof(unsigned long long) * 32);
     (void)reset;
@@ -622,7 +741,7 @@ int bfa_assort_batch(const BfaParams* p, int32_t B, const int32_t* T, const int6
     AssortArgs aa;
     aa.p = *p; aa.B = B; aa.C = 0; aa.max_stamps = max_stamps; aa.logp = nullptr; aa.row_off = nullptr; aa.T = T;
     aa.frame_off = (const long long*)frame_off; aa.frame_ph = frame_ph; aa.frame_idx = frame_idx; aa.status = status;
-    aa.stamps = stamps; aa.conf = nullptr; aa.n_stamps = n_stamps; aa.path_lp = nullptr;
+    aa.stamps = stamps; aa.conf = nullptr; aa.n_stamps = n_stamps; aa.path_lp = nullptr; aa.uflag = nullptr;
     aa.ts = 0; aa.ss = assort_ss(max_stamps);     // utterance lengths are only known on the device here: frames are read in place
     assort_confidence_kernel<<<(B + ASSORT_WARPS - 1) / ASSORT_WARPS, ASSORT_WARPS * 32, assort_smem(aa.ts, aa.ss), (cudaStream_t)stream>>>(aa);
     LAUNCH_CHECK();

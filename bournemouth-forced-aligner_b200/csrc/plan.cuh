@@ -44,6 +44,8 @@ struct PlanArgs {
     float* padded;             // [B][max_T + 16]
     uint32_t* anchors;         // [B][anchor_words]
     float* path_lp;            // [total_frames] raw log-prob of the class each frame was assigned to (for confidences), or null
+    const int* deferred;       // when non-null: plan only the utterances deferred[0 .. *n_deferred) (what the direct kernel left)
+    const int* n_deferred;
 };
 
 // ---- target-class bitmask: unique_targets = set(seq) - {blank, -100}, p < C (:44-49) ----
@@ -382,7 +384,8 @@ __device__ int plan_segmented(const UttCtx& c, Item* loc, int32_t* lists, uint32
 }
 
 __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ PlanArgs a) {
-    const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     int n_items = 0;
     Item* loc = nullptr;
     Item single;                 // the common case, one item = the whole utterance, never leaves lane 0's registers
@@ -390,6 +393,12 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
     bool tok = false;
     __shared__ uint32_t s_mask[8][MAX_WORDS];
     pdl_release();               // the banded kernel's CTAs may take their SMs while this grid drains
+    if (a.deferred) {            // the direct kernel went first: only what it handed back
+        pdl_wait();
+        const int nd = *a.n_deferred;
+        if (blockIdx.x * (blockDim.x >> 5) >= nd) return;      // uniform over the CTA
+        u = u < nd ? a.deferred[u] : a.B;
+    }
     if (u < a.B) {
     const BfaParams& p = a.p;
     UttCtx c;

@@ -61,6 +61,7 @@
 #pragma once
 #include <type_traits>
 
+#include "assort.cuh"
 #include "bfa_common.cuh"
 
 namespace bfa {
@@ -98,7 +99,29 @@ struct Band3Args {
         long long bp_slab_words;
         int smem_per_warp;     // bytes of shared memory per (DP, helper) pair
         int npairs;            // pairs per CTA that fit
+        int region;            // bytes of the pair's staging region (stage ring / back-trace staging), see band3_off_*
     } cls[3];
+    // ---- direct mode (viterbi_band3_direct_kernel): the kernel plans its utterances itself (task q = utterances 4q .. 4q+3),
+    //      emits timestamps and confidences from its own back-trace, and needs no item list.  cls[0] describes its window class.
+    int B;
+    const long long* row_off;
+    const int32_t* T;
+    const long long* tgt_off;
+    const long long* frame_off;
+    int32_t* status;
+    BfaStamp* stamps;          // may be null (frames only)
+    float* conf;               // may be null
+    int32_t* n_stamps;
+    int max_stamps;
+    int32_t* uflag;            // [B] 1: finished here, stamps included; 0: left to the planner chain.  Null in direct-only mode
+    int* deferred;             // utterances left to the planner chain (null in direct-only mode: status = BFA_ST_DEFERRED instead)
+    int* n_deferred;
+    float* pscr_lp;            // per-SM, per-pair scratch [slot][pair][UPW][tpitch]: raw log-prob of the frame-wise best class ...
+    unsigned char* pscr_gs;    // ... and that class (the confidence inputs wherever the path agrees with the guess)
+    int tpitch;                // frames per utterance in the scratch / shared staging arrays (multiple of 16, >= max_T)
+    int ncap;                  // phonemes per utterance the shared event / stamp arrays hold (>= max_N of the batch)
+    int nslots;                // SM slots the per-SM scratch and slabs were sized for (> every %smid)
+    int direct_only;           // no planner chain follows: utterances that do not qualify get status BFA_ST_DEFERRED
 };
 
 template <int G>
@@ -132,16 +155,35 @@ __host__ __device__ inline size_t band3_stage_region(int C, int G) {
 }
 // word offset of the visited-cell buffers inside the back-trace staging area (after the record buffers)
 __host__ __device__ inline int band3_bt_keep_words(int G) { return B3_NREC * (6 * G + 1) * 32; }
-// shared memory of one pair: stage ring | class weights | (lnS, eb) per staged row | target classes | helper flags | mbarriers
+// shared memory of one pair: staging region (stage ring, later the back-trace staging) | class weights | (lnS, eb) per staged row |
+// target classes | helper flags + utterance states | the pair's work items (direct mode) | mbarriers.  R = bytes of the region.
 enum : int { B3_BAR_FULL = 0, B3_BAR_READY = B3_NST, B3_BAR_FREE = 2 * B3_NST, B3_BAR_REC = 3 * B3_NST, B3_BAR_KREADY = 3 * B3_NST + B3_NREC,
-             B3_BAR_KFREE = 3 * B3_NST + B3_NREC + 2, B3_NBARS = 3 * B3_NST + B3_NREC + 4 };
-__host__ __device__ inline size_t band3_off_kk(int C, int G) { return band3_stage_region(C, G); }
-__host__ __device__ inline size_t band3_off_stats(int C, int G) { return band3_off_kk(C, G) + (size_t)B3_UPW * B3_KK * 4; }
-__host__ __device__ inline size_t band3_off_cls(int C, int G) { return band3_off_stats(C, G) + (size_t)B3_NST * B3_UPW * B3_STP * 8; }
-__host__ __device__ inline size_t band3_off_flags(int C, int G) { return band3_off_cls(C, G) + (size_t)B3_UPW * B3_NMAX; }
-__host__ __device__ inline size_t band3_off_bars(int C, int G) { return band3_off_flags(C, G) + 16; }
-__host__ __device__ inline size_t band3_smem_per_warp(int C, int G) {   // per PAIR of warps
-    return (band3_off_bars(C, G) + (size_t)B3_NBARS * 8 + 127) / 128 * 128;
+             B3_BAR_KFREE = 3 * B3_NST + B3_NREC + 2, B3_BAR_PLAN = 3 * B3_NST + B3_NREC + 4, B3_NBARS = 3 * B3_NST + B3_NREC + 5 };
+__host__ __device__ inline size_t band3_off_kk(size_t R) { return R; }
+__host__ __device__ inline size_t band3_off_stats(size_t R) { return band3_off_kk(R) + (size_t)B3_UPW * B3_KK * 4; }
+__host__ __device__ inline size_t band3_off_cls(size_t R) { return band3_off_stats(R) + (size_t)B3_NST * B3_UPW * B3_STP * 8; }
+__host__ __device__ inline size_t band3_off_flags(size_t R) { return band3_off_cls(R) + (size_t)B3_UPW * B3_NMAX; }
+__host__ __device__ inline size_t band3_off_items(size_t R) { return band3_off_flags(R) + 32; }
+__host__ __device__ inline size_t band3_off_bars(size_t R) { return band3_off_items(R) + (size_t)B3_UPW * sizeof(Item); }
+__host__ __device__ inline size_t band3_smem_per_pair(size_t R) { return (band3_off_bars(R) + (size_t)B3_NBARS * 8 + 127) / 128 * 128; }
+__host__ __device__ inline size_t band3_smem_per_warp(int C, int G) { return band3_smem_per_pair(band3_stage_region(C, G)); }   // per PAIR of warps
+
+// Direct mode: what the back-trace keeps in the staging region (G = 3).  Byte offsets:
+//   events [UPW][evcap] | (verdict, final score) [UPW] + event counts [UPW] | (start, end) per phoneme [UPW][ncap2] |
+//   record buffers during the walk, afterwards per warp of the pair: ph_s [tpitch] + ix_s [tpitch] int32 (the frame labels of the
+//   utterance it is finishing) | per utterance: lp_s [tpitch] floats + gs_s [tpitch] bytes (confidence inputs kept by the fill)
+__host__ __device__ inline int band3_evcap(int ncap) { return (3 * ncap + 8 + 3) & ~3; }
+__host__ __device__ inline size_t band3_d_off_ev() { return 0; }
+__host__ __device__ inline size_t band3_d_off_fin(int ncap) { return (size_t)B3_UPW * band3_evcap(ncap) * 4; }
+__host__ __device__ inline size_t band3_d_off_se(int ncap) { return band3_d_off_fin(ncap) + 64; }
+__host__ __device__ inline size_t band3_d_off_rec(int ncap) { return (band3_d_off_se(ncap) + (size_t)B3_UPW * ((ncap + 1) & ~1) * 8 + 127) / 128 * 128; }
+__host__ __device__ inline size_t band3_d_off_lp(int ncap, int tpitch) {
+    const size_t rec = (size_t)B3_NREC * (6 * 3 + 1) * 128, lab = (size_t)16 * tpitch;
+    return band3_d_off_rec(ncap) + (rec > lab ? rec : lab);
+}
+__host__ __device__ inline size_t band3_direct_region(int C, int tpitch, int ncap) {
+    const size_t st = band3_stage_region(C, 3), bt = band3_d_off_lp(ncap, tpitch) + (size_t)B3_UPW * 5 * tpitch;
+    return ((st > bt ? st : bt) + 15) / 16 * 16;
 }
 
 __device__ __forceinline__ float b3_ex2(float x) {
@@ -193,6 +235,10 @@ __device__ __forceinline__ void b3_push(uint32_t& acc, float earlier, float late
 __device__ unsigned long long g_b3_phase[32];
 __device__ unsigned long long g_b3_warp[32];
 __device__ unsigned long long g_b3_cta[160 * 2];   // [cta]: max DP task cycles, [160 + cta]: physical SM id   // [warp id]: summed task cycles, [16 + warp id]: tasks
+__device__ unsigned long long g_b3_fin[32];   // band3_direct_finish sub-phases: [which * 16 + i]
+#define FIN_DECL long long fin_last = clock64(); long long fin_acc[10] = {0,0,0,0,0,0,0,0,0,0}
+#define FIN_T(i) do { const long long fin_now = clock64(); fin_acc[i] += fin_now - fin_last; fin_last = fin_now; } while (0)
+#define FIN_FLUSH do { if (lane == 0) { for (int i = 0; i < 10; ++i) atomicAdd(&g_b3_fin[which * 16 + i], (unsigned long long)fin_acc[i]); } } while (0)
 #define PH_DECL long long ph_last = clock64(); long long ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; const int ph_base = 0
 #define PH_DECL_H long long ph_last = clock64(); long long ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; const int ph_base = 16
 #define PH_RESET ph_last = clock64()
@@ -202,6 +248,9 @@ __device__ unsigned long long g_b3_cta[160 * 2];   // [cta]: max DP task cycles,
     atomicAdd(&g_b3_warp[threadIdx.x >> 5], (unsigned long long)ph_tot); atomicAdd(&g_b3_warp[16 + (threadIdx.x >> 5)], 1ull); \
     if (ph_base == 0 && blockIdx.x < 160) { unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); atomicMax(&g_b3_cta[blockIdx.x], (unsigned long long)ph_tot); g_b3_cta[160 + blockIdx.x] = smid; } } } while (0)
 #else
+#define FIN_DECL
+#define FIN_T(i)
+#define FIN_FLUSH
 #define PH_DECL
 #define PH_DECL_H
 #define PH_RESET
@@ -209,7 +258,9 @@ __device__ unsigned long long g_b3_cta[160 * 2];   // [cta]: max DP task cycles,
 #define PH_FLUSH
 #endif
 
-// What both warps of a pair derive from the item list (uniform within an 8-lane segment).
+// What both warps of a pair derive from the item list (uniform within an 8-lane segment).  `my_item` is this lane's segment's
+// item: an entry of the global list (list mode) or the copy the helper warp planned into shared memory (direct mode); `on` says
+// whether the segment has work.
 template <int G, int CT>
 struct Band3Task {
     int seg, l8, C;
@@ -224,11 +275,11 @@ struct Band3Task {
     uint32_t bar0;
     const float* my_src;
     bool use_stats, warp_stats;
-    __device__ __forceinline__ Band3Task(const Band3Args& a, const Item* items, int first, int n_valid, unsigned char* smem_pair, int lane) {
+    __device__ __forceinline__ Band3Task(const Band3Args& a, const Item* my_item, bool on, unsigned char* smem_pair, size_t R, int lane) {
         seg = lane >> 3; l8 = lane & 7;
         C = CT ? CT : a.C;
-        seg_on = seg < n_valid;
-        it = &items[first + (seg_on ? seg : 0)];
+        seg_on = on;
+        it = my_item;
         T = seg_on ? it->T : 0;
         Tmax = T;
 #pragma unroll
@@ -238,51 +289,162 @@ struct Band3Task {
         lead = seg_on ? it->lead : 0;
         stage_floats = B3_UPW * seg_stride;
         stage_buf = reinterpret_cast<float*>(smem_pair);
-        kk = reinterpret_cast<float*>(smem_pair + band3_off_kk(C, G));                   // [UPW][B3_KK]
-        stats = reinterpret_cast<float2*>(smem_pair + band3_off_stats(C, G));            // [NST][UPW][B3_STP]
-        cls8 = smem_pair + band3_off_cls(C, G);                                          // [UPW][B3_NMAX]
-        hflags = reinterpret_cast<int*>(smem_pair + band3_off_flags(C, G));              // [UPW] helper verdict: rows not sane
-        bar0 = smem_u32(smem_pair + band3_off_bars(C, G));
+        kk = reinterpret_cast<float*>(smem_pair + band3_off_kk(R));                   // [UPW][B3_KK]
+        stats = reinterpret_cast<float2*>(smem_pair + band3_off_stats(R));            // [NST][UPW][B3_STP]
+        cls8 = smem_pair + band3_off_cls(R);                                          // [UPW][B3_NMAX]
+        hflags = reinterpret_cast<int*>(smem_pair + band3_off_flags(R));              // [UPW] helper verdict: rows not sane; then [UPW] utterance states (direct mode)
+        bar0 = smem_u32(smem_pair + band3_off_bars(R));
         my_src = a.logp + it->lp_off;
-        use_stats = (it->flags & ITEM_STATS) != 0;
+        use_stats = seg_on && (it->flags & ITEM_STATS) != 0;
         warp_stats = __any_sync(FULL, use_stats);   // every item of a call shares the mode
     }
 };
+// the segment's item and whether it is on: list mode (items of the window class) / direct mode (planned into shared memory)
+__device__ __forceinline__ const Item* band3_list_item(const Item* items, int first, int n_valid, int lane, bool& on) {
+    const int seg = lane >> 3;
+    on = seg < n_valid;
+    return &items[first + (on ? seg : 0)];
+}
+__device__ __forceinline__ const Item* band3_direct_item(unsigned char* smem_pair, size_t R, int lane, bool& on) {
+    const Item* it = reinterpret_cast<const Item*>(smem_pair + band3_off_items(R)) + (lane >> 3);
+    on = it->T > 0;
+    return it;
+}
+// utterance states of a direct-mode task (shared memory, after the helper flags)
+enum : int { B3_U_RUN = 0, B3_U_NONE = 1, B3_U_DEFER = 2 };
+
+// Direct mode: the helper warp plans the four utterances of task `task` (what plan_kernel's single-item branch does,
+// forced_alignment.py:153-190 / :963-976) and leaves their items in shared memory.  An utterance is taken here when it is a single
+// stride-4 DP problem that fits the 24-group window and its targets are plain phoneme classes; when silence anchoring is on and
+// the target holds silence_id (a segmentation attempt, :133), or anything else is unusual, it is left to the planner chain.
+template <int CT>
+__device__ __forceinline__ void band3_direct_plan(const Band3Args& a, int task, unsigned char* smem_pair, size_t R, int lane) {
+    constexpr float LOG2E = 1.4426950408889634f;
+    const int seg = lane >> 3, l8 = lane & 7;
+    const int C = CT ? CT : a.C;
+    const BfaParams& p = a.p;
+    Item* items = reinterpret_cast<Item*>(smem_pair + band3_off_items(R));
+    int* ustate = reinterpret_cast<int*>(smem_pair + band3_off_flags(R)) + B3_UPW;
+    unsigned char* cls8 = smem_pair + band3_off_cls(R) + seg * B3_NMAX;
+    float* kk = reinterpret_cast<float*>(smem_pair + band3_off_kk(R)) + seg * B3_KK;
+    const int u = task * B3_UPW + seg;
+    int state = B3_U_NONE;
+    Item it;
+    it.lp_off = 0; it.stat_off = 0; it.out_off = 0; it.out_lim = 0; it.seq_off = 0;
+    it.T = 0; it.L = 0; it.band = 0; it.stride = 4; it.n = 0; it.idx0 = 0; it.trim = 0; it.n_out = 0;
+    it.utt = u; it.anchor_off = 0; it.flags = 0; it.lead = 0;
+    int T = 0, N = 0;
+    const bool boost = p.boost_targets && p.mode == BFA_MODE_FULL;
+    if (u < a.B) {
+        state = B3_U_DEFER;
+        T = a.T[u];
+        const long long t0 = a.tgt_off[u], t1 = a.tgt_off[u + 1];
+        const long long ro = a.row_off[u], fo0 = a.frame_off[u], fo1 = a.frame_off[u + 1];
+        N = (int)min(t1 - t0, (long long)(1 << 20));
+        const int L = 4 * N + 1;
+        bool ok = N >= 1 && N <= B3_NMAX && N <= a.ncap && T >= 2 && T <= a.tpitch;
+        if (p.mode == BFA_MODE_SIMPLE) ok = ok && !((double)L > (double)T * 0.9) && !((double)L > (double)T * 0.8);   // :963-968: stride stays 4 (both tests see stride 4)
+        else ok = ok && L <= T;                                                          // :153-157
+        const int band = (L > 60) ? max(L / 4, 20) : 0;                                   // :190 / :976
+        ok = ok && L <= T && band3_window_need(N, T, L, band) <= B3_LPU * 3;
+        const int lead = (int)(((unsigned long long)(a.logp + ro) & 15ull) >> 2);
+        if (lead != 0 && (ro < lead || (C == 66 && (lead & 1)))) ok = false;     // same rule as the planner's fast_class
+        it.lp_off = ro; it.stat_off = fo0; it.out_off = fo0; it.out_lim = fo1; it.seq_off = t0;
+        it.L = L; it.band = band; it.n = N; it.n_out = T; it.lead = lead;
+        it.flags = ITEM_FINAL;
+        if (p.mode == BFA_MODE_FULL) it.flags |= (p.boost_targets ? ITEM_STATS : 0) | (p.enforce_minimum ? ITEM_FLOOR : 0);
+        if (ok) state = B3_U_RUN;
+    }
+    // targets: byte-sized class table + the class weights of the fused log-sum-exp, exp(x + boost*[c in targets] - boost) =
+    // 2^(x*log2e + kk[c]); every id must be a plain class, and none may be silence_id while silence anchoring is on
+    if (boost) {
+        for (int c = l8; c < B3_KK; c += B3_LPU) kk[c] = c < C ? -p.boost_factor * LOG2E : -INFINITY;
+    }
+    __syncwarp();
+    bool tbad = false;
+    if (state == B3_U_RUN) {
+        const bool segmenting = p.mode == BFA_MODE_FULL && p.silence_anchors > 0 && p.silence_id >= 0;
+        const int32_t* seq = a.tgt + it.seq_off;
+        int cv[B3_NMAX / B3_LPU];                  // all of this lane's targets in flight at once (one memory round trip)
+#pragma unroll
+        for (int i = 0; i < B3_NMAX / B3_LPU; ++i) {
+            const int j = l8 + B3_LPU * i;
+            cv[i] = j < N ? seq[j] : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < B3_NMAX / B3_LPU; ++i) {
+            const int j = l8 + B3_LPU * i;
+            if (j < N) {
+                const int c = cv[i];
+                if (c < 0 || c >= C || c == p.blank_id || (segmenting && c == p.silence_id)) tbad = true;
+                else {
+                    cls8[j] = (unsigned char)c;
+                    if (boost) kk[c] = 0.0f;
+                }
+            }
+        }
+    }
+    const unsigned bm = __ballot_sync(FULL, tbad);
+    if ((bm >> (seg * B3_LPU)) & 0xffu) state = B3_U_DEFER;
+    if (l8 == 0) {
+        it.T = state == B3_U_RUN ? T : 0;
+        items[seg] = it;
+        ustate[seg] = state;
+    }
+    __syncwarp();
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // Helper warp: tables, bulk copies, row statistics.
 // ------------------------------------------------------------------------------------------------------------
-template <int G, int CT>
-__device__ void band3_helper(const Band3Args& a, const Item* items, int first, int n_valid, unsigned char* smem_pair, uint32_t& phase, bool not_first,
-                             int lane, uint64_t pol) {
+// both warps of a pair meet here (named barrier 1 + pair, 64 threads): hand-overs of the direct mode
+__device__ __forceinline__ void band3_pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+
+template <int CT>
+__device__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair, size_t R, int seg0, int which, int lane, uint32_t& phase,
+                                    const float* pscr_lp, const unsigned char* pscr_gs);
+
+template <int G, int CT, bool DIRECT>
+__device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int first, int n_valid, unsigned char* smem_pair, uint32_t& phase, bool not_first,
+                             int lane, uint64_t pol, int pair, float* pscr_lp, unsigned char* pscr_gs) {
     constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-    const Band3Task<G, CT> k(a, items, first, n_valid, smem_pair, lane);
+    const size_t R = (size_t)kc.region;
+    // This warp finished the previous task last (it wrote that task's outputs; direct mode: both warps met at the pair barrier),
+    // so tables and staging area are free; the area was last written through the generic proxy and is about to be written by
+    // bulk copies.
+    PH_DECL_H;
+    if (not_first) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (DIRECT) band3_direct_plan<CT>(a, first, smem_pair, R, lane);      // `first` is the task number
+    PH_T(8);
+    bool on;
+    const Item* my_item = DIRECT ? band3_direct_item(smem_pair, R, lane, on) : band3_list_item(kc.items, first, n_valid, lane, on);
+    const Band3Task<G, CT> k(a, my_item, on, smem_pair, R, lane);
     const int seg = k.seg, l8 = k.l8, C = k.C, T = k.T;
     const int blank = a.p.blank_id;
     const float boostv = a.p.boost_factor;
     const bool warp_stats = k.warp_stats;
-    PH_DECL_H;
 
-    // This warp finished the previous task last (it wrote that task's outputs), so tables and staging area are free;
-    // the area was last written through the generic proxy and is about to be written by bulk copies.
-    if (not_first) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     // ---- per-utterance tables (built before the first bulk copies are issued: behind them these small loads would queue
     //      for microseconds): target classes (bytes) and the class weights of the fused log-sum-exp:
-    //      exp(x + boost*[c in targets] - boost) = 2^(x*log2e + kk[c]) ----
-    if (k.seg_on) {
-        const int32_t* seq = a.tgt + k.it->seq_off;
-        const int N = k.it->n;
-        for (int j = l8; j < N; j += B3_LPU) k.cls8[seg * B3_NMAX + j] = (unsigned char)seq[j];
-    }
-    if (warp_stats) {
-        const int utt = k.it->utt;
-        for (int c = l8; c < B3_KK; c += B3_LPU) {
-            const bool ok = c < C;
-            const bool tg = ok && k.seg_on && ((a.tmask[(size_t)utt * MAX_WORDS + (c >> 5)] >> (c & 31)) & 1u);
-            k.kk[seg * B3_KK + c] = ok ? (tg ? 0.0f : -boostv * LOG2E) : -INFINITY;
+    //      exp(x + boost*[c in targets] - boost) = 2^(x*log2e + kk[c]) ----   (direct mode: band3_direct_plan built them)
+    if (!DIRECT) {
+        if (k.seg_on) {
+            const int32_t* seq = a.tgt + k.it->seq_off;
+            const int N = k.it->n;
+            for (int j = l8; j < N; j += B3_LPU) k.cls8[seg * B3_NMAX + j] = (unsigned char)seq[j];
+        }
+        if (warp_stats) {
+            const int utt = k.it->utt;
+            for (int c = l8; c < B3_KK; c += B3_LPU) {
+                const bool ok = c < C;
+                const bool tg = ok && k.seg_on && ((a.tmask[(size_t)utt * MAX_WORDS + (c >> 5)] >> (c & 31)) & 1u);
+                k.kk[seg * B3_KK + c] = ok ? (tg ? 0.0f : -boostv * LOG2E) : -INFINITY;
+            }
         }
     }
     __syncwarp();
+    if (DIRECT && lane == 0) mbar_arrive(k.bar0 + 8u * B3_BAR_PLAN);      // the DP warp may read the items and the class table
+    PH_T(9);
     // lanes with l8 == 0 issue their own utterance's copy and arrive once per chunk on the stage's full barrier (count = UPW)
     const uint32_t dst0 = smem_u32(k.stage_buf + seg * k.seg_stride);
     const uint32_t full_bytes = (uint32_t)B3_ROWS * C * 4;
@@ -317,7 +479,7 @@ __device__ void band3_helper(const Band3Args& a, const Item* items, int first, i
     // only known after the back-trace, when the row has long left the chip.  While a row is in shared memory this warp
     // stores the raw log-prob of its frame-wise best (boosted) class together with that class; the back-trace then only
     // has to fetch the frames where the path disagrees with the guess.
-    const bool spec = warp_stats && a.path_lp != nullptr && a.guess_cls != nullptr;
+    const bool spec = DIRECT ? (warp_stats && pscr_lp != nullptr) : (warp_stats && a.path_lp != nullptr && a.guess_cls != nullptr);
     const int o_trim = k.it->trim;
     const long long o_out = k.it->out_off;
     int rel_hi = 0;                  // frames [trim, trim + rel_hi) of the item are written out (:447-448, :465-467)
@@ -326,8 +488,9 @@ __device__ void band3_helper(const Band3Args& a, const Item* items, int first, i
         rel_hi = (int)min((long long)k.it->n_out, max(room, 0LL));
         rel_hi = min(rel_hi, T - o_trim);
     }
-    float* const plp_row = a.path_lp ? a.path_lp + (o_out - o_trim) : nullptr;           // indexed by the item's frame number
-    unsigned char* const gcl_row = a.guess_cls ? a.guess_cls + (o_out - o_trim) : nullptr;
+    // indexed by the item's frame number; direct mode: the pair's private scratch, read back by this task's own back-trace
+    float* const plp_row = DIRECT ? (pscr_lp ? pscr_lp + seg * a.tpitch : nullptr) : (a.path_lp ? a.path_lp + (o_out - o_trim) : nullptr);
+    unsigned char* const gcl_row = DIRECT ? (pscr_gs ? pscr_gs + seg * a.tpitch : nullptr) : (a.guess_cls ? a.guess_cls + (o_out - o_trim) : nullptr);
 
     float emax = -INFINITY;          // raw mode: emissions must be <= 0 (log-probabilities)
     float lse_chk = 0.f;             // running sum of the rows' log-sum-exp (finite <=> all rows sane)
@@ -429,6 +592,60 @@ __device__ void band3_helper(const Band3Args& a, const Item* items, int first, i
     }
 
     if (a.p.reserved & BFA_FLAG_FILL_ONLY) return;   // measurement switch, see bfa_b200.h
+    if constexpr (DIRECT) {
+        // direct mode: the DP warp walks the path by itself (transitions only); then the two warps turn the transitions of two
+        // utterances each into frame labels, timestamps and confidences (band3_direct_finish)
+        // While the DP warp walks: bring the confidence inputs the fill kept (raw log-prob of the frame-wise best class + that
+        // class, all four utterances) back from the pair's scratch with bulk copies and turn them into probabilities, frame by
+        // frame; the finishing pass then only has to fetch the frames where the path disagrees with the guess.
+        if (k.n_chunks > 0 && spec) {
+            asm volatile("fence.proxy.async.global;" ::: "memory");   // the scratch this warp wrote with ordinary stores is read back by bulk copies
+            mbar_wait(k.bar0 + 8u * B3_BAR_KFREE, (phase >> B3_BAR_KFREE) & 1u);   // the DP warp has left the fill: the stage ring is free
+            phase ^= 1u << B3_BAR_KFREE;
+            unsigned char* lpb = smem_pair + band3_d_off_lp(a.ncap, a.tpitch);
+            const uint32_t cbar = k.bar0 + 8u * (B3_BAR_KREADY + 1);
+            int Tq[B3_UPW];
+            uint32_t nb_all = 0;
+#pragma unroll
+            for (int sg = 0; sg < B3_UPW; ++sg) {
+                Tq[sg] = __shfl_sync(FULL, T, sg * B3_LPU);
+                nb_all += (uint32_t)((Tq[sg] + 3) & ~3) * 4u + (uint32_t)((Tq[sg] + 15) & ~15);
+            }
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(cbar, nb_all);           // one arrival (the barrier counts 1), all eight copies on it
+#pragma unroll
+                for (int sg = 0; sg < B3_UPW; ++sg)
+                    if (Tq[sg] > 0) {
+                        bulk_g2s(smem_u32(lpb + (size_t)sg * 5 * a.tpitch), pscr_lp + (size_t)sg * a.tpitch, (uint32_t)((Tq[sg] + 3) & ~3) * 4u, cbar);
+                        bulk_g2s(smem_u32(lpb + (size_t)sg * 5 * a.tpitch + (size_t)4 * a.tpitch), pscr_gs + (size_t)sg * a.tpitch,
+                                 (uint32_t)((Tq[sg] + 15) & ~15), cbar);
+                    }
+            }
+            mbar_wait(cbar, (phase >> (B3_BAR_KREADY + 1)) & 1u);
+            phase ^= 1u << (B3_BAR_KREADY + 1);
+#pragma unroll 1
+            for (int sg = 0; sg < B3_UPW; ++sg) {
+                const int Ts = Tq[sg];
+                float4* v = reinterpret_cast<float4*>(lpb + (size_t)sg * 5 * a.tpitch);
+                for (int i = lane; i < (Ts + 3) / 4; i += 32) {
+                    float4 x = v[i];
+                    x.x = expf(x.x); x.y = expf(x.y); x.z = expf(x.z); x.w = expf(x.w);
+                    v[i] = x;
+                }
+            }
+            __syncwarp();
+        }
+        PH_RESET;
+        band3_pair_sync(pair);                  // the walk is done
+        PH_T(0);
+        band3_direct_finish<CT>(a, smem_pair, R, 2, 1, lane, phase, pscr_lp, pscr_gs);
+        PH_T(1);
+        band3_pair_sync(pair);                  // both warps are done with the task
+        PH_T(2);
+        PH_FLUSH;
+        return;
+    } else {
     // ---- back-trace, output side.  The DP warp walks the path one 32-frame block at a time and hands over the visited
     //      cells (8 * absolute cell of frames 32b + 8i + l8, lane for lane); this warp turns them into frame_phonemes /
     //      frame_phonemes_idx (:695-703), checks that the path stayed inside the band, and fetches the confidence inputs
@@ -538,17 +755,35 @@ __device__ void band3_helper(const Band3Args& a, const Item* items, int first, i
         PH_T(4);
         PH_FLUSH;
     }
+    }   // !DIRECT
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // DP warp: frame loop, decision records, back-trace, outputs.
 // ------------------------------------------------------------------------------------------------------------
-template <int G, int CT, bool EXACT>
-__device__ void band3_dp(const Band3Args& a, const Item* items, int first, int n_valid, unsigned char* smem_pair, uint32_t* slab, uint32_t& phase,
-                         int lane) {
+template <int G, int CT, bool EXACT, bool DIRECT>
+__device__ void band3_dp(const Band3Args& a, const Band3Args::Class& kc, int first, int n_valid, unsigned char* smem_pair, uint32_t* slab, uint32_t& phase,
+                         int lane, int pair, const float* pscr_lp, const unsigned char* pscr_gs) {
     using S = Band3Shape<G>;
     PH_DECL;
-    const Band3Task<G, CT> k(a, items, first, n_valid, smem_pair, lane);
+    const size_t R = (size_t)kc.region;
+    if (DIRECT) {                                      // the helper warp has planned the task: items and class table are in shared memory
+        const uint32_t pb = smem_u32(smem_pair + band3_off_bars(R)) + 8u * B3_BAR_PLAN;
+        mbar_wait(pb, (phase >> B3_BAR_PLAN) & 1u);
+        phase ^= 1u << B3_BAR_PLAN;
+    }
+    bool on;
+    const Item* my_item = DIRECT ? band3_direct_item(smem_pair, R, lane, on) : band3_list_item(kc.items, first, n_valid, lane, on);
+    const Band3Task<G, CT> k(a, my_item, on, smem_pair, R, lane);
+    if constexpr (DIRECT) {
+        if (k.n_chunks == 0) {                         // nothing of this task runs here (no such utterances, or all left to the planner chain)
+            if (a.p.reserved & BFA_FLAG_FILL_ONLY) return;
+            band3_pair_sync(pair);
+            band3_direct_finish<CT>(a, smem_pair, R, 0, 0, lane, phase, pscr_lp, pscr_gs);
+            band3_pair_sync(pair);
+            return;
+        }
+    }
     const int seg = k.seg, l8 = k.l8, C = k.C, T = k.T, Tmax = k.Tmax, n_chunks = k.n_chunks;
     const bool seg_on = k.seg_on;
     const Item& it = *k.it;
@@ -824,6 +1059,106 @@ __device__ void band3_dp(const Band3Args& a, const Item* items, int first, int n
         PH_FLUSH;
         return;
     }
+    if constexpr (DIRECT) {
+        if (lane == 0) mbar_arrive(bar0 + 8u * B3_BAR_KFREE);   // the stage ring is free: the helper may stage the confidence inputs there
+        // ---- back-trace (:686-703), direct mode: the walk only notes where the path ENTERS a cell (one event per run:
+        //      cell and first frame, latest first); band3_direct_finish turns the events into everything else.  Same records,
+        //      same run-per-iteration walk as the list mode below, without the per-frame hand-over to the helper warp ----
+        const bool walk = seg_on && !bad && T > 0;
+        const int last_blk = (T - 1) >> 5;
+        uint32_t* recbuf = reinterpret_cast<uint32_t*>(smem_pair + band3_d_off_rec(a.ncap));   // [B3_NREC][REC][32]
+        const int evcap = band3_evcap(a.ncap);
+        uint32_t* ev = reinterpret_cast<uint32_t*>(smem_pair + band3_d_off_ev()) + seg * evcap;
+        float* finv = reinterpret_cast<float*>(smem_pair + band3_d_off_fin(a.ncap));           // [UPW] (verdict, final score)
+        int* nevs = reinterpret_cast<int*>(smem_pair + band3_d_off_fin(a.ncap) + 32);          // [UPW] events per utterance
+        constexpr uint32_t RECB = (uint32_t)S::REC * 128u;
+        const uint32_t rec_s = smem_u32(recbuf);
+        const uint32_t cellbase = rec_s + (uint32_t)seg * S::CELLS * 8u;
+        uint32_t A = cellbase + 8u * (uint32_t)fin_cell;
+        uint32_t K = 24u * (uint32_t)fin_base - cellbase;                                      // A + K = 8 * cabs
+        const int nblk = (Tmax + 31) >> 5;
+        const uint32_t rbar0 = bar0 + 8u * B3_BAR_REC;
+        auto issue_rec = [&](int blk) {
+            if (lane == 0) {
+                const uint32_t bar = rbar0 + 8u * (blk % B3_NREC);
+                mbar_expect_tx(bar, RECB);
+                bulk_g2s(rec_s + (uint32_t)(blk % B3_NREC) * RECB, slab + (size_t)blk * S::REC * 32, RECB, bar);
+            }
+        };
+        asm volatile("fence.proxy.async.global;" ::: "memory");   // the slab was written with ordinary stores
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage ring was read through the generic proxy
+        __syncwarp();
+#pragma unroll
+        for (int d = 1; d <= B3_NREC; ++d)
+            if (nblk - d >= 0) issue_rec(nblk - d);
+        uint32_t rphase = phase >> B3_BAR_REC;
+        int nev = 0;
+        int last_f = -1;
+        PH_T(6);
+        for (int b = nblk - 1; b >= 0; --b) {
+            mbar_wait(rbar0 + 8u * (b % B3_NREC), (rphase >> (b % B3_NREC)) & 1u);
+            rphase ^= 1u << (b % B3_NREC);
+            const bool live = walk && b <= last_blk;
+            const uint32_t boff = (uint32_t)(b % B3_NREC) * RECB;
+            const uint32_t sfw = live ? recbuf[(b % B3_NREC) * S::REC * 32 + B3_UPW * S::CELLS * 2 + lane] : 0u;
+            const uint32_t nsl = (sfw & 15u) + ((sfw >> 4) & 15u) + ((sfw >> 8) & 15u) + ((sfw >> 12) & 15u);
+            PH_T(7);
+            A += boff;
+            K -= boff;
+            uint32_t mask = live ? 0xffffffffu : 0u;
+            uint32_t c0, c1, p0, p1, q0, q1;
+            auto lds2 = [](uint32_t addr, uint32_t& x, uint32_t& y) {
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(addr) : "memory");
+            };
+            lds2(A, c0, c1);
+            lds2(A - 8u, p0, p1);
+            lds2(A - 16u, q0, q1);
+            const uint32_t fbase = (uint32_t)b * 32u;
+            while (mask != 0u) {
+                const uint32_t stop = (c0 | c1) & mask;
+                const uint32_t bit = stop & (0u - stop);      // frame whose decision ends the run (0: none left in this block)
+                const uint32_t maskn = bit * 0xfffffffeu;     // frames strictly before it
+                if (bit != 0u) {                              // the path entered cell (A + K) / 8 at frame fbase + clz(bit)
+                    last_f = (int)(fbase + (uint32_t)__clz(bit));
+                    if (l8 == 0 && nev < evcap) ev[nev] = ((A + K) << 19) | (uint32_t)last_f;
+                    ++nev;
+                }
+                const bool m1 = (c0 & bit) != 0u, m2 = (c1 & bit) != 0u;
+                A = m2 ? A - 16u : (m1 ? A - 8u : A);
+                c0 = m2 ? q0 : (m1 ? p0 : c0);
+                c1 = m2 ? q1 : (m1 ? p1 : c1);
+                mask = maskn;
+                lds2(A - 8u, p0, p1);
+                lds2(A - 16u, q0, q1);
+            }
+            __syncwarp();                          // every lane is done with this record buffer
+            if (b >= B3_NREC) issue_rec(b - B3_NREC);
+            A += 24u * nsl - boff;
+            K -= 24u * nsl - boff;
+            PH_T(8);
+        }
+        // the run the utterance starts in has no entry decision: note it as entered at frame 0
+        if (walk && last_f != 0) {
+            if (l8 == 0 && nev < evcap) ev[nev] = ((A + K) << 19);
+            ++nev;
+        }
+        if (nev > evcap) bad = true;               // cannot happen on a monotone path (<= 3 events per phoneme); defensive
+        if (l8 == 0) {
+            finv[2 * seg] = __uint_as_float((bad || !seg_on) ? 1u : 0u);
+            finv[2 * seg + 1] = fin_val;
+            nevs[seg] = nev;
+        }
+        phase = (phase & ~(((1u << B3_NREC) - 1u) << B3_BAR_REC)) | ((rphase & ((1u << B3_NREC) - 1u)) << B3_BAR_REC);
+        __syncwarp();
+        band3_pair_sync(pair);                     // events and verdicts are in shared memory
+        PH_T(9);
+        band3_direct_finish<CT>(a, smem_pair, R, 0, 0, lane, phase, pscr_lp, pscr_gs);
+        PH_T(10);
+        band3_pair_sync(pair);                     // both warps are done with the task
+        PH_T(12);
+        PH_FLUSH;
+        return;
+    } else {
     // ---- back-trace (:686-703), walking side ----
     // A cell is addressed by its window-relative index ci = 3*(group - base) + k.  Staging lays a record out as
     // bt2[seg][ci] = (first decision word, second decision word or 0), so one 64-bit shared load per run yields
@@ -927,21 +1262,195 @@ __device__ void band3_dp(const Band3Args& a, const Item* items, int first, int n
     phase = (phase & ~(((1u << B3_NREC) - 1u) << B3_BAR_REC)) | ((rphase & ((1u << B3_NREC) - 1u)) << B3_BAR_REC);
     PH_T(10);
     PH_FLUSH;
+    }   // !DIRECT
 }
 
-// One window class of one launch: every CTA works through the tasks dealt to it, then moves on to the next class without
-// waiting for anybody else (the item lists are disjoint).
-template <int G, int CT, bool EXACT>
-__device__ void band3_run(const Band3Args& a, const Band3Args::Class& k, unsigned char* smem_raw, int warp, int lane) {
-    const int n_items = *k.n_items;
-    if (n_items == 0) return;                 // nothing of this window class in the batch (uniform over the CTA)
-    const int npairs = min((int)(blockDim.x >> 6), k.npairs);   // as many pairs as the shared memory of one SM holds
-    // Roles.  A DP warp issues about 1.45x the instructions of a helper warp, and warp w issues on scheduler w % 4.  With 14
-    // warps the schedulers hold 4, 4, 3, 3 of them; giving the two 4-warp schedulers one DP warp + three helpers each and
-    // the 3-warp schedulers 2 + 1 and 3 + 0 keeps the busiest scheduler ~9 % lighter than any contiguous split.
-    bool is_dp = warp < npairs;               // default: warps [0, npairs) run the DP, [npairs, 2 npairs) are their helpers
-    int pair = is_dp ? warp : warp - npairs;
-    bool idle = warp >= 2 * npairs;
+// Direct mode, last phase.  One warp of the pair finishes two utterances (seg0, seg0 + 1), one after the other, `which` = 0 for
+// the DP warp, 1 for the helper warp (each owns one pair of frame-label arrays in shared memory):
+//   1. the events of the walk (cell, first frame; latest first) become one (start, end) pair per phoneme -- on a monotone path
+//      every phoneme state is entered exactly once, and its run ends where the next event begins -- and the band-legality check
+//      of the lazy band (header, 2.) runs on the two end frames of every run (the distance to the band centre is linear in between);
+//   2. frame_phonemes / frame_phonemes_idx (:695-703) are painted in shared memory, one phoneme run per lane over a background
+//      of (blank, -1), and leave with one bulk store each; while painting a run the lane compares the fill's guess (the
+//      frame-wise best class, whose probability the helper warp has already left in lp_s) with the phoneme and fetches
+//      lp[f, phoneme] from the posteriors where they differ (4-byte asynchronous copies, all in flight together);
+//   3. one lane per phoneme emits its timestamp (assort_frames, :777-834: with ignore_noise the stamps are exactly the phoneme
+//      runs, blanks always separate two phonemes) and its confidence (utils.py:70-113, sequential fp32 like the reference).
+// Utterances that cannot be finished here (not planned, illegal path, degenerate end) are left to the planner chain, or flagged
+// BFA_ST_DEFERRED when no chain follows.
+__device__ __forceinline__ void band3_store_frames(int32_t* dst, const int32_t* src_s, int n, int lane) {
+    // n frame labels from shared memory to global memory: one bulk store when both sides are 16-byte aligned, else by hand
+    const bool aligned = ((unsigned long long)dst & 15ull) == 0;
+    const int nb = aligned ? (n & ~3) : 0;
+    if (nb > 0 && lane == 0)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_s)), "r"(nb * 4) : "memory");
+    for (int f = nb + lane; f < n; f += 32) dst[f] = src_s[f];
+}
+
+template <int CT>
+__device__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair, size_t R, int seg0, int which, int lane, uint32_t& phase,
+                                    const float* pscr_lp, const unsigned char* pscr_gs) {
+    const int C = CT ? CT : a.C;
+    const Item* items = reinterpret_cast<const Item*>(smem_pair + band3_off_items(R));
+    const int* ustate = reinterpret_cast<const int*>(smem_pair + band3_off_flags(R)) + B3_UPW;
+    const unsigned char* cls_all = smem_pair + band3_off_cls(R);
+    const int evcap = band3_evcap(a.ncap), ncap2 = (a.ncap + 1) & ~1;
+    const uint32_t* ev_all = reinterpret_cast<const uint32_t*>(smem_pair + band3_d_off_ev());
+    const float* finv = reinterpret_cast<const float*>(smem_pair + band3_d_off_fin(a.ncap));
+    const int* nevs = reinterpret_cast<const int*>(smem_pair + band3_d_off_fin(a.ncap) + 32);
+    int2* se_all = reinterpret_cast<int2*>(smem_pair + band3_d_off_se(a.ncap));
+    int32_t* ph_s = reinterpret_cast<int32_t*>(smem_pair + band3_d_off_rec(a.ncap) + (size_t)which * 8 * a.tpitch);
+    int32_t* ix_s = ph_s + a.tpitch;
+    unsigned char* lpb = smem_pair + band3_d_off_lp(a.ncap, a.tpitch);
+    const int blank = a.p.blank_id;
+    const bool want_stamps = a.stamps != nullptr;
+    const bool want_conf = want_stamps && a.conf != nullptr;
+    bool waited = false;                       // griddepcontrol.wait executed (before the first write another grid could see)
+    bool stores_open = false;                  // bulk stores of the previous utterance may still be reading ph_s / ix_s
+    FIN_DECL;
+    for (int q = 0; q < 2; ++q) {
+        const int seg = seg0 + q;
+        const int state = ustate[seg];
+        if (state == B3_U_NONE) continue;      // no such utterance (uniform over the warp)
+        const Item& it = items[seg];
+        const int u = it.utt, T = it.T, N = it.n;
+        bool bad = state != B3_U_RUN || __float_as_uint(finv[2 * seg]) != 0u;
+        // the helper warp has left exp(raw log-prob of the frame-wise best class) and that class here (see band3_helper)
+        const bool spec = want_conf && pscr_lp != nullptr && (it.flags & ITEM_STATS) != 0;
+        float* lp_s = reinterpret_cast<float*>(lpb + (size_t)seg * 5 * a.tpitch);
+        const unsigned char* gs_s = lpb + (size_t)seg * 5 * a.tpitch + (size_t)4 * a.tpitch;
+        int2* se = se_all + seg * ncap2;
+        if (!bad) {
+            // ---- 1. events -> (start, end) per phoneme, legality; background of the frame labels ----
+            if (stores_open) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                stores_open = false;
+            }
+            __syncwarp();
+            {
+                const int4 bk = make_int4(blank, blank, blank, blank), m1 = make_int4(-1, -1, -1, -1);
+                for (int i = lane; i < (T + 3) / 4; i += 32) {
+                    reinterpret_cast<int4*>(ph_s)[i] = bk;
+                    reinterpret_cast<int4*>(ix_s)[i] = m1;
+                }
+            }
+            for (int g = lane; g < N; g += 32) se[g] = make_int2(0, 0);
+            __syncwarp();
+            const uint32_t* ev = ev_all + seg * evcap;
+            const int nev = nevs[seg];
+            const int L = it.L, band = it.band;
+            const bool use_band = band > 0 && T > 1 && L > 1;
+            const float pace_f = use_band ? (float)((double)(L - 1) / (double)(T - 1)) : 0.0f;
+            const float lim_f = use_band ? (float)(band - B3_MARGIN) : INFINITY;
+            bool illegal = false;
+            int pcount = 0;
+            for (int i = lane; i < nev; i += 32) {
+                const uint32_t e = ev[i];
+                const uint32_t cabs = e >> 22;
+                const int f = (int)(e & 0x3fffffu);
+                const int f_end = i == 0 ? T : (int)(ev[i - 1] & 0x3fffffu);         // the run ends where the next (later) one begins
+                const int g = (int)((cabs * 43691u) >> 17);                            // cabs / 3 (cabs < 2^15)
+                const int kc = (int)cabs - 3 * g;
+                // band legality (:650-653), conservative: the centre of the (merged) state stays B3_MARGIN states inside the band
+                const float s_c = (float)(4 * g) - (kc == 0 ? 3.0f : (kc == 1 ? 1.5f : 0.0f));
+                illegal |= f_end <= f || fabsf(s_c - (float)f * pace_f) > lim_f || fabsf(s_c - (float)(f_end - 1) * pace_f) > lim_f;
+                if (kc == 0) {
+                    if (g >= 1 && g <= N) { se[g - 1] = make_int2(f, f_end); ++pcount; }
+                    else illegal = true;
+                }
+            }
+            pcount = __reduce_add_sync(FULL, pcount);
+            bad = __any_sync(FULL, illegal) || pcount != N;
+            __syncwarp();
+            FIN_T(1);
+        }
+        if (!waited) { pdl_wait(); waited = true; }
+        FIN_T(4);
+        if (!bad) {
+            // ---- 2. paint the phoneme runs; fetch the confidence inputs the fill guessed wrong ----
+            const unsigned char* my_cls = cls_all + seg * B3_NMAX;
+            const float* src = a.logp + it.lp_off;
+            const uint32_t lp_sa = smem_u32(lp_s);
+            int nmiss = 0;
+            for (int g = lane; g < N; g += 32) {
+                const int2 r = se[g];
+                const int pc = my_cls[g], ix = it.idx0 + g;
+                for (int f = r.x; f < r.y; ++f) {
+                    ph_s[f] = pc;
+                    ix_s[f] = ix;
+                    if (want_conf && !(spec && gs_s[f] == pc)) {
+                        cp_async4(lp_sa + 4u * (uint32_t)f, src + (long long)f * C + pc);
+                        ++nmiss;
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the labels leave through the async proxy
+            __syncwarp();
+            FIN_T(5);
+            {
+                const int room = (int)min((long long)T, max(it.out_lim - it.out_off, 0LL));
+                band3_store_frames(a.frame_ph + it.out_off, ph_s, room, lane);
+                band3_store_frames(a.frame_idx + it.out_off, ix_s, room, lane);
+                if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                stores_open = true;
+            }
+            if (__any_sync(FULL, nmiss > 0)) {
+                cp_async_wait_all();
+                __syncwarp();
+                FIN_T(6);
+                for (int g = lane; g < N; g += 32) {                           // what arrived is a log-prob: exponentiate it in place
+                    const int2 r = se[g];
+                    const int pc = my_cls[g];
+                    for (int f = r.x; f < r.y; ++f)
+                        if (!(spec && gs_s[f] == pc)) lp_s[f] = expf(lp_s[f]);
+                }
+                __syncwarp();
+            }
+            FIN_T(7);
+            // ---- 3. timestamps + confidences, one phoneme per lane ----
+            int st = BFA_ST_OK;
+            if (want_stamps) {
+                BfaStamp* out = a.stamps + (size_t)u * a.max_stamps;
+                for (int g = lane; g < N && g < a.max_stamps; g += 32) {
+                    const int2 r = se[g];
+                    BfaStamp sv;
+                    sv.phoneme = my_cls[g]; sv.start = r.x; sv.end = r.y; sv.target_idx = it.idx0 + g;
+                    out[g] = sv;
+                    if (want_conf) a.conf[(size_t)u * a.max_stamps + g] = stamp_confidence_prob(lp_s, T, r.x, r.y);
+                }
+                if (N > a.max_stamps) st |= BFA_ST_STAMP_OVERFLOW;
+            }
+            if (lane == 0) {
+                if (want_stamps) a.n_stamps[u] = min(N, a.max_stamps);
+                a.status[u] = st;
+                if (a.dp_final) a.dp_final[u] = finv[2 * seg + 1];
+                if (a.uflag) a.uflag[u] = 1;
+            }
+        } else if (lane == 0) {
+            if (a.deferred) {
+                a.deferred[atomicAdd(a.n_deferred, 1)] = u;
+                if (a.uflag) a.uflag[u] = 0;
+            } else {
+                a.status[u] = BFA_ST_DEFERRED;
+                if (want_stamps) a.n_stamps[u] = 0;
+                if (a.dp_final) a.dp_final[u] = 0.0f;
+            }
+        }
+        __syncwarp();
+        FIN_T(8);
+    }
+    if (stores_open && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the stores have read it
+    __syncwarp();
+    FIN_FLUSH;
+}
+
+// Role and pair of a warp.  A DP warp issues about 1.45x the instructions of a helper warp, and warp w issues on scheduler w % 4.
+// With 14 warps the schedulers hold 4, 4, 3, 3 of them; giving the two 4-warp schedulers one DP warp + three helpers each and
+// the 3-warp schedulers 2 + 1 and 3 + 0 keeps the busiest scheduler ~9 % lighter than any contiguous split.
+__device__ __forceinline__ void band3_roles(int warp, int npairs, bool& is_dp, int& pair, bool& idle) {
+    is_dp = warp < npairs;                    // default: warps [0, npairs) run the DP, [npairs, 2 npairs) are their helpers
+    pair = is_dp ? warp : warp - npairs;
+    idle = warp >= 2 * npairs;
 #ifndef BFA_ROLES_CONTIG
     if (npairs == 7) {
         constexpr uint32_t DP_WARPS = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3) | (1u << 6) | (1u << 7) | (1u << 11);
@@ -950,14 +1459,23 @@ __device__ void band3_run(const Band3Args& a, const Band3Args::Class& k, unsigne
         idle = warp >= 14;
     }
 #endif
+}
+
+template <int G, int CT, bool EXACT>
+__device__ void band3_run(const Band3Args& a, const Band3Args::Class& k, unsigned char* smem_raw, int warp, int lane) {
+    const int n_items = *k.n_items;
+    if (n_items == 0) return;                 // nothing of this window class in the batch (uniform over the CTA)
+    const int npairs = min((int)(blockDim.x >> 6), k.npairs);   // as many pairs as the shared memory of one SM holds
+    bool is_dp, idle;
+    int pair;
+    band3_roles(warp, npairs, is_dp, pair, idle);
     unsigned char* smem_pair = smem_raw + (size_t)pair * k.smem_per_warp;
     __syncthreads();                          // the previous class is done with the shared memory
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // its generic-proxy writes are ordered before this class's bulk copies
     if (!idle && is_dp && lane == 0) {
         // No zero fill: slots that are never loaded (rows past the end of an utterance, unused segments) may hold
         // anything, NaN included; whatever is computed from them is never looked at.
-        const int C = CT ? CT : a.C;
-        const uint32_t b0 = smem_u32(smem_pair + band3_off_bars(C, G));
+        const uint32_t b0 = smem_u32(smem_pair + band3_off_bars((size_t)k.region));
         for (int i = 0; i < B3_NBARS; ++i) mbar_init(b0 + 8u * i, (i >= B3_BAR_FULL && i < B3_BAR_FULL + B3_NST) ? B3_UPW : 1);
         fence_mbar_init();
     }
@@ -974,21 +1492,20 @@ __device__ void band3_run(const Band3Args& a, const Band3Args::Class& k, unsigne
         uint32_t* slab = k.bp_scratch + (size_t)(blockIdx.x * npairs + pair) * k.bp_slab_words;
         for (int q = blockIdx.x + gridDim.x * pair; q < n_tasks; q += gridDim.x * npairs) {
             const int j = REV ? n_tasks - 1 - q : q;
-            band3_dp<G, CT, EXACT>(a, k.items, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, slab, phase, lane);
+            band3_dp<G, CT, EXACT, false>(a, k, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, slab, phase, lane, pair, nullptr, nullptr);
         }
     } else {
         const uint64_t pol = policy_evict_first();
         bool not_first = false;
         for (int q = blockIdx.x + gridDim.x * pair; q < n_tasks; q += gridDim.x * npairs) {
             const int j = REV ? n_tasks - 1 - q : q;
-            band3_helper<G, CT>(a, k.items, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, phase, not_first, lane, pol);
+            band3_helper<G, CT, false>(a, k, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, phase, not_first, lane, pol, pair, nullptr, nullptr);
             not_first = true;
         }
     }
     __syncthreads();                          // every pair of this CTA is done with this class
     if (!idle && is_dp && lane == 0) {        // the barrier words are about to become ordinary shared memory again
-        const int C = CT ? CT : a.C;
-        const uint32_t b0 = smem_u32(smem_pair + band3_off_bars(C, G));
+        const uint32_t b0 = smem_u32(smem_pair + band3_off_bars((size_t)k.region));
         for (int i = 0; i < B3_NBARS; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(b0 + 8u * i) : "memory");
     }
 }
@@ -1003,6 +1520,54 @@ __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_kernel(Band3Ar
     band3_run<3, CT, EXACT>(a, a.cls[0], smem_raw, warp, lane);
     band3_run<5, CT, EXACT>(a, a.cls[1], smem_raw, warp, lane);
     band3_run<8, CT, EXACT>(a, a.cls[2], smem_raw, warp, lane);
+}
+
+// Direct mode: ONE kernel per batch on the common path.  Task q = utterances 4q .. 4q+3, planned by the helper warp itself,
+// 24-group window; fill, walk, frame labels, timestamps and confidences all happen here; whatever does not qualify is handed to
+// the planner chain (or flagged).  The kernel reads nothing another kernel of the call produces, so it never waits for its
+// predecessor in the stream before the fill: launched with programmatic stream serialization it starts, SM by SM, while the
+// previous launch (normally the previous batch's instance of this kernel) drains, and executes griddepcontrol.wait only before
+// its first write another grid could see (band3_direct_finish).  The fill's private scratch (decision records, confidence
+// inputs) is indexed by the PHYSICAL SM: a CTA of this kernel owns its SM's shared memory, so two launches never use the same
+// SM's scratch at the same time.
+template <int CT, bool EXACT>
+__global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_direct_kernel(const __grid_constant__ Band3Args a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_release();
+    const Band3Args::Class& k = a.cls[0];
+    const int npairs = min((int)(blockDim.x >> 6), k.npairs);
+    bool is_dp, idle;
+    int pair;
+    band3_roles(warp, npairs, is_dp, pair, idle);
+    unsigned char* smem_pair = smem_raw + (size_t)pair * k.smem_per_warp;
+    if (!idle && is_dp && lane == 0) {
+        const uint32_t b0 = smem_u32(smem_pair + band3_off_bars((size_t)k.region));
+        for (int i = 0; i < B3_NBARS; ++i) mbar_init(b0 + 8u * i, (i >= B3_BAR_FULL && i < B3_BAR_FULL + B3_NST) ? B3_UPW : 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (idle) return;
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    if ((int)smid >= a.nslots) __trap();      // the host sized the per-SM scratch from %nsmid
+    const size_t slot = (size_t)smid * npairs + pair;
+    uint32_t* slab = k.bp_scratch + slot * k.bp_slab_words;
+    float* pscr_lp = a.pscr_lp ? a.pscr_lp + slot * B3_UPW * a.tpitch : nullptr;
+    unsigned char* pscr_gs = a.pscr_lp ? a.pscr_gs + slot * B3_UPW * a.tpitch : nullptr;
+    uint32_t phase = 0;
+    const int n_tasks = (a.B + B3_UPW - 1) / B3_UPW;
+    if (is_dp) {
+        for (int q = blockIdx.x + gridDim.x * pair; q < n_tasks; q += gridDim.x * npairs)
+            band3_dp<3, CT, EXACT, true>(a, k, q, B3_UPW, smem_pair, slab, phase, lane, pair, pscr_lp, pscr_gs);
+    } else {
+        const uint64_t pol = policy_evict_first();
+        bool not_first = false;
+        for (int q = blockIdx.x + gridDim.x * pair; q < n_tasks; q += gridDim.x * npairs) {
+            band3_helper<3, CT, true>(a, k, q, B3_UPW, smem_pair, phase, not_first, lane, pol, pair, pscr_lp, pscr_gs);
+            not_first = true;
+        }
+    }
 }
 
 }  // namespace bfa

@@ -51,6 +51,8 @@ extern "C" {
 #define BFA_ST_TOO_SHORT 2     /* T < N: the reference raises ValueError (:161-165) */
 #define BFA_ST_PROPORTIONAL 3  /* T == N proportional assignment (:170-176) */
 #define BFA_ST_SEGMENTED 4     /* silence-anchored segmentation accepted (:133-145) */
+#define BFA_ST_DEFERRED 5      /* only with BFA_FLAG_DIRECT_ONLY: the utterance needs the full planner chain and was NOT aligned;
+                                  run it again without that flag (the Python facade does) */
 #define BFA_ST_DEGENERATE 8    /* flag: winning DP score <= -1000 (the reference's "-inf") */
 #define BFA_ST_STAMP_OVERFLOW 16 /* flag: more than max_stamps runs; stamps truncated */
 
@@ -93,6 +95,21 @@ typedef struct BfaParams {
                                  * uses it to time the fill phase by itself; never set it in production. */
 #define BFA_FLAG_NO_SPEC 8       /* the banded kernel fetches every confidence input during its back-trace instead of keeping the
                                  * frame-wise best class's value while the row is on chip (measurement / A-B switch) */
+
+#define BFA_FLAG_NO_DIRECT 32    /* A/B switch: never use the direct kernel, every utterance goes through planner + item lists */
+#define BFA_FLAG_DIRECT_ONLY 64  /* Launch ONLY the direct kernel (one kernel per call: in-kernel planning, banded stride-4 Viterbi,
+                                  * frame labels, timestamps, confidences).  Utterances it cannot finish -- silence_id in the target
+                                  * while silence anchoring is on, more phonemes than 4N+1 <= T allows, T == N, empty targets, paths
+                                  * that touch the band edge, ... -- are reported as status BFA_ST_DEFERRED with n_stamps = 0 and must
+                                  * be run again without this flag.  Nothing is ever silently different: an utterance is either
+                                  * finished exactly as without the flag or flagged.  Ignored (full chain) when the direct kernel
+                                  * cannot be used at all (ignore_noise == 0, C > 72, very long utterances). */
+#define BFA_FLAG_PIPELINED 128   /* With BFA_FLAG_DIRECT_ONLY: the caller asserts that every INPUT of this call (logp, offsets,
+                                  * lengths, targets) was complete before the operation that precedes this call in the stream was
+                                  * enqueued (e.g. the posteriors are resident, or their producer is older than the previous call).
+                                  * The kernel is then launched with programmatic stream serialization and starts reading its inputs
+                                  * while its predecessor in the stream is still draining, SM by SM; it waits for the predecessor's
+                                  * completion before writing any output.  Back-to-back calls overlap their ramp-up and tail. */
 
 /* framestamp tuple (phoneme_id, start_frame, end_frame_exclusive, target_seq_idx)
  * = the 4-tuples returned by ViterbiDecoder.assort_frames (forced_alignment.py:777-834). */
@@ -228,6 +245,7 @@ int bfa_debug_phases(unsigned long long *out32, int reset);
 int bfa_debug_warps(unsigned long long *out32, int reset);
 int bfa_debug_item_counts(int32_t *out4);
 int bfa_debug_ctas(unsigned long long *out320, int reset);
+int bfa_debug_fin(unsigned long long *out32, int reset);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 int64_t bfa_launch_count(void);

@@ -21,15 +21,20 @@ for it in range(3):
     _cabi.lib().bfa_debug_warps(wout, 1)
     cout = (C.c_ulonglong * 320)()
     _cabi.lib().bfa_debug_ctas(cout, 1)
-names = ["setup", "slide", "barrier wait", "-", "frames", "loop end", "pre-walk", "rec wait+stage", "walk", "handoff", "tail", "flush+sync", "keep-free wait"]
+    fout = (C.c_ulonglong * 32)()
+    _cabi.lib().bfa_debug_fin(fout, 1)
+names = ["setup", "slide", "barrier wait", "-", "frames", "loop end", "pre-walk", "rec wait", "walk", "pair sync", "finish", "flush+sync", "end sync"]
 tot = sum(out[:14]); nw = (B + 3) // 4
 print(f"warps {nw}; cycles per warp-task {tot / nw:.0f} = {tot / nw / 1.965e3:.1f} us")
 for n, v in zip(names, out):
     print(f"{n:14s} {v / nw:10.0f} cyc/task  {100 * v / tot:5.1f}%")
-hn = ["kready wait", "decode+stores", "gather wait", "write gathered", "final", "fill: full wait", "fill: row stats", "fill: free wait+issue"]
+hn = ["wait for walk", "finish", "end sync", "-", "-", "fill: full wait", "fill: row stats", "fill: free wait+issue", "plan", "task+tables"]
 print("helper warp:")
 for n, v in zip(hn, out[16:30]):
     print(f"{n:14s} {v / nw:10.0f} cyc/task")
+fn = ["-", "events+legality", "-", "-", "pdl wait", "paint", "miss wait", "stores+miss exp", "stamps+final"]
+for w in range(2):
+    print("finish, " + ("DP warp: " if w == 0 else "helper:  ") + "  ".join(f"{n} {fout[w * 16 + i] / nw:.0f}" for i, n in enumerate(fn)))
 print(f"DP task cycles: max {out[14]} min {out[15]}  ({out[14]/1.965e3:.1f} / {out[15]/1.965e3:.1f} us);  helper: max {out[30]} min {out[31]} ({out[30]/1.965e3:.1f} / {out[31]/1.965e3:.1f} us)")
 print("mean task us by warp id (scheduler = id % 4):", " ".join(f"w{i}:{wout[i] / max(wout[16 + i], 1) / 1.965e3:.0f}" for i in range(14)))
 ct = sorted((cout[i] / 1.965e3, int(cout[160 + i]), i) for i in range(148))
