@@ -170,17 +170,15 @@ __host__ __device__ inline size_t band3_smem_per_warp(int C, int G) { return ban
 
 // Direct mode: what the back-trace keeps in the staging region (G = 3).  Byte offsets:
 //   events [UPW][evcap] | (verdict, final score) [UPW] + event counts [UPW] | (start, end) per phoneme [UPW][ncap2] |
-//   record buffers during the walk, afterwards per warp of the pair: ph_s [tpitch] + ix_s [tpitch] int32 (the frame labels of the
-//   utterance it is finishing) | per utterance: lp_s [tpitch] floats + gs_s [tpitch] bytes (confidence inputs kept by the fill)
+//   per warp of the pair: run-boundary bits (tpitch / 32 + 1 words) + fetched-frame nibbles (tpitch / 4 bytes) | record buffers of the walk |
+//   per utterance: lp_s [tpitch] floats + gs_s [tpitch] bytes (confidence inputs kept by the fill)
 __host__ __device__ inline int band3_evcap(int ncap) { return (3 * ncap + 8 + 3) & ~3; }
 __host__ __device__ inline size_t band3_d_off_ev() { return 0; }
 __host__ __device__ inline size_t band3_d_off_fin(int ncap) { return (size_t)B3_UPW * band3_evcap(ncap) * 4; }
 __host__ __device__ inline size_t band3_d_off_se(int ncap) { return band3_d_off_fin(ncap) + 64; }
-__host__ __device__ inline size_t band3_d_off_rec(int ncap) { return (band3_d_off_se(ncap) + (size_t)B3_UPW * ((ncap + 1) & ~1) * 8 + 127) / 128 * 128; }
-__host__ __device__ inline size_t band3_d_off_lp(int ncap, int tpitch) {
-    const size_t rec = (size_t)B3_NREC * (6 * 3 + 1) * 128, lab = (size_t)16 * tpitch;
-    return band3_d_off_rec(ncap) + (rec > lab ? rec : lab);
-}
+__host__ __device__ inline size_t band3_d_off_bits(int ncap) { return band3_d_off_se(ncap) + (size_t)B3_UPW * ((ncap + 1) & ~1) * 8; }
+__host__ __device__ inline size_t band3_d_off_rec(int ncap, int tpitch) { return (band3_d_off_bits(ncap) + (size_t)8 * (tpitch / 32 + 1) * 4 + 127) / 128 * 128; }
+__host__ __device__ inline size_t band3_d_off_lp(int ncap, int tpitch) { return band3_d_off_rec(ncap, tpitch) + (size_t)B3_NREC * (6 * 3 + 1) * 128; }
 __host__ __device__ inline size_t band3_direct_region(int C, int tpitch, int ncap) {
     const size_t st = band3_stage_region(C, 3), bt = band3_d_off_lp(ncap, tpitch) + (size_t)B3_UPW * 5 * tpitch;
     return ((st > bt ? st : bt) + 15) / 16 * 16;
@@ -318,7 +316,7 @@ enum : int { B3_U_RUN = 0, B3_U_NONE = 1, B3_U_DEFER = 2 };
 // stride-4 DP problem that fits the 24-group window and its targets are plain phoneme classes; when silence anchoring is on and
 // the target holds silence_id (a segmentation attempt, :133), or anything else is unusual, it is left to the planner chain.
 template <int CT>
-__device__ __forceinline__ void band3_direct_plan(const Band3Args& a, int task, unsigned char* smem_pair, size_t R, int lane) {
+__device__ __noinline__ void band3_direct_plan(const Band3Args& a, int task, unsigned char* smem_pair, size_t R, int lane) {
     constexpr float LOG2E = 1.4426950408889634f;
     const int seg = lane >> 3, l8 = lane & 7;
     const int C = CT ? CT : a.C;
@@ -401,8 +399,7 @@ __device__ __forceinline__ void band3_direct_plan(const Band3Args& a, int task, 
 __device__ __forceinline__ void band3_pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
 
 template <int CT>
-__device__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair, size_t R, int seg0, int which, int lane, uint32_t& phase,
-                                    const float* pscr_lp, const unsigned char* pscr_gs);
+__device__ __noinline__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair, size_t R, int seg0, int which, int lane, bool have_spec);
 
 template <int G, int CT, bool DIRECT>
 __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int first, int n_valid, unsigned char* smem_pair, uint32_t& phase, bool not_first,
@@ -639,7 +636,7 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
         PH_RESET;
         band3_pair_sync(pair);                  // the walk is done
         PH_T(0);
-        band3_direct_finish<CT>(a, smem_pair, R, 2, 1, lane, phase, pscr_lp, pscr_gs);
+        band3_direct_finish<CT>(a, smem_pair, R, 2, 1, lane, pscr_lp != nullptr);
         PH_T(1);
         band3_pair_sync(pair);                  // both warps are done with the task
         PH_T(2);
@@ -779,7 +776,7 @@ __device__ void band3_dp(const Band3Args& a, const Band3Args::Class& kc, int fir
         if (k.n_chunks == 0) {                         // nothing of this task runs here (no such utterances, or all left to the planner chain)
             if (a.p.reserved & BFA_FLAG_FILL_ONLY) return;
             band3_pair_sync(pair);
-            band3_direct_finish<CT>(a, smem_pair, R, 0, 0, lane, phase, pscr_lp, pscr_gs);
+            band3_direct_finish<CT>(a, smem_pair, R, 0, 0, lane, pscr_lp != nullptr);
             band3_pair_sync(pair);
             return;
         }
@@ -1066,7 +1063,7 @@ __device__ void band3_dp(const Band3Args& a, const Band3Args::Class& kc, int fir
         //      same run-per-iteration walk as the list mode below, without the per-frame hand-over to the helper warp ----
         const bool walk = seg_on && !bad && T > 0;
         const int last_blk = (T - 1) >> 5;
-        uint32_t* recbuf = reinterpret_cast<uint32_t*>(smem_pair + band3_d_off_rec(a.ncap));   // [B3_NREC][REC][32]
+        uint32_t* recbuf = reinterpret_cast<uint32_t*>(smem_pair + band3_d_off_rec(a.ncap, a.tpitch));   // [B3_NREC][REC][32]
         const int evcap = band3_evcap(a.ncap);
         uint32_t* ev = reinterpret_cast<uint32_t*>(smem_pair + band3_d_off_ev()) + seg * evcap;
         float* finv = reinterpret_cast<float*>(smem_pair + band3_d_off_fin(a.ncap));           // [UPW] (verdict, final score)
@@ -1152,7 +1149,7 @@ __device__ void band3_dp(const Band3Args& a, const Band3Args::Class& kc, int fir
         __syncwarp();
         band3_pair_sync(pair);                     // events and verdicts are in shared memory
         PH_T(9);
-        band3_direct_finish<CT>(a, smem_pair, R, 0, 0, lane, phase, pscr_lp, pscr_gs);
+        band3_direct_finish<CT>(a, smem_pair, R, 0, 0, lane, pscr_lp != nullptr);
         PH_T(10);
         band3_pair_sync(pair);                     // both warps are done with the task
         PH_T(12);
@@ -1266,30 +1263,24 @@ __device__ void band3_dp(const Band3Args& a, const Band3Args::Class& kc, int fir
 }
 
 // Direct mode, last phase.  One warp of the pair finishes two utterances (seg0, seg0 + 1), one after the other, `which` = 0 for
-// the DP warp, 1 for the helper warp (each owns one pair of frame-label arrays in shared memory):
+// the DP warp, 1 for the helper warp:
 //   1. the events of the walk (cell, first frame; latest first) become one (start, end) pair per phoneme -- on a monotone path
-//      every phoneme state is entered exactly once, and its run ends where the next event begins -- and the band-legality check
-//      of the lazy band (header, 2.) runs on the two end frames of every run (the distance to the band centre is linear in between);
-//   2. frame_phonemes / frame_phonemes_idx (:695-703) are painted in shared memory, one phoneme run per lane over a background
-//      of (blank, -1), and leave with one bulk store each; while painting a run the lane compares the fill's guess (the
-//      frame-wise best class, whose probability the helper warp has already left in lp_s) with the phoneme and fetches
-//      lp[f, phoneme] from the posteriors where they differ (4-byte asynchronous copies, all in flight together);
+//      every phoneme state is entered exactly once, and its run ends where the next event begins -- the band-legality check of
+//      the lazy band (header, 2.) runs on the two end frames of every run (the distance to the band centre is linear in between),
+//      and both ends of every phoneme run are marked in a bit map over the frames;
+//   2. one sweep over the frames, 32 per step (lane = frame, nothing data-dependent in the control flow): the number of marks at
+//      or before a frame says whether it lies in a phoneme run and in which; frame_phonemes / frame_phonemes_idx (:695-703) go
+//      straight to global memory, coalesced; where the fill's guess (the frame-wise best class, whose probability the helper warp
+//      has already left in lp_s) is not the frame's phoneme, lp[f, phoneme] is fetched from the posteriors (4-byte asynchronous
+//      copies, all in flight together) and exponentiated afterwards;
 //   3. one lane per phoneme emits its timestamp (assort_frames, :777-834: with ignore_noise the stamps are exactly the phoneme
 //      runs, blanks always separate two phonemes) and its confidence (utils.py:70-113, sequential fp32 like the reference).
 // Utterances that cannot be finished here (not planned, illegal path, degenerate end) are left to the planner chain, or flagged
 // BFA_ST_DEFERRED when no chain follows.
-__device__ __forceinline__ void band3_store_frames(int32_t* dst, const int32_t* src_s, int n, int lane) {
-    // n frame labels from shared memory to global memory: one bulk store when both sides are 16-byte aligned, else by hand
-    const bool aligned = ((unsigned long long)dst & 15ull) == 0;
-    const int nb = aligned ? (n & ~3) : 0;
-    if (nb > 0 && lane == 0)
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_s)), "r"(nb * 4) : "memory");
-    for (int f = nb + lane; f < n; f += 32) dst[f] = src_s[f];
-}
-
+// Not inlined on purpose: this is run-once code, and one copy shared by all fourteen warps of the CTA (which arrive here at about
+// the same time) keeps its instruction-cache misses to one warp's worth.
 template <int CT>
-__device__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair, size_t R, int seg0, int which, int lane, uint32_t& phase,
-                                    const float* pscr_lp, const unsigned char* pscr_gs) {
+__device__ __noinline__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair, size_t R, int seg0, int which, int lane, bool have_spec) {
     const int C = CT ? CT : a.C;
     const Item* items = reinterpret_cast<const Item*>(smem_pair + band3_off_items(R));
     const int* ustate = reinterpret_cast<const int*>(smem_pair + band3_off_flags(R)) + B3_UPW;
@@ -1299,14 +1290,14 @@ __device__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair
     const float* finv = reinterpret_cast<const float*>(smem_pair + band3_d_off_fin(a.ncap));
     const int* nevs = reinterpret_cast<const int*>(smem_pair + band3_d_off_fin(a.ncap) + 32);
     int2* se_all = reinterpret_cast<int2*>(smem_pair + band3_d_off_se(a.ncap));
-    int32_t* ph_s = reinterpret_cast<int32_t*>(smem_pair + band3_d_off_rec(a.ncap) + (size_t)which * 8 * a.tpitch);
-    int32_t* ix_s = ph_s + a.tpitch;
+    const int wpitch = a.tpitch / 32 + 1;
+    uint32_t* bnd = reinterpret_cast<uint32_t*>(smem_pair + band3_d_off_bits(a.ncap)) + (size_t)which * 4 * wpitch;   // run-boundary bits
+    unsigned char* mnib = reinterpret_cast<unsigned char*>(bnd + wpitch);               // [quad of frames] which of its frames were fetched
     unsigned char* lpb = smem_pair + band3_d_off_lp(a.ncap, a.tpitch);
     const int blank = a.p.blank_id;
     const bool want_stamps = a.stamps != nullptr;
     const bool want_conf = want_stamps && a.conf != nullptr;
     bool waited = false;                       // griddepcontrol.wait executed (before the first write another grid could see)
-    bool stores_open = false;                  // bulk stores of the previous utterance may still be reading ph_s / ix_s
     FIN_DECL;
     for (int q = 0; q < 2; ++q) {
         const int seg = seg0 + q;
@@ -1316,24 +1307,14 @@ __device__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair
         const int u = it.utt, T = it.T, N = it.n;
         bool bad = state != B3_U_RUN || __float_as_uint(finv[2 * seg]) != 0u;
         // the helper warp has left exp(raw log-prob of the frame-wise best class) and that class here (see band3_helper)
-        const bool spec = want_conf && pscr_lp != nullptr && (it.flags & ITEM_STATS) != 0;
+        const bool spec = want_conf && have_spec && (it.flags & ITEM_STATS) != 0;
         float* lp_s = reinterpret_cast<float*>(lpb + (size_t)seg * 5 * a.tpitch);
         const unsigned char* gs_s = lpb + (size_t)seg * 5 * a.tpitch + (size_t)4 * a.tpitch;
         int2* se = se_all + seg * ncap2;
+        const int nw = (T + 31) >> 5;
         if (!bad) {
-            // ---- 1. events -> (start, end) per phoneme, legality; background of the frame labels ----
-            if (stores_open) {
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                stores_open = false;
-            }
-            __syncwarp();
-            {
-                const int4 bk = make_int4(blank, blank, blank, blank), m1 = make_int4(-1, -1, -1, -1);
-                for (int i = lane; i < (T + 3) / 4; i += 32) {
-                    reinterpret_cast<int4*>(ph_s)[i] = bk;
-                    reinterpret_cast<int4*>(ix_s)[i] = m1;
-                }
-            }
+            // ---- 1. events -> (start, end) per phoneme, legality, run-boundary bits ----
+            for (int i = lane; i < nw; i += 32) bnd[i] = 0u;
             for (int g = lane; g < N; g += 32) se[g] = make_int2(0, 0);
             __syncwarp();
             const uint32_t* ev = ev_all + seg * evcap;
@@ -1353,10 +1334,14 @@ __device__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair
                 const int kc = (int)cabs - 3 * g;
                 // band legality (:650-653), conservative: the centre of the (merged) state stays B3_MARGIN states inside the band
                 const float s_c = (float)(4 * g) - (kc == 0 ? 3.0f : (kc == 1 ? 1.5f : 0.0f));
-                illegal |= f_end <= f || fabsf(s_c - (float)f * pace_f) > lim_f || fabsf(s_c - (float)(f_end - 1) * pace_f) > lim_f;
+                illegal |= f_end <= f || f_end > T || fabsf(s_c - (float)f * pace_f) > lim_f || fabsf(s_c - (float)(f_end - 1) * pace_f) > lim_f;
                 if (kc == 0) {
-                    if (g >= 1 && g <= N) { se[g - 1] = make_int2(f, f_end); ++pcount; }
-                    else illegal = true;
+                    if (g >= 1 && g <= N && f_end <= T) {
+                        se[g - 1] = make_int2(f, f_end);
+                        ++pcount;
+                        atomicOr(&bnd[f >> 5], 1u << (f & 31));
+                        if (f_end < T) atomicOr(&bnd[f_end >> 5], 1u << (f_end & 31));
+                    } else illegal = true;
                 }
             }
             pcount = __reduce_add_sync(FULL, pcount);
@@ -1367,45 +1352,88 @@ __device__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair
         if (!waited) { pdl_wait(); waited = true; }
         FIN_T(4);
         if (!bad) {
-            // ---- 2. paint the phoneme runs; fetch the confidence inputs the fill guessed wrong ----
+            // ---- 2. frame sweep: every lane takes four consecutive frames per step (128 frames per step of the warp) ----
             const unsigned char* my_cls = cls_all + seg * B3_NMAX;
             const float* src = a.logp + it.lp_off;
+            int32_t* fph = a.frame_ph + it.out_off;
+            int32_t* fidx = a.frame_idx + it.out_off;
+            const int room = (int)min((long long)T, max(it.out_lim - it.out_off, 0LL));
+            const bool vec_ok = (((unsigned long long)fph | (unsigned long long)fidx) & 15ull) == 0;
             const uint32_t lp_sa = smem_u32(lp_s);
-            int nmiss = 0;
-            for (int g = lane; g < N; g += 32) {
-                const int2 r = se[g];
-                const int pc = my_cls[g], ix = it.idx0 + g;
-                for (int f = r.x; f < r.y; ++f) {
-                    ph_s[f] = pc;
-                    ix_s[f] = ix;
-                    if (want_conf && !(spec && gs_s[f] == pc)) {
-                        cp_async4(lp_sa + 4u * (uint32_t)f, src + (long long)f * C + pc);
-                        ++nmiss;
+            const int idx0 = it.idx0;
+            bool my_miss = false;
+            int carry = 0;                                       // marks before the current group of 32 words
+            for (int w0 = 0; w0 < nw; w0 += 32) {
+                // exclusive prefix of the marks per word over this group of 32 words (lane = word)
+                const int mine = (w0 + lane < nw) ? __popc(bnd[w0 + lane]) : 0;
+                int inc = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(FULL, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                const int excl = carry + inc - mine;
+                carry += __shfl_sync(FULL, inc, 31);
+                const int qn = (min(32, nw - w0) + 3) >> 2;      // steps of 4 words = 128 frames in this group
+#pragma unroll 2
+                for (int i = 0; i < qn; ++i) {
+                    const int wj = 4 * i + (lane >> 3);          // this lane's word within the group
+                    const int f0 = (w0 + wj) * 32 + 4 * (lane & 7);
+                    const int bo = 4 * (lane & 7);
+                    const uint32_t word = (w0 + wj < nw) ? bnd[w0 + wj] : 0u;
+                    int cnt = __shfl_sync(FULL, excl, wj) + __popc(word & ((1u << bo) - 1u));
+                    int pcv[4], ixv[4];
+                    uint32_t nib = 0;
+                    const uint32_t gw = (spec && f0 < T) ? *reinterpret_cast<const uint32_t*>(gs_s + f0) : 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        cnt += (int)((word >> (bo + k)) & 1u);
+                        const bool inside = (cnt & 1) != 0 && f0 + k < T;
+                        const int g = (cnt + 1) >> 1;            // 1-based phoneme of the run the frame lies in
+                        pcv[k] = blank; ixv[k] = -1;
+                        if (inside) {
+                            pcv[k] = my_cls[g - 1];
+                            ixv[k] = idx0 + g - 1;
+                            bool miss = want_conf && !(spec && (int)((gw >> (8 * k)) & 255u) == pcv[k]);
+#ifdef BFA_DBG_NOMISS
+                            miss = false;
+#endif
+                            if (miss) {
+                                cp_async4(lp_sa + 4u * (uint32_t)(f0 + k), src + (long long)(f0 + k) * C + pcv[k]);
+                                nib |= 1u << k;
+                            }
+                        }
+                    }
+#ifndef BFA_DBG_NOSTORE
+                    if (vec_ok && f0 + 3 < room) {
+                        *reinterpret_cast<int4*>(fph + f0) = make_int4(pcv[0], pcv[1], pcv[2], pcv[3]);
+                        *reinterpret_cast<int4*>(fidx + f0) = make_int4(ixv[0], ixv[1], ixv[2], ixv[3]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (f0 + k < room) { fph[f0 + k] = pcv[k]; fidx[f0 + k] = ixv[k]; }
+                    }
+#endif
+                    if (f0 < T) mnib[f0 >> 2] = (unsigned char)nib;
+                    my_miss |= nib != 0u;
+                }
+            }
+            FIN_T(5);
+            if (__any_sync(FULL, my_miss)) {                     // what arrived is a log-prob: exponentiate it in place
+                cp_async_wait_all();
+                FIN_T(6);
+                __syncwarp();                                    // every lane's copies have landed
+                for (int q4 = 0; q4 < (T + 3) >> 2; q4 += 32) {
+                    const int qq = q4 + lane;
+                    if (qq < (T + 3) >> 2) {
+                        const uint32_t nib = mnib[qq];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if ((nib >> k) & 1u) lp_s[4 * qq + k] = expf(lp_s[4 * qq + k]);
                     }
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the labels leave through the async proxy
             __syncwarp();
-            FIN_T(5);
-            {
-                const int room = (int)min((long long)T, max(it.out_lim - it.out_off, 0LL));
-                band3_store_frames(a.frame_ph + it.out_off, ph_s, room, lane);
-                band3_store_frames(a.frame_idx + it.out_off, ix_s, room, lane);
-                if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                stores_open = true;
-            }
-            if (__any_sync(FULL, nmiss > 0)) {
-                cp_async_wait_all();
-                __syncwarp();
-                FIN_T(6);
-                for (int g = lane; g < N; g += 32) {                           // what arrived is a log-prob: exponentiate it in place
-                    const int2 r = se[g];
-                    const int pc = my_cls[g];
-                    for (int f = r.x; f < r.y; ++f)
-                        if (!(spec && gs_s[f] == pc)) lp_s[f] = expf(lp_s[f]);
-                }
-                __syncwarp();
-            }
             FIN_T(7);
             // ---- 3. timestamps + confidences, one phoneme per lane ----
             int st = BFA_ST_OK;
@@ -1439,8 +1467,6 @@ __device__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair
         __syncwarp();
         FIN_T(8);
     }
-    if (stores_open && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the stores have read it
-    __syncwarp();
     FIN_FLUSH;
 }
 

@@ -32,7 +32,7 @@ hn = ["wait for walk", "finish", "end sync", "-", "-", "fill: full wait", "fill:
 print("helper warp:")
 for n, v in zip(hn, out[16:30]):
     print(f"{n:14s} {v / nw:10.0f} cyc/task")
-fn = ["-", "events+legality", "-", "-", "pdl wait", "paint", "miss wait", "stores+miss exp", "stamps+final"]
+fn = ["-", "events+legality", "-", "-", "pdl wait", "frame sweep", "miss wait", "miss exp", "stamps+final"]
 for w in range(2):
     print("finish, " + ("DP warp: " if w == 0 else "helper:  ") + "  ".join(f"{n} {fout[w * 16 + i] / nw:.0f}" for i, n in enumerate(fn)))
 print(f"DP task cycles: max {out[14]} min {out[15]}  ({out[14]/1.965e3:.1f} / {out[15]/1.965e3:.1f} us);  helper: max {out[30]} min {out[31]} ({out[30]/1.965e3:.1f} / {out[31]/1.965e3:.1f} us)")
