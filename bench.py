@@ -266,6 +266,21 @@ def main():
                 pending[i].wait()
                 pending[i] = None
 
+    # Clock sampling starts here (nvidia-smi is already polling when the timed region begins).  Then the GPU is brought to its
+    # sustained clocks: an idle B200 sits at 120 MHz and needs milliseconds of load to ramp up, far longer than W = 5 steps of
+    # 0.15 ms -- so PREWARM_S seconds of untimed steps come first, then the contract's W warm-up steps, then (after the barrier)
+    # the K timed steps, with no host-side pause in between.
+    sampler = ClockSampler(local)
+    sampler.start()
+    PREWARM_S = 0.4
+    t_pre = time.perf_counter()
+    n_pre = 0
+    while time.perf_counter() - t_pre < PREWARM_S:
+        for _ in range(16):
+            r = step()
+        n_pre += 16
+        drain()
+        torch.cuda.synchronize()
     for _ in range(max(a.warmup, 3)):
         r = step()
     drain()
@@ -297,14 +312,16 @@ def main():
     PROFILE_EVERY = 1 if world == 1 else 4
     lib.bfa_profile_enable(0 if one_kernel else (1 | (PROFILE_EVERY << 8)))
     lib.bfa_profile_read(None, None)
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.25)
+    for _ in range(max(a.warmup, 3)):      # the W warm-up steps, immediately before the timed region
+        step()
+    drain()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    th0 = time.perf_counter()
     for _ in range(a.steps):
         step()
+    host_us_per_call = (time.perf_counter() - th0) / a.steps * 1e6     # how long the host needs to enqueue one step
     drain()                    # every gather has completed inside the timed region
     e1.record()
     barrier()
@@ -451,7 +468,7 @@ def main():
                                                         if pusher is not None else "NCCL all_gather_into_tensor"), "sharding": f"{world} rank(s) x {B} utterances, no data-path collective; "
                                                          f"when n_gpus>1 every rank pushes its packed result arrays to all peers each step (copy-engine P2P writes over NVLink on a side stream; NCCL all_gather as fallback), completed inside the timed region"}),
                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-               "uninstrumented_step": plain}
+               "uninstrumented_step": plain, "host_enqueue_us_per_step": host_us_per_call, "prewarm_steps": n_pre}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -340,6 +340,7 @@ class AlignmentUtils:
         self.viterbi_decoder = ViterbiDecoder(blank_id, silence_id, silence_anchors=self.silence_anchors,
                                               ignore_noise=ignore_noise, truly_forced=self.truly_forced)
         self.last_result: Optional[BatchResult] = None
+        self.last_params_reserved = 0
 
     @staticmethod
     def _lens(x, B, default):
@@ -387,6 +388,7 @@ class AlignmentUtils:
                                                  max_stamps=max(T_max, 1))
             st = r.status[:B].cpu().numpy()
         self.last_result = r
+        self.last_params_reserved = int(params.reserved)     # which path the batch finally took (FLAG_DIRECT_ONLY: one kernel)
         self.viterbi_decoder._raise_if_too_short(st, T, N)
         return r
 

@@ -62,6 +62,7 @@ __device__ __forceinline__ float stamp_confidence_prob(const float* pr_s, int T,
         const float half = avg / 2.0f;
         int good = 1;
         float mx = 0.f;
+#pragma unroll 4
         for (int f = s + 1; f < e; ++f) {
             const float pr = pr_s[f];
             mx = fmaxf(mx, pr);

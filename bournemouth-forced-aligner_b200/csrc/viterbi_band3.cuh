@@ -178,7 +178,9 @@ __host__ __device__ inline size_t band3_d_off_fin(int ncap) { return (size_t)B3_
 __host__ __device__ inline size_t band3_d_off_se(int ncap) { return band3_d_off_fin(ncap) + 64; }
 __host__ __device__ inline size_t band3_d_off_bits(int ncap) { return band3_d_off_se(ncap) + (size_t)B3_UPW * ((ncap + 1) & ~1) * 8; }
 __host__ __device__ inline size_t band3_d_off_rec(int ncap, int tpitch) { return (band3_d_off_bits(ncap) + (size_t)8 * (tpitch / 32 + 1) * 4 + 127) / 128 * 128; }
-__host__ __device__ inline size_t band3_d_off_lp(int ncap, int tpitch) { return band3_d_off_rec(ncap, tpitch) + (size_t)B3_NREC * (6 * 3 + 1) * 128; }
+__host__ __device__ inline size_t band3_d_off_lp(int ncap, int tpitch) {
+    return band3_d_off_rec(ncap, tpitch) + (size_t)B3_NREC * (6 * 3 + 1) * 128;
+}
 __host__ __device__ inline size_t band3_direct_region(int C, int tpitch, int ncap) {
     const size_t st = band3_stage_region(C, 3), bt = band3_d_off_lp(ncap, tpitch) + (size_t)B3_UPW * 5 * tpitch;
     return ((st > bt ? st : bt) + 15) / 16 * 16;
@@ -1439,11 +1441,13 @@ __device__ __noinline__ void band3_direct_finish(const Band3Args& a, unsigned ch
             int st = BFA_ST_OK;
             if (want_stamps) {
                 BfaStamp* out = a.stamps + (size_t)u * a.max_stamps;
+                const bool out16 = ((unsigned long long)out & 15ull) == 0;
                 for (int g = lane; g < N && g < a.max_stamps; g += 32) {
                     const int2 r = se[g];
                     BfaStamp sv;
                     sv.phoneme = my_cls[g]; sv.start = r.x; sv.end = r.y; sv.target_idx = it.idx0 + g;
-                    out[g] = sv;
+                    if (out16) *reinterpret_cast<int4*>(out + g) = make_int4(sv.phoneme, sv.start, sv.end, sv.target_idx);
+                    else out[g] = sv;
                     if (want_conf) a.conf[(size_t)u * a.max_stamps + g] = stamp_confidence_prob(lp_s, T, r.x, r.y);
                 }
                 if (N > a.max_stamps) st |= BFA_ST_STAMP_OVERFLOW;
@@ -1479,7 +1483,11 @@ __device__ __forceinline__ void band3_roles(int warp, int npairs, bool& is_dp, i
     idle = warp >= 2 * npairs;
 #ifndef BFA_ROLES_CONTIG
     if (npairs == 7) {
+#ifdef BFA_DP_WARPS
+        constexpr uint32_t DP_WARPS = BFA_DP_WARPS;
+#else
         constexpr uint32_t DP_WARPS = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3) | (1u << 6) | (1u << 7) | (1u << 11);
+#endif
         is_dp = (DP_WARPS >> warp) & 1u;
         pair = __popc((is_dp ? DP_WARPS : ~DP_WARPS) & ((1u << warp) - 1u));
         idle = warp >= 14;

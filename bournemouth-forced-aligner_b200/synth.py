@@ -68,3 +68,45 @@ def ragged_batch(B, *, C=66, t_range=(60, 1800), n_range=(4, 120), seed=0, peak=
         lp, tgt, _ = planted_batch(1, T, N, C, seed=seed * 100003 + u, peak=peak, device=device)
         out.append((lp[0], tgt[0]))
     return out
+
+
+def pack_ragged(utts, C, device="cpu", align_floats=4):
+    """Pack a list of (log_probs [T,C], targets [N]) back to back (every utterance starts on a multiple of `align_floats`
+    floats) -> (flat fp32 rows, row_off int64 [B], Ts, flat int32 targets, Ns), the arguments of ViterbiDecoder.align_batch."""
+    Ts = [int(l.shape[0]) for l, _ in utts]
+    Ns = [int(t.shape[0]) for _, t in utts]
+    offs, cur = [], 0
+    for t in Ts:
+        offs.append(cur)
+        cur += (t * C + align_floats - 1) // align_floats * align_floats
+    flat = torch.empty(max(cur, 1), dtype=torch.float32, device=device)
+    for (l, _), o, t in zip(utts, offs, Ts):
+        flat[o:o + t * C] = l.reshape(-1)
+    tg = torch.cat([t for _, t in utts]).to(torch.int32).contiguous() if utts else torch.zeros(0, dtype=torch.int32)
+    return flat, torch.tensor(offs, dtype=torch.int64, device=device), Ts, tg.to(device), Ns
+
+
+def baseline_config(n, *, C=66, device="cpu", B=None, seed=None, sort_ragged=True):
+    """The synthetic workloads of BASELINE.json `configs`, as align_batch arguments:
+       2: B=1024, T=600, N=40      3: B=256, T=3600, N=200 with SIL anchors (silence-anchored segmentation)
+       4: ragged B=8192, T in [60,1800], N in [4,120], rows packed (ordered by length like a bucketing loader)
+    Returns dict(lp=flat rows, row_off, Ts, tgt=flat int32 targets, Ns, name)."""
+    if n == 2:
+        B = B or 1024
+        lp, tgt, _ = planted_batch(B, 600, 40, C, seed=21 if seed is None else seed, device=device)
+        return dict(name=f"2: B={B} T=600 N=40", lp=lp.reshape(-1), row_off=torch.arange(B, dtype=torch.int64, device=device) * 600 * C,
+                    Ts=[600] * B, tgt=tgt.to(torch.int32).reshape(-1).contiguous(), Ns=[40] * B)
+    if n == 3:
+        B = B or 256
+        lp, tgt, _ = planted_batch(B, 3600, 200, C, seed=22 if seed is None else seed, peak=12.0, sil_every=40, sil_frames=18, device=device)
+        return dict(name=f"3: B={B} T=3600 N=200 SIL anchors", lp=lp.reshape(-1), row_off=torch.arange(B, dtype=torch.int64, device=device) * 3600 * C,
+                    Ts=[3600] * B, tgt=tgt.to(torch.int32).reshape(-1).contiguous(), Ns=[200] * B)
+    if n == 4:
+        B = B or 8192
+        utts = ragged_batch(B, C=C, seed=23 if seed is None else seed, device=device)
+        if sort_ragged:
+            utts.sort(key=lambda u: -int(u[0].shape[0]))
+        flat, row_off, Ts, tg, Ns = pack_ragged(utts, C, device=device)
+        return dict(name=f"4: ragged B={B} T in [60,1800] N in [4,120] packed" + (", ordered by length" if sort_ragged else ""),
+                    lp=flat, row_off=row_off, Ts=Ts, tgt=tg, Ns=Ns)
+    raise ValueError(n)

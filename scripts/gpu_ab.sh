@@ -5,7 +5,7 @@ run() {
   python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read()); r = d['roofline']
-print('$1: value %.3e ms/step %.4f frac %.3f isolated %.4f fill %.4f' % (d['value'], d['ms_per_step'], r['frac'], r.get('isolated_launch_ms', 0), r.get('fill_phase', {}).get('kernel_ms', 0)))"
+print('$1: value %.3e ms/step %.4f frac %.3f isolated %.4f fill %.4f host_us %.1f plain %.4f' % (d['value'], d['ms_per_step'], r['frac'], r.get('isolated_launch_ms', 0), r.get('fill_phase', {}).get('kernel_ms', 0), d.get('host_enqueue_us_per_step', 0), d['uninstrumented_step']['ms_per_step']))"
 }
 run default
 for v in "$@"; do
