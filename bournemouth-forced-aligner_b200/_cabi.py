@@ -13,7 +13,7 @@ LIB_PATH = Path(os.environ["BFA_B200_LIB"]) if os.environ.get("BFA_B200_LIB") el
 
 BFA_OK, BFA_E_INVALID, BFA_E_UNSUPPORTED, BFA_E_WORKSPACE, BFA_E_CUDA = 0, -1, -2, -3, -4
 ST_OK, ST_EMPTY_TARGET, ST_TOO_SHORT, ST_PROPORTIONAL, ST_SEGMENTED = 0, 1, 2, 3, 4
-ST_DEFERRED = 5
+ST_DEFERRED, ST_UNSUPPORTED = 5, 6
 ST_DEGENERATE, ST_STAMP_OVERFLOW = 8, 16
 MODE_FULL, MODE_SIMPLE = 0, 1
 FLAG_EXACT_ONLY, HINT_NO_SIL = 1, 2

@@ -35,13 +35,15 @@ def _require_cuda(t: torch.Tensor, what: str):
 
 
 class _Workspace:
-    """Grow-only device scratch, one per (aligner, device)."""
+    """Grow-only device scratch, one per (aligner, device, CUDA stream): calls in flight on different streams never share
+    counters, item lists or back-pointer slabs.  A buffer that is outgrown is handed back to the caching allocator, which
+    only reuses it for work enqueued later on the same stream."""
 
     def __init__(self):
         self.buf = {}
 
     def get(self, nbytes: int, device) -> torch.Tensor:
-        key = str(device)
+        key = (str(device), int(torch.cuda.current_stream(device).cuda_stream))
         b = self.buf.get(key)
         if b is None or b.numel() < nbytes:
             b = torch.empty(int(nbytes * 1.1) + 256, dtype=torch.uint8, device=device)
@@ -77,16 +79,25 @@ class BatchResult:
 
     def stamp_lists(self, with_conf: bool = False) -> List[List[tuple]]:
         """list[B] of list[(phoneme, start, end_exclusive, target_idx[, conf])] -- forced_alignment.py:871-872."""
-        n = self.n_stamps.cpu().numpy()
-        st = self.stamps.cpu().numpy()
-        cf = self.conf.cpu().numpy() if (with_conf and self.conf is not None) else None
-        out = []
-        for b in range(n.shape[0]):
-            rows = st[b, : n[b]].tolist()
-            if cf is None:
-                out.append([tuple(r) for r in rows])
-            else:
-                out.append([tuple(r) + (float(c),) for r, c in zip(rows, cf[b, : n[b]].tolist())])
+        B = len(self.T) if self.T is not None else int(self.n_stamps.shape[0])
+        if B == 0:
+            return []
+        # one device->host copy of the packed arena when there is one (stamps | conf | n_stamps live in a single allocation)
+        n = self.n_stamps[:B].cpu().numpy()
+        st = self.stamps[:B].cpu().numpy()
+        cf = self.conf[:B].cpu().numpy() if (with_conf and self.conf is not None) else None
+        # vectorised: all valid rows flattened once, converted to Python objects in one go, then cut per utterance
+        valid = np.arange(st.shape[1])[None, :] < n[:, None]
+        rows = st[valid]                                   # [sum n, 4]
+        cols = [rows[:, i].tolist() for i in range(4)]
+        if cf is None:
+            flat = list(zip(*cols))
+        else:
+            flat = list(zip(*cols, cf[valid].tolist()))
+        out, pos = [], 0
+        for k in n.tolist():
+            out.append(flat[pos:pos + k])
+            pos += k
         return out
 
 
@@ -350,7 +361,9 @@ class AlignmentUtils:
             return [int(v) for v in x.tolist()]
         return [int(v) for v in x]
 
-    def _dense_batch(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf):
+    def _dense_launch(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf):
+        """Enqueue the alignment of a padded batch on the current stream and return without waiting for it: the first half of
+        decode_alignments.  Two heads (core.py:900-920) can be launched back to back before either result is looked at."""
         _require_cuda(log_probs, "log_probs")
         lp = log_probs if (log_probs.dtype == torch.float32 and log_probs.is_contiguous()) else log_probs.contiguous().float()
         B, T_max, C_ = lp.shape
@@ -369,7 +382,7 @@ class AlignmentUtils:
                 params.reserved |= _cabi.HINT_NO_SIL
                 may_segment = False
         # Without segmentation every utterance that is a plain stride-4 problem is finished by ONE kernel (in-kernel planning,
-        # Viterbi, stamps, confidences): launch only that kernel; whatever it flags as deferred is run again below
+        # Viterbi, stamps, confidences): launch only that kernel; whatever it flags as deferred is run again in _dense_finish
         if not may_segment and S > 0 and direct_only_worthwhile(T, N, params):
             params.reserved |= _cabi.FLAG_DIRECT_ONLY
         seqs = true_seqs.to(dev)
@@ -378,19 +391,48 @@ class AlignmentUtils:
         tgt = seqs[mask].to(torch.int32).contiguous()
         row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T_max * C_)
         r = self.viterbi_decoder.align_batch(lp, row_off, T, C_, tgt, N, params=params, want_stamps=True, want_conf=want_conf)
+        return dict(r=r, lp=lp, row_off=row_off, T=T, N=N, C=C_, tgt=tgt, params=params, want_conf=want_conf, B=B, T_max=T_max)
+
+    def _dense_finish(self, h):
+        """Second half: wait for the statuses, repeat the call where the library asked for it, raise what the reference raises."""
+        r, params, B, T, N = h["r"], h["params"], h["B"], h["T"], h["N"]
+        again = lambda **kw: self.viterbi_decoder.align_batch(h["lp"], h["row_off"], T, h["C"], h["tgt"], N, params=params, want_stamps=True,
+                                                              want_conf=h["want_conf"], **kw)
         st = r.status[:B].cpu().numpy()
         if ((st & 7) == _cabi.ST_DEFERRED).any():  # the one-kernel path handed utterances back: the full chain takes the batch
             params.reserved &= ~(_cabi.FLAG_DIRECT_ONLY | _cabi.FLAG_PIPELINED)
-            r = self.viterbi_decoder.align_batch(lp, row_off, T, C_, tgt, N, params=params, want_stamps=True, want_conf=want_conf)
+            r = again()
             st = r.status[:B].cpu().numpy()
         if (st & _cabi.ST_STAMP_OVERFLOW).any():   # more runs than the default stamp pitch (degenerate paths): use the safe pitch
-            r = self.viterbi_decoder.align_batch(lp, row_off, T, C_, tgt, N, params=params, want_stamps=True, want_conf=want_conf,
-                                                 max_stamps=max(T_max, 1))
+            r = again(max_stamps=max(h["T_max"], 1))
             st = r.status[:B].cpu().numpy()
+        if ((st & 7) == _cabi.ST_UNSUPPORTED).any():
+            import warnings
+            bad = np.nonzero((st & 7) == _cabi.ST_UNSUPPORTED)[0]
+            warnings.warn(f"{bad.size} utterance(s) (first: #{int(bad[0])}, {int(N[int(bad[0])])} phonemes) need a CTC path of more than "
+                          f"{_cabi.MAX_L} states and were not aligned (no timestamps returned for them); split such segments")
         self.last_result = r
         self.last_params_reserved = int(params.reserved)     # which path the batch finally took (FLAG_DIRECT_ONLY: one kernel)
         self.viterbi_decoder._raise_if_too_short(st, T, N)
         return r
+
+    def _dense_batch(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf):
+        return self._dense_finish(self._dense_launch(log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf))
+
+    def decode_alignments_launch(self, log_probs, true_seqs, pred_lens=None, true_seqs_lens=None, boost_targets=True, enforce_minimum=True,
+                                 with_confidence=False):
+        """decode_alignments split in two: this half only enqueues the kernels (no host synchronisation) and returns a handle for
+        decode_alignments_finish.  core.py:900-920 aligns the phoneme head and the group head one after the other; with the two
+        halves both heads are in flight before the host looks at either."""
+        if (true_seqs is None) or (true_seqs_lens is None):
+            raise ValueError("Phoneme sequences and lengths required for forced alignment")  # :878-879
+        p = self.viterbi_decoder._params(boost_targets, enforce_minimum, self.silence_anchors > 0)
+        h = self._dense_launch(log_probs, true_seqs, pred_lens, true_seqs_lens, p, with_confidence)
+        h["with_confidence"] = with_confidence
+        return h
+
+    def decode_alignments_finish(self, handle):
+        return self._dense_finish(handle).stamp_lists(with_conf=handle["with_confidence"])
 
     def decode_alignments(self, log_probs, true_seqs=None, pred_lens=None, true_seqs_lens=None, forced_alignment=True,
                           boost_targets=True, enforce_minimum=True, debug=False, with_confidence=False):
@@ -435,7 +477,10 @@ def _calculate_confidences(log_probs: torch.Tensor, framestamps):
         if est and not (s2 < T and e2 <= T):  # utils.py:88-91
             raise ValueError(f"Invalid frame range for estimated timestamp: start_frame={s2}, end_frame={e2}, "
                              f"log_probs shape={tuple(lp.shape)}, is_estimated={est}, phoneme_id={ph}")
-    st = torch.tensor([[int(f[0]), int(f[1]), int(f[2]), int(f[3])] for f in framestamps], dtype=torch.int32, device=dev)
+    for (ph, s, e, _i, est) in framestamps:
+        if not (-C_ <= int(ph) < C_) or max(0, int(s)) >= T:   # utils.py:89 indexes probs[start_frame, phoneme_id]
+            raise IndexError(f"stamp (phoneme_id={ph}, start_frame={s}) is out of bounds for log_probs of shape {(T, C_)}")
+    st = torch.tensor([[int(f[0]) % C_, int(f[1]), int(f[2]), int(f[3])] for f in framestamps], dtype=torch.int32, device=dev)
     conf = torch.empty(n, dtype=torch.float32, device=dev)
     i64 = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)
     i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
@@ -467,7 +512,9 @@ def _calculate_confidences_batch(log_probs: torch.Tensor, framestamps, pred_lens
     st = np.zeros((B, ms, 4), np.int32)
     for b, fs in enumerate(framestamps):
         for i, f in enumerate(fs):
-            st[b, i] = (int(f[0]), int(f[1]), int(f[2]), int(f[3]))
+            if not (-C_ <= int(f[0]) < C_) or max(0, int(f[1])) >= T[b]:   # utils.py:89 indexes probs[start_frame, phoneme_id]
+                raise IndexError(f"stamp (phoneme_id={f[0]}, start_frame={f[1]}) of item {b} is out of bounds for log_probs of shape {(T[b], C_)}")
+            st[b, i] = (int(f[0]) % C_, int(f[1]), int(f[2]), int(f[3]))
     st_d = torch.from_numpy(st).to(dev)
     n_d = torch.tensor([len(f) for f in framestamps], dtype=torch.int32, device=dev)
     T_d = torch.tensor(T, dtype=torch.int32, device=dev)

@@ -12,6 +12,7 @@ namespace bfa {
 // rewrite that element, so the max of :107 runs over {avg, p[start+1 .. end-1]}.
 __device__ __forceinline__ float stamp_confidence(const float* lp, int T, int C, int ph, int start, int end) {
     int s = max(0, start), e = min(T, end);                     // :86-87
+    if (s >= T || ph < 0 || ph >= C) return __int_as_float(0x7fc00000);   // the reference raises IndexError here (probs[start, ph], :89); never read out of bounds
     float avg = expf(lp[(long long)s * C + ph]);                // :89
     if (s < e && ph < C) {                                      // :93
         const float half = avg / 2.0f;                          // :95
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(As
     if (u >= a.B) return;
     if (a.uflag && a.uflag[u]) return;
     const int st = a.status[u] & 7;
-    if (st == BFA_ST_EMPTY_TARGET || st == BFA_ST_TOO_SHORT) {   // :894-897 -> [] ; ValueError
+    if (st == BFA_ST_EMPTY_TARGET || st == BFA_ST_TOO_SHORT || st == BFA_ST_UNSUPPORTED) {   // :894-897 -> [] ; ValueError ; refused
         if (lane == 0) a.n_stamps[u] = 0;
         return;
     }

@@ -82,6 +82,10 @@ cudaError_t band_set_attr(int bytes) {
     cudaError_t e = cudaFuncSetAttribute(viterbi_band3_kernel<66, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_kernel<67, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_kernel<17, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<67, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<17, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<66, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -115,6 +119,8 @@ void direct_launch(const Band3Args& ba, bool exact, int grid, cudaStream_t st, b
     const size_t smem = std::max((size_t)ba.cls[0].npairs * ba.cls[0].smem_per_warp, (size_t)116 * 1024);
     if (exact) launch_maybe_pdl(viterbi_band3_direct_kernel<0, true>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
     else if (ba.C == 66) launch_maybe_pdl(viterbi_band3_direct_kernel<66, false>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
+    else if (ba.C == 67) launch_maybe_pdl(viterbi_band3_direct_kernel<67, false>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
+    else if (ba.C == 17) launch_maybe_pdl(viterbi_band3_direct_kernel<17, false>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
     else launch_maybe_pdl(viterbi_band3_direct_kernel<0, false>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
 }
 // One launch for the three window classes.  exact: the items carry the caller's log-probs unchanged (no fused log-softmax),
@@ -124,6 +130,8 @@ void band_launch(const Band3Args& ba, bool exact, int grid, cudaStream_t st) {
     for (int v = 0; v < BAND_NV; ++v) smem = std::max(smem, (size_t)ba.cls[v].npairs * ba.cls[v].smem_per_warp);
     if (exact) launch_pdl(viterbi_band3_kernel<0, true>, grid, BAND_WARPS * 64, smem, st, ba);
     else if (ba.C == 66) launch_pdl(viterbi_band3_kernel<66, false>, grid, BAND_WARPS * 64, smem, st, ba);
+    else if (ba.C == 67) launch_pdl(viterbi_band3_kernel<67, false>, grid, BAND_WARPS * 64, smem, st, ba);
+    else if (ba.C == 17) launch_pdl(viterbi_band3_kernel<17, false>, grid, BAND_WARPS * 64, smem, st, ba);
     else launch_pdl(viterbi_band3_kernel<0, false>, grid, BAND_WARPS * 64, smem, st, ba);
 }
 
@@ -134,6 +142,7 @@ struct Fork {
     cudaStream_t s = nullptr, s2 = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr;
     bool ok = false, tried = false;
+    std::mutex use;   // one call at a time enqueues its fork / side-stream launches / join on these shared events and streams
 };
 Fork* fork_stream() {
     static std::mutex mu;
@@ -172,6 +181,7 @@ int device_info(DeviceInfo& out) {
         if (d.vg_ctas_per_sm_big < 1) d.vg_ctas_per_sm_big = 1;
         CUDA_TRY(cudaFuncSetAttribute(assort_confidence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)assort_smem(ASSORT_TS_MAX, ASSORT_SS_MAX)));
+        CUDA_TRY(cudaFuncSetAttribute(soft_boundaries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         const int band_smem_max = BAND_SMEM_MAX;
         d.band_ok = band_set_attr(band_smem_max) == cudaSuccess;
         if (!d.band_ok) (void)cudaGetLastError();   // do not leave a sticky error behind: the exact kernel still runs
@@ -227,7 +237,7 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
         long long byT = (long long)(1.2 * (double)(s.max_T + 2 * p.boundary_pad)) + 1;
         if (byT < maxL) maxL = byT;
     }
-    if (maxL > BFA_MAX_L) return BFA_E_UNSUPPORTED;
+    if (maxL > BFA_MAX_L) maxL = BFA_MAX_L;   // longer paths are refused per utterance by the planner (BFA_ST_UNSUPPORTED), not per batch
     L.max_L = (int)maxL;
     L.bp_words_per_lane = (maxL > 512) ? 2 : 1;
     L.resident_warps = d.sms * d.vg_ctas_per_sm * VG_WARPS;
@@ -323,7 +333,7 @@ const char* bfa_strerror(int code) {
     switch (code) {
         case BFA_OK: return "ok";
         case BFA_E_INVALID: return "invalid argument";
-        case BFA_E_UNSUPPORTED: return "shape outside compiled limits (C > 256 or CTC path longer than 1024 states)";
+        case BFA_E_UNSUPPORTED: return "shape outside compiled limits (C > 256)";
         case BFA_E_WORKSPACE: return "workspace too small";
         case BFA_E_CUDA: return "CUDA runtime error";
         default: return "unknown error";
@@ -500,6 +510,10 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         // kernel sends back is done afterwards.  One CTA of the exact kernel (8 items at a time) per reserved SM.
         const int hint = shape->reserved > 0 ? shape->reserved : 0;
         Fork* fk = hint > 0 ? fork_stream() : nullptr;
+        // the events and side streams are shared by every call on this device: two host threads must not interleave their
+        // record / wait sequences (thread A's side-stream pass would wait for thread B's planner); held until the join is enqueued
+        std::unique_lock<std::mutex> fork_guard;
+        if (fk) fork_guard = std::unique_lock<std::mutex>(fk->use);
         int band_grid = L.band_grid;
         if (fk) {
             const bool two = L.max_L > 256;      // short-path and long-path classes of the exact kernel side by side
@@ -533,6 +547,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
             CUDA_TRY(cudaStreamWaitEvent(st, fk->join, 0));
             if (L.max_L > 256) CUDA_TRY(cudaStreamWaitEvent(st, fk->join2, 0));
         }
+        if (fork_guard.owns_lock()) fork_guard.unlock();
         // the exact kernel: what the planner gave it (unless that ran on the side stream) plus what the banded kernel sent back
         rc = launch_viterbi(va, max_items_i, L.max_L, d, st, false);
         if (rc) return rc;
@@ -622,8 +637,9 @@ int bfa_soft_boundaries_batch(int32_t B, int32_t C, const float* logp, const int
     if (B <= 0) return B == 0 ? BFA_OK : BFA_E_INVALID;
     const size_t smem = (size_t)SOFT_WARPS * max_stamps * sizeof(double);
     if (smem > 200 * 1024) return BFA_E_UNSUPPORTED;
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(soft_boundaries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    DeviceInfo d;
+    int rc = device_info(d);     // sets the kernel's shared-memory attribute once per DEVICE
+    if (rc) return rc;
     const double t1 = pow(10.0, -1.0 * 3.0), t2 = pow(10.0, -1.0 * (double)boundary_softness);   // core.py:699-701
     soft_boundaries_kernel<<<(B + SOFT_WARPS - 1) / SOFT_WARPS, SOFT_WARPS * 32, smem, (cudaStream_t)stream>>>(
         B, C, logp, (const long long*)row_off, T, stamps, n_stamps, max_stamps, t1, t2);

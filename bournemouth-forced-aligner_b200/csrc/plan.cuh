@@ -355,6 +355,7 @@ __device__ int plan_segmented(const UttCtx& c, Item* loc, int32_t* lists, uint32
         if ((double)(stride * n + 1) > (double)Ts * 0.8) stride = 2;
         const int L = stride * n + 1;
         if ((double)L > (double)Ts * 1.2) return -1;                              // :427-429
+        if (L > BFA_MAX_L) return -2;                                             // beyond the exact kernel's state capacity
         if (n_items >= a.item_cap) return -1;  // cannot happen (item_cap = gmax + 1); defensive
         if (lane == 0) {
             Item it;
@@ -431,6 +432,12 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
         if (p.mode == BFA_MODE_FULL && p.silence_anchors > 0 && p.silence_id >= 0 && T > 0 && ti.has_sil) {
             int r = plan_segmented(c, loc, a.lists + (size_t)u * a.list_ints, a.anchors + (size_t)u * a.anchor_words);
             if (r >= 0) { n_items = r; st = BFA_ST_SEGMENTED; done = true; }
+            else if (r == -2) {          // a segment's path is longer than BFA_MAX_L states: this utterance is refused, the batch goes on
+                st = BFA_ST_UNSUPPORTED;
+                __syncwarp();
+                fill_frames(c, o_base, o_lim, T, p.blank_id, -1);
+                done = true;
+            }
         }
         if (!done) {
             int stride = 4;
@@ -457,6 +464,11 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
                         }
                     }
                 }
+            }
+            if (ok && T > 0 && stride * N + 1 > BFA_MAX_L) {   // more states than the exact kernel holds (N > 255 at stride 4)
+                ok = false;
+                st = BFA_ST_UNSUPPORTED;
+                fill_frames(c, o_base, o_lim, T, p.blank_id, -1);
             }
             if (ok && T > 0) {
                 const int L = stride * N + 1;

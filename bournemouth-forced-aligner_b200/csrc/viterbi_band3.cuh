@@ -72,6 +72,8 @@ constexpr int B3_NST = 3;          // pipeline stages (chunk c is consumed while
 constexpr int B3_ROWS = 8;         // rows per stage per utterance (8*C*4 bytes is always a multiple of 16)
 constexpr int B3_PAIRS = 7;        // (DP warp, helper warp) pairs per CTA, one CTA per SM
 constexpr int B3_KK = 72;          // floats per utterance in the class-weight table (C <= 72)
+constexpr int B3_KK2 = 2 * B3_KK;  // per utterance: the table, then a copy shifted by B3_KSH floats (odd class counts: rows that
+constexpr int B3_KSH = 3;          // start on an odd float pair up classes (1,2),(3,4),..; the copy puts class 1 on a 16-byte boundary)
 constexpr int B3_STP = 9;          // float2 pitch of the per-utterance (lnS, eb) array (bank spreading)
 constexpr int B3_SLOT_PAD = 4;      // floats of slack per staged (utterance, chunk) slot: room for an item's lead-in (Item::lead)
 constexpr int B3_NMAX = 128;       // phonemes per item on this path (byte-sized class table in shared memory)
@@ -160,7 +162,7 @@ __host__ __device__ inline int band3_bt_keep_words(int G) { return B3_NREC * (6 
 enum : int { B3_BAR_FULL = 0, B3_BAR_READY = B3_NST, B3_BAR_FREE = 2 * B3_NST, B3_BAR_REC = 3 * B3_NST, B3_BAR_KREADY = 3 * B3_NST + B3_NREC,
              B3_BAR_KFREE = 3 * B3_NST + B3_NREC + 2, B3_BAR_PLAN = 3 * B3_NST + B3_NREC + 4, B3_NBARS = 3 * B3_NST + B3_NREC + 5 };
 __host__ __device__ inline size_t band3_off_kk(size_t R) { return R; }
-__host__ __device__ inline size_t band3_off_stats(size_t R) { return band3_off_kk(R) + (size_t)B3_UPW * B3_KK * 4; }
+__host__ __device__ inline size_t band3_off_stats(size_t R) { return band3_off_kk(R) + (size_t)B3_UPW * B3_KK2 * 4; }
 __host__ __device__ inline size_t band3_off_cls(size_t R) { return band3_off_stats(R) + (size_t)B3_NST * B3_UPW * B3_STP * 8; }
 __host__ __device__ inline size_t band3_off_flags(size_t R) { return band3_off_cls(R) + (size_t)B3_UPW * B3_NMAX; }
 __host__ __device__ inline size_t band3_off_items(size_t R) { return band3_off_flags(R) + 32; }
@@ -326,7 +328,7 @@ __device__ __noinline__ void band3_direct_plan(const Band3Args& a, int task, uns
     Item* items = reinterpret_cast<Item*>(smem_pair + band3_off_items(R));
     int* ustate = reinterpret_cast<int*>(smem_pair + band3_off_flags(R)) + B3_UPW;
     unsigned char* cls8 = smem_pair + band3_off_cls(R) + seg * B3_NMAX;
-    float* kk = reinterpret_cast<float*>(smem_pair + band3_off_kk(R)) + seg * B3_KK;
+    float* kk = reinterpret_cast<float*>(smem_pair + band3_off_kk(R)) + seg * B3_KK2;
     const int u = task * B3_UPW + seg;
     int state = B3_U_NONE;
     Item it;
@@ -348,7 +350,7 @@ __device__ __noinline__ void band3_direct_plan(const Band3Args& a, int task, uns
         const int band = (L > 60) ? max(L / 4, 20) : 0;                                   // :190 / :976
         ok = ok && L <= T && band3_window_need(N, T, L, band) <= B3_LPU * 3;
         const int lead = (int)(((unsigned long long)(a.logp + ro) & 15ull) >> 2);
-        if (lead != 0 && (ro < lead || (C == 66 && (lead & 1)))) ok = false;     // same rule as the planner's fast_class
+        if (lead != 0 && (ro < lead || (C == 66 && (lead & 1)))) ok = false;     // same rule as the planner's fast_class (C = 66 reads 8-byte pairs from an even float)
         it.lp_off = ro; it.stat_off = fo0; it.out_off = fo0; it.out_lim = fo1; it.seq_off = t0;
         it.L = L; it.band = band; it.n = N; it.n_out = T; it.lead = lead;
         it.flags = ITEM_FINAL;
@@ -358,7 +360,10 @@ __device__ __noinline__ void band3_direct_plan(const Band3Args& a, int task, uns
     // targets: byte-sized class table + the class weights of the fused log-sum-exp, exp(x + boost*[c in targets] - boost) =
     // 2^(x*log2e + kk[c]); every id must be a plain class, and none may be silence_id while silence anchoring is on
     if (boost) {
-        for (int c = l8; c < B3_KK; c += B3_LPU) kk[c] = c < C ? -p.boost_factor * LOG2E : -INFINITY;
+        for (int c = l8; c < B3_KK; c += B3_LPU) {
+            kk[c] = c < C ? -p.boost_factor * LOG2E : -INFINITY;
+            if (c + B3_KSH < B3_KK) kk[B3_KK + B3_KSH + c] = kk[c];
+        }
     }
     __syncwarp();
     bool tbad = false;
@@ -379,7 +384,10 @@ __device__ __noinline__ void band3_direct_plan(const Band3Args& a, int task, uns
                 if (c < 0 || c >= C || c == p.blank_id || (segmenting && c == p.silence_id)) tbad = true;
                 else {
                     cls8[j] = (unsigned char)c;
-                    if (boost) kk[c] = 0.0f;
+                    if (boost) {
+                        kk[c] = 0.0f;
+                        if (c + B3_KSH < B3_KK) kk[B3_KK + B3_KSH + c] = 0.0f;
+                    }
                 }
             }
         }
@@ -437,7 +445,9 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
             for (int c = l8; c < B3_KK; c += B3_LPU) {
                 const bool ok = c < C;
                 const bool tg = ok && k.seg_on && ((a.tmask[(size_t)utt * MAX_WORDS + (c >> 5)] >> (c & 31)) & 1u);
-                k.kk[seg * B3_KK + c] = ok ? (tg ? 0.0f : -boostv * LOG2E) : -INFINITY;
+                const float kv = ok ? (tg ? 0.0f : -boostv * LOG2E) : -INFINITY;
+                k.kk[seg * B3_KK2 + c] = kv;
+                if (c + B3_KSH < B3_KK) k.kk[seg * B3_KK2 + B3_KK + B3_KSH + c] = kv;
             }
         }
     }
@@ -513,13 +523,54 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
                 // immediate); deriving it from a run-time value keeps ptxas from folding it back into a second immediate
                 const uint32_t tagmask = 0xffffff80u | ((uint32_t)a.C >> 16);
                 auto tag = [&](float v, int c) { return __uint_as_float((__float_as_uint(v) & tagmask) | (uint32_t)c); };
-                const float* kp = k.kk + seg * B3_KK;
+                const float* kp = k.kk + seg * B3_KK2;
                 auto term = [&](float x, float kc, int c, float& acc) {
                     const float v = fmaf(x, LOG2E, kc);
                     acc += b3_ex2(v);
                     best = fmaxf(best, tag(v, c));
                 };
-                if (CT != 0 && (CT & 1) == 0) {
+                if (CT != 0 && (CT & 1) == 1) {
+                    // Odd compiled class count (67 = the reference's phoneme head, 17 = its group head): a row of CT floats starts
+                    // on an even or an odd float, alternately.  Classes are still taken two per instruction: a row on an even
+                    // float pairs (0,1),(2,3),.. and leaves class CT-1 single, a row on an odd float leaves class 0 single and
+                    // pairs (1,2),(3,4),.. (aligned again), with the class weights read from the shifted copy of the table.
+                    // Pair elements carry the tag "position in the pair sequence" (class = tag + first paired class), the
+                    // single class the tag 127.
+                    const int odd = (k.lead + l8) & 1;         // parity of the row's first float (stage slot and seg pitch are even)
+                    const unsigned long long* x64 = reinterpret_cast<const unsigned long long*>(rowp + odd);
+                    const float* kq = odd ? kp + B3_KK + B3_KSH + 1 : kp;                  // weights of the first paired class, 16-byte aligned
+                    const ulonglong2* k128 = reinterpret_cast<const ulonglong2*>(kq);
+                    unsigned long long sA = 0ull, sB = 0ull;
+                    auto pair_term = [&](unsigned long long x, unsigned long long kc, int c, unsigned long long& acc2) {
+                        const unsigned long long v = b3_fma2(x, LOG2E, kc);
+                        float v0, v1;
+                        b3_unpack2(v, v0, v1);
+                        acc2 = b3_add2(acc2, b3_pack2(b3_ex2(v0), b3_ex2(v1)));
+                        best = fmaxf(best, fmaxf(tag(v0, c), tag(v1, c + 1)));
+                    };
+                    constexpr int NP = (CT - 1) / 2;           // pairs
+#pragma unroll
+                    for (int i = 0; i < NP / 2; ++i) {
+                        const ulonglong2 kv = k128[i];
+                        pair_term(x64[2 * i], kv.x, 4 * i, sA);
+                        pair_term(x64[2 * i + 1], kv.y, 4 * i + 2, sB);
+                    }
+                    if (NP & 1) pair_term(x64[NP - 1], reinterpret_cast<const unsigned long long*>(kq)[NP - 1], 2 * (NP - 1), sA);
+                    b3_unpack2(sA, s0, s1);
+                    b3_unpack2(sB, s2, s3);
+                    {   // the single class: CT-1 (row on an even float) or 0 (row on an odd float)
+                        const int cs1 = odd ? 0 : CT - 1;
+                        const float v = fmaf(rowp[cs1], LOG2E, kp[cs1]);
+                        s0 += b3_ex2(v);
+                        best = fmaxf(best, tag(v, 127));
+                    }
+                    // tag -> class
+                    {
+                        const int tg = (int)(__float_as_uint(best) & 127u);
+                        const int cls_best = tg == 127 ? (odd ? 0 : CT - 1) : tg + odd;
+                        best = __uint_as_float((__float_as_uint(best) & ~127u) | (uint32_t)cls_best);
+                    }
+                } else if (CT != 0 && (CT & 1) == 0) {
                     // two classes per instruction where the ISA allows it (FFMA2 / FADD2, same IEEE results lane by lane):
                     // the issue slots, not the FP pipe, are what this warp competes for
                     const unsigned long long* x64 = reinterpret_cast<const unsigned long long*>(rowp);

@@ -63,21 +63,52 @@ def gather_results(stamps: torch.Tensor, conf: torch.Tensor, n_stamps: torch.Ten
     return tuple(outs)
 
 
-def gather_packed(result, counts: Sequence[int], group=None):
+def global_stamp_pitch(max_N: int, max_T: int, ignore_noise: bool, group=None, device=None) -> int:
+    """The stamp pitch (BfaShape.max_stamps) every rank must use so that the packed result arenas of all ranks have one
+    layout: the default pitch of align_batch depends on the rank's own longest target, and ranks own different utterances.
+    One small all-reduce (MAX) before the first batch; pass the result as `max_stamps` to plan_batch / align_batch."""
+    mine = (max_N + 8) if ignore_noise else max(max_T, 1)
+    t = torch.tensor([mine], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
+
+
+def gather_packed(result, counts: Sequence[int], group=None, dst=None):
     """The same gather as gather_results in ONE collective: `result` is a BatchResult whose per-utterance arrays are
     views of a single allocation (`result.arena`, see aligner.result_arena_words).  Returns
-    (stamps [sum B_r, P, 4] i32, conf [sum B_r, P] f32 or None, n_stamps, status, dp_final) over all utterances."""
+    (stamps [sum B_r, P, 4] i32, conf [sum B_r, P] f32 or None, n_stamps, status, dp_final) over all utterances.
+    Every rank must have used the same stamp pitch (global_stamp_pitch); this is checked, not assumed.
+    dst = None: all-gather (every rank gets everything).  dst = r: gather to rank r only (north_star's "final gather of the
+    timestamp arrays"): the other ranks return None."""
     from .aligner import result_arena_words
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     ms = result.max_stamps
     want_conf = result.conf is not None
+    # the layouts must agree: pitch, confidence section, and this rank's count as the caller sees it
+    meta = torch.tensor([ms, int(want_conf), int(counts[rank])], dtype=torch.int64, device=result.arena.device)
+    metas = meta.new_empty(world * 3)
+    dist.all_gather_into_tensor(metas, meta, group=group)
+    metas = metas.view(world, 3).cpu()
+    if not (bool((metas[:, 0] == ms).all()) and bool((metas[:, 1] == int(want_conf)).all())):
+        raise ValueError(f"gather_packed: ranks used different result layouts (max_stamps per rank {metas[:, 0].tolist()}); "
+                         "agree on one pitch first (sharding.global_stamp_pitch)")
+    if metas[:, 2].tolist() != [int(c) for c in counts]:
+        raise ValueError(f"gather_packed: counts {list(counts)} do not match what the ranks hold {metas[:, 2].tolist()}")
     sizes = [result_arena_words(max(int(c), 1), ms, True, want_conf) for c in counts]
     wmax = max(sz["total"] for sz in sizes)
     arena = result.arena
     if arena.numel() < wmax:
         arena = torch.cat([arena, arena.new_zeros(wmax - arena.numel())])
-    buf = arena.new_empty(world * wmax)
-    dist.all_gather_into_tensor(buf, arena[:wmax].contiguous(), group=group)
+    if dst is None:
+        buf = arena.new_empty(world * wmax)
+        dist.all_gather_into_tensor(buf, arena[:wmax].contiguous(), group=group)
+    else:
+        parts = [arena.new_empty(wmax) for _ in range(world)] if rank == dst else None
+        dist.gather(arena[:wmax].contiguous(), parts, dst=dst, group=group)
+        if rank != dst:
+            return None
+        buf = torch.cat(parts)
     buf = buf.view(world, wmax)
     st, cf, ns, ss, dp = [], [], [], [], []
     for r in range(world):
@@ -106,17 +137,30 @@ class PushGather:
     that the PEERS' pushes have landed is known after a barrier of the group (or any later collective).
     Raises if symmetric memory is not available (callers fall back to gather_packed / all_gather_into_tensor)."""
 
-    def __init__(self, n_words: int, device, group=None, buffers: int = 2):
+    def __init__(self, n_words: int, device, group=None, buffers: int = 2, dst=None):
+        """dst = None: push to every peer (an all-gather).  dst = r: push to rank r only -- the final gather to one place,
+        streamed: with `buffers` = the number of batches, rank r ends up holding recv[i].view(world, -1)[q] = rank q's arena of
+        batch i for every batch, and each rank has sent 1 / (world - 1) of what the all-gather sends."""
         import torch.distributed._symmetric_memory as symm
         group = group if group is not None else dist.group.WORLD
         self.world, self.rank, self.n = dist.get_world_size(group), dist.get_rank(group), int(n_words)
+        self.dst = dst
+        # every rank must push arenas of one size: agree on it (ranks own different utterances)
+        sz = torch.tensor([self.n], dtype=torch.int64, device=device)
+        szs = sz.new_empty(self.world)
+        dist.all_gather_into_tensor(szs, sz, group=group)
+        if not bool((szs == self.n).all()):
+            raise ValueError(f"PushGather: ranks have different arena sizes {szs.tolist()}; use one stamp pitch and one batch size "
+                             "(sharding.global_stamp_pitch) or pad the arenas")
         self.stream = torch.cuda.Stream(device=device)
         self.recv, self._peers, self._done = [], [], []
-        for _ in range(buffers):
-            buf = symm.empty(self.world * self.n, dtype=torch.int32, device=device)
-            hdl = symm.rendezvous(buf, group)
-            self.recv.append(buf)
-            self._peers.append([hdl.get_buffer(q, (self.world * self.n,), torch.int32) for q in range(self.world)])
+        per = self.world * self.n
+        big = symm.empty(buffers * per, dtype=torch.int32, device=device)        # one symmetric allocation, one rendezvous
+        hdl = symm.rendezvous(big, group)
+        peers = [hdl.get_buffer(q, (buffers * per,), torch.int32) for q in range(self.world)]
+        for b in range(buffers):
+            self.recv.append(big[b * per:(b + 1) * per])
+            self._peers.append([pq[b * per:(b + 1) * per] for pq in peers])
             self._done.append(None)
 
     def push(self, i: int, arena: torch.Tensor) -> None:
@@ -124,8 +168,10 @@ class PushGather:
         ready.record()                                        # the batch's kernels on the current stream
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
-            for k in range(self.world):                       # start with the next rank: spreads the load over the links
-                q = (self.rank + k) % self.world
+            if arena.numel() != self.n:
+                raise ValueError(f"PushGather.push: arena of {arena.numel()} words, expected {self.n}")
+            targets = [(self.rank + k) % self.world for k in range(self.world)] if self.dst is None else [self.dst]
+            for q in targets:                                 # all peers: start with the next rank, spreads the load over the links
                 self._peers[i][q][self.rank * self.n:(self.rank + 1) * self.n].copy_(arena, non_blocking=True)
             done = torch.cuda.Event()
             done.record()

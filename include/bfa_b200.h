@@ -41,7 +41,7 @@ extern "C" {
 /* return codes */
 #define BFA_OK 0
 #define BFA_E_INVALID (-1)     /* null pointer / bad size / C <= blank_id */
-#define BFA_E_UNSUPPORTED (-2) /* shape outside compiled limits (C > 256, L > BFA_MAX_L) */
+#define BFA_E_UNSUPPORTED (-2) /* shape outside compiled limits (C > 256); paths longer than BFA_MAX_L are a per-utterance status */
 #define BFA_E_WORKSPACE (-3)   /* workspace too small: call bfa_workspace_bytes */
 #define BFA_E_CUDA (-4)        /* CUDA runtime error, see bfa_last_cuda_error */
 
@@ -53,6 +53,8 @@ extern "C" {
 #define BFA_ST_SEGMENTED 4     /* silence-anchored segmentation accepted (:133-145) */
 #define BFA_ST_DEFERRED 5      /* only with BFA_FLAG_DIRECT_ONLY: the utterance needs the full planner chain and was NOT aligned;
                                   run it again without that flag (the Python facade does) */
+#define BFA_ST_UNSUPPORTED 6   /* the utterance's CTC path has more than BFA_MAX_L states (more than 255 phonemes in one DP problem):
+                                  it was NOT aligned (frames = blank, no stamps); every other utterance of the batch is unaffected */
 #define BFA_ST_DEGENERATE 8    /* flag: winning DP score <= -1000 (the reference's "-inf") */
 #define BFA_ST_STAMP_OVERFLOW 16 /* flag: more than max_stamps runs; stamps truncated */
 

@@ -54,6 +54,14 @@ def load():
     return tuple(mods)
 
 
+def _noop(_):
+    """Pool warm-up: the worker imports torch and the staged reference once."""
+    import torch
+    torch.set_num_threads(1)
+    load()
+    return 0
+
+
 def _worker(args):
     """One process = one host core: the reference's own batch entry on a slice of the sample."""
     import time

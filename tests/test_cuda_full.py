@@ -308,3 +308,85 @@ def test_free_decoding_matches_reference_semantics(bfa, dev):
                 want.append((pred[t], t, e, -1))
             t = e
     assert got == want
+
+
+# ---- round-1 advisor findings --------------------------------------------------------------------------------------
+def test_long_target_is_refused_per_utterance(bfa, orc, dev):
+    """A target of more than 255 phonemes needs more than BFA_MAX_L = 1024 path states: that utterance is reported as
+    BFA_ST_UNSUPPORTED (blank frames, no stamps) and every other utterance of the batch is aligned as usual."""
+    from bfa_b200 import synth, _cabi
+    Cc = 67
+    utts = []
+    for i, (T, N) in enumerate([(300, 30), (1900, 350), (500, 60), (1300, 260), (200, 12)]):
+        l, t, _ = synth.planted_batch(1, T, N, Cc, seed=70 + i, peak=10.0)
+        utts.append((l[0], t[0]))
+    flat, row_off, Ts, tg, Ns = synth.pack_ragged(utts, Cc)
+    w = dict(lp=flat, row_off=row_off, Ts=Ts, tgt=tg, Ns=Ns)
+    r = _align(bfa, dev, w, Cc)
+    st = r.status[:5].cpu().numpy()
+    assert (st & 7).tolist() == [0, _cabi.ST_UNSUPPORTED, 0, _cabi.ST_UNSUPPORTED, 0]
+    assert r.n_stamps[:5].cpu().tolist()[1] == 0 and r.n_stamps[:5].cpu().tolist()[3] == 0
+    fo = np.zeros(6, np.int64); np.cumsum(np.asarray(Ts, np.int64), out=fo[1:])
+    assert (r.frame_ph[fo[1]:fo[2]] == Cc - 1).all() and (r.frame_idx[fo[1]:fo[2]] == -1).all()
+    for b in (0, 2, 4):
+        l, t = utts[b]
+        o = orc.align_batch(orc.params(Cc - 1, 0), l.numpy().reshape(1, Ts[b], Cc), np.zeros(1, np.int64), np.asarray([Ts[b]], np.int32), Cc,
+                            t.numpy().astype(np.int32), np.asarray([0, Ns[b]], np.int64), max_stamps=r.max_stamps, n_threads=1)
+        np.testing.assert_array_equal(r.frame_ph[fo[b]:fo[b + 1]].cpu().numpy(), o["frame_ph"])
+        n = int(o["n_stamps"][0])
+        assert int(r.n_stamps[b]) == n
+        np.testing.assert_array_equal(r.stamps[b, :n, 1].cpu().numpy(), o["stamps"]["start"][0][:n])
+    # the reference-shaped entry warns and returns no stamps for the refused utterance
+    au = bfa.AlignmentUtils(Cc - 1, 0)
+    Tm, Nm = max(Ts), max(Ns)
+    lp = torch.full((5, Tm, Cc), -20.0); tg2 = torch.zeros((5, Nm), dtype=torch.long)
+    for b, (l, t) in enumerate(utts):
+        lp[b, :Ts[b]] = l; tg2[b, :Ns[b]] = t
+    with pytest.warns(UserWarning, match="were not aligned"):
+        got = au.decode_alignments(lp.to(dev), true_seqs=tg2, pred_lens=torch.tensor(Ts), true_seqs_lens=torch.tensor(Ns))
+    assert got[1] == [] and got[3] == [] and len(got[0]) == 30 and len(got[2]) == 60
+
+
+def test_two_host_threads_one_device(bfa, dev):
+    """Two host threads aligning different ragged batches on the same device at the same time, each on its own stream (the
+    side-stream pass of the exact kernel is shared per device and is serialised by a mutex): same results as one after the other."""
+    import threading
+    from bfa_b200 import synth
+    Cc = 66
+    batches = []
+    for s in range(2):
+        utts = synth.ragged_batch(96, C=Cc, t_range=(60, 500), n_range=(4, 120), seed=810 + s)
+        batches.append(synth.pack_ragged(utts, Cc, device=dev))
+    dec = bfa.AlignmentUtils(Cc - 1, 0).viterbi_decoder
+
+    def run(k, out, stream=None):
+        flat, row_off, Ts, tg, Ns = batches[k]
+        p = dec._params(True, True, True)
+        ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())
+        with ctx:
+            for _ in range(6):
+                r = dec.align_batch(flat, row_off, Ts, Cc, tg, Ns, params=p)
+            (stream or torch.cuda.current_stream()).synchronize()
+        out[k] = (r.frame_ph.clone(), r.frame_idx.clone(), r.status.clone(), r.n_stamps.clone())
+    ref, got = {}, {}
+    for k in range(2):
+        run(k, ref)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    th = [threading.Thread(target=run, args=(k, got, streams[k])) for k in range(2)]
+    for t in th: t.start()
+    for t in th: t.join()
+    torch.cuda.synchronize()
+    for k in range(2):
+        for a_, b_ in zip(ref[k], got[k]):
+            assert torch.equal(a_, b_), f"batch {k} differs when two threads share the device"
+
+
+def test_confidence_rejects_out_of_range_stamps(bfa, dev):
+    """utils.py:89 indexes probs[start_frame, phoneme_id]: a stamp outside the matrix raises (IndexError in the reference)."""
+    lp = torch.log_softmax(torch.randn(20, 9), -1).to(dev)
+    with pytest.raises(IndexError):
+        bfa._calculate_confidences(lp, [(3, 25, 30, 0, False)])
+    with pytest.raises(IndexError):
+        bfa._calculate_confidences(lp, [(9, 2, 5, 0, False)])
+    ok = bfa._calculate_confidences(lp, [(3, 2, 5, 0, False)])
+    assert len(ok) == 1 and 0.0 < ok[0][5] <= 1.0

@@ -60,6 +60,28 @@ def _worker(rank, world, port, q):
     res.arena = arena
     h = gather_packed(res, counts)
     ok = ok and all(bool((x == y).all()) for x, y in zip(h[:4], g)) and bool((h[4] == -torch.arange(11).float()).all())
+    # gather to ONE rank (north_star: "NCCL used only for the final gather of timestamp arrays"): rank 0 gets everything
+    h0 = gather_packed(res, counts, dst=0)
+    if rank == 0:
+        ok = ok and all(bool((x == y).all()) for x, y in zip(h0[:4], g))
+    else:
+        ok = ok and h0 is None
+    # ragged corpora: ranks whose longest targets differ would pick different default stamp pitches; the pitch is agreed on
+    # with one all-reduce, and a gather over mismatched layouts raises instead of mis-slicing
+    from bfa_b200.sharding import global_stamp_pitch
+    ok = ok and global_stamp_pitch(10 + 20 * rank, 500, True) == 38 and global_stamp_pitch(10, 300 + rank, False) == 301
+    P2 = P + 3 * rank
+    w2 = result_arena_words(bp, P2, True, True)
+    arena2 = torch.zeros(w2["total"], dtype=torch.int32)
+    res2 = BatchResult(None, None, None, arena2[w2["dp_final"]:w2["dp_final"] + bp].view(torch.float32), arena2[w2["status"]:w2["status"] + bp],
+                       arena2[w2["stamps"]:w2["stamps"] + bp * P2 * 4].view(bp, P2, 4), arena2[w2["conf"]:w2["conf"] + bp * P2].view(torch.float32).view(bp, P2),
+                       arena2[w2["n_stamps"]:w2["n_stamps"] + bp], None, P2)
+    res2.arena = arena2
+    try:
+        gather_packed(res2, counts)
+        ok = False
+    except ValueError as e:
+        ok = ok and "different result layouts" in str(e)
     q.put((rank, ok))
     dist.destroy_process_group()
 
