@@ -182,6 +182,7 @@ int device_info(DeviceInfo& out) {
         CUDA_TRY(cudaFuncSetAttribute(assort_confidence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)assort_smem(ASSORT_TS_MAX, ASSORT_SS_MAX)));
         CUDA_TRY(cudaFuncSetAttribute(soft_boundaries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(silprob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BAND_SMEM_MAX));
         const int band_smem_max = BAND_SMEM_MAX;
         d.band_ok = band_set_attr(band_smem_max) == cudaSuccess;
         if (!d.band_ok) (void)cudaGetLastError();   // do not leave a sticky error behind: the exact kernel still runs
@@ -206,13 +207,14 @@ inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 // Workspace carve-up shared by bfa_workspace_bytes and bfa_align_batch.
 struct Layout {
-    bool segmenting, want_rowstat;
+    bool segmenting, want_sil;
+    int cb_pitch, sil_nst;
     int item_cap, gmax, amax, anchor_words, list_ints, max_L, bp_words_per_lane;
     int resident_warps;
     long long slab_words;
     int band_grid, band_smem_per_warp[BAND_NV];
     long long band_slab_words[BAND_NV];
-    size_t off_tmask, off_tgtok, off_need, off_rowstat, off_items_local, off_items, off_fast[BAND_NV], off_lists, off_padded, off_anchors, off_counters,
+    size_t off_tmask, off_tgtok, off_need, off_sild, off_silunits, off_items_local, off_items, off_fast[BAND_NV], off_lists, off_cbase, off_anchors, off_counters,
         off_pathlp, off_gcls, off_bp, off_bp_band[BAND_NV], total;
     // direct kernel
     bool direct;                 // usable for this shape / parameter set
@@ -252,13 +254,17 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
     L.off_tmask = o; o = align_up(o + (size_t)s.B * MAX_WORDS * 4);
     L.off_tgtok = o; o = align_up(o + (size_t)s.B * 4);
     L.off_need = o; o = align_up(o + (size_t)s.B * 4);
-    L.want_rowstat = p.boost_targets && L.segmenting && !(p.reserved & BFA_HINT_NO_SIL);
-    L.off_rowstat = o; o = align_up(o + (L.want_rowstat ? (size_t)s.total_frames * 8 : 0));
+    // running sums of the silence probabilities (silprob_kernel) for the planner's silence scan: one double per frame
+    L.want_sil = L.segmenting && !(p.reserved & BFA_HINT_NO_SIL);
+    L.sil_nst = ss_stages(s.C, (size_t)BAND_SMEM_MAX);
+    L.cb_pitch = s.max_T / SS_CHUNK + 2;
+    L.off_sild = o; o = align_up(o + (L.segmenting ? (size_t)s.total_frames * 8 : 0));    // also when the caller hinted "no SIL": a wrong hint costs time, never results
+    L.off_silunits = o; o = align_up(o + (L.want_sil ? ((size_t)s.total_frames / SS_CHUNK + s.B) * 8 : 0));
     L.off_items_local = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
     L.off_items = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
     for (int v = 0; v < BAND_NV; ++v) { L.off_fast[v] = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item)); }
     L.off_lists = o; o = align_up(o + (size_t)s.B * L.list_ints * 4);
-    L.off_padded = o; o = align_up(o + (L.segmenting ? (size_t)s.B * (s.max_T + 16) * 4 : 0));
+    L.off_cbase = o; o = align_up(o + (L.segmenting ? (size_t)s.B * L.cb_pitch * 8 : 0));
     L.off_anchors = o; o = align_up(o + (size_t)s.B * L.anchor_words * 4);
     L.off_counters = o; o = align_up(o + 64);
     L.off_pathlp = o; o = align_up(o + (size_t)s.total_frames * 4);
@@ -395,7 +401,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
 
     if (stamps && shape->max_stamps <= 0) return BFA_E_INVALID;
     uint32_t* tmask = (uint32_t*)(ws + L.off_tmask);
-    float2* rowstat = L.want_rowstat ? (float2*)(ws + L.off_rowstat) : nullptr;
+    double* sild = L.segmenting ? (double*)(ws + L.off_sild) : nullptr;
     float* path_lp = (stamps && conf && !(p->reserved & BFA_FLAG_UNFUSED_CONF)) ? (float*)(ws + L.off_pathlp) : nullptr;
     // counter slots: 0 items of the exact kernel (planner + retries), 1-2 its work counters (short / long class), 3 5 7 items of
     // the banded window classes, 10 the planner's exact-item count (side-stream pass), 11-12 work counters of the second exact
@@ -447,19 +453,26 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         if (direct_only) return BFA_OK;
     }
 
-    // Row statistics are only materialised for the planner's silence scan (utterances whose target holds
-    // SIL); the Viterbi kernels fuse boost + log_softmax + floor into their row loads.
-    if (rowstat && shape->max_T > 0) {
-        // ~64 rows per warp: one CTA of 8 warps per 512 rows of the longest utterance
-        const int ysplit = std::max(1, std::min(64, (shape->max_T + 511) / 512));
-        rowstat_kernel<<<dim3(B, ysplit), 256, 0, st>>>(C, p->blank_id, p->silence_id, p->boost_factor, logp, (const long long*)row_off, T, tgt,
-                                          (const long long*)tgt_off, (const long long*)frame_off, rowstat);
+    // The planner's silence scan needs exp(modified_lp[t, silence_id]) of every row of the utterances whose target holds
+    // silence_id (forced_alignment.py:297, :503-512): one streaming read of those utterances, left behind as running sums
+    // (silscan.cuh).  The Viterbi kernels fuse boost + log_softmax + floor into their own row loads.
+    if (L.want_sil && shape->max_T > 0) {
+        SilArgs sa;
+        sa.p = *p; sa.B = B; sa.C = C; sa.nst = L.sil_nst;
+        sa.logp = logp; sa.row_off = (const long long*)row_off; sa.T = T; sa.tgt = tgt; sa.tgt_off = (const long long*)tgt_off;
+        sa.frame_off = (const long long*)frame_off; sa.D = sild; sa.deferred = deferred; sa.n_deferred = counters + 13;
+        sa.tmask = tmask; sa.units = (int2*)(ws + L.off_silunits); sa.n_units = counters + 14;
+        launch_maybe_pdl(silunits_kernel, (B + 7) / 8, 256, 0, st, sa, use_direct);
+        LAUNCH_CHECK();
+        const long long units = (long long)shape->total_frames / SS_CHUNK + B;      // upper bound; the real count stays on the device
+        const int grid = (int)std::max(1LL, std::min((long long)d.sms, (units + SS_WARPS - 1) / SS_WARPS));
+        launch_maybe_pdl(silprob_kernel, grid, SS_WARPS * 32, ss_smem_per_warp(C, sa.nst) * SS_WARPS, st, sa, false);
         LAUNCH_CHECK();
     }
     PlanArgs pa;
     pa.p = *p; pa.B = B; pa.C = C; pa.max_T = shape->max_T; pa.max_N = shape->max_N;
     pa.logp = logp; pa.row_off = (const long long*)row_off; pa.T = T; pa.tgt = tgt; pa.tgt_off = (const long long*)tgt_off;
-    pa.frame_off = (const long long*)frame_off; pa.rowstat = rowstat; pa.tmask = tmask;
+    pa.frame_off = (const long long*)frame_off; pa.D = sild; pa.sil_ready = L.want_sil ? 1 : 0; pa.tmask = tmask;
     pa.frame_ph = frame_ph; pa.frame_idx = frame_idx; pa.dp_final = dp_final; pa.status = status;
     pa.item_cap = L.item_cap; pa.gmax = L.gmax; pa.amax = L.amax; pa.anchor_words = L.anchor_words;
     pa.items_local = (Item*)(ws + L.off_items_local); pa.items = (Item*)(ws + L.off_items);
@@ -467,7 +480,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     pa.deferred = deferred; pa.n_deferred = counters + 13;
     for (int v = 0; v < BAND_NV; ++v) { pa.fast_items[v] = (Item*)(ws + L.off_fast[v]); pa.n_fast[v] = counters + 3 + 2 * v; }
     pa.fast_enable = fast ? 1 : 0; pa.path_lp = path_lp;
-    pa.padded = (float*)(ws + L.off_padded); pa.anchors = (uint32_t*)(ws + L.off_anchors);
+    pa.cbase = (double*)(ws + L.off_cbase); pa.cb_pitch = L.cb_pitch; pa.anchors = (uint32_t*)(ws + L.off_anchors);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_prof.mu);

@@ -84,6 +84,35 @@ __device__ __forceinline__ int warp_max_i(int v) {
     return v;
 }
 
+// ---- target-class bitmask: unique_targets = set(seq) - {blank, -100}, p < C (:44-49) ----
+// Warp-cooperative; returns this lane's view: w[i] = mask word i (all lanes), all_ok = every id is a valid
+// non-blank class, has_sil = the target holds silence_id.
+struct TgtInfo {
+    uint32_t w[MAX_WORDS];
+    bool all_ok, has_sil;
+};
+// `sw` = MAX_WORDS words of shared memory owned by the calling warp: the lanes OR their targets' bits into it (one
+// shared atomic per target instead of a MAX_WORDS-way select on register words), then every lane reads the mask back.
+__device__ __forceinline__ TgtInfo target_info(const int32_t* tgt, long long b, long long e, int C, int blank_id, int silence_id,
+                                               int lane, uint32_t* sw) {
+    TgtInfo r;
+    if (lane < MAX_WORDS) sw[lane] = 0;
+    __syncwarp();
+    bool all_ok = true, has_sil = false;
+    for (long long j = b + lane; j < e; j += 32) {
+        const int c = tgt[j];
+        has_sil |= (c == silence_id);
+        if (c == blank_id || c == -100 || c < 0 || c >= C) { all_ok = false; continue; }
+        atomicOr(&sw[c >> 5], 1u << (c & 31));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < MAX_WORDS; ++i) r.w[i] = sw[i];
+    r.all_ok = __all_sync(FULL, all_ok);
+    r.has_sil = __any_sync(FULL, has_sil);
+    return r;
+}
+
 // Row statistics of the boosted row (forced_alignment.py:51-54): (max, log sum exp(x + b - max)).
 // One warp per row, lane owns classes lane + 32*i; `get(c)` returns the raw value of class c.  Shared by
 // rowstat_kernel (planner's silence scan) and the generic Viterbi kernel so both see identical bits.

@@ -10,6 +10,7 @@
 // its length stay on the device.
 #pragma once
 #include "bfa_common.cuh"
+#include "silscan.cuh"
 #include "viterbi_band3.cuh"
 
 namespace bfa {
@@ -23,7 +24,9 @@ struct PlanArgs {
     const int32_t* tgt;
     const long long* tgt_off;
     const long long* frame_off;
-    const float2* rowstat;     // valid when p.boost_targets
+    double* D;                 // chunk-local running sums of the silence probabilities (silscan.cuh), or null (no segmentation)
+    int sil_ready;             // silprob_kernel ran: D holds every utterance whose target has silence_id.  0: the caller hinted that
+                               // no target does; an utterance that has one anyway gets its sums from the planner itself (slow, same values)
     uint32_t* tmask;           // [B][MAX_WORDS]
     int32_t* frame_ph;
     int32_t* frame_idx;
@@ -41,41 +44,13 @@ struct PlanArgs {
     int fast_enable;
     int32_t* lists;            // [B][list_ints]
     int list_ints;
-    float* padded;             // [B][max_T + 16]
+    double* cbase;             // [B][cb_pitch] chunk bases of the running sums
+    int cb_pitch;
     uint32_t* anchors;         // [B][anchor_words]
     float* path_lp;            // [total_frames] raw log-prob of the class each frame was assigned to (for confidences), or null
     const int* deferred;       // when non-null: plan only the utterances deferred[0 .. *n_deferred) (what the direct kernel left)
     const int* n_deferred;
 };
-
-// ---- target-class bitmask: unique_targets = set(seq) - {blank, -100}, p < C (:44-49) ----
-// Warp-cooperative; returns this lane's view: w[i] = mask word i (all lanes), all_ok = every id is a valid
-// non-blank class, has_sil = the target holds silence_id.
-struct TgtInfo {
-    uint32_t w[MAX_WORDS];
-    bool all_ok, has_sil;
-};
-// `sw` = MAX_WORDS words of shared memory owned by the calling warp: the lanes OR their targets' bits into it (one
-// shared atomic per target instead of a MAX_WORDS-way select on register words), then every lane reads the mask back.
-__device__ __forceinline__ TgtInfo target_info(const int32_t* tgt, long long b, long long e, int C, int blank_id, int silence_id,
-                                               int lane, uint32_t* sw) {
-    TgtInfo r;
-    if (lane < MAX_WORDS) sw[lane] = 0;
-    __syncwarp();
-    bool all_ok = true, has_sil = false;
-    for (long long j = b + lane; j < e; j += 32) {
-        const int c = tgt[j];
-        has_sil |= (c == silence_id);
-        if (c == blank_id || c == -100 || c < 0 || c >= C) { all_ok = false; continue; }
-        atomicOr(&sw[c >> 5], 1u << (c & 31));
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < MAX_WORDS; ++i) r.w[i] = sw[i];
-    r.all_ok = __all_sync(FULL, all_ok);
-    r.has_sil = __any_sync(FULL, has_sil);
-    return r;
-}
 
 // Which kernel runs an item: 0 / 1 / 2 = banded kernel with a 24 / 40 / 64-group window, -1 = exact generic kernel.
 __device__ __forceinline__ int fast_class(const Item& it, int C, const float* logp, bool tgt_ok, int fast_enable) {
@@ -92,112 +67,95 @@ __device__ __forceinline__ int fast_class(const Item& it, int C, const float* lo
     return -1;
 }
 
-// ---- row statistics of the boosted row: max and log(sum exp(x - max)) (:51-54) ----
-// Only the planner's silence scan needs them materialised (the Viterbi kernels fuse them), i.e. only
-// utterances whose target contains SIL while silence anchoring is on (forced_alignment.py:291-297).
-// One CTA per utterance (8 warps, one row per warp per step); other utterances exit at once.
-__global__ void rowstat_kernel(int C, int blank_id, int silence_id, float boost, const float* __restrict__ logp,
-                               const long long* row_off, const int32_t* T, const int32_t* tgt, const long long* tgt_off,
-                               const long long* frame_off, float2* rowstat) {
-    const int u = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ uint32_t s_mask[32][MAX_WORDS];
-    const TgtInfo ti = target_info(tgt, tgt_off[u], tgt_off[u + 1], C, blank_id, silence_id, lane, s_mask[warp]);
-    if (!ti.has_sil) return;
-    const int Tu = T[u];
-    uint32_t tbits = 0;
-#pragma unroll
-    for (int i = 0; i < MAX_WORDS; ++i) tbits |= ((ti.w[i] >> lane) & 1u) << i;
-    // gridDim.y CTAs share an utterance's rows: enough rows in flight to pull them at HBM speed
-    const int nw = (blockDim.x >> 5) * gridDim.y;
-    for (int t = warp + (blockDim.x >> 5) * blockIdx.y; t < Tu; t += nw) {
-        const float* row = logp + row_off[u] + (long long)t * C;
-        float2 st = row_stats_warp([&](int c) { return row[c]; }, C, lane, tbits, boost);
-        if (lane == 0) rowstat[frame_off[u] + t] = st;
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 struct UttCtx {
     const PlanArgs* a;
     int u, lane, T, N;
     const float* lp;         // utterance rows
     const int32_t* seq;
-    const float2* stat;      // utterance row stats (or null)
-    bool sil_is_target;
-    float* padded;
-    uint32_t tw[MAX_WORDS];  // target-class mask words
+    const double* D;         // running sums of the silence probabilities, local to chunks of SS_CHUNK rows (silprob_kernel), or null
+    double* cbase;           // [T / SS_CHUNK + 1] sum of everything before each chunk (chunk_bases)
+    const uint32_t* mw;      // the utterance's target-class mask words (shared memory)
 };
 
-// exp(modified_lp[row, silence_id]) (:503-504)
-__device__ __forceinline__ float sil_prob(const UttCtx& c, int row) {
-    const BfaParams& p = c.a->p;
-    float x = c.lp[(long long)row * c.a->C + p.silence_id];
-    float m = 0.f, ls = 0.f;
-    if (p.boost_targets) {
-        if (c.stat) { float2 s = c.stat[row]; m = s.x; ls = s.y; }
-        else {   // no materialised statistics: this lane walks its own row (slow path, same formula)
-            const float* r = c.lp + (long long)row * c.a->C;
-            const int Cn = c.a->C;
-            m = -INFINITY;
-            for (int q = 0; q < Cn; ++q) m = fmaxf(m, r[q] + (((c.tw[q >> 5] >> (q & 31)) & 1u) ? p.boost_factor : 0.0f));
-            float sum = 0.f;
-            for (int q = 0; q < Cn; ++q) sum += expf(r[q] + (((c.tw[q >> 5] >> (q & 31)) & 1u) ? p.boost_factor : 0.0f) - m);
-            ls = logf(sum);
+// Sum of the silence probabilities of rows 0 .. t of the utterance (0 for t < 0): chunk-local running sum + chunk base.
+__device__ __forceinline__ double sil_prefix(const UttCtx& c, int t) {
+    return t < 0 ? 0.0 : c.D[t] + c.cbase[t >> SS_CHUNK_SHIFT];
+}
+// cbase[j] = sum of the probabilities of all rows before chunk j (an fp64 scan over the chunks' last values).
+__device__ void chunk_bases(const UttCtx& c) {
+    const int nch = (c.T + SS_CHUNK - 1) >> SS_CHUNK_SHIFT;
+    double carry = 0.0;
+    for (int b = 0; b < nch; b += 32) {
+        const int j = b + c.lane;
+        double v = 0.0;
+        if (j < nch) v = c.D[min(j * SS_CHUNK + SS_CHUNK - 1, c.T - 1)];
+        const double own = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o = __shfl_up_sync(FULL, v, d);
+            if (c.lane >= d) v += o;
         }
+        v += carry;
+        if (j < nch) c.cbase[j] = v - own;
+        carry = __shfl_sync(FULL, v, 31);
     }
-    x = mod_value(x, c.sil_is_target, p.boost_targets != 0, p.enforce_minimum != 0, p.boost_factor, m, ls, p.min_log_prob);
-    return expf(x);
+    __syncwarp();
 }
 
-// _detect_silence_segments (:471-541) over rows [r0, r0+Tn).  Writes (start,end) pairs to out
-// (lane 0) and returns the count (uniform).  k-frame moving average through a prefix sum that is
-// accumulated in fp64 and stored as fp32, like torch.cumsum on CPU.
+// _detect_silence_segments (:471-541) over rows [r0, r0+Tn).  Writes (start,end) pairs to out (lane 0) and returns the
+// count (uniform).  The reference's k-frame moving average comes from a prefix sum of the range (torch.cumsum: accumulated
+// in fp64, stored as fp32, :506-512); here every prefix value is a difference of two running sums of the utterance, rounded
+// to fp32 the same way.  The silence bits of 1024 windows are formed first (independent loads, four 32-window groups in
+// flight), then the run logic walks them.
 __device__ int detect_silence(const UttCtx& c, int r0, int Tn, float thr, int k, int32_t* out, int max_out) {
     const BfaParams& p = c.a->p;
-    if (p.silence_id >= c.a->C) return 0;   // :497
-    if (Tn < k || Tn <= 0) return 0;        // :499
+    if (p.silence_id >= c.a->C || c.D == nullptr) return 0;   // :497
+    if (Tn < k || Tn <= 0) return 0;                            // :499
     const int lane = c.lane;
-    float* padded = c.padded;
-    if (k > 1) {
-        double carry = 0.0;
-        if (lane == 0) padded[0] = 0.0f;
-        for (int base = 0; base < Tn; base += 32) {
-            int t = base + lane;
-            double v = (t < Tn) ? (double)sil_prob(c, r0 + t) : 0.0;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                double o = __shfl_up_sync(FULL, v, d);
-                if (lane >= d) v += o;
-            }
-            v += carry;
-            if (t < Tn) padded[t + 1] = (float)v;
-            carry = __shfl_sync(FULL, v, 31);
-        }
-        __syncwarp();
-    }
     const int nwin = (k > 1) ? Tn - k + 1 : Tn;
+    const double base0 = sil_prefix(c, r0 - 1);
+    const float kf = (float)k;
     int n = 0, in_sil = 0, start = 0;
-    for (int base = 0; base < nwin; base += 32) {
-        int i = base + lane;
-        bool sil = false;
-        if (i < nwin) {
-            float avg = (k > 1) ? (padded[i + k] - padded[i]) / (float)k : sil_prob(c, r0 + i);   // :510-512
-            sil = avg >= thr;                                                                      // :517
+    for (int w0 = 0; w0 < nwin; w0 += 1024) {
+        const int nb = min(32, (nwin - w0 + 31) >> 5);
+        uint32_t myword = 0;
+        for (int j = 0; j < nb; j += 4) {
+            float av[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = w0 + 32 * (j + q) + lane;
+                av[q] = -INFINITY;
+                if (j + q < nb && i < nwin) {
+                    // padded[i + k] - padded[i] (:510-512): padded[j] = fp32(sum of the range's first j probabilities)
+                    const float hi = (float)(sil_prefix(c, r0 + i + k - 1) - base0);
+                    const float lo = (k > 1) ? (i == 0 ? 0.0f : (float)(sil_prefix(c, r0 + i - 1) - base0)) : 0.0f;
+                    av[q] = (k > 1) ? (hi - lo) / kf : (float)(sil_prefix(c, r0 + i) - sil_prefix(c, r0 + i - 1));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t bits = __ballot_sync(FULL, av[q] >= thr);                           // :517
+                if (lane == j + q) myword = bits;
+            }
         }
-        uint32_t bits = __ballot_sync(FULL, sil);
-        uint32_t vmask = (nwin - base >= 32) ? FULL : ((1u << (nwin - base)) - 1u);
-        uint32_t trans = (bits ^ ((bits << 1) | (in_sil ? 1u : 0u))) & vmask;
-        while (trans) {                                                                           // :524-533
-            int b = __ffs(trans) - 1;
-            trans &= trans - 1;
-            int i2 = base + b;
-            if (!in_sil) { in_sil = 1; start = i2; }
-            else {
-                in_sil = 0;
-                int e = min(i2 + k - 1, Tn);
-                if (e - start >= k && n < max_out) {
-                    if (lane == 0) { out[2 * n] = start; out[2 * n + 1] = e; }
-                    ++n;
+        for (int j = 0; j < nb; ++j) {
+            const int base = w0 + 32 * j;
+            const uint32_t bits = __shfl_sync(FULL, myword, j);
+            const uint32_t vmask = (nwin - base >= 32) ? FULL : ((1u << (nwin - base)) - 1u);
+            uint32_t trans = (bits ^ ((bits << 1) | (in_sil ? 1u : 0u))) & vmask;
+            while (trans) {                                                                       // :524-533
+                const int b = __ffs(trans) - 1;
+                trans &= trans - 1;
+                const int i2 = base + b;
+                if (!in_sil) { in_sil = 1; start = i2; }
+                else {
+                    in_sil = 0;
+                    const int e = min(i2 + k - 1, Tn);
+                    if (e - start >= k && n < max_out) {
+                        if (lane == 0) { out[2 * n] = start; out[2 * n + 1] = e; }
+                        ++n;
+                    }
                 }
             }
         }
@@ -244,6 +202,15 @@ __device__ int plan_segmented(const UttCtx& c, Item* loc, int32_t* lists, uint32
         } else ++i;
     }
     if (ng == 0) return -1;                                                       // :293-295
+    if (c.D) {
+        if (!a.sil_ready) {          // a wrong BFA_HINT_NO_SIL: nobody streamed this utterance's rows
+            const bool sil_tgt = (c.mw[p.silence_id >> 5] >> (p.silence_id & 31)) & 1u;
+            for (int r0 = 0; r0 < T; r0 += SS_CHUNK)
+                ss_gather_rows(p, C, c.lp + (long long)r0 * C, min(SS_CHUNK, T - r0), a.D + a.frame_off[c.u] + r0, lane, c.mw, sil_tgt);
+            __syncwarp();
+        }
+        chunk_bases(c);
+    }
     int k = p.silence_anchors;                                                    // :296
     int na = detect_silence(c, 0, T, 0.9f, k, asil, a.amax);                      // :297
     if (na == 0 && N > 200) {                                                     // :298-304
@@ -408,15 +375,12 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
     c.N = (int)(a.tgt_off[u + 1] - a.tgt_off[u]);
     c.lp = a.logp + a.row_off[u];
     c.seq = a.tgt + a.tgt_off[u];
-    c.stat = a.rowstat ? a.rowstat + a.frame_off[u] : nullptr;
-    c.padded = a.padded + (size_t)u * (a.max_T + 16);
+    c.D = a.D ? a.D + a.frame_off[u] : nullptr;
+    c.cbase = a.cbase + (size_t)u * a.cb_pitch;
     uint32_t* sw = s_mask[threadIdx.x >> 5];
+    c.mw = sw;
     const TgtInfo ti = target_info(a.tgt, a.tgt_off[u], a.tgt_off[u + 1], a.C, p.blank_id, p.silence_id, lane, sw);
     if (lane < MAX_WORDS) a.tmask[(size_t)u * MAX_WORDS + lane] = sw[lane];      // consumed by the Viterbi kernels
-#pragma unroll
-    for (int i = 0; i < MAX_WORDS; ++i) c.tw[i] = ti.w[i];
-    c.sil_is_target = false;
-    if (p.silence_id >= 0 && p.silence_id < a.C) c.sil_is_target = (sw[p.silence_id >> 5] >> (p.silence_id & 31)) & 1u;
     const int T = c.T, N = c.N;
     const long long o_base = a.frame_off[u], o_lim = a.frame_off[u + 1];
     loc = a.items_local + (size_t)u * a.item_cap;
