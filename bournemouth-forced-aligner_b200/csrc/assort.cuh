@@ -79,7 +79,8 @@ __device__ __forceinline__ float stamp_confidence_prob(const float* pr_s, int T,
 }
 
 constexpr int ASSORT_WARPS = 4;
-constexpr int ASSORT_TS_MAX = 2048;   // longest utterance whose per-frame arrays are staged in shared memory
+constexpr int ASSORT_R = 6;           // rounds of 32 x 32 frames the staged run-length sweep keeps in registers
+constexpr int ASSORT_TS_MAX = ASSORT_R * 1024;   // longest utterance whose per-frame arrays are staged in shared memory (8 bytes per frame per warp)
 constexpr int ASSORT_SS_MAX = 512;    // largest stamp pitch assembled in shared memory
 // staged frames / stamps per warp for a batch shape, and the dynamic shared memory of one CTA
 __host__ __device__ inline int assort_ts(int max_T) { return max_T <= ASSORT_TS_MAX ? (max_T + 31) / 32 * 32 : 0; }
@@ -164,11 +165,14 @@ __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(As
     int n = 0;            // provisional stamps so far (uniform)
     int open = -1;        // index of the provisional stamp whose end is still unknown
     if (pk_s) {
-        // Staged utterances (T <= 2048 = 64 blocks of 32 frames).  (A) one sweep turns the packed (idx, phoneme) words into
-        // run-start / candidate bit masks, block j kept by lane j % 32; (B) every lane emits the stamps that start in its own
-        // blocks: slots from a prefix count over the blocks, ends from the next run start (same mask, or the first later
-        // non-empty block, found with one ballot and one indexed shuffle).
-        uint32_t sb[2] = {0u, 0u}, cb[2] = {0u, 0u};
+        // Staged utterances (T <= ASSORT_TS_MAX: ASSORT_R rounds of 32 blocks of 32 frames).  (A) one sweep turns the packed
+        // (idx, phoneme) words into run-start / candidate bit masks, block j kept by lane j % 32 in round j / 32; (B) every lane
+        // emits the stamps that start in its own blocks: slots from a prefix count over the blocks, ends from the next run
+        // start (same mask, a later block of the same round found with one indexed shuffle, or the first run start of the
+        // next non-empty round, which is uniform).
+        uint32_t sb[ASSORT_R], cb[ASSORT_R];
+#pragma unroll
+        for (int r = 0; r < ASSORT_R; ++r) { sb[r] = 0u; cb[r] = 0u; }
         const int nb = (T + 31) >> 5;
         int32_t carry = 0;
         for (int b = 0; b < nb; ++b) {
@@ -181,14 +185,18 @@ __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(As
             const bool cand = startf && ((w & 0xffff) != blank || !a.p.ignore_noise);
             const uint32_t sbits = __ballot_sync(FULL, startf), cbits = __ballot_sync(FULL, cand);
             if (lane == (b & 31)) {
-                if (b < 32) { sb[0] = sbits; cb[0] = cbits; }
-                else { sb[1] = sbits; cb[1] = cbits; }
+#pragma unroll
+                for (int r = 0; r < ASSORT_R; ++r)
+                    if ((b >> 5) == r) { sb[r] = sbits; cb[r] = cbits; }
             }
         }
-        // exclusive prefix of the candidate counts over the blocks (two rounds of 32 blocks)
-        int ex[2], tot = 0;
+        // exclusive prefix of the candidate counts over the blocks, round by round
+        const int nr = (nb + 31) >> 5;       // rounds in use (uniform)
+        int ex[ASSORT_R], tot = 0;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < ASSORT_R; ++r) {
+            ex[r] = tot;
+            if (r >= nr) continue;
             const int c = __popc(cb[r]);
             int inc = c;
 #pragma unroll
@@ -200,17 +208,26 @@ __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(As
             tot += __shfl_sync(FULL, inc, 31);
         }
         n = tot;
-        // first run start after each block: position inside the nearest later block that holds one (T if none)
-        const uint32_t nz0 = __ballot_sync(FULL, sb[0] != 0u), nz1 = __ballot_sync(FULL, sb[1] != 0u);
+        // per round: which blocks hold a run start, and the round's first run start (uniform; -1: none)
+        uint32_t nz[ASSORT_R];
+        int first[ASSORT_R];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const uint32_t later_same = (r == 0 ? nz0 : nz1) & ~((2u << lane) - 1u);   // blocks after mine in my round
-            const uint32_t other = r == 0 ? nz1 : 0u;                                    // the round after mine
-            const int src = later_same ? __ffs(later_same) - 1 : (other ? __ffs(other) - 1 : 0);
-            const uint32_t m0 = __shfl_sync(FULL, sb[0], src), m1 = __shfl_sync(FULL, sb[1], src);
-            int next_start = T;
-            if (later_same) next_start = (r * 32 + src) * 32 + __ffs(r == 0 ? m0 : m1) - 1;
-            else if (other) next_start = (32 + src) * 32 + __ffs(m1) - 1;
+        for (int r = 0; r < ASSORT_R; ++r) {
+            nz[r] = 0u; first[r] = -1;
+            if (r >= nr) continue;
+            nz[r] = __ballot_sync(FULL, sb[r] != 0u);
+            const int src = nz[r] ? __ffs(nz[r]) - 1 : 0;
+            const uint32_t m = __shfl_sync(FULL, sb[r], src);
+            first[r] = nz[r] ? (r * 32 + src) * 32 + __ffs(m) - 1 : -1;
+        }
+        int after = T;               // first run start of the rounds after r (walking r downwards)
+#pragma unroll
+        for (int r = ASSORT_R - 1; r >= 0; --r) {
+            if (r >= nr) continue;
+            const uint32_t later_same = nz[r] & ~((2u << lane) - 1u);                    // blocks after mine in my round
+            const int src = later_same ? __ffs(later_same) - 1 : 0;
+            const uint32_t m = __shfl_sync(FULL, sb[r], src);
+            const int next_start = later_same ? (r * 32 + src) * 32 + __ffs(m) - 1 : after;
             uint32_t cbl = cb[r];
             int slot = ex[r];
             const int blk = r * 32 + lane;
@@ -230,6 +247,7 @@ __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(As
                 }
                 ++slot;
             }
+            if (first[r] >= 0) after = first[r];
         }
         __syncwarp();
     } else

@@ -258,7 +258,7 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
     L.want_sil = L.segmenting && !(p.reserved & BFA_HINT_NO_SIL);
     L.sil_nst = ss_stages(s.C, (size_t)BAND_SMEM_MAX);
     L.cb_pitch = s.max_T / SS_CHUNK + 2;
-    L.off_sild = o; o = align_up(o + (L.segmenting ? (size_t)s.total_frames * 8 : 0));    // also when the caller hinted "no SIL": a wrong hint costs time, never results
+    L.off_sild = o; o = align_up(o + (L.segmenting ? (size_t)s.total_frames * 8 + 16 : 0));    // also when the caller hinted "no SIL": a wrong hint costs time, never results
     L.off_silunits = o; o = align_up(o + (L.want_sil ? ((size_t)s.total_frames / SS_CHUNK + s.B) * 8 : 0));
     L.off_items_local = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));
     L.off_items = o; o = align_up(o + (size_t)s.B * L.item_cap * sizeof(Item));

@@ -76,7 +76,13 @@ struct UttCtx {
     const double* D;         // running sums of the silence probabilities, local to chunks of SS_CHUNK rows (silprob_kernel), or null
     double* cbase;           // [T / SS_CHUNK + 1] sum of everything before each chunk (chunk_bases)
     const uint32_t* mw;      // the utterance's target-class mask words (shared memory)
+    double* ds;              // this warp's staging buffer for a slab of running sums: [PLAN_SLAB + PLAN_KMAX + 4] doubles + 4 chunk bases
+    uint32_t bar;            // its mbarrier
+    uint32_t* phase;         // parity of the next completion of that barrier
 };
+constexpr int PLAN_SLAB = 512;     // windows of the silence scan per staged slab
+constexpr int PLAN_KMAX = 64;      // longest moving average the staged scan handles (silence_anchors; 10 by default)
+constexpr int PLAN_DS = PLAN_SLAB + PLAN_KMAX + 4;
 
 // Sum of the silence probabilities of rows 0 .. t of the utterance (0 for t < 0): chunk-local running sum + chunk base.
 __device__ __forceinline__ double sil_prefix(const UttCtx& c, int t) {
@@ -103,69 +109,116 @@ __device__ void chunk_bases(const UttCtx& c) {
     __syncwarp();
 }
 
+// Run logic of _detect_silence_segments (:519-539) over the silence bits of windows [base, base + 32): carries (in_sil, start, n).
+struct SilRuns {
+    int n = 0, in_sil = 0, start = 0;
+    __device__ __forceinline__ void feed(uint32_t bits, int base, int nwin, int k, int Tn, int lane, int32_t* out, int max_out) {
+        const uint32_t vmask = (nwin - base >= 32) ? FULL : ((1u << (nwin - base)) - 1u);
+        uint32_t trans = (bits ^ ((bits << 1) | (in_sil ? 1u : 0u))) & vmask;
+        while (trans) {                                                                           // :524-533
+            const int b = __ffs(trans) - 1;
+            trans &= trans - 1;
+            const int i2 = base + b;
+            if (!in_sil) { in_sil = 1; start = i2; }
+            else {
+                in_sil = 0;
+                const int e = min(i2 + k - 1, Tn);
+                if (e - start >= k && n < max_out) {
+                    if (lane == 0) { out[2 * n] = start; out[2 * n + 1] = e; }
+                    ++n;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ int finish(int k, int Tn, int lane, int32_t* out, int max_out) {
+        if (in_sil && Tn - start >= k && n < max_out) {                                          // :536-539
+            if (lane == 0) { out[2 * n] = start; out[2 * n + 1] = Tn; }
+            ++n;
+        }
+        __syncwarp();
+        return n;
+    }
+};
+
+// Moving averages longer than the staged scan holds, or k == 1 (the probability itself): every prefix value straight from
+// global memory.  Same arithmetic as detect_silence.
+__device__ __noinline__ int detect_silence_direct(const double* D, const double* cbase, int lane, int r0, int Tn, float thr, int k,
+                                                  int32_t* out, int max_out) {
+    UttCtx c;
+    c.D = D; c.cbase = const_cast<double*>(cbase);
+    const int nwin = (k > 1) ? Tn - k + 1 : Tn;
+    const double base0 = sil_prefix(c, r0 - 1);
+    const float kf = (float)k;
+    SilRuns runs;
+    for (int base = 0; base < nwin; base += 32) {
+        const int i = base + lane;
+        float av = -INFINITY;
+        if (i < nwin) {
+            if (k > 1) {
+                const float hi = (float)(sil_prefix(c, r0 + i + k - 1) - base0);
+                const float lo = i == 0 ? 0.0f : (float)(sil_prefix(c, r0 + i - 1) - base0);
+                av = (hi - lo) / kf;
+            } else {
+                av = (float)(sil_prefix(c, r0 + i) - sil_prefix(c, r0 + i - 1));
+            }
+        }
+        runs.feed(__ballot_sync(FULL, av >= thr), base, nwin, k, Tn, lane, out, max_out);
+    }
+    return runs.finish(k, Tn, lane, out, max_out);
+}
+
 // _detect_silence_segments (:471-541) over rows [r0, r0+Tn).  Writes (start,end) pairs to out (lane 0) and returns the
 // count (uniform).  The reference's k-frame moving average comes from a prefix sum of the range (torch.cumsum: accumulated
 // in fp64, stored as fp32, :506-512); here every prefix value is a difference of two running sums of the utterance, rounded
-// to fp32 the same way.  The silence bits of 1024 windows are formed first (independent loads, four 32-window groups in
-// flight), then the run logic walks them.
+// to fp32 the same way.  The running sums a slab of PLAN_SLAB windows needs come into shared memory with ONE bulk copy
+// (one memory round trip per slab instead of one per group of windows).
 __device__ int detect_silence(const UttCtx& c, int r0, int Tn, float thr, int k, int32_t* out, int max_out) {
     const BfaParams& p = c.a->p;
     if (p.silence_id >= c.a->C || c.D == nullptr) return 0;   // :497
     if (Tn < k || Tn <= 0) return 0;                            // :499
+    if (k <= 1 || k > PLAN_KMAX) return detect_silence_direct(c.D, c.cbase, c.lane, r0, Tn, thr, k, out, max_out);
     const int lane = c.lane;
-    const int nwin = (k > 1) ? Tn - k + 1 : Tn;
+    const int nwin = Tn - k + 1;
     const double base0 = sil_prefix(c, r0 - 1);
     const float kf = (float)k;
-    int n = 0, in_sil = 0, start = 0;
-    for (int w0 = 0; w0 < nwin; w0 += 1024) {
-        const int nb = min(32, (nwin - w0 + 31) >> 5);
-        uint32_t myword = 0;
-        for (int j = 0; j < nb; j += 4) {
-            float av[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = w0 + 32 * (j + q) + lane;
-                av[q] = -INFINITY;
-                if (j + q < nb && i < nwin) {
-                    // padded[i + k] - padded[i] (:510-512): padded[j] = fp32(sum of the range's first j probabilities)
-                    const float hi = (float)(sil_prefix(c, r0 + i + k - 1) - base0);
-                    const float lo = (k > 1) ? (i == 0 ? 0.0f : (float)(sil_prefix(c, r0 + i - 1) - base0)) : 0.0f;
-                    av[q] = (k > 1) ? (hi - lo) / kf : (float)(sil_prefix(c, r0 + i) - sil_prefix(c, r0 + i - 1));
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t bits = __ballot_sync(FULL, av[q] >= thr);                           // :517
-                if (lane == j + q) myword = bits;
-            }
+    const double* cbs = c.ds + PLAN_DS;
+    SilRuns runs;
+    for (int w0 = 0; w0 < nwin; w0 += PLAN_SLAB) {
+        // prefix value j of the range, padded[j] (:508-509), is fp32(sum of rows r0 .. r0+j-1) = fp32(S(r0+j-1) - S(r0-1));
+        // the slab needs j in [w0, min(w0 + PLAN_SLAB + k, Tn)]
+        const int t_lo = max(r0 + w0 - 1, 0);
+        const int t_hi = min(r0 + w0 + PLAN_SLAB + k - 1, r0 + Tn - 1);
+        const double* src = c.D + t_lo;
+        const int skew = (int)(((unsigned long long)src >> 3) & 1ull);      // bulk copies start on 16-byte boundaries
+        const int ch0 = t_lo >> SS_CHUNK_SHIFT;
+        __syncwarp();                                                       // the previous slab's readers are done
+        if (lane == 0) {
+            const uint32_t bytes = ((uint32_t)(t_hi - t_lo + 1 + skew) * 8u + 15u) & ~15u;
+            mbar_expect_tx(c.bar, bytes);
+            bulk_g2s(smem_u32(c.ds), src - skew, bytes, c.bar);
         }
-        for (int j = 0; j < nb; ++j) {
-            const int base = w0 + 32 * j;
-            const uint32_t bits = __shfl_sync(FULL, myword, j);
-            const uint32_t vmask = (nwin - base >= 32) ? FULL : ((1u << (nwin - base)) - 1u);
-            uint32_t trans = (bits ^ ((bits << 1) | (in_sil ? 1u : 0u))) & vmask;
-            while (trans) {                                                                       // :524-533
-                const int b = __ffs(trans) - 1;
-                trans &= trans - 1;
-                const int i2 = base + b;
-                if (!in_sil) { in_sil = 1; start = i2; }
-                else {
-                    in_sil = 0;
-                    const int e = min(i2 + k - 1, Tn);
-                    if (e - start >= k && n < max_out) {
-                        if (lane == 0) { out[2 * n] = start; out[2 * n + 1] = e; }
-                        ++n;
-                    }
-                }
+        if (lane < 4) c.ds[PLAN_DS + lane] = c.cbase[min(ch0 + lane, (c.T - 1) >> SS_CHUNK_SHIFT)];
+        mbar_wait(c.bar, *c.phase & 1u);
+        *c.phase ^= 1u;
+        __syncwarp();
+        const double* dsk = c.ds + (skew - t_lo);
+        auto S = [&](int t) -> double {      // running sum through row t of the utterance (t >= 0), from the staged slab
+            return dsk[t] + cbs[(t >> SS_CHUNK_SHIFT) - ch0];
+        };
+        const int wend = min(w0 + PLAN_SLAB, nwin);
+#pragma unroll 2
+        for (int base = w0; base < wend; base += 32) {
+            const int i = base + lane;
+            float av = -INFINITY;
+            if (i < nwin) {
+                const float hi = (float)(S(r0 + i + k - 1) - base0);
+                const float lo = (r0 + i == 0) ? 0.0f : (float)(S(r0 + i - 1) - base0);
+                av = (hi - lo) / kf;                                                               // :510-512
             }
+            runs.feed(__ballot_sync(FULL, av >= thr), base, nwin, k, Tn, lane, out, max_out);       // :517
         }
     }
-    if (in_sil && Tn - start >= k && n < max_out) {                                              // :536-539
-        if (lane == 0) { out[2 * n] = start; out[2 * n + 1] = Tn; }
-        ++n;
-    }
-    __syncwarp();
-    return n;
+    return runs.finish(k, Tn, lane, out, max_out);
 }
 
 __device__ __forceinline__ void fill_frames(const UttCtx& c, long long o0, long long olim, int nf, int ph, int idx) {
@@ -207,6 +260,8 @@ __device__ int plan_segmented(const UttCtx& c, Item* loc, int32_t* lists, uint32
             const bool sil_tgt = (c.mw[p.silence_id >> 5] >> (p.silence_id & 31)) & 1u;
             for (int r0 = 0; r0 < T; r0 += SS_CHUNK)
                 ss_gather_rows(p, C, c.lp + (long long)r0 * C, min(SS_CHUNK, T - r0), a.D + a.frame_off[c.u] + r0, lane, c.mw, sil_tgt);
+            __threadfence();
+            asm volatile("fence.proxy.async.global;" ::: "memory");      // detect_silence reads these sums back with bulk copies
             __syncwarp();
         }
         chunk_bases(c);
@@ -360,6 +415,14 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
     bool have_single = false;
     bool tok = false;
     __shared__ uint32_t s_mask[8][MAX_WORDS];
+    __shared__ __align__(16) double s_ds[8][PLAN_DS + 4];      // per warp: a slab of running sums + 4 chunk bases (detect_silence)
+    __shared__ __align__(8) unsigned long long s_bar[8];
+    uint32_t ds_phase = 0;
+    if (lane == 0) {
+        mbar_init(smem_u32(&s_bar[threadIdx.x >> 5]), 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
     pdl_release();               // the banded kernel's CTAs may take their SMs while this grid drains
     if (a.deferred) {            // the direct kernel went first: only what it handed back
         pdl_wait();
@@ -379,6 +442,9 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
     c.cbase = a.cbase + (size_t)u * a.cb_pitch;
     uint32_t* sw = s_mask[threadIdx.x >> 5];
     c.mw = sw;
+    c.ds = s_ds[threadIdx.x >> 5];
+    c.bar = smem_u32(&s_bar[threadIdx.x >> 5]);
+    c.phase = &ds_phase;
     const TgtInfo ti = target_info(a.tgt, a.tgt_off[u], a.tgt_off[u + 1], a.C, p.blank_id, p.silence_id, lane, sw);
     if (lane < MAX_WORDS) a.tmask[(size_t)u * MAX_WORDS + lane] = sw[lane];      // consumed by the Viterbi kernels
     const int T = c.T, N = c.N;
