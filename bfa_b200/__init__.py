@@ -11,7 +11,7 @@ from .aligner import (AlignmentUtils, BatchResult, ViterbiDecoder, _calculate_co
 
 from .postprocess import (CoverageError, align_words, analyze_alignment_coverage, convert_to_ms,  # noqa: E402,F401
                           ensure_target_coverage, post_process_segment, stamps_to_ms)
-from .pipeline import PhonemeTimestampAligner  # noqa: E402,F401
+from .pipeline import PhonemeTimestampAligner, log_softmax_rows, stitch_log_softmax  # noqa: E402,F401
 
-__all__ = ["PhonemeTimestampAligner", "AlignmentUtils", "ViterbiDecoder", "_calculate_confidences", "align_host", "BatchResult", "convert_to_ms", "stamps_to_ms", "extend_soft_boundaries_func", "_calculate_confidences_batch", "ensure_target_coverage", "CoverageError", "align_words", "analyze_alignment_coverage", "post_process_segment",
+__all__ = ["PhonemeTimestampAligner", "stitch_log_softmax", "log_softmax_rows", "AlignmentUtils", "ViterbiDecoder", "_calculate_confidences", "align_host", "BatchResult", "convert_to_ms", "stamps_to_ms", "extend_soft_boundaries_func", "_calculate_confidences_batch", "ensure_target_coverage", "CoverageError", "align_words", "analyze_alignment_coverage", "post_process_segment",
            "BfaError", "BfaParams", "BfaShape", "default_params"]

@@ -308,10 +308,20 @@ class ViterbiDecoder:
         return dict(frame_ph=frame_ph[:total], frame_idx=frame_idx[:total], frame_off=f_off, dp_final=dp_final, final_state=fstate)
 
     def _calculate_alignment_score(self, log_probs, frame_phonemes):
-        """forced_alignment.py:767-773 (off the hot path: core.py passes return_scores=False)."""
-        valid = frame_phonemes < log_probs.shape[1]
-        g = log_probs.gather(1, frame_phonemes.clamp_max(log_probs.shape[1] - 1).unsqueeze(1)).squeeze(1)
-        return float((g.double() * valid).sum().item())
+        """forced_alignment.py:767-773: sum of log_probs[t, frame_phonemes[t]] (bfa_alignment_score_batch, one warp per utterance,
+        accumulated in double like the reference's Python float)."""
+        _require_cuda(log_probs, "log_probs")
+        lp = log_probs if (log_probs.dtype == torch.float32 and log_probs.is_contiguous()) else log_probs.contiguous().float()
+        dev = lp.device
+        T_, C_ = lp.shape
+        ph = torch.as_tensor(frame_phonemes).to(device=dev, dtype=torch.int32).contiguous()
+        n = min(T_, int(ph.numel()))
+        score = torch.empty(1, dtype=torch.float64, device=dev)
+        z = torch.zeros(1, dtype=torch.int64, device=dev)
+        rc = _cabi.lib().bfa_alignment_score_batch(1, C_, _ptr(lp), _ptr(z), _ptr(torch.tensor([n], dtype=torch.int32, device=dev)), _ptr(ph),
+                                                   _ptr(z), _ptr(score), _stream(dev))
+        _cabi.check(rc)
+        return float(score.item())
 
     def assort_frames(self, frame_phonemes, frame_phonemes_idx, max_blanks=10) -> List[Stamp]:
         """forced_alignment.py:777-834."""

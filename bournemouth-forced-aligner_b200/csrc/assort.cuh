@@ -175,19 +175,19 @@ __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(As
         for (int r = 0; r < ASSORT_R; ++r) { sb[r] = 0u; cb[r] = 0u; }
         const int nb = (T + 31) >> 5;
         int32_t carry = 0;
-        for (int b = 0; b < nb; ++b) {
-            const int t = b * 32 + lane;
-            const int32_t w = t < T ? pk_s[t] : 0;
-            int32_t wp = __shfl_up_sync(FULL, w, 1);
-            if (lane == 0) wp = carry;
-            carry = __shfl_sync(FULL, w, 31);
-            const bool startf = t < T && (t == 0 || w != wp);                                  // :798-801
-            const bool cand = startf && ((w & 0xffff) != blank || !a.p.ignore_noise);
-            const uint32_t sbits = __ballot_sync(FULL, startf), cbits = __ballot_sync(FULL, cand);
-            if (lane == (b & 31)) {
 #pragma unroll
-                for (int r = 0; r < ASSORT_R; ++r)
-                    if ((b >> 5) == r) { sb[r] = sbits; cb[r] = cbits; }
+        for (int r = 0; r < ASSORT_R; ++r) {         // the round index is static: the masks stay in registers
+            const int b_end = min(32, nb - r * 32);
+            for (int bb = 0; bb < b_end; ++bb) {
+                const int t = (r * 32 + bb) * 32 + lane;
+                const int32_t w = t < T ? pk_s[t] : 0;
+                int32_t wp = __shfl_up_sync(FULL, w, 1);
+                if (lane == 0) wp = carry;
+                carry = __shfl_sync(FULL, w, 31);
+                const bool startf = t < T && (t == 0 || w != wp);                                  // :798-801
+                const bool cand = startf && ((w & 0xffff) != blank || !a.p.ignore_noise);
+                const uint32_t sbits = __ballot_sync(FULL, startf), cbits = __ballot_sync(FULL, cand);
+                if (lane == bb) { sb[r] = sbits; cb[r] = cbits; }
             }
         }
         // exclusive prefix of the candidate counts over the blocks, round by round

@@ -12,6 +12,7 @@
 
 #include "assort.cuh"
 #include "bfa_common.cuh"
+#include "frontend.cuh"
 #include "plan.cuh"
 #include "viterbi_band3.cuh"
 #include "viterbi_generic.cuh"
@@ -632,6 +633,37 @@ int bfa_viterbi_paths(const BfaParams* p, int32_t n_items, int32_t C, int32_t ma
     va.path_lp = nullptr;
     va.bp_scratch = bp; va.bp_slab_words = (long long)(max_T + 2) * 32 * (max_L > 512 ? 2 : 1);
     return launch_viterbi(va, n_items, max_L, d, st);
+}
+
+int bfa_alignment_score_batch(int32_t B, int32_t C, const float* logp, const int64_t* row_off, const int32_t* T,
+                              const int32_t* frame_ph, const int64_t* frame_off, double* score, void* stream) {
+    if (!logp || !row_off || !T || !frame_ph || !frame_off || !score || C <= 0) return BFA_E_INVALID;
+    if (B <= 0) return B == 0 ? BFA_OK : BFA_E_INVALID;
+    alignment_score_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(B, C, logp, (const long long*)row_off, T, frame_ph,
+                                                                          (const long long*)frame_off, score);
+    LAUNCH_CHECK();
+    return BFA_OK;
+}
+
+int bfa_stitch_log_softmax(int32_t B, int32_t n_windows, int32_t frames_per_window, int32_t C, int32_t total_frames,
+                           const float* window_logits, int64_t in_pitch, const float* window_weights, float* logp_out,
+                           int64_t out_pitch, void* stream) {
+    if (!window_logits || !logp_out || C <= 0 || total_frames < 0 || frames_per_window < 0) return BFA_E_INVALID;
+    if (C > BFA_MAX_C) return BFA_E_UNSUPPORTED;
+    if (frames_per_window > 0 && (!window_weights || n_windows <= 0 || frames_per_window < 2)) return BFA_E_INVALID;
+    if (B <= 0 || total_frames == 0) return B >= 0 ? BFA_OK : BFA_E_INVALID;
+    DeviceInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    StitchArgs a;
+    a.B = B; a.W = n_windows; a.fpw = frames_per_window; a.C = C; a.total_frames = total_frames;
+    a.sf = frames_per_window > 0 ? frames_per_window / 2 : 1;                     // stride_frames (windowing.py:128)
+    a.in = window_logits; a.weights = window_weights; a.out = logp_out; a.in_pitch_b = in_pitch; a.out_pitch_b = out_pitch;
+    const long long rows = (long long)B * total_frames;
+    const int grid = (int)std::min((rows + STITCH_WARPS - 1) / STITCH_WARPS, (long long)d.sms * 8);
+    stitch_log_softmax_kernel<<<grid, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    LAUNCH_CHECK();
+    return BFA_OK;
 }
 
 int bfa_confidence_batch(int32_t B, int32_t C, const float* logp, const int64_t* row_off, const int32_t* T_conf,

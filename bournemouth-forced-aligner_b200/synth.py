@@ -110,3 +110,75 @@ def baseline_config(n, *, C=66, device="cpu", B=None, seed=None, sort_ragged=Tru
         return dict(name=f"4: ragged B={B} T in [60,1800] N in [4,120] packed" + (", ordered by length" if sort_ragged else ""),
                     lp=flat, row_off=row_off, Ts=Ts, tgt=tg, Ns=Ns)
     raise ValueError(n)
+
+
+class FakePhonemizer:
+    """Deterministic stand-in for ipamappers/ph66_phonemeizer.Phonemizer (espeak is not part of the path): the same record
+    layout (ph66 / pg16 / eipa / mipa / words / word_num / text, ph66_phonemeizer.py:347-470) and label tables; every word maps
+    to 2-5 phoneme ids derived from its letters, commas and full stops become SIL like the reference's <SIL> words."""
+    phonemes_key, phoneme_groups_key, phonemes_ipa_key = "ph66", "pg16", "eipa"
+
+    def __init__(self, n_ph=66, n_grp=16):
+        self.index_to_plabel = {0: "SIL", **{i: f"p{i}" for i in range(1, n_ph)}, n_ph: "noise"}
+        self.index_to_glabel = {0: "SIL", **{i: f"g{i}" for i in range(1, n_grp)}, n_grp: "noise"}
+        self.phoneme_id_to_group_id = {0: 0, **{i: 1 + (i - 1) % (n_grp - 1) for i in range(1, n_ph)}, n_ph: n_grp}
+        self.n_ph = n_ph
+
+    def phonemize_sentence(self, text):
+        words = text.replace(",", " <SIL> ").replace(".", " <SIL> ").split()
+        out = {"ph66": [], "pg16": [], "eipa": [], "mipa": [], "word_num": [], "words": [], "text": text}
+        for wi, w in enumerate(words):
+            if w == "<SIL>":
+                ids = [0]
+                out["words"].append("<sil>")
+            else:
+                h = sum((i + 1) * ord(ch) for i, ch in enumerate(w))
+                ids = [1 + (h * (k + 3) + 7 * k) % (self.n_ph - 1) for k in range(2 + h % 4)]
+                out["words"].append(w)
+            for p in ids:
+                out["ph66"].append(p); out["pg16"].append(self.phoneme_id_to_group_id[p])
+                out["eipa"].append(self.index_to_plabel[p]); out["mipa"].append(self.index_to_plabel[p]); out["word_num"].append(wi)
+        return out
+
+
+def planted_logits(targets, T, C, *, seed=0, peak=9.0, sil_frames=12, blank_id=None):
+    """[T, C] raw logits (not normalised) whose frame-wise peaks follow `targets` in order, target 0 (SIL) held for
+    `sil_frames` frames, the rest spread evenly with blank frames in between: what an acoustic model would hand to
+    core.py:898 for an utterance that really contains the targets."""
+    blank_id = C - 1 if blank_id is None else blank_id
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(T, C, generator=g)
+    n = len(targets)
+    n_sil = sum(1 for t in targets if t == 0)
+    per = max(2, (T - n_sil * sil_frames) // max(n - n_sil, 1))
+    t = 0
+    for ph in targets:
+        dur = sil_frames if ph == 0 else per
+        hold = dur if ph == 0 else max(1, dur // 2)
+        for f in range(t, min(t + dur, T)):
+            logits[f, ph if f - t < hold else blank_id] += peak
+        t += dur
+    for f in range(t, T):
+        logits[f, blank_id] += peak
+    return logits
+
+
+class PlantedPosteriorProvider:
+    """Stands where PhonemeTimestampAligner._cupe_prediction_batch (core.py:370-460) stands in tests: logits planted along each
+    utterance's own targets (set `pending` to the batch's phoneme sequences before the call), 20 ms frames, seeded call by
+    call.  Returns (logits_class [B, T, 67], logits_group [B, T, 17], None, spectral_lens) on the CPU."""
+
+    def __init__(self, phoneme_id_to_group_id, seed):
+        self.p2g, self.seed, self.n_calls, self.pending = phoneme_id_to_group_id, seed, 0, None
+
+    def __call__(self, wavs, wav_lens, extract_embeddings=False):
+        B = wavs.shape[0]
+        spectral = [max(8, int(wl) // 320) for wl in wav_lens]
+        T = max(spectral)
+        lp, lg = torch.zeros(B, T, 67), torch.zeros(B, T, 17)
+        for b in range(B):
+            tg = [int(p) for p in self.pending[b]]
+            lp[b, :spectral[b]] = planted_logits(tg, spectral[b], 67, seed=self.seed + 10 * self.n_calls + b)
+            lg[b, :spectral[b]] = planted_logits([self.p2g[p] for p in tg], spectral[b], 17, seed=self.seed + 10 * self.n_calls + b + 5)
+        self.n_calls += 1
+        return lp, lg, None, spectral

@@ -197,6 +197,28 @@ int bfa_confidence_batch(int32_t B, int32_t C, const float *logp, const int64_t 
                          int32_t max_stamps, float *conf, void *stream);
 
 /*
+ * == ViterbiDecoder._calculate_alignment_score (forced_alignment.py:767-773) for a batch:
+ *    score[u] = sum over t < T[u] of logp[row_off[u] + t*C + frame_ph[frame_off[u] + t]] (labels >= C skipped),
+ *    accumulated in double like the reference's Python float.
+ */
+int bfa_alignment_score_batch(int32_t B, int32_t C, const float *logp, const int64_t *row_off,
+                              const int32_t *T, const int32_t *frame_ph, const int64_t *frame_off,
+                              double *score, void *stream);
+
+/*
+ * == the step in front of the aligner: stich_window_predictions (cupe2i/windowing.py:103-173) followed by
+ *    F.log_softmax(.., dim=2) (core.py:898-899), in one pass.  window_logits is [B, n_windows, frames_per_window, C]
+ *    (utterance b at window_logits + b*in_pitch), window_weights the reference's cross-fade window
+ *    cos(linspace(-pi/2, pi/2, frames_per_window)) (:130, passed in so that it carries the caller's bits), logp_out
+ *    [B, total_frames, C] (utterance b at logp_out + b*out_pitch).  The cross-fade follows the reference's arithmetic
+ *    operation by operation; the result agrees with torch's stitch + log_softmax to 1e-5.
+ *    frames_per_window == 0: no stitching, window_logits holds [B, total_frames, C] logits (plain log-softmax).
+ */
+int bfa_stitch_log_softmax(int32_t B, int32_t n_windows, int32_t frames_per_window, int32_t C,
+                           int32_t total_frames, const float *window_logits, int64_t in_pitch,
+                           const float *window_weights, float *logp_out, int64_t out_pitch, void *stream);
+
+/*
  * Host-buffer convenience entry (what a CPU-side caller binds): same semantics as bfa_align_batch
  * with every pointer a HOST pointer.  Copies inputs host->device in chunks of utterances on two
  * streams (copy of chunk i+1 overlaps the kernels of chunk i), runs the device pipeline, copies

@@ -61,3 +61,21 @@ def _native_library_is_built():
     if b._stale() and shutil.which("nvcc"):
         b.build()
     yield
+
+
+@pytest.fixture(scope="session")
+def dev():
+    import torch
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="session")
+def bfa():
+    import bfa_b200
+    return bfa_b200
+
+
+@pytest.fixture(scope="session")
+def orc():
+    from oracle import oracle
+    return oracle

@@ -15,23 +15,6 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-4
 
 
-@pytest.fixture(scope="module")
-def dev():
-    return torch.device("cuda:0")
-
-
-@pytest.fixture(scope="module")
-def bfa():
-    import bfa_b200
-    return bfa_b200
-
-
-@pytest.fixture(scope="module")
-def orc():
-    from oracle import oracle
-    return oracle
-
-
 def _oracle(orc, p, w, Cc, max_stamps, threads=None):
     Ts, Ns = w["Ts"], w["Ns"]
     toff = np.zeros(len(Ns) + 1, np.int64); np.cumsum(np.asarray(Ns, np.int64), out=toff[1:])

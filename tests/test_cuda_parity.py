@@ -13,23 +13,6 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-4
 
 
-@pytest.fixture(scope="module")
-def dev():
-    return torch.device("cuda:0")
-
-
-@pytest.fixture(scope="module")
-def bfa():
-    import bfa_b200
-    return bfa_b200
-
-
-@pytest.fixture(scope="module")
-def orc():
-    from oracle import oracle
-    return oracle
-
-
 def _cases(npz):
     return [str(c) for c in npz["__cases__"]]
 
@@ -545,7 +528,7 @@ def test_shim_aligner_from_posteriors_vs_reference(bfa, dev):
     from bfa_b200 import synth
     g = np.load(Path(__file__).parent / "golden" / "pipeline.npz")
     utts = sorted({k.split("/")[0] for k in g.files}, key=lambda c: int(c[1:]))
-    al = bfa.PhonemeTimestampAligner(blank_class=66, silence_class=0)
+    al = bfa.PhonemeTimestampAligner(blank_class=66, silence_class=0, ensure_completeness=True)
     batches = {}
     for u in utts:                                   # utterances of one golden batch share (N, C) and the padded length
         T, N, Cc, b = (int(x) for x in g[f"{u}/meta"])
