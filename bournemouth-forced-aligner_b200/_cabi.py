@@ -19,7 +19,7 @@ MODE_FULL, MODE_SIMPLE = 0, 1
 FLAG_EXACT_ONLY, HINT_NO_SIL = 1, 2
 FLAG_UNFUSED_CONF, FLAG_NO_SPEC, FLAG_FILL_ONLY = 4, 8, 16
 FLAG_NO_DIRECT, FLAG_DIRECT_ONLY, FLAG_PIPELINED = 32, 64, 128
-MAX_C, MAX_L = 256, 1024
+MAX_C, MAX_L = 256, 8192
 
 
 class BfaParams(C.Structure):

@@ -16,6 +16,7 @@
 #include "plan.cuh"
 #include "viterbi_band3.cuh"
 #include "viterbi_generic.cuh"
+#include "viterbi_wide.cuh"
 
 using namespace bfa;
 
@@ -73,6 +74,7 @@ __global__ void nsmid_kernel(int* out) {
 
 // The banded-kernel variants launched per call: 8 lanes per utterance, G groups per lane -> window 24 / 40 / 64 groups;
 // each exists specialised for C = 66 (the benchmark width, class loop fully unrolled) and for a run-time C.
+constexpr int VW_CTAS = 16;      // DP problems of more than 1024 states in flight (each owns a back-pointer slab)
 constexpr int BAND_NV = 3;
 constexpr int BAND_G[BAND_NV] = {3, 5, 8};
 constexpr int BAND_WARPS = B3_PAIRS;   // (DP, helper) warp pairs per CTA
@@ -176,6 +178,7 @@ int device_info(DeviceInfo& out) {
         const size_t smem = sizeof(WarpSmem) * VG_WARPS;
         CUDA_TRY(cudaFuncSetAttribute(viterbi_generic_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(viterbi_generic_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(viterbi_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * VW_WARPS)));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.vg_ctas_per_sm, viterbi_generic_kernel<0>, VG_WARPS * 32, smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.vg_ctas_per_sm_big, viterbi_generic_kernel<1>, VG_WARPS * 32, smem));
         if (d.vg_ctas_per_sm < 1) d.vg_ctas_per_sm = 1;
@@ -210,6 +213,9 @@ inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 struct Layout {
     bool segmenting, want_sil;
     int cb_pitch, sil_nst;
+    int wide_L, wide_ctas;       // > 0: some utterance may need more than 1024 path states (viterbi_wide_kernel)
+    long long wide_slab_words;
+    size_t off_bp_wide;
     int item_cap, gmax, amax, anchor_words, list_ints, max_L, bp_words_per_lane;
     int resident_warps;
     long long slab_words;
@@ -241,6 +247,11 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
         if (byT < maxL) maxL = byT;
     }
     if (maxL > BFA_MAX_L) maxL = BFA_MAX_L;   // longer paths are refused per utterance by the planner (BFA_ST_UNSUPPORTED), not per batch
+    // paths of more than 1024 states (targets of more than 255 phonemes in one piece) go to the wide kernel: one CTA per problem
+    L.wide_L = maxL > VW_SPAN ? (int)maxL : 0;
+    L.wide_ctas = L.wide_L ? std::max(1, std::min(s.B, VW_CTAS)) : 0;
+    L.wide_slab_words = L.wide_L ? vw_slab_words(s.max_T, L.wide_L) : 0;
+    if (maxL > VW_SPAN) maxL = VW_SPAN;
     L.max_L = (int)maxL;
     L.bp_words_per_lane = (maxL > 512) ? 2 : 1;
     L.resident_warps = d.sms * d.vg_ctas_per_sm * VG_WARPS;
@@ -272,6 +283,7 @@ int make_layout(const BfaParams& p, const BfaShape& s, const DeviceInfo& d, Layo
     L.off_gcls = o; o = align_up(o + (size_t)s.total_frames);
     // the banded variants and the exact kernel run concurrently (internal streams): every kernel owns its slabs
     L.off_bp = o; o = align_up(o + (size_t)L.resident_warps * (size_t)L.slab_words * 4);
+    L.off_bp_wide = o; o = align_up(o + (size_t)L.wide_ctas * (size_t)L.wide_slab_words * 4);
     for (int v = 0; v < BAND_NV; ++v) {
         L.off_bp_band[v] = o;
         o = align_up(o + (size_t)L.band_grid * BAND_WARPS * (size_t)L.band_slab_words[v] * 4);
@@ -569,6 +581,13 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         rc = launch_viterbi(va, max_items_i, L.max_L, d, st, true);
         if (rc) return rc;
     }
+    if (L.wide_L) {          // what the exact kernel skipped: the planner's items of more than 1024 states, anywhere in its list
+        VitArgs vw = va;
+        vw.n_items = counters; vw.first = nullptr; vw.work_counter = counters + 15; vw.warp_base = 0;
+        vw.bp_scratch = (uint32_t*)(ws + L.off_bp_wide); vw.bp_slab_words = L.wide_slab_words;
+        viterbi_wide_kernel<<<L.wide_ctas, VW_WARPS * 32, sizeof(WarpSmem) * VW_WARPS, st>>>(vw);
+        LAUNCH_CHECK();
+    }
 
     if (stamps) {
         AssortArgs aa;
@@ -610,7 +629,7 @@ int bfa_viterbi_paths(const BfaParams* p, int32_t n_items, int32_t C, int32_t ma
                       void* stream) {
     if (!p || !logp || !row_off || !T || !path || !path_off || !Lp || !band || !frame_ph || !frame_idx || !frame_off) return BFA_E_INVALID;
     if (n_items <= 0) return n_items == 0 ? BFA_OK : BFA_E_INVALID;
-    if (C <= 0 || C > BFA_MAX_C || max_L > BFA_MAX_L) return BFA_E_UNSUPPORTED;
+    if (C <= 0 || C > BFA_MAX_C || max_L > VW_SPAN) return BFA_E_UNSUPPORTED;   // explicit paths: the per-warp exact kernel only
     if (p->blank_id < 0 || p->blank_id >= C) return BFA_E_INVALID;
     DeviceInfo d;
     int rc = device_info(d);

@@ -377,7 +377,7 @@ __device__ int plan_segmented(const UttCtx& c, Item* loc, int32_t* lists, uint32
         if ((double)(stride * n + 1) > (double)Ts * 0.8) stride = 2;
         const int L = stride * n + 1;
         if ((double)L > (double)Ts * 1.2) return -1;                              // :427-429
-        if (L > BFA_MAX_L) return -2;                                             // beyond the exact kernel's state capacity
+        if (L > BFA_MAX_L) return -2;                                             // beyond the wide exact kernel's state capacity
         if (n_items >= a.item_cap) return -1;  // cannot happen (item_cap = gmax + 1); defensive
         if (lane == 0) {
             Item it;
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
                     }
                 }
             }
-            if (ok && T > 0 && stride * N + 1 > BFA_MAX_L) {   // more states than the exact kernel holds (N > 255 at stride 4)
+            if (ok && T > 0 && stride * N + 1 > BFA_MAX_L) {   // more states than the wide exact kernel holds (N > 2047 at stride 4)
                 ok = false;
                 st = BFA_ST_UNSUPPORTED;
                 fill_frames(c, o_base, o_lim, T, p.blank_id, -1);

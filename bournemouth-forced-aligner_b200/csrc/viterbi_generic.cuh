@@ -106,62 +106,21 @@ __device__ __forceinline__ void stream_advance(WarpSmem& sm, Stream& st, int pb,
     }
 }
 
-template <int J>
-__device__ __forceinline__ float get_state(const float (&dp)[J], int s, int lane) {
-    float v = 0.f;
-#pragma unroll
-    for (int j = 0; j < J; ++j)
-        if (j == (s % J)) v = dp[j];
-    return __shfl_sync(FULL, v, s / J);
-}
+// Transform row t of the item into rowbuf[t & 1]: target boost + log_softmax + floor (:121-129) and the sub-silence
+// anchoring of silence-anchored segments (:543-561), from the warp's ring.
+struct RowProducer {
+    const VitArgs& a;
+    const Item& it;
+    WarpSmem& sm;
+    Stream& st;
+    const int lane;
+    const uint64_t pol;
+    const uint32_t tbits;
+    const bool use_stats, do_floor, has_anchor;
+    uint32_t anc_blk;                           // lane q holds anchor word q of the current 256-frame block
+    __device__ __forceinline__ void operator()(int t) {
+        const int C = a.C, T = it.T, blank = a.p.blank_id;
 
-template <int J>
-__device__ void run_item(const VitArgs& a, const Item& it, WarpSmem& sm, Stream& st, uint32_t* bp, int lane, uint64_t pol) {
-    using bpw_t = typename std::conditional<(J > 16), unsigned long long, uint32_t>::type;
-    constexpr int BPW = (J > 16) ? 2 : 1;
-    const int T = it.T, L = it.L, C = a.C;
-    const float NEG = a.p.neg_inf;
-    const bool use_stats = (it.flags & ITEM_STATS) != 0;
-    const bool do_floor = (it.flags & ITEM_FLOOR) != 0;
-    const bool has_anchor = (it.flags & ITEM_ANCHOR) != 0;
-    const int blank = a.p.blank_id;
-
-    // ---- per-lane path description ----
-    int pid[J];
-    uint32_t skipmask = 0;
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        int s = lane * J + j;
-        int cls = blank;
-        if (s < L) {
-            cls = state_class(a, it, s);
-            if (s >= 2 && cls != state_class(a, it, s - 2)) skipmask |= 1u << j;  // can_skip (:603-605)
-        }
-        pid[j] = min(max(cls, 0), C - 1);
-    }
-    // target-class bits for the classes this lane transforms: class lane + 32*i
-    uint32_t tbits = 0;
-    if (a.tmask && (use_stats || do_floor)) {
-#pragma unroll
-        for (int i = 0; i < MAX_WORDS; ++i) tbits |= ((a.tmask[(size_t)it.utt * MAX_WORDS + i] >> lane) & 1u) << i;
-    }
-
-    // ---- stream set-up ----
-    {
-        const float* g = a.logp + it.lp_off;
-        uintptr_t addr = (uintptr_t)g;
-        st.g16 = (const float*)(addr & ~(uintptr_t)15);
-        st.shift = (int)((addr & 15) >> 2);
-        st.total = st.shift + T * C;
-        st.n_chunks = (st.total + CHUNK - 1) / CHUNK;
-        st.issued = 0;
-        st.ready = 0;
-    }
-
-    uint32_t anc_blk = 0;                       // lane q holds anchor word q of the current 256-frame block
-
-    // transform row t into rowbuf[t & 1]
-    auto produce = [&](int t) {
         int pos = st.shift + t * C;
         stream_advance(sm, st, pos, pos + C - 1, lane, pol);
         __syncwarp();
@@ -223,7 +182,62 @@ __device__ void run_item(const VitArgs& a, const Item& it, WarpSmem& sm, Stream&
             for (int i = 0; i < MAX_WORDS; ++i)
                 if (lane + 32 * i < C) rb[lane + 32 * i] = v[i];
         }
-    };
+    }
+};
+
+template <int J>
+__device__ __forceinline__ float get_state(const float (&dp)[J], int s, int lane) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+        if (j == (s % J)) v = dp[j];
+    return __shfl_sync(FULL, v, s / J);
+}
+
+template <int J>
+__device__ void run_item(const VitArgs& a, const Item& it, WarpSmem& sm, Stream& st, uint32_t* bp, int lane, uint64_t pol) {
+    using bpw_t = typename std::conditional<(J > 16), unsigned long long, uint32_t>::type;
+    constexpr int BPW = (J > 16) ? 2 : 1;
+    const int T = it.T, L = it.L, C = a.C;
+    const float NEG = a.p.neg_inf;
+    const bool use_stats = (it.flags & ITEM_STATS) != 0;
+    const bool do_floor = (it.flags & ITEM_FLOOR) != 0;
+    const bool has_anchor = (it.flags & ITEM_ANCHOR) != 0;
+    const int blank = a.p.blank_id;
+
+    // ---- per-lane path description ----
+    int pid[J];
+    uint32_t skipmask = 0;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        int s = lane * J + j;
+        int cls = blank;
+        if (s < L) {
+            cls = state_class(a, it, s);
+            if (s >= 2 && cls != state_class(a, it, s - 2)) skipmask |= 1u << j;  // can_skip (:603-605)
+        }
+        pid[j] = min(max(cls, 0), C - 1);
+    }
+    // target-class bits for the classes this lane transforms: class lane + 32*i
+    uint32_t tbits = 0;
+    if (a.tmask && (use_stats || do_floor)) {
+#pragma unroll
+        for (int i = 0; i < MAX_WORDS; ++i) tbits |= ((a.tmask[(size_t)it.utt * MAX_WORDS + i] >> lane) & 1u) << i;
+    }
+
+    // ---- stream set-up ----
+    {
+        const float* g = a.logp + it.lp_off;
+        uintptr_t addr = (uintptr_t)g;
+        st.g16 = (const float*)(addr & ~(uintptr_t)15);
+        st.shift = (int)((addr & 15) >> 2);
+        st.total = st.shift + T * C;
+        st.n_chunks = (st.total + CHUNK - 1) / CHUNK;
+        st.issued = 0;
+        st.ready = 0;
+    }
+
+    RowProducer produce{a, it, sm, st, lane, pol, tbits, use_stats, do_floor, has_anchor, 0u};
 
     // ---- t = 0 (:594-596) ----
     produce(0);
@@ -414,7 +428,7 @@ __global__ void __launch_bounds__(VG_WARPS * 32, KCLASS == 0 ? 2 : 1) viterbi_ge
             else if (J <= 4) run_item<4>(a, it, sm, st, bp, lane, pol);
             else run_item<8>(a, it, sm, st, bp, lane, pol);
         } else {
-            if (J <= 8) continue;
+            if (J <= 8 || J > 32) continue;        // J > 32: viterbi_wide_kernel
             if (J <= 16) run_item<16>(a, it, sm, st, bp, lane, pol);
             else run_item<32>(a, it, sm, st, bp, lane, pol);
         }

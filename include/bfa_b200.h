@@ -53,7 +53,7 @@ extern "C" {
 #define BFA_ST_SEGMENTED 4     /* silence-anchored segmentation accepted (:133-145) */
 #define BFA_ST_DEFERRED 5      /* only with BFA_FLAG_DIRECT_ONLY: the utterance needs the full planner chain and was NOT aligned;
                                   run it again without that flag (the Python facade does) */
-#define BFA_ST_UNSUPPORTED 6   /* the utterance's CTC path has more than BFA_MAX_L states (more than 255 phonemes in one DP problem):
+#define BFA_ST_UNSUPPORTED 6   /* the utterance's CTC path has more than BFA_MAX_L states (more than 2047 phonemes in one DP problem):
                                   it was NOT aligned (frames = blank, no stamps); every other utterance of the batch is unaffected */
 #define BFA_ST_DEGENERATE 8    /* flag: winning DP score <= -1000 (the reference's "-inf") */
 #define BFA_ST_STAMP_OVERFLOW 16 /* flag: more than max_stamps runs; stamps truncated */
@@ -62,7 +62,7 @@ extern "C" {
 #define BFA_MODE_SIMPLE 1 /* AlignmentUtils.decode_alignments_simple (:932-986) */
 
 #define BFA_MAX_C 256
-#define BFA_MAX_L 1024  /* CTC-path states per DP problem (N <= 255 at stride 4) */
+#define BFA_MAX_L 8192  /* CTC-path states per DP problem (N <= 2047 at stride 4); more than 1024 states: one CTA per problem */
 
 /* Constants of ViterbiDecoder/AlignmentUtils (forced_alignment.py:16-23, :29, :226, :269, :418,
  * :777, :841).  Replaces the reference's constructor arguments + hard-coded literals. */

@@ -294,40 +294,58 @@ def test_free_decoding_matches_reference_semantics(bfa, dev):
 
 
 # ---- round-1 advisor findings --------------------------------------------------------------------------------------
-def test_long_target_is_refused_per_utterance(bfa, orc, dev):
-    """A target of more than 255 phonemes needs more than BFA_MAX_L = 1024 path states: that utterance is reported as
-    BFA_ST_UNSUPPORTED (blank frames, no stamps) and every other utterance of the batch is aligned as usual."""
+def test_long_targets_wide_kernel_and_per_utterance_refusal(bfa, orc, dev):
+    """Targets of more than 255 phonemes need more than 1024 path states: they are aligned by the one-CTA-per-problem exact kernel
+    (the reference aligns them whole when silence anchoring does not split them, forced_alignment.py:298-308, :153-190).  Beyond
+    BFA_MAX_L = 8192 states an utterance is reported as BFA_ST_UNSUPPORTED (blank frames, no stamps) and every other utterance of
+    the batch is aligned as usual."""
     from bfa_b200 import synth, _cabi
     Cc = 67
     utts = []
-    for i, (T, N) in enumerate([(300, 30), (1900, 350), (500, 60), (1300, 260), (200, 12)]):
+    shapes = [(300, 30), (1900, 350), (500, 60), (1300, 260), (200, 12), (8600, 2100), (2500, 600), (1105, 276)]
+    for i, (T, N) in enumerate(shapes):
         l, t, _ = synth.planted_batch(1, T, N, Cc, seed=70 + i, peak=10.0)
         utts.append((l[0], t[0]))
     flat, row_off, Ts, tg, Ns = synth.pack_ragged(utts, Cc)
     w = dict(lp=flat, row_off=row_off, Ts=Ts, tgt=tg, Ns=Ns)
     r = _align(bfa, dev, w, Cc)
-    st = r.status[:5].cpu().numpy()
-    assert (st & 7).tolist() == [0, _cabi.ST_UNSUPPORTED, 0, _cabi.ST_UNSUPPORTED, 0]
-    assert r.n_stamps[:5].cpu().tolist()[1] == 0 and r.n_stamps[:5].cpu().tolist()[3] == 0
-    fo = np.zeros(6, np.int64); np.cumsum(np.asarray(Ts, np.int64), out=fo[1:])
-    assert (r.frame_ph[fo[1]:fo[2]] == Cc - 1).all() and (r.frame_idx[fo[1]:fo[2]] == -1).all()
-    for b in (0, 2, 4):
+    nb = len(shapes)
+    st = r.status[:nb].cpu().numpy()
+    assert (st & 7).tolist() == [0, 0, 0, 0, 0, _cabi.ST_UNSUPPORTED, 0, 0]
+    assert r.n_stamps[:nb].cpu().tolist()[5] == 0
+    fo = np.zeros(nb + 1, np.int64); np.cumsum(np.asarray(Ts, np.int64), out=fo[1:])
+    assert (r.frame_ph[fo[5]:fo[6]] == Cc - 1).all() and (r.frame_idx[fo[5]:fo[6]] == -1).all()
+    for b in (0, 1, 2, 3, 4, 6, 7):
         l, t = utts[b]
         o = orc.align_batch(orc.params(Cc - 1, 0), l.numpy().reshape(1, Ts[b], Cc), np.zeros(1, np.int64), np.asarray([Ts[b]], np.int32), Cc,
                             t.numpy().astype(np.int32), np.asarray([0, Ns[b]], np.int64), max_stamps=r.max_stamps, n_threads=1)
-        np.testing.assert_array_equal(r.frame_ph[fo[b]:fo[b + 1]].cpu().numpy(), o["frame_ph"])
+        np.testing.assert_array_equal(r.frame_ph[fo[b]:fo[b + 1]].cpu().numpy(), o["frame_ph"], err_msg=f"utterance {b} {shapes[b]}")
+        np.testing.assert_array_equal(r.frame_idx[fo[b]:fo[b + 1]].cpu().numpy(), o["frame_idx"], err_msg=f"utterance {b} {shapes[b]}")
         n = int(o["n_stamps"][0])
         assert int(r.n_stamps[b]) == n
         np.testing.assert_array_equal(r.stamps[b, :n, 1].cpu().numpy(), o["stamps"]["start"][0][:n])
+        np.testing.assert_allclose(float(r.dp_final[b]), float(o["dp_final"][0]), rtol=1e-4)
+    # degenerate long problems (flat posteriors: ties, unreachable end states) follow the same exact semantics
+    T, N = 1500, 300
+    flat_lp = torch.log_softmax(torch.zeros(1, T, Cc), -1)
+    tg1 = torch.randint(1, Cc - 1, (1, N), generator=torch.Generator().manual_seed(5))
+    w1 = dict(lp=flat_lp.reshape(-1), row_off=torch.zeros(1, dtype=torch.int64), Ts=[T], tgt=tg1.to(torch.int32).reshape(-1), Ns=[N])
+    r1 = _align(bfa, dev, w1, Cc)
+    o1 = orc.align_batch(orc.params(Cc - 1, 0), flat_lp.numpy(), np.zeros(1, np.int64), np.asarray([T], np.int32), Cc, tg1.numpy().astype(np.int32).reshape(-1),
+                         np.asarray([0, N], np.int64), max_stamps=r1.max_stamps, n_threads=1)
+    np.testing.assert_array_equal(r1.frame_ph[:T].cpu().numpy(), o1["frame_ph"])
+    np.testing.assert_array_equal(r1.frame_idx[:T].cpu().numpy(), o1["frame_idx"])
     # the reference-shaped entry warns and returns no stamps for the refused utterance
     au = bfa.AlignmentUtils(Cc - 1, 0)
-    Tm, Nm = max(Ts), max(Ns)
-    lp = torch.full((5, Tm, Cc), -20.0); tg2 = torch.zeros((5, Nm), dtype=torch.long)
-    for b, (l, t) in enumerate(utts):
-        lp[b, :Ts[b]] = l; tg2[b, :Ns[b]] = t
+    sel = [0, 5, 3]
+    Tm, Nm = max(Ts[b] for b in sel), max(Ns[b] for b in sel)
+    lp = torch.full((3, Tm, Cc), -20.0); tg2 = torch.zeros((3, Nm), dtype=torch.long)
+    for k, b in enumerate(sel):
+        l, t = utts[b]
+        lp[k, :Ts[b]] = l; tg2[k, :Ns[b]] = t
     with pytest.warns(UserWarning, match="were not aligned"):
-        got = au.decode_alignments(lp.to(dev), true_seqs=tg2, pred_lens=torch.tensor(Ts), true_seqs_lens=torch.tensor(Ns))
-    assert got[1] == [] and got[3] == [] and len(got[0]) == 30 and len(got[2]) == 60
+        got = au.decode_alignments(lp.to(dev), true_seqs=tg2, pred_lens=torch.tensor([Ts[b] for b in sel]), true_seqs_lens=torch.tensor([Ns[b] for b in sel]))
+    assert got[1] == [] and len(got[0]) == 30 and len(got[2]) == 260
 
 
 def test_two_host_threads_one_device(bfa, dev):
