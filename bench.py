@@ -542,6 +542,10 @@ def main():
         w = dict(lp=lpv, row_off=row_off, Ts=Ts, Ns=Ns, tgt=tgv.to(torch.int32).reshape(-1).contiguous())
         variants.append(run_variant(torch, lib, dec, dev, "metric shape with silence_id at every 10th target (anchoring on, no hints, full chain)", w, Cc,
                                     hinted(dec, False), peak))
+        psil = hinted(dec, False)
+        psil.reserved |= _cabi.FLAG_NO_DIRECT        # what the facade sets when the host-side targets (nearly) all hold silence_id
+        variants.append(run_variant(torch, lib, dec, dev, "metric shape with silence_id at every 10th target, one-kernel pass skipped (BFA_FLAG_NO_DIRECT)", w, Cc,
+                                    psil, peak))
         del lpv, w
         torch.cuda.empty_cache()
         for n in (2, 3, 4):        # BASELINE.json configs[1..3]

@@ -387,10 +387,14 @@ class AlignmentUtils:
             # targets still live on the host (core.py builds them there): a free check lets the library skip the
             # row-statistics pass that only the silence scan needs (BFA_HINT_NO_SIL; purely a performance hint)
             lens = torch.as_tensor(N)[:, None]
-            has_sil = bool(((true_seqs == params.silence_id) & (torch.arange(S)[None, :] < lens)).any())
-            if not has_sil:
+            sil_utts = ((true_seqs == params.silence_id) & (torch.arange(S)[None, :] < lens)).any(dim=1)
+            if not bool(sil_utts.any()):
                 params.reserved |= _cabi.HINT_NO_SIL
                 may_segment = False
+            elif float(sil_utts.float().mean()) > 0.75:
+                # (nearly) every target holds silence_id: the one-kernel pass would hand (nearly) everything back to the
+                # planner chain; skip it (BFA_FLAG_NO_DIRECT; a performance switch, results do not depend on it)
+                params.reserved |= _cabi.FLAG_NO_DIRECT
         # Without segmentation every utterance that is a plain stride-4 problem is finished by ONE kernel (in-kernel planning,
         # Viterbi, stamps, confidences): launch only that kernel; whatever it flags as deferred is run again in _dense_finish
         if not may_segment and S > 0 and direct_only_worthwhile(T, N, params):

@@ -417,8 +417,8 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     double* sild = L.segmenting ? (double*)(ws + L.off_sild) : nullptr;
     float* path_lp = (stamps && conf && !(p->reserved & BFA_FLAG_UNFUSED_CONF)) ? (float*)(ws + L.off_pathlp) : nullptr;
     // counter slots: 0 items of the exact kernel (planner + retries), 1-2 its work counters (short / long class), 3 5 7 items of
-    // the banded window classes, 10 the planner's exact-item count (side-stream pass), 11-12 work counters of the second exact
-    // pass, 13 utterances the direct kernel handed back
+    // the banded window classes (4 6 8 their frames), 10 the planner's exact-item count (side-stream pass), 11-12 work counters of the second exact
+    // pass, 13 utterances the direct kernel handed back, 14 silence-scan work units, 15 work counter of the wide exact kernel
     int* counters = (int*)(ws + L.off_counters);
     g_last_counters = counters;
     g_last_direct_B = 0;
@@ -491,7 +491,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     pa.items_local = (Item*)(ws + L.off_items_local); pa.items = (Item*)(ws + L.off_items);
     pa.n_items = counters; pa.lists = (int32_t*)(ws + L.off_lists); pa.list_ints = L.list_ints;
     pa.deferred = deferred; pa.n_deferred = counters + 13;
-    for (int v = 0; v < BAND_NV; ++v) { pa.fast_items[v] = (Item*)(ws + L.off_fast[v]); pa.n_fast[v] = counters + 3 + 2 * v; }
+    for (int v = 0; v < BAND_NV; ++v) { pa.fast_items[v] = (Item*)(ws + L.off_fast[v]); pa.n_fast[v] = counters + 3 + 2 * v; pa.frames_fast[v] = counters + 4 + 2 * v; }
     pa.fast_enable = fast ? 1 : 0; pa.path_lp = path_lp;
     pa.cbase = (double*)(ws + L.off_cbase); pa.cb_pitch = L.cb_pitch; pa.anchors = (uint32_t*)(ws + L.off_anchors);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
@@ -524,7 +524,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         ba.frame_ph = frame_ph; ba.frame_idx = frame_idx; ba.dp_final = dp_final; ba.path_lp = path_lp;
         ba.guess_cls = (path_lp && !(p->reserved & BFA_FLAG_NO_SPEC)) ? (unsigned char*)(ws + L.off_gcls) : nullptr;
         for (int v = 0; v < BAND_NV; ++v) {
-            ba.cls[v].items = pa.fast_items[v]; ba.cls[v].n_items = pa.n_fast[v];
+            ba.cls[v].items = pa.fast_items[v]; ba.cls[v].n_items = pa.n_fast[v]; ba.cls[v].n_frames = pa.frames_fast[v];
             ba.cls[v].bp_scratch = (uint32_t*)(ws + L.off_bp_band[v]);
             ba.cls[v].bp_slab_words = L.band_slab_words[v];
             ba.cls[v].smem_per_warp = L.band_smem_per_warp[v];

@@ -41,6 +41,7 @@ struct PlanArgs {
     int* n_items;              // device counter
     Item* fast_items[3];       // compacted lists for the banded kernel (window 24 / 40 / 64 groups)
     int* n_fast[3];
+    int* frames_fast[3];       // frames of each list's items (the banded kernel sizes the classes' CTA shares with them)
     int fast_enable;
     int32_t* lists;            // [B][list_ints]
     int list_ints;
@@ -529,8 +530,8 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
 
     // ---- publish the items into the compact global lists (banded kernels / exact kernel).  Counts are aggregated per
     //      CTA in shared memory first: one global atomic per list per CTA instead of one per utterance ----
-    __shared__ int s_cnt[4], s_base[4];
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    __shared__ int s_cnt[4], s_base[4], s_frm[4];
+    if (threadIdx.x < 4) { s_cnt[threadIdx.x] = 0; s_frm[threadIdx.x] = 0; }
     __syncthreads();
     int my_cnt[4] = {0, 0, 0, 0}, my_off[4] = {0, 0, 0, 0};
     int cl0 = -2;                // class of item `lane` (the first, usually the only, pass over the items)
@@ -539,8 +540,15 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
         int cl = -2;
         if (i < n_items) cl = have_single ? fast_class(single, a.C, a.logp, tok, a.fast_enable) : fast_class(loc[i], a.C, a.logp, tok, a.fast_enable);
         if (i0 == 0) cl0 = cl;
+        const int Ti = (i < n_items) ? (have_single ? single.T : loc[i].T) : 0;
 #pragma unroll
-        for (int c = -1; c <= 2; ++c) my_cnt[c + 1] += __popc(__ballot_sync(FULL, cl == c));
+        for (int c = -1; c <= 2; ++c) {
+            my_cnt[c + 1] += __popc(__ballot_sync(FULL, cl == c));
+            if (c >= 0) {
+                const int fr = __reduce_add_sync(FULL, cl == c ? Ti : 0);
+                if (fr && lane == 0) atomicAdd(&s_frm[c + 1], fr);
+            }
+        }
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -551,6 +559,7 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
     if (threadIdx.x < 4 && s_cnt[threadIdx.x]) {
         int* cnt = (threadIdx.x == 0) ? a.n_items : a.n_fast[threadIdx.x - 1];
         s_base[threadIdx.x] = atomicAdd(cnt, s_cnt[threadIdx.x]);
+        if (threadIdx.x > 0 && s_frm[threadIdx.x]) atomicAdd(a.frames_fast[threadIdx.x - 1], s_frm[threadIdx.x]);
     }
     __syncthreads();
     for (int i0 = 0; i0 < n_items; i0 += 32) {

@@ -97,6 +97,7 @@ struct Band3Args {
     struct Class {             // one per window class (24 / 40 / 64 groups)
         const Item* items;
         const int* n_items;
+        const int* n_frames;   // frames of the class's items (the planner's sum; list mode with several classes: the CTA shares)
         uint32_t* bp_scratch;  // decision-record slabs, one per resident pair
         long long bp_slab_words;
         int smem_per_warp;     // bytes of shared memory per (DP, helper) pair
@@ -1546,8 +1547,10 @@ __device__ __forceinline__ void band3_roles(int warp, int npairs, bool& is_dp, i
 #endif
 }
 
+// cta / ncta: this CTA's rank among the CTAs that work on the class, and their number (uniform over the CTA); rev: hand the list
+// out back to front.
 template <int G, int CT, bool EXACT>
-__device__ void band3_run(const Band3Args& a, const Band3Args::Class& k, unsigned char* smem_raw, int warp, int lane) {
+__device__ void band3_run(const Band3Args& a, const Band3Args::Class& k, unsigned char* smem_raw, int warp, int lane, int cta, int ncta, bool rev) {
     const int n_items = *k.n_items;
     if (n_items == 0) return;                 // nothing of this window class in the batch (uniform over the CTA)
     const int npairs = min((int)(blockDim.x >> 6), k.npairs);   // as many pairs as the shared memory of one SM holds
@@ -1567,23 +1570,20 @@ __device__ void band3_run(const Band3Args& a, const Band3Args::Class& k, unsigne
     __syncthreads();
     uint32_t phase = 0;
     const int n_tasks = (n_items + B3_UPW - 1) / B3_UPW;
-    // static deal: slot q -> CTA q % grid, pair (q / grid) % npairs.  With one CTA per SM this spreads ceil(n_tasks / SMs)
-    // tasks evenly over the SMs and over the four schedulers of each SM.  The widest window class hands its list out front to
-    // back, the other two back to front: when the caller orders the utterances by length (a length-bucketing loader), the pair
-    // that gets the longest task of one class gets the shortest of the others.
-    constexpr bool REV = G != 8;
+    // static deal: slot q -> CTA q % ncta, pair (q / ncta) % npairs.  With one CTA per SM this spreads ceil(n_tasks / CTAs)
+    // tasks evenly over the SMs and over the four schedulers of each SM.
     if (idle) {
     } else if (is_dp) {
         uint32_t* slab = k.bp_scratch + (size_t)(blockIdx.x * npairs + pair) * k.bp_slab_words;
-        for (int q = blockIdx.x + gridDim.x * pair; q < n_tasks; q += gridDim.x * npairs) {
-            const int j = REV ? n_tasks - 1 - q : q;
+        for (int q = cta + ncta * pair; q < n_tasks; q += ncta * npairs) {
+            const int j = rev ? n_tasks - 1 - q : q;
             band3_dp<G, CT, EXACT, false>(a, k, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, slab, phase, lane, pair, nullptr, nullptr);
         }
     } else {
         const uint64_t pol = policy_evict_first();
         bool not_first = false;
-        for (int q = blockIdx.x + gridDim.x * pair; q < n_tasks; q += gridDim.x * npairs) {
-            const int j = REV ? n_tasks - 1 - q : q;
+        for (int q = cta + ncta * pair; q < n_tasks; q += ncta * npairs) {
+            const int j = rev ? n_tasks - 1 - q : q;
             band3_helper<G, CT, false>(a, k, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, phase, not_first, lane, pol, pair, nullptr, nullptr);
             not_first = true;
         }
@@ -1602,9 +1602,32 @@ __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_kernel(Band3Ar
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_release();
     pdl_wait();                               // the planner's item lists
-    band3_run<3, CT, EXACT>(a, a.cls[0], smem_raw, warp, lane);
-    band3_run<5, CT, EXACT>(a, a.cls[1], smem_raw, warp, lane);
-    band3_run<8, CT, EXACT>(a, a.cls[2], smem_raw, warp, lane);
+    // One class in the batch (the usual case): every CTA works on it.  Several: the classes run SIDE BY SIDE, each on a share of
+    // the CTAs proportional to its work (frames x cost of a chunk at that window width / pairs an SM holds at that width) --
+    // run one after the other each class costs about one longest task, however few tasks it has.  Lists are handed out back to
+    // front then (a caller that orders utterances by length gets longest-first).
+    const int n0 = *a.cls[0].n_items, n1 = *a.cls[1].n_items, n2 = *a.cls[2].n_items;
+    const int G_ = (int)gridDim.x, c_ = (int)blockIdx.x;
+    if ((n0 > 0) + (n1 > 0) + (n2 > 0) <= 1 || G_ < 6) {
+        band3_run<3, CT, EXACT>(a, a.cls[0], smem_raw, warp, lane, c_, G_, true);
+        band3_run<5, CT, EXACT>(a, a.cls[1], smem_raw, warp, lane, c_, G_, true);
+        band3_run<8, CT, EXACT>(a, a.cls[2], smem_raw, warp, lane, c_, G_, false);
+        return;
+    }
+    const int np = (int)(blockDim.x >> 6);
+    const float w0 = n0 ? fmaxf(1.f, (float)*a.cls[0].n_frames) * 1.0f / (float)min(np, a.cls[0].npairs) : 0.f;
+    const float w1 = n1 ? fmaxf(1.f, (float)*a.cls[1].n_frames) * 1.6f / (float)min(np, a.cls[1].npairs) : 0.f;
+    const float w2 = n2 ? fmaxf(1.f, (float)*a.cls[2].n_frames) * 2.5f / (float)min(np, a.cls[2].npairs) : 0.f;
+    const float ws = w0 + w1 + w2;
+    int g0 = n0 ? max(1, (int)(G_ * w0 / ws + 0.5f)) : 0;
+    int g1 = n1 ? max(1, (int)(G_ * w1 / ws + 0.5f)) : 0;
+    int g2 = n2 ? max(1, (int)(G_ * w2 / ws + 0.5f)) : 0;
+    // make the shares add up: take from / give to the largest
+    int* gl = (g0 >= g1 && g0 >= g2) ? &g0 : (g1 >= g2 ? &g1 : &g2);
+    *gl += G_ - (g0 + g1 + g2);
+    if (c_ < g0) band3_run<3, CT, EXACT>(a, a.cls[0], smem_raw, warp, lane, c_, g0, true);
+    else if (c_ < g0 + g1) band3_run<5, CT, EXACT>(a, a.cls[1], smem_raw, warp, lane, c_ - g0, g1, true);
+    else band3_run<8, CT, EXACT>(a, a.cls[2], smem_raw, warp, lane, c_ - g0 - g1, g2, true);
 }
 
 // Direct mode: ONE kernel per batch on the common path.  Task q = utterances 4q .. 4q+3, planned by the helper warp itself,

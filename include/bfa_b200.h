@@ -98,7 +98,8 @@ typedef struct BfaParams {
 #define BFA_FLAG_NO_SPEC 8       /* the banded kernel fetches every confidence input during its back-trace instead of keeping the
                                  * frame-wise best class's value while the row is on chip (measurement / A-B switch) */
 
-#define BFA_FLAG_NO_DIRECT 32    /* A/B switch: never use the direct kernel, every utterance goes through planner + item lists */
+#define BFA_FLAG_NO_DIRECT 32    /* never use the direct kernel, every utterance goes through planner + item lists: worth setting when
+                                    (nearly) every target holds silence_id, i.e. the direct kernel would hand everything back; results are the same */
 #define BFA_FLAG_DIRECT_ONLY 64  /* Launch ONLY the direct kernel (one kernel per call: in-kernel planning, banded stride-4 Viterbi,
                                   * frame labels, timestamps, confidences).  Utterances it cannot finish -- silence_id in the target
                                   * while silence anchoring is on, more phonemes than 4N+1 <= T allows, T == N, empty targets, paths
