@@ -460,7 +460,7 @@ def main():
     # ---- roofline of the dominant kernel
     peak, peak_src = measured_peak()
     alg = algorithmic_bytes(Ts, Ns, Cc)
-    ctag = f"<{Cc},false>" if Cc == 66 else "<0,false> (run-time class count)"
+    ctag = f"<{Cc},false>" if Cc in (66, 67, 17) else "<0,false> (run-time class count)"     # the compiled class counts (bfa_api.cu: direct_launch)
     if one_kernel:
         dom_avg_ms = ms / a.steps
         kname = f"viterbi_band3_direct_kernel{ctag} (the whole step: in-kernel planning, fill, back-trace, frame labels, stamps, confidences)"

@@ -161,7 +161,9 @@ __host__ __device__ inline int band3_bt_keep_words(int G) { return B3_NREC * (6 
 // shared memory of one pair: staging region (stage ring, later the back-trace staging) | class weights | (lnS, eb) per staged row |
 // target classes | helper flags + utterance states | the pair's work items (direct mode) | mbarriers.  R = bytes of the region.
 enum : int { B3_BAR_FULL = 0, B3_BAR_READY = B3_NST, B3_BAR_FREE = 2 * B3_NST, B3_BAR_REC = 3 * B3_NST, B3_BAR_KREADY = 3 * B3_NST + B3_NREC,
-             B3_BAR_KFREE = 3 * B3_NST + B3_NREC + 2, B3_BAR_PLAN = 3 * B3_NST + B3_NREC + 4, B3_NBARS = 3 * B3_NST + B3_NREC + 5 };
+             B3_BAR_KFREE = 3 * B3_NST + B3_NREC + 2, B3_BAR_PLAN = 3 * B3_NST + B3_NREC + 4, B3_BAR_PAIR = 3 * B3_NST + B3_NREC + 5, B3_NBARS = 3 * B3_NST + B3_NREC + 6 };
+// arrivals that complete a phase of barrier i: every utterance's copy on the stage-full barriers, both warps on the pair rendezvous, one elsewhere
+__host__ __device__ inline uint32_t band3_bar_count(int i) { return (i >= B3_BAR_FULL && i < B3_BAR_FULL + B3_NST) ? B3_UPW : (i == B3_BAR_PAIR ? 2u : 1u); }
 __host__ __device__ inline size_t band3_off_kk(size_t R) { return R; }
 __host__ __device__ inline size_t band3_off_stats(size_t R) { return band3_off_kk(R) + (size_t)B3_UPW * B3_KK2 * 4; }
 __host__ __device__ inline size_t band3_off_cls(size_t R) { return band3_off_stats(R) + (size_t)B3_NST * B3_UPW * B3_STP * 8; }
@@ -407,7 +409,16 @@ __device__ __noinline__ void band3_direct_plan(const Band3Args& a, int task, uns
 // Helper warp: tables, bulk copies, row statistics.
 // ------------------------------------------------------------------------------------------------------------
 // both warps of a pair meet here (named barrier 1 + pair, 64 threads): hand-overs of the direct mode
-__device__ __forceinline__ void band3_pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+// A rendezvous on the pair's own mbarrier (two arrivals per phase, release / acquire like the other hand-overs): unlike a named
+// hardware barrier it involves nobody but the two warps, whatever the rest of the CTA is doing or has already left.
+__device__ __forceinline__ void band3_pair_sync(uint32_t bar0, uint32_t& phase, int lane) {
+    const uint32_t bar = bar0 + 8u * B3_BAR_PAIR;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+    mbar_wait(bar, (phase >> B3_BAR_PAIR) & 1u);
+    phase ^= 1u << B3_BAR_PAIR;
+    __syncwarp();
+}
 
 template <int CT>
 __device__ __noinline__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair, size_t R, int seg0, int which, int lane, bool have_spec);
@@ -688,11 +699,11 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
             __syncwarp();
         }
         PH_RESET;
-        band3_pair_sync(pair);                  // the walk is done
+        band3_pair_sync(k.bar0, phase, lane);                  // the walk is done
         PH_T(0);
         band3_direct_finish<CT>(a, smem_pair, R, 2, 1, lane, pscr_lp != nullptr);
         PH_T(1);
-        band3_pair_sync(pair);                  // both warps are done with the task
+        band3_pair_sync(k.bar0, phase, lane);                  // both warps are done with the task
         PH_T(2);
         PH_FLUSH;
         return;
@@ -829,9 +840,9 @@ __device__ void band3_dp(const Band3Args& a, const Band3Args::Class& kc, int fir
     if constexpr (DIRECT) {
         if (k.n_chunks == 0) {                         // nothing of this task runs here (no such utterances, or all left to the planner chain)
             if (a.p.reserved & BFA_FLAG_FILL_ONLY) return;
-            band3_pair_sync(pair);
+            band3_pair_sync(k.bar0, phase, lane);
             band3_direct_finish<CT>(a, smem_pair, R, 0, 0, lane, pscr_lp != nullptr);
-            band3_pair_sync(pair);
+            band3_pair_sync(k.bar0, phase, lane);
             return;
         }
     }
@@ -1201,11 +1212,11 @@ __device__ void band3_dp(const Band3Args& a, const Band3Args::Class& kc, int fir
         }
         phase = (phase & ~(((1u << B3_NREC) - 1u) << B3_BAR_REC)) | ((rphase & ((1u << B3_NREC) - 1u)) << B3_BAR_REC);
         __syncwarp();
-        band3_pair_sync(pair);                     // events and verdicts are in shared memory
+        band3_pair_sync(k.bar0, phase, lane);                     // events and verdicts are in shared memory
         PH_T(9);
         band3_direct_finish<CT>(a, smem_pair, R, 0, 0, lane, pscr_lp != nullptr);
         PH_T(10);
-        band3_pair_sync(pair);                     // both warps are done with the task
+        band3_pair_sync(k.bar0, phase, lane);                     // both warps are done with the task
         PH_T(12);
         PH_FLUSH;
         return;
@@ -1564,7 +1575,7 @@ __device__ void band3_run(const Band3Args& a, const Band3Args::Class& k, unsigne
         // No zero fill: slots that are never loaded (rows past the end of an utterance, unused segments) may hold
         // anything, NaN included; whatever is computed from them is never looked at.
         const uint32_t b0 = smem_u32(smem_pair + band3_off_bars((size_t)k.region));
-        for (int i = 0; i < B3_NBARS; ++i) mbar_init(b0 + 8u * i, (i >= B3_BAR_FULL && i < B3_BAR_FULL + B3_NST) ? B3_UPW : 1);
+        for (int i = 0; i < B3_NBARS; ++i) mbar_init(b0 + 8u * i, band3_bar_count(i));
         fence_mbar_init();
     }
     __syncthreads();
@@ -1651,7 +1662,7 @@ __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_direct_kernel(
     unsigned char* smem_pair = smem_raw + (size_t)pair * k.smem_per_warp;
     if (!idle && is_dp && lane == 0) {
         const uint32_t b0 = smem_u32(smem_pair + band3_off_bars((size_t)k.region));
-        for (int i = 0; i < B3_NBARS; ++i) mbar_init(b0 + 8u * i, (i >= B3_BAR_FULL && i < B3_BAR_FULL + B3_NST) ? B3_UPW : 1);
+        for (int i = 0; i < B3_NBARS; ++i) mbar_init(b0 + 8u * i, band3_bar_count(i));
         fence_mbar_init();
     }
     __syncthreads();

@@ -24,7 +24,10 @@ struct WideShared {
     int item;
 };
 
-__device__ __forceinline__ void vw_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+__device__ __forceinline__ void vw_bar(int nthreads) {
+    __syncwarp();
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
 
 // words per frame of a wide item's back-pointer slab: nw warps x 32 lanes x one 64-bit word (2 bits per state)
 __host__ __device__ inline long long vw_slab_words(int max_T, int max_L) {
