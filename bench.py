@@ -206,7 +206,7 @@ def reference_main(a):
         return 0
     steps, warmup = max(1, a.steps), max(0, a.warmup)
     # bounded samples: the Python reference aligns ~11 utterances of this shape per second and core
-    ref, ref_step = python_reference_arm(a, 1, min(steps, 6), min(warmup, 1))
+    ref, ref_step = python_reference_arm(a, 2, min(steps, 6), min(warmup, 1))
     n = a.cpu_sample or a.batch
     port, port_step = cpu_port_arm(a, n, min(steps, 8), min(warmup, 1))
     base, step_s = (ref, ref_step) if ref is not None else (port, port_step)
