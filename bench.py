@@ -536,6 +536,32 @@ def main():
             variants.append(run_variant(torch, lib, decv, dev, f"metric shape at C={Cv} (blank {Cv - 1}), one kernel per step", w, Cv, hinted(decv, True), peak))
             del lpv, w
             torch.cuda.empty_cache()
+        # both heads of one batch the way the shim enqueues them (core.py:900-922 aligns the phoneme head and the group head of every
+        # batch): prepared first, then the two alignment kernels next to each other in the stream, the second one pipelined
+        lp67, tg67, _ = synth.planted_batch(B, T, N, 67, seed=5067, device=dev)
+        lp17, tg17, _ = synth.planted_batch(B, T, N, 17, seed=5017, device=dev)
+        au67, au17 = bfa_b200.AlignmentUtils(blank_id=66, silence_id=0), bfa_b200.AlignmentUtils(blank_id=16, silence_id=0)
+        lens_t, nl_t = torch.full((B,), T), torch.full((B,), N)
+        h67 = au67.decode_alignments_prepare(lp67, tg67.cpu(), lens_t, nl_t)
+        h17 = au17.decode_alignments_prepare(lp17, tg17.cpu(), lens_t, nl_t)
+
+        def two_heads():
+            au67.decode_alignments_enqueue(h67)
+            au17.decode_alignments_enqueue(h17, after_sibling=True)
+        for _ in range(4):
+            two_heads()
+        torch.cuda.synchronize()
+        ms2 = time_steps(torch, two_heads, 10)
+        ok2 = int((h67["r"].status[:B] & 7 != 0).sum()) == 0 and int((h17["r"].status[:B] & 7 != 0).sum()) == 0
+        alg2 = algorithmic_bytes(Ts, Ns, 67) + algorithmic_bytes(Ts, Ns, 17)
+        variants.append({"name": "both heads of the metric shape per step (C=67 then C=17, prepared first, second kernel pipelined): what core.py:900-922 costs",
+                         "B": B, "C": [67, 17], "frames": B * T, "ms_per_step": ms2, "value": B * T / (ms2 / 1e3), "unit": "frames/s (utterance frames, both heads aligned)",
+                         "launches_per_step": 2.0, "all_finished": ok2,
+                         "roofline": {"algorithmic_bytes": alg2, "achieved": alg2 / (ms2 / 1e3) / 1e9, "frac": alg2 / (ms2 / 1e3) / 1e9 / peak, "unit": "GB/s",
+                                      "of": "both kernels, CUDA events around 10 steps"},
+                         "items": {"exact_kernel": 0, "window_24_40_64": [0, 0, 0]}})
+        del lp67, lp17, h67, h17
+        torch.cuda.empty_cache()
         # SIL at every 10th target (what punctuation does to real targets): silence anchoring really runs -- row statistics for the
         # silence scan (a second read of the rows), planner, segments through the list-mode banded kernel, stamp kernel
         lpv, tgv, _ = synth.planted_batch(B, T, N, Cc, seed=6001, peak=10.0, sil_every=10, sil_frames=15, device=dev)

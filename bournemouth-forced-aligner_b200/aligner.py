@@ -371,9 +371,9 @@ class AlignmentUtils:
             return [int(v) for v in x.tolist()]
         return [int(v) for v in x]
 
-    def _dense_launch(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf):
-        """Enqueue the alignment of a padded batch on the current stream and return without waiting for it: the first half of
-        decode_alignments.  Two heads (core.py:900-920) can be launched back to back before either result is looked at."""
+    def _dense_prepare(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf):
+        """Everything of a padded batch's alignment call that is not the call itself: lengths, flat targets, offsets and the batch
+        plan on the device (small torch ops on the current stream), and the choice of launch sequence."""
         _require_cuda(log_probs, "log_probs")
         lp = log_probs if (log_probs.dtype == torch.float32 and log_probs.is_contiguous()) else log_probs.contiguous().float()
         B, T_max, C_ = lp.shape
@@ -404,8 +404,25 @@ class AlignmentUtils:
         mask = torch.arange(S, device=dev)[None, :] < N_dev[:, None]
         tgt = seqs[mask].to(torch.int32).contiguous()
         row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T_max * C_)
-        r = self.viterbi_decoder.align_batch(lp, row_off, T, C_, tgt, N, params=params, want_stamps=True, want_conf=want_conf)
-        return dict(r=r, lp=lp, row_off=row_off, T=T, N=N, C=C_, tgt=tgt, params=params, want_conf=want_conf, B=B, T_max=T_max)
+        plan = self.viterbi_decoder.plan_batch(T, N, C_, params=params, device=dev)
+        return dict(r=None, lp=lp, row_off=row_off, T=T, N=N, C=C_, tgt=tgt, params=params, want_conf=want_conf, B=B, T_max=T_max, plan=plan)
+
+    def _dense_enqueue(self, h, after_sibling=False):
+        """Enqueue the prepared call (kernels only, no host synchronisation).  after_sibling: the operation before this one in the
+        stream is the alignment kernel of ANOTHER prepared call whose preparation was enqueued after this call's preparation (the
+        other head of the same batch, core.py:900-920): every input of this call was complete before that kernel was enqueued, so
+        a one-kernel call may start while it drains (BFA_FLAG_PIPELINED)."""
+        params = h["params"]
+        if after_sibling and (params.reserved & _cabi.FLAG_DIRECT_ONLY):
+            params.reserved |= _cabi.FLAG_PIPELINED
+        h["r"] = self.viterbi_decoder.align_batch(h["lp"], h["row_off"], h["T"], h["C"], h["tgt"], h["N"], params=params, want_stamps=True,
+                                                  want_conf=h["want_conf"], plan=h["plan"])
+        return h
+
+    def _dense_launch(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf):
+        """Enqueue the alignment of a padded batch on the current stream and return without waiting for it: the first half of
+        decode_alignments.  Two heads (core.py:900-920) can be launched back to back before either result is looked at."""
+        return self._dense_enqueue(self._dense_prepare(log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf))
 
     def _dense_finish(self, h):
         """Second half: wait for the statuses, repeat the call where the library asked for it, raise what the reference raises."""
@@ -444,6 +461,20 @@ class AlignmentUtils:
         h = self._dense_launch(log_probs, true_seqs, pred_lens, true_seqs_lens, p, with_confidence)
         h["with_confidence"] = with_confidence
         return h
+
+    def decode_alignments_prepare(self, log_probs, true_seqs, pred_lens=None, true_seqs_lens=None, boost_targets=True, enforce_minimum=True,
+                                  with_confidence=False):
+        """decode_alignments_launch without the launch: a handle for decode_alignments_enqueue.  Preparing both heads of a batch
+        first and enqueueing them afterwards puts the two alignment kernels next to each other in the stream."""
+        if (true_seqs is None) or (true_seqs_lens is None):
+            raise ValueError("Phoneme sequences and lengths required for forced alignment")  # :878-879
+        p = self.viterbi_decoder._params(boost_targets, enforce_minimum, self.silence_anchors > 0)
+        h = self._dense_prepare(log_probs, true_seqs, pred_lens, true_seqs_lens, p, with_confidence)
+        h["with_confidence"] = with_confidence
+        return h
+
+    def decode_alignments_enqueue(self, handle, after_sibling=False):
+        return self._dense_enqueue(handle, after_sibling)
 
     def decode_alignments_finish(self, handle):
         return self._dense_finish(handle).stamp_lists(with_conf=handle["with_confidence"])

@@ -117,9 +117,9 @@ class PhonemeTimestampAligner:
         self.stats.clear()
 
     # ---- the post-acoustic half of extract_timestamps_from_segment_batch --------------------------------------------------------
-    def _launch(self, utils, log_probs, seqs, seq_lens, spectral_lens):
-        return utils.decode_alignments_launch(log_probs, true_seqs=seqs, pred_lens=spectral_lens, true_seqs_lens=seq_lens,          # :902-922
-                                              boost_targets=self.boost_targets, enforce_minimum=self.enforce_minimum)
+    def _prepare(self, utils, log_probs, seqs, seq_lens, spectral_lens):
+        return utils.decode_alignments_prepare(log_probs, true_seqs=seqs, pred_lens=spectral_lens, true_seqs_lens=seq_lens,         # :902-922
+                                               boost_targets=self.boost_targets, enforce_minimum=self.enforce_minimum)
 
     def _finish(self, utils, handle, log_probs, seqs, seq_lens, spectral_lens, wav_lens, offsets, silence):
         frames = utils.decode_alignments_finish(handle)
@@ -143,8 +143,13 @@ class PhonemeTimestampAligner:
         (id, start_frame, end_frame, target_idx, is_estimated, confidence, start_ms, end_ms) per head.
         Both heads are enqueued on the device before the host waits for either (core.py:900-922 runs them one after the other)."""
         groups = log_probs_g is not None and grp_seqs is not None
-        hp = self._launch(self.alignment_utils_p, log_probs_p, ph_seqs, ph_seq_lens, spectral_lens)
-        hg = self._launch(self.alignment_utils_g, log_probs_g, grp_seqs, ph_seq_lens, spectral_lens) if groups else None
+        # both heads are prepared (targets, offsets, plans on the device) before either alignment is enqueued: the two alignment
+        # kernels sit next to each other in the stream and the second may start while the first drains
+        hp = self._prepare(self.alignment_utils_p, log_probs_p, ph_seqs, ph_seq_lens, spectral_lens)
+        hg = self._prepare(self.alignment_utils_g, log_probs_g, grp_seqs, ph_seq_lens, spectral_lens) if groups else None
+        self.alignment_utils_p.decode_alignments_enqueue(hp)
+        if groups:
+            self.alignment_utils_g.decode_alignments_enqueue(hg, after_sibling=True)
         ph = self._finish(self.alignment_utils_p, hp, log_probs_p, ph_seqs, ph_seq_lens, spectral_lens, wav_lens, start_offset_times,
                           self.silence_class)
         gr = (self._finish(self.alignment_utils_g, hg, log_probs_g, grp_seqs, ph_seq_lens, spectral_lens, wav_lens, start_offset_times,
