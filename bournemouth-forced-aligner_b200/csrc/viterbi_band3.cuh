@@ -333,6 +333,12 @@ __device__ __noinline__ void band3_direct_plan(const Band3Args& a, int task, uns
     unsigned char* cls8 = smem_pair + band3_off_cls(R) + seg * B3_NMAX;
     float* kk = reinterpret_cast<float*>(smem_pair + band3_off_kk(R)) + seg * B3_KK2;
     const int u = task * B3_UPW + seg;
+#ifdef BFA_PHASE_PROF
+    long long pp_last = clock64();
+#define PP_T(i) do { const long long pp_now = clock64(); if (lane == 0) atomicAdd(&g_b3_phase[16 + (i)], (unsigned long long)(pp_now - pp_last)); pp_last = pp_now; } while (0)
+#else
+#define PP_T(i)
+#endif
     int state = B3_U_NONE;
     Item it;
     it.lp_off = 0; it.stat_off = 0; it.out_off = 0; it.out_lim = 0; it.seq_off = 0;
@@ -360,6 +366,7 @@ __device__ __noinline__ void band3_direct_plan(const Band3Args& a, int task, uns
         if (p.mode == BFA_MODE_FULL) it.flags |= (p.boost_targets ? ITEM_STATS : 0) | (p.enforce_minimum ? ITEM_FLOOR : 0);
         if (ok) state = B3_U_RUN;
     }
+    PP_T(10);
     // targets: byte-sized class table + the class weights of the fused log-sum-exp, exp(x + boost*[c in targets] - boost) =
     // 2^(x*log2e + kk[c]); every id must be a plain class, and none may be silence_id while silence anchoring is on
     if (boost) {
@@ -369,6 +376,7 @@ __device__ __noinline__ void band3_direct_plan(const Band3Args& a, int task, uns
         }
     }
     __syncwarp();
+    PP_T(11);
     bool tbad = false;
     if (state == B3_U_RUN) {
         const bool segmenting = p.mode == BFA_MODE_FULL && p.silence_anchors > 0 && p.silence_id >= 0;
@@ -396,6 +404,7 @@ __device__ __noinline__ void band3_direct_plan(const Band3Args& a, int task, uns
         }
     }
     const unsigned bm = __ballot_sync(FULL, tbad);
+    PP_T(12);
     if ((bm >> (seg * B3_LPU)) & 0xffu) state = B3_U_DEFER;
     if (l8 == 0) {
         it.T = state == B3_U_RUN ? T : 0;
@@ -403,6 +412,8 @@ __device__ __noinline__ void band3_direct_plan(const Band3Args& a, int task, uns
         ustate[seg] = state;
     }
     __syncwarp();
+    PP_T(13);
+#undef PP_T
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -833,6 +844,7 @@ __device__ void band3_dp(const Band3Args& a, const Band3Args::Class& kc, int fir
         const uint32_t pb = smem_u32(smem_pair + band3_off_bars(R)) + 8u * B3_BAR_PLAN;
         mbar_wait(pb, (phase >> B3_BAR_PLAN) & 1u);
         phase ^= 1u << B3_BAR_PLAN;
+        PH_T(3);
     }
     bool on;
     const Item* my_item = DIRECT ? band3_direct_item(smem_pair, R, lane, on) : band3_list_item(kc.items, first, n_valid, lane, on);
@@ -1660,6 +1672,7 @@ __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_direct_kernel(
     int pair;
     band3_roles(warp, npairs, is_dp, pair, idle);
     unsigned char* smem_pair = smem_raw + (size_t)pair * k.smem_per_warp;
+    const int n_tasks = (a.B + B3_UPW - 1) / B3_UPW;
     if (!idle && is_dp && lane == 0) {
         const uint32_t b0 = smem_u32(smem_pair + band3_off_bars((size_t)k.region));
         for (int i = 0; i < B3_NBARS; ++i) mbar_init(b0 + 8u * i, band3_bar_count(i));
@@ -1675,7 +1688,6 @@ __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_direct_kernel(
     float* pscr_lp = a.pscr_lp ? a.pscr_lp + slot * B3_UPW * a.tpitch : nullptr;
     unsigned char* pscr_gs = a.pscr_lp ? a.pscr_gs + slot * B3_UPW * a.tpitch : nullptr;
     uint32_t phase = 0;
-    const int n_tasks = (a.B + B3_UPW - 1) / B3_UPW;
     if (is_dp) {
         for (int q = blockIdx.x + gridDim.x * pair; q < n_tasks; q += gridDim.x * npairs)
             band3_dp<3, CT, EXACT, true>(a, k, q, B3_UPW, smem_pair, slab, phase, lane, pair, pscr_lp, pscr_gs);

@@ -23,12 +23,12 @@ for it in range(3):
     _cabi.lib().bfa_debug_ctas(cout, 1)
     fout = (C.c_ulonglong * 32)()
     _cabi.lib().bfa_debug_fin(fout, 1)
-names = ["setup", "slide", "barrier wait", "-", "frames", "loop end", "pre-walk", "rec wait", "walk", "pair sync", "finish", "flush+sync", "end sync"]
+names = ["setup", "slide", "barrier wait", "wait for the plan", "frames", "loop end", "pre-walk", "rec wait", "walk", "pair sync", "finish", "flush+sync", "end sync"]
 tot = sum(out[:14]); nw = (B + 3) // 4
 print(f"warps {nw}; cycles per warp-task {tot / nw:.0f} = {tot / nw / 1.965e3:.1f} us")
 for n, v in zip(names, out):
     print(f"{n:14s} {v / nw:10.0f} cyc/task  {100 * v / tot:5.1f}%")
-hn = ["wait for walk", "finish", "end sync", "-", "-", "fill: full wait", "fill: row stats", "fill: free wait+issue", "plan", "task+tables"]
+hn = ["wait for walk", "finish", "end sync", "-", "-", "fill: full wait", "fill: row stats", "fill: free wait+issue", "plan", "task+tables", "plan: metadata+rules", "plan: weight table", "plan: targets", "plan: items"]
 print("helper warp:")
 for n, v in zip(hn, out[16:30]):
     print(f"{n:14s} {v / nw:10.0f} cyc/task")
