@@ -1593,19 +1593,26 @@ __device__ void band3_run(const Band3Args& a, const Band3Args::Class& k, unsigne
     __syncthreads();
     uint32_t phase = 0;
     const int n_tasks = (n_items + B3_UPW - 1) / B3_UPW;
-    // static deal: slot q -> CTA q % ncta, pair (q / ncta) % npairs.  With one CTA per SM this spreads ceil(n_tasks / CTAs)
-    // tasks evenly over the SMs and over the four schedulers of each SM.
+    // static deal, round by round: a pair is slot (cta + ncta * pair) of n_slots; even rounds hand their tasks out in slot order,
+    // odd rounds in reverse (a snake): when the list is ordered by length -- a length-bucketing caller, handed out longest first --
+    // the slot that got the longest task of one round gets the shortest of the next, and every slot ends up with about the same
+    // number of frames.  With one CTA per SM consecutive slots are different SMs, so a round spreads evenly over the SMs.
+    const int n_slots = ncta * npairs, slot = cta + ncta * pair;
     if (idle) {
     } else if (is_dp) {
         uint32_t* slab = k.bp_scratch + (size_t)(blockIdx.x * npairs + pair) * k.bp_slab_words;
-        for (int q = cta + ncta * pair; q < n_tasks; q += ncta * npairs) {
+        for (int r = 0; r * n_slots < n_tasks; ++r) {
+            const int q = r * n_slots + ((r & 1) ? n_slots - 1 - slot : slot);
+            if (q >= n_tasks) continue;
             const int j = rev ? n_tasks - 1 - q : q;
             band3_dp<G, CT, EXACT, false>(a, k, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, slab, phase, lane, pair, nullptr, nullptr);
         }
     } else {
         const uint64_t pol = policy_evict_first();
         bool not_first = false;
-        for (int q = cta + ncta * pair; q < n_tasks; q += ncta * npairs) {
+        for (int r = 0; r * n_slots < n_tasks; ++r) {
+            const int q = r * n_slots + ((r & 1) ? n_slots - 1 - slot : slot);
+            if (q >= n_tasks) continue;
             const int j = rev ? n_tasks - 1 - q : q;
             band3_helper<G, CT, false>(a, k, j * B3_UPW, min(B3_UPW, n_items - j * B3_UPW), smem_pair, phase, not_first, lane, pol, pair, nullptr, nullptr);
             not_first = true;
@@ -1627,14 +1634,16 @@ __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_kernel(Band3Ar
     pdl_wait();                               // the planner's item lists
     // One class in the batch (the usual case): every CTA works on it.  Several: the classes run SIDE BY SIDE, each on a share of
     // the CTAs proportional to its work (frames x cost of a chunk at that window width / pairs an SM holds at that width) --
-    // run one after the other each class costs about one longest task, however few tasks it has.  Lists are handed out back to
-    // front then (a caller that orders utterances by length gets longest-first).
+    // run one after the other each class costs about one longest task, however few tasks it has.
     const int n0 = *a.cls[0].n_items, n1 = *a.cls[1].n_items, n2 = *a.cls[2].n_items;
     const int G_ = (int)gridDim.x, c_ = (int)blockIdx.x;
+    // every list is handed out from its longer end (a caller that orders utterances by length, either way, gets longest-first)
+    auto from_back = [](const Band3Args::Class& k, int n) { return n > 1 && k.items[0].T < k.items[n - 1].T; };
+    const bool r0 = from_back(a.cls[0], n0), r1 = from_back(a.cls[1], n1), r2 = from_back(a.cls[2], n2);
     if ((n0 > 0) + (n1 > 0) + (n2 > 0) <= 1 || G_ < 6) {
-        band3_run<3, CT, EXACT>(a, a.cls[0], smem_raw, warp, lane, c_, G_, true);
-        band3_run<5, CT, EXACT>(a, a.cls[1], smem_raw, warp, lane, c_, G_, true);
-        band3_run<8, CT, EXACT>(a, a.cls[2], smem_raw, warp, lane, c_, G_, false);
+        band3_run<3, CT, EXACT>(a, a.cls[0], smem_raw, warp, lane, c_, G_, r0);
+        band3_run<5, CT, EXACT>(a, a.cls[1], smem_raw, warp, lane, c_, G_, r1);
+        band3_run<8, CT, EXACT>(a, a.cls[2], smem_raw, warp, lane, c_, G_, r2);
         return;
     }
     const int np = (int)(blockDim.x >> 6);
@@ -1648,9 +1657,9 @@ __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_kernel(Band3Ar
     // make the shares add up: take from / give to the largest
     int* gl = (g0 >= g1 && g0 >= g2) ? &g0 : (g1 >= g2 ? &g1 : &g2);
     *gl += G_ - (g0 + g1 + g2);
-    if (c_ < g0) band3_run<3, CT, EXACT>(a, a.cls[0], smem_raw, warp, lane, c_, g0, true);
-    else if (c_ < g0 + g1) band3_run<5, CT, EXACT>(a, a.cls[1], smem_raw, warp, lane, c_ - g0, g1, true);
-    else band3_run<8, CT, EXACT>(a, a.cls[2], smem_raw, warp, lane, c_ - g0 - g1, g2, true);
+    if (c_ < g0) band3_run<3, CT, EXACT>(a, a.cls[0], smem_raw, warp, lane, c_, g0, r0);
+    else if (c_ < g0 + g1) band3_run<5, CT, EXACT>(a, a.cls[1], smem_raw, warp, lane, c_ - g0, g1, r1);
+    else band3_run<8, CT, EXACT>(a, a.cls[2], smem_raw, warp, lane, c_ - g0 - g1, g2, r2);
 }
 
 // Direct mode: ONE kernel per batch on the common path.  Task q = utterances 4q .. 4q+3, planned by the helper warp itself,
