@@ -472,6 +472,7 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     if (L.want_sil && shape->max_T > 0) {
         SilArgs sa;
         sa.p = *p; sa.B = B; sa.C = C; sa.nst = L.sil_nst;
+        sa.keep_in_l2 = (double)shape->total_frames * C * 4.0 < 48.0 * 1024 * 1024 ? 1 : 0;   // well inside the 126 MB L2
         sa.logp = logp; sa.row_off = (const long long*)row_off; sa.T = T; sa.tgt = tgt; sa.tgt_off = (const long long*)tgt_off;
         sa.frame_off = (const long long*)frame_off; sa.D = sild; sa.deferred = deferred; sa.n_deferred = counters + 13;
         sa.tmask = tmask; sa.units = (int2*)(ws + L.off_silunits); sa.n_units = counters + 14;

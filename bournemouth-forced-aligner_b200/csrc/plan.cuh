@@ -245,15 +245,30 @@ __device__ int plan_segmented(const UttCtx& c, Item* loc, int32_t* lists, uint32
     int32_t* segs = mt + 2 * a.gmax;           // [5*(2*gmax+2)]
     int32_t* sub = segs + 5 * (2 * a.gmax + 2);// [2*amax]
 
-    // Step 1: target SIL groups (:203-224)
+    // Step 1: target SIL groups (:203-224): maximal runs of silence_id in the target, 32 targets per step
     int ng = 0;
-    for (int i = 0; i < N;) {
-        if (c.seq[i] == p.silence_id) {
-            int s = i;
-            while (i < N && c.seq[i] == p.silence_id) ++i;
-            if (lane == 0) { grp[2 * ng] = s; grp[2 * ng + 1] = i; }
+    {
+        int in_run = 0, start = 0;
+        for (int base = 0; base < N; base += 32) {
+            const int i = base + lane;
+            const uint32_t bits = __ballot_sync(FULL, i < N && c.seq[i] == p.silence_id);
+            const uint32_t vmask = (N - base >= 32) ? FULL : ((1u << (N - base)) - 1u);
+            uint32_t trans = (bits ^ ((bits << 1) | (in_run ? 1u : 0u))) & vmask;
+            while (trans) {
+                const int pos = base + __ffs(trans) - 1;
+                trans &= trans - 1;
+                if (!in_run) { in_run = 1; start = pos; }
+                else {
+                    in_run = 0;
+                    if (lane == 0) { grp[2 * ng] = start; grp[2 * ng + 1] = pos; }
+                    ++ng;
+                }
+            }
+        }
+        if (in_run) {
+            if (lane == 0) { grp[2 * ng] = start; grp[2 * ng + 1] = N; }
             ++ng;
-        } else ++i;
+        }
     }
     if (ng == 0) return -1;                                                       // :293-295
     if (c.D) {

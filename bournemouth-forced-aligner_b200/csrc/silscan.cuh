@@ -28,6 +28,7 @@ constexpr int SS_PAD = 8;          // floats of slack per stage (lead-in of a mi
 struct SilArgs {
     BfaParams p;
     int B, C, nst;
+    int keep_in_l2;            // the batch fits in L2: leave the rows there for the banded kernel's read (no evict-first hint)
     const float* logp;
     const long long* row_off;
     const int32_t* T;
@@ -188,7 +189,10 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 1) silprob_kernel(const __grid_
                     const uint32_t bulk = last ? (bytes & ~15u) : ((bytes + 15u) & ~15u);
                     for (uint32_t w = bulk >> 2; w < (bytes >> 2); ++w) d[w] = s[w];   // < 4 tail floats of the last copy
                     mbar_expect_tx(bar, bulk);
-                    if (bulk) bulk_g2s_hint(smem_u32(d), s, bulk, bar, pol);
+                    if (bulk) {
+                        if (a.keep_in_l2) bulk_g2s(smem_u32(d), s, bulk, bar);
+                        else bulk_g2s_hint(smem_u32(d), s, bulk, bar, pol);
+                    }
                 }
             };
             for (int b = 0; b < nst && b < nblk; ++b) issue(b);

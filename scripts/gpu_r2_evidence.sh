@@ -24,4 +24,5 @@ if [ -f bournemouth-forced-aligner_b200/lib/libbfa_b200_prof.so ]; then
 BFA_B200_LIB=$PWD/bournemouth-forced-aligner_b200/lib/libbfa_b200_prof.so timeout 300 python scripts/phase_prof.py 4096 > gpurun_out/phase.log 2>&1
 head -20 gpurun_out/phase.log
 fi
-bash scripts/gpu_sanitize.sh 2>&1 | tail -30
+bash scripts/gpu_sanitize.sh 2>&1 | tail -12
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
