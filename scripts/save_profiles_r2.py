@@ -27,7 +27,7 @@ def ncu(rep, page, *extra):
 for src, dst in [("bench_full.log", "bench.json"), ("bench_ref.log", "bench_reference_arm.json")]:
     l = last_json(g / src)
     if l: (out / f"{tag}_{dst}").write_text(l + "\n")
-for n in (2, 8):
+for n in (2, 4, 8):
     for src, dst in [(f"bench_n{n}.log", f"bench_n{n}.json"), (f"corpus_n{n}.log", f"corpus_n{n}.json")]:
         if (g / src).exists():
             l = last_json(g / src)
