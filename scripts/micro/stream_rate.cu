@@ -54,17 +54,19 @@ int main(int argc, char** argv) {
     float* x; float* sink; cudaMalloc(&x, (size_t)B * T * C * 4); cudaMalloc(&sink, 4); cudaMemset(x, 0, (size_t)B * T * C * 4);
     cudaFuncSetAttribute(stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const int cfg[][2] = {{8, 3}, {8, 2}, {4, 6}, {12, 2}, {20, 1}, {24, 1}, {8, 1}, {4, 3}};
+    // third column: CTAs (fewer than 148: can a part of the SMs pull the whole HBM bandwidth?)
+    const int cfg[][3] = {{8, 3, 148}, {8, 2, 148}, {4, 6, 148}, {12, 2, 148}, {20, 1, 148}, {24, 1, 148}, {8, 1, 148}, {4, 3, 148},
+                          {8, 3, 111}, {8, 3, 74}, {8, 3, 37}, {8, 1, 74}, {8, 2, 74}};
     for (auto& c : cfg) {
-        const int rows = c[0], nst = c[1];
+        const int rows = c[0], nst = c[1], grid = c[2];
         const size_t smem = (size_t)WARPS * (((size_t)nst * UPW * rows * C * 4 + 64 + 127) / 128 * 128);
         if (smem > 227 * 1024 || T % rows) { printf("rows %d stages %d: skipped\n", rows, nst); continue; }
         float best = 1e9;
         for (int rep = 0; rep < 5; ++rep) {
-            cudaEventRecord(e0); stream<<<148, WARPS * 32, smem>>>(x, B, rows, nst, sink); cudaEventRecord(e1); cudaEventSynchronize(e1);
+            cudaEventRecord(e0); stream<<<grid, WARPS * 32, smem>>>(x, B, rows, nst, sink); cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
         }
-        printf("rows/chunk %2d stages %d (%5.1f KB in flight per SM): %.1f us  %.0f GB/s  %s\n", rows, nst, smem / 1024.0, best * 1e3, (double)B * T * C * 4 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+        printf("CTAs %3d rows/chunk %2d stages %d (%5.1f KB in flight per SM): %.1f us  %.0f GB/s  %s\n", grid, rows, nst, smem / 1024.0, best * 1e3, (double)B * T * C * 4 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
 }
