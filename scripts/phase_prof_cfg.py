@@ -3,9 +3,14 @@ import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bfa_b200
 from bfa_b200 import synth, _cabi
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 dev = torch.device("cuda:0")
-w = synth.baseline_config(n, C=66, device=dev)
+if len(sys.argv) > 1 and sys.argv[1] == "sil":      # the metric shape with silence_id at every 10th target (bench.py's variant)
+    lpv, tgv, _ = synth.planted_batch(4096, 600, 40, 66, seed=6001, peak=10.0, sil_every=10, sil_frames=15, device=dev)
+    w = dict(lp=lpv, row_off=torch.arange(4096, dtype=torch.int64, device=dev) * 600 * 66, Ts=[600] * 4096, Ns=[40] * 4096,
+             tgt=tgv.to(torch.int32).reshape(-1).contiguous())
+else:
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    w = synth.baseline_config(n, C=66, device=dev)
 dec = bfa_b200.AlignmentUtils(65, 0).viterbi_decoder
 p = dec._params(True, True, True)
 plan = dec.plan_batch(w["Ts"], w["Ns"], 66, params=p, device=dev)

@@ -6,7 +6,7 @@ import torch
 import bfa_b200
 from bfa_b200 import _cabi, synth
 
-B, T, N, Cc = 4096, 600, 40, int(sys.argv[1]) if len(sys.argv) > 1 else 66
+B, T, N, Cc = int(os.environ.get("QT_B", "4096")), 600, 40, int(sys.argv[1]) if len(sys.argv) > 1 else 66
 dev = torch.device("cuda:0")
 lib = _cabi.lib()
 lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=4242, device=dev)
@@ -22,7 +22,7 @@ Ts, Ns = [T] * B, [N] * B
 def run(p, n, profile):
     plan = dec.plan_batch(Ts, Ns, Cc, params=p, device=dev)
     out = None
-    for _ in range(200):
+    for _ in range(int(os.environ.get("QT_WARM", "200"))):
         out = dec.align_batch(lp, row_off, Ts, Cc, tgt32, Ns, params=p, want_stamps=True, want_conf=True, plan=plan, out=out)
     torch.cuda.synchronize()
     if profile:
