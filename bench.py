@@ -51,9 +51,11 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU baseline sample (0 = auto)")
     ap.add_argument("--chain", action="store_true", help="A/B: always launch the full planner chain (no BFA_FLAG_DIRECT_ONLY)")
     ap.add_argument("--no-pipeline", action="store_true", help="A/B: no BFA_FLAG_PIPELINED (launches do not overlap)")
-    ap.add_argument("--gather", default="root", choices=["root", "all", "nccl"],
-                    help="N>1: root = every rank streams its result arrays to rank 0 (copy-engine pushes, the final gather to one place); "
-                         "all = every rank pushes to every peer each step (stress variant); nccl = one all_gather per step")
+    ap.add_argument("--gather", default="peer", choices=["peer", "root", "all", "nccl"],
+                    help="N>1: peer = the alignment kernels write their result arrays straight into rank 0's memory (peer-mapped "
+                         "stores over NVLink: the gather to one place costs no extra step); root = every rank streams its result arrays "
+                         "to rank 0 with copy-engine pushes; all = every rank pushes to every peer each step (stress variant); "
+                         "nccl = one all_gather per step")
     ap.add_argument("--corpus", type=int, default=0, help="BASELINE config 5: align a corpus of this many utterances sharded over the ranks")
     return ap.parse_args()
 
@@ -317,12 +319,13 @@ def main():
     #      the alignment, no SM taken from the kernel that needs all of them, 1/(N-1) of the traffic of an all-gather.
     #      --gather all: every rank pushes to every peer each step (round 1's design, kept as a stress variant);
     #      --gather nccl: one NCCL all_gather per step.
-    n_slots = max(a.steps, 2) if (a.gather == "root" and world > 1) else 2
+    n_slots = max(a.steps, 2) if (a.gather in ("root", "peer") and world > 1) else 2
     result = [None] * n_slots
     pending = [None] * n_slots
     nstep = [0]
     gather_bufs = None
     pusher = None
+    peer = [None]
     gather_mode = a.gather if world > 1 else "none (1 GPU)"
 
     def step():
@@ -334,6 +337,22 @@ def main():
         if pending[i] is not None:     # the gather that still reads this result set
             pending[i].wait()
             pending[i] = None
+        if world > 1 and gather_mode == "peer":
+            # the result arrays of slot i live in rank 0's memory: this rank's kernels store them there directly
+            if peer[0] is None:
+                try:
+                    from bfa_b200.aligner import result_arena_words
+                    from bfa_b200.sharding import PeerArena
+                    peer[0] = PeerArena(result_arena_words(B, bplan.max_stamps, True, True)["total"], dev, buffers=n_slots, dst=0)
+                except Exception as e:   # noqa: BLE001
+                    gather_mode = "root"
+                    if rank == 0:
+                        print(f"# peer-mapped result arrays unavailable ({e}); using copy-engine pushes", file=sys.stderr)
+            if peer[0] is not None:
+                r = dec.align_batch(lp, row_off, Ts, Cc, tgt32, Ns, params=params, want_stamps=True, want_conf=True, plan=bplan, out=result[i],
+                                    arena=peer[0].arena(i) if result[i] is None else None)
+                result[i] = r
+                return r
         r = dec.align_batch(lp, row_off, Ts, Cc, tgt32, Ns, params=params, want_stamps=True, want_conf=True, plan=bplan, out=result[i])
         result[i] = r
         if world > 1:
@@ -352,6 +371,18 @@ def main():
                     gather_bufs = [torch.empty(world * r.arena.numel(), dtype=r.arena.dtype, device=dev) for _ in range(n_slots)]
                 pending[i] = dist.all_gather_into_tensor(gather_bufs[i], r.arena, async_op=True)
         return r
+
+    def local_checksum(r):
+        # what this rank computed, summed on this rank.  With peer-mapped arenas r.arena IS rank 0's memory, so the reference sum
+        # comes from one more (untimed) alignment of the same batch into a zero-initialised local arena (the receive buffer
+        # starts zeroed too, and the kernels leave unused stamp slots untouched)
+        if peer[0] is None:
+            return r.arena.to(torch.int64).sum().reshape(1)
+        from bfa_b200.aligner import result_arena_words
+        loc = dec.align_batch(lp, row_off, Ts, Cc, tgt32, Ns, params=params, want_stamps=True, want_conf=True, plan=bplan,
+                              arena=torch.zeros(result_arena_words(B, bplan.max_stamps, True, True)["total"], dtype=torch.int32, device=dev))
+        torch.cuda.synchronize()
+        return loc.arena.to(torch.int64).sum().reshape(1)      # every step aligns the same batch: the same arrays, computed into LOCAL memory
 
     def drain():
         for i in range(n_slots):
@@ -382,16 +413,17 @@ def main():
         n_pre += 16
         drain()
         torch.cuda.synchronize()
-    if world > 1 and pusher is not None:
-        # untimed check of the push gather: what landed in the receive buffer is what the ranks computed
+    if world > 1 and (pusher is not None or peer[0] is not None):
+        # untimed check of the gather: what landed in the receive buffer is what the ranks computed
         barrier()
         i_last = (nstep[0] - 1) % n_slots
-        mine = result[i_last].arena.to(torch.int64).sum().reshape(1)
+        mine = local_checksum(result[i_last])
         sums = torch.empty(world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(sums, mine)
         if gather_mode == "all" or rank == 0:
-            got = pusher.recv[i_last].view(world, -1).to(torch.int64).sum(1)
-            assert bool((got == sums).all()), "push gather: receive buffer does not match the ranks' results"
+            got = (pusher or peer[0]).recv[i_last].view(world, -1).to(torch.int64).sum(1)
+            assert bool((got == sums).all()), "gather: receive buffer does not match the ranks' results"
+        barrier()
     assert int((r.status[:B] & 7 != 0).sum()) == 0, "unexpected non-OK status on the synthetic workload"
 
     l0 = lib.bfa_launch_count()
@@ -432,16 +464,17 @@ def main():
         ms = float(t.item())
     value = world * B * T * a.steps / (ms / 1e3)
     gather_check = None
-    if world > 1 and pusher is not None and gather_mode == "root":
+    if world > 1 and (pusher is not None or peer[0] is not None) and gather_mode in ("root", "peer"):
         # rank 0 now holds the timestamp arrays of every rank and every timed step: verify one (untimed)
         k = a.steps - 1
-        mine = result[k % n_slots].arena.to(torch.int64).sum().reshape(1)
+        mine = local_checksum(result[k % n_slots])
         sums = torch.empty(world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(sums, mine)
         if rank == 0:
-            got = pusher.recv[k % n_slots].view(world, -1).to(torch.int64).sum(1)
+            got = (pusher or peer[0]).recv[k % n_slots].view(world, -1).to(torch.int64).sum(1)
             gather_check = bool((got == sums).all())
             assert gather_check, "final gather: rank 0 does not hold the ranks' results of the last step"
+        barrier()
 
     # ---- the same K steps once more (nothing differs when the step is one kernel; with the chain this run carries no per-kernel
     #      events).  Reported beside the contract's numbers, not instead of them.
@@ -654,6 +687,9 @@ def main():
 
     if rank == 0:
         gather_txt = {"none (1 GPU)": "none (1 GPU)",
+                      "peer": "the alignment kernels of every rank store their packed result arrays of every step straight into rank 0's memory "
+                              "(peer-mapped stores over NVLink inside the kernel, torch symmetric memory, sharding.PeerArena(dst=0)): no copy, no side "
+                              "stream, nothing between two launches; complete when the last kernel is, verified after the timed region",
                       "root": "every rank streams its packed result arrays of every step to rank 0 (copy-engine P2P writes over NVLink on a side stream, "
                               "sharding.PushGather(dst=0)); completed inside and verified after the timed region",
                       "all": "every rank pushes its packed result arrays to ALL peers each step (stress variant)",
@@ -715,11 +751,20 @@ def corpus_main(a, world, rank, local, dev, lib):
     r0 = dec.align_batch(pool[0][0], row_off, Ts, Cc, pool[0][1], Ns, params=params, plan=plan)
     words = r0.arena.numel()
     pusher = None
+    peer = None
     if world > 1:
-        from bfa_b200.sharding import PushGather
-        pusher = PushGather(words, dev, buffers=n_chunks_max, dst=0)
-    for c in range(n_chunks):               # result sets allocated up front (the local copy of this rank's timestamp arrays)
-        results[c] = dec.align_batch(pool[c % POOL][0], row_off, Ts, Cc, pool[c % POOL][1], Ns, params=params, plan=plan)
+        from bfa_b200.sharding import PeerArena, PushGather
+        if a.gather == "peer":
+            try:
+                peer = PeerArena(words, dev, buffers=n_chunks_max, dst=0)
+            except Exception as e:   # noqa: BLE001
+                if rank == 0:
+                    print(f"# peer-mapped result arrays unavailable ({e}); using copy-engine pushes", file=sys.stderr)
+        if peer is None:
+            pusher = PushGather(words, dev, buffers=n_chunks_max, dst=0)
+    for c in range(n_chunks):               # result sets allocated up front: local arenas (pushed) or this rank's slots in rank 0's memory
+        results[c] = dec.align_batch(pool[c % POOL][0], row_off, Ts, Cc, pool[c % POOL][1], Ns, params=params, plan=plan,
+                                     arena=peer.arena(c) if peer is not None else None)
     t_pre = time.perf_counter()
     while time.perf_counter() - t_pre < 0.4:   # clocks
         for k in range(8):
@@ -753,11 +798,17 @@ def corpus_main(a, world, rank, local, dev, lib):
     verified = None
     if world > 1:                           # rank 0 holds every rank's arrays: check the last chunk every rank has
         last = min(chunks_per_rank) - 1
-        mine_sum = results[last].arena.to(torch.int64).sum().reshape(1)
+        if peer is not None:                # the arena is rank 0's memory: the reference sum comes from the same chunk aligned into local memory
+            loc = dec.align_batch(pool[last % POOL][0], row_off, Ts, Cc, pool[last % POOL][1], Ns, params=params, plan=plan,
+                                  arena=torch.zeros(words, dtype=torch.int32, device=dev))
+            torch.cuda.synchronize()
+            mine_sum = loc.arena.to(torch.int64).sum().reshape(1)
+        else:
+            mine_sum = results[last].arena.to(torch.int64).sum().reshape(1)
         sums = torch.empty(world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(sums, mine_sum)
         if rank == 0:
-            got = pusher.recv[last].view(world, -1).to(torch.int64).sum(1)
+            got = (peer or pusher).recv[last].view(world, -1).to(torch.int64).sum(1)
             verified = bool((got == sums).all())
     if rank == 0:
         frames = n_total * T
@@ -767,8 +818,10 @@ def corpus_main(a, world, rank, local, dev, lib):
                "value": frames / (float(tt[2]) / 1e3), "unit": "frames/s", "value_device_timed": frames / ((float(tt[0]) + float(tt[1])) / 1e3),
                "gathered_bytes_on_rank0": int(words * 4 * sum(chunks_per_rank)) if world > 1 else 0,
                "statuses_ok": ok, "gather_verified": verified,
-               "how": "every rank aligns its contiguous share chunk by chunk (one kernel per chunk, pipelined launches) and streams each chunk's packed "
-                      "result arrays to rank 0 with copy-engine P2P writes; the only synchronisation is the barrier at the end",
+               "how": "every rank aligns its contiguous share chunk by chunk (one kernel per chunk, pipelined launches)"
+                      + (" and its kernels store each chunk's packed result arrays straight into rank 0's memory (peer-mapped stores over NVLink)"
+                         if peer is not None else " and streams each chunk's packed result arrays to rank 0 with copy-engine P2P writes")
+                      + "; the only synchronisation is the barrier at the end",
                "data": f"synthetic, {POOL} distinct chunks per rank generated on the device and cycled (the whole corpus would be {frames * Cc * 4 / 1e9:.0f} GB of posteriors); "
                        "utterances beyond the corpus size in the last chunk of a rank are aligned too (whole chunks)"}
         print(json.dumps(out))

@@ -196,10 +196,14 @@ class ViterbiDecoder:
 
     def align_batch(self, log_probs: torch.Tensor, row_off: torch.Tensor, T: Sequence[int], C_: int, tgt: torch.Tensor,
                     N: Sequence[int], *, params: BfaParams, want_stamps=True, want_conf=True, max_stamps=None,
-                    plan: Optional["BatchPlan"] = None, out: Optional[BatchResult] = None) -> BatchResult:
+                    plan: Optional["BatchPlan"] = None, out: Optional[BatchResult] = None,
+                    arena: Optional[torch.Tensor] = None) -> BatchResult:
         """Ragged batch through bfa_align_batch.  log_probs: flat/any-shape fp32 CUDA tensor holding the rows,
         row_off int64[B] element offsets (CUDA), T/N python sequences, tgt flat int32 CUDA targets.
-        `plan` (from plan_batch) skips the per-call metadata upload, `out` reuses a previous result's buffers."""
+        `plan` (from plan_batch) skips the per-call metadata upload, `out` reuses a previous result's buffers.
+        `arena`: caller-owned int32 storage for the packed per-utterance results (>= result_arena_words(..)["total"] words,
+        16-byte aligned) instead of a fresh allocation -- e.g. this rank's slice of ANOTHER GPU's symmetric-memory buffer
+        (sharding.PeerArena): the kernels then write the timestamp arrays straight into the gathering rank's memory."""
         _require_cuda(log_probs, "log_probs")
         dev = log_probs.device
         if log_probs.dtype != torch.float32 or not log_probs.is_contiguous():
@@ -214,7 +218,12 @@ class ViterbiDecoder:
             # so that the multi-GPU gather of the timestamp arrays is a single collective (sharding.gather_packed)
             Bp = max(B, 1)
             words = result_arena_words(Bp, ms, want_stamps, want_conf)
-            arena = torch.empty(words["total"], dtype=torch.int32, device=dev)
+            if arena is None:
+                arena = torch.empty(words["total"], dtype=torch.int32, device=dev)
+            else:
+                if arena.dtype != torch.int32 or arena.dim() != 1 or arena.numel() < words["total"] or not arena.is_cuda or arena.data_ptr() % 16:
+                    raise BfaError(f"arena must be a 16-byte aligned 1-D int32 CUDA tensor of >= {words['total']} words")
+                arena = arena[:words["total"]]
             dp_final = arena[words["dp_final"]:words["dp_final"] + Bp].view(torch.float32)
             status = arena[words["status"]:words["status"] + Bp]
             stamps = conf = n_stamps = None

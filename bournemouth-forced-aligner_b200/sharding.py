@@ -181,3 +181,45 @@ class PushGather:
         if self._done[i] is not None:
             torch.cuda.current_stream().wait_event(self._done[i])
             self._done[i] = None
+
+
+class PeerArena:
+    """The gather without a gather step: every rank's alignment kernels write their packed result arrays (stamps | conf |
+    n_stamps | status | dp_final, `align_batch(..., arena=...)`) STRAIGHT into the gathering rank's memory -- ordinary stores to a
+    peer-mapped address, carried by NVLink while the kernel computes.  No copy, no side stream, no event between two launches (so
+    back-to-back launches keep overlapping their ramp-up and tail), no SM taken from the aligner.
+
+        pa = PeerArena(n_words, device, buffers=K, dst=0)        # collective: one symmetric allocation, one rendezvous
+        r = align_batch(..., arena=pa.arena(i))                  # first call for buffer i; later: out=r
+        ... torch.cuda.synchronize(); barrier of the group ...   # every rank's kernels are done: their stores have landed
+        pa.recv[i].view(world, -1)[q]                            # on rank dst: rank q's arena of buffer i
+
+    The traffic is what the result arrays weigh (4 MB per 4096 utterances), written once.  Raises if symmetric memory is not
+    available (callers fall back to PushGather / gather_packed)."""
+
+    def __init__(self, n_words: int, device, group=None, buffers: int = 2, dst: int = 0):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.dst = dist.get_world_size(group), dist.get_rank(group), int(dst)
+        self.n = (int(n_words) + 3) // 4 * 4                      # 16-byte pitch: the kernels store timestamps 16 bytes at a time
+        sz = torch.tensor([self.n], dtype=torch.int64, device=device)
+        szs = sz.new_empty(self.world)
+        dist.all_gather_into_tensor(szs, sz, group=group)
+        if not bool((szs == self.n).all()):
+            raise ValueError(f"PeerArena: ranks have different arena sizes {szs.tolist()}; use one stamp pitch and one batch size "
+                             "(sharding.global_stamp_pitch)")
+        per = self.world * self.n
+        big = symm.empty(buffers * per, dtype=torch.int32, device=device)
+        hdl = symm.rendezvous(big, group)
+        big.zero_()                                               # unused stamp slots stay zero (checksums over whole arenas)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                       # nobody stores into rank dst's buffer before it is zeroed
+        self._big = big
+        self._at_dst = big if self.rank == self.dst else hdl.get_buffer(self.dst, (buffers * per,), torch.int32)
+        self.recv = [big[b * per:(b + 1) * per] for b in range(buffers)]     # meaningful on rank dst
+        self._per = per
+
+    def arena(self, i: int) -> torch.Tensor:
+        """This rank's slot of buffer i in rank dst's memory (a peer-mapped tensor on every rank but dst)."""
+        o = i * self._per + self.rank * self.n
+        return self._at_dst[o:o + self.n]

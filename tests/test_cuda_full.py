@@ -225,6 +225,35 @@ def test_pipelined_calls_back_to_back(bfa, orc, dev):
         assert torch.equal(r.stamps[:B, :N], ref[k][2]) and torch.equal(r.conf[:B, :N], ref[k][3]) and torch.equal(r.dp_final[:B], ref[k][4])
 
 
+def test_caller_owned_arena(bfa, dev):
+    """align_batch(arena=...): the packed per-utterance results go into storage the caller owns (the multi-GPU path hands in this
+    rank's slot of the gathering rank's symmetric-memory buffer, sharding.PeerArena).  Same results as a library-allocated arena,
+    nothing written outside the arena's words, bad arenas refused."""
+    from bfa_b200 import synth
+    from bfa_b200.aligner import result_arena_words, BfaError
+    Cc, B, T, N = 66, 300, 200, 16
+    lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=77, device=dev)
+    tg = tgt.to(torch.int32).reshape(-1).contiguous()
+    dec = bfa.AlignmentUtils(Cc - 1, 0).viterbi_decoder
+    row_off = torch.arange(B, dtype=torch.int64, device=dev) * T * Cc
+    p = dec._params(True, True, True)
+    ref = dec.align_batch(lp, row_off, [T] * B, Cc, tg, [N] * B, params=p)
+    words = result_arena_words(B, ref.max_stamps, True, True)["total"]
+    big = torch.full((words + 64,), 0x5a5a5a5a, dtype=torch.int32, device=dev)
+    r = dec.align_batch(lp, row_off, [T] * B, Cc, tg, [N] * B, params=p, arena=big[32:32 + words + 8])
+    torch.cuda.synchronize()
+    assert r.arena.data_ptr() == big[32:].data_ptr() and r.arena.numel() == words
+    assert (big[:32] == 0x5a5a5a5a).all() and (big[32 + words:] == 0x5a5a5a5a).all()
+    assert torch.equal(r.frame_ph, ref.frame_ph) and torch.equal(r.n_stamps[:B], ref.n_stamps[:B]) and torch.equal(r.status[:B], ref.status[:B])
+    assert torch.equal(r.stamps[:B, :N], ref.stamps[:B, :N]) and torch.equal(r.conf[:B, :N], ref.conf[:B, :N])
+    assert torch.equal(r.dp_final[:B], ref.dp_final[:B])
+    r2 = dec.align_batch(lp, row_off, [T] * B, Cc, tg, [N] * B, params=p, out=r)      # reuse keeps writing into the caller's storage
+    assert r2.arena.data_ptr() == big[32:].data_ptr()
+    for bad in (big[33:33 + words], big[32:32 + words - 4], big[32:32 + words].to(torch.int64), torch.zeros(words, dtype=torch.int32)):
+        with pytest.raises(BfaError):
+            dec.align_batch(lp, row_off, [T] * B, Cc, tg, [N] * B, params=p, arena=bad)
+
+
 # ---- near-ties: how often does the fused log-softmax flip a back-trace decision? -------------------------------
 @pytest.mark.parametrize("Cc,sil", [(66, 0), (67, 0), (17, 0), (67, 9)])
 def test_flip_rate_at_low_peaks(bfa, orc, dev, Cc, sil):
