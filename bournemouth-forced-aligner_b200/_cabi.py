@@ -53,6 +53,7 @@ _SIGNATURES = {
     "bfa_default_params": (None, [C.POINTER(BfaParams), C.c_int32, C.c_int32]),
     "bfa_workspace_bytes": (C.c_size_t, [C.POINTER(BfaParams), C.POINTER(BfaShape)]),
     "bfa_align_batch": (C.c_int, [C.POINTER(BfaParams), C.POINTER(BfaShape)] + [_P] * 13 + [_P, C.c_size_t, _P]),
+    "bfa_align_batch_logits": (C.c_int, [C.POINTER(BfaParams), C.POINTER(BfaShape)] + [_P] * 14 + [_P, C.c_size_t, _P]),
     "bfa_viterbi_paths_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "bfa_viterbi_paths": (C.c_int, [C.POINTER(BfaParams), C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [_P] * 13
                           + [_P, C.c_size_t, _P]),

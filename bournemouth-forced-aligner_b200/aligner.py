@@ -76,6 +76,7 @@ class BatchResult:
         self.stamps, self.conf, self.n_stamps = stamps, conf, n_stamps
         self.T, self.max_stamps = T, max_stamps
         self.arena = None   # the single allocation behind stamps/conf/n_stamps/status/dp_final (align_batch), or None
+        self.row_lse = None  # align_batch(logits=True): float32[total_frames] log-sum-exp of the rows (see bfa_align_batch_logits)
 
     def stamp_lists(self, with_conf: bool = False) -> List[List[tuple]]:
         """list[B] of list[(phoneme, start, end_exclusive, target_idx[, conf])] -- forced_alignment.py:871-872."""
@@ -197,13 +198,16 @@ class ViterbiDecoder:
     def align_batch(self, log_probs: torch.Tensor, row_off: torch.Tensor, T: Sequence[int], C_: int, tgt: torch.Tensor,
                     N: Sequence[int], *, params: BfaParams, want_stamps=True, want_conf=True, max_stamps=None,
                     plan: Optional["BatchPlan"] = None, out: Optional[BatchResult] = None,
-                    arena: Optional[torch.Tensor] = None) -> BatchResult:
+                    arena: Optional[torch.Tensor] = None, logits: bool = False) -> BatchResult:
         """Ragged batch through bfa_align_batch.  log_probs: flat/any-shape fp32 CUDA tensor holding the rows,
         row_off int64[B] element offsets (CUDA), T/N python sequences, tgt flat int32 CUDA targets.
         `plan` (from plan_batch) skips the per-call metadata upload, `out` reuses a previous result's buffers.
         `arena`: caller-owned int32 storage for the packed per-utterance results (>= result_arena_words(..)["total"] words,
         16-byte aligned) instead of a fresh allocation -- e.g. this rank's slice of ANOTHER GPU's symmetric-memory buffer
-        (sharding.PeerArena): the kernels then write the timestamp arrays straight into the gathering rank's memory."""
+        (sharding.PeerArena): the kernels then write the timestamp arrays straight into the gathering rank's memory.
+        `logits=True`: the rows hold the acoustic model's UN-NORMALISED logits (core.py:898-899 skipped); one kernel aligns them
+        and leaves `result.row_lse` (float32[total_frames], log-sum-exp of every row of the utterances it finished) behind;
+        utterances it cannot finish come back with status ST_DEFERRED (bfa_align_batch_logits; full mode with boosting only)."""
         _require_cuda(log_probs, "log_probs")
         dev = log_probs.device
         if log_probs.dtype != torch.float32 or not log_probs.is_contiguous():
@@ -234,6 +238,8 @@ class ViterbiDecoder:
                     conf = arena[words["conf"]:words["conf"] + Bp * ms].view(torch.float32).view(Bp, ms)
             out = BatchResult(frame_ph, frame_idx, plan.frame_off, dp_final, status, stamps, conf, n_stamps, plan.T_np, ms)
             out.arena = arena
+        if logits and getattr(out, "row_lse", None) is None:
+            out.row_lse = torch.zeros(max(total, 1), dtype=torch.float32, device=dev)
         l = _cabi.lib()
         with torch.cuda.device(dev):
             if plan.ws_bytes is None:
@@ -241,10 +247,16 @@ class ViterbiDecoder:
                 if plan.ws_bytes == 0 and B > 0:
                     _cabi.check(_cabi.BFA_E_UNSUPPORTED)
             ws = self._ws.get(max(plan.ws_bytes, 256), dev)
-            rc = l.bfa_align_batch(C.byref(params), C.byref(plan.shape), _ptr(log_probs), _ptr(row_off), _ptr(plan.T_dev), _ptr(tgt),
-                                   _ptr(plan.tgt_off), _ptr(out.frame_ph), _ptr(out.frame_idx), _ptr(plan.frame_off), _ptr(out.dp_final),
-                                   _ptr(out.status), _ptr(out.stamps), _ptr(out.conf), _ptr(out.n_stamps), _ptr(ws), ws.numel(),
-                                   _stream(dev))
+            if logits:
+                rc = l.bfa_align_batch_logits(C.byref(params), C.byref(plan.shape), _ptr(log_probs), _ptr(row_off), _ptr(plan.T_dev), _ptr(tgt),
+                                              _ptr(plan.tgt_off), _ptr(out.frame_ph), _ptr(out.frame_idx), _ptr(plan.frame_off),
+                                              _ptr(out.dp_final), _ptr(out.status), _ptr(out.stamps), _ptr(out.conf), _ptr(out.n_stamps),
+                                              _ptr(out.row_lse), _ptr(ws), ws.numel(), _stream(dev))
+            else:
+                rc = l.bfa_align_batch(C.byref(params), C.byref(plan.shape), _ptr(log_probs), _ptr(row_off), _ptr(plan.T_dev), _ptr(tgt),
+                                       _ptr(plan.tgt_off), _ptr(out.frame_ph), _ptr(out.frame_idx), _ptr(plan.frame_off), _ptr(out.dp_final),
+                                       _ptr(out.status), _ptr(out.stamps), _ptr(out.conf), _ptr(out.n_stamps), _ptr(ws), ws.numel(),
+                                       _stream(dev))
         _cabi.check(rc)
         return out
 

@@ -92,6 +92,10 @@ cudaError_t band_set_attr(int bytes) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<66, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<66, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<67, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<17, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(viterbi_band3_direct_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     return e;
 }
 constexpr int BAND_SMEM_MAX = 227 * 1024;   // dynamic shared memory one CTA may opt in to on sm_100
@@ -118,8 +122,15 @@ cudaError_t launch_maybe_pdl(void (*k)(A), int grid, int block, size_t smem, cud
 }
 // The direct kernel (one launch per batch on the common path).  At least half of an SM's shared memory is requested so that two
 // CTAs of it can never share an SM: its scratch is indexed by the physical SM.
-void direct_launch(const Band3Args& ba, bool exact, int grid, cudaStream_t st, bool pdl) {
+void direct_launch(const Band3Args& ba, bool exact, int grid, cudaStream_t st, bool pdl, bool logits = false) {
     const size_t smem = std::max((size_t)ba.cls[0].npairs * ba.cls[0].smem_per_warp, (size_t)116 * 1024);
+    if (logits) {       // un-normalised logits in (boosting on, hence never `exact`): the reduction also carries the rows' plain log-sum-exp
+        if (ba.C == 66) launch_maybe_pdl(viterbi_band3_direct_kernel<66, false, true>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
+        else if (ba.C == 67) launch_maybe_pdl(viterbi_band3_direct_kernel<67, false, true>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
+        else if (ba.C == 17) launch_maybe_pdl(viterbi_band3_direct_kernel<17, false, true>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
+        else launch_maybe_pdl(viterbi_band3_direct_kernel<0, false, true>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
+        return;
+    }
     if (exact) launch_maybe_pdl(viterbi_band3_direct_kernel<0, true>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
     else if (ba.C == 66) launch_maybe_pdl(viterbi_band3_direct_kernel<66, false>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
     else if (ba.C == 67) launch_maybe_pdl(viterbi_band3_direct_kernel<67, false>, grid, BAND_WARPS * 64, smem, st, ba, pdl);
@@ -391,10 +402,33 @@ size_t bfa_workspace_bytes(const BfaParams* p, const BfaShape* shape) {
     return L.total;
 }
 
+static int align_impl(const BfaParams* p, const BfaShape* shape, const float* logp, const int64_t* row_off, const int32_t* T,
+                      const int32_t* tgt, const int64_t* tgt_off, int32_t* frame_ph, int32_t* frame_idx,
+                      const int64_t* frame_off, float* dp_final, int32_t* status, BfaStamp* stamps, float* conf,
+                      int32_t* n_stamps, float* row_lse, void* workspace, size_t workspace_bytes, void* stream);
+
 int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp, const int64_t* row_off, const int32_t* T,
                     const int32_t* tgt, const int64_t* tgt_off, int32_t* frame_ph, int32_t* frame_idx,
                     const int64_t* frame_off, float* dp_final, int32_t* status, BfaStamp* stamps, float* conf,
                     int32_t* n_stamps, void* workspace, size_t workspace_bytes, void* stream) {
+    return align_impl(p, shape, logp, row_off, T, tgt, tgt_off, frame_ph, frame_idx, frame_off, dp_final, status, stamps, conf, n_stamps,
+                      nullptr, workspace, workspace_bytes, stream);
+}
+
+int bfa_align_batch_logits(const BfaParams* p, const BfaShape* shape, const float* logits, const int64_t* row_off, const int32_t* T,
+                           const int32_t* tgt, const int64_t* tgt_off, int32_t* frame_ph, int32_t* frame_idx,
+                           const int64_t* frame_off, float* dp_final, int32_t* status, BfaStamp* stamps, float* conf,
+                           int32_t* n_stamps, float* row_lse, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!row_lse || !p) return BFA_E_INVALID;
+    if (p->mode != BFA_MODE_FULL || !p->boost_targets) return BFA_E_UNSUPPORTED;   // without boosting nothing re-normalises the rows
+    return align_impl(p, shape, logits, row_off, T, tgt, tgt_off, frame_ph, frame_idx, frame_off, dp_final, status, stamps, conf, n_stamps,
+                      row_lse, workspace, workspace_bytes, stream);
+}
+
+static int align_impl(const BfaParams* p, const BfaShape* shape, const float* logp, const int64_t* row_off, const int32_t* T,
+                      const int32_t* tgt, const int64_t* tgt_off, int32_t* frame_ph, int32_t* frame_idx,
+                      const int64_t* frame_off, float* dp_final, int32_t* status, BfaStamp* stamps, float* conf,
+                      int32_t* n_stamps, float* row_lse, void* workspace, size_t workspace_bytes, void* stream) {
     if (!p || !shape || !logp || !row_off || !T || !tgt_off || !frame_ph || !frame_idx || !frame_off || !status) return BFA_E_INVALID;
     if ((stamps == nullptr) != (n_stamps == nullptr)) return BFA_E_INVALID;
     if (p->blank_id < 0 || p->blank_id >= shape->C) return BFA_E_INVALID;
@@ -427,7 +461,9 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
     // confidences); the planner chain below then only sees what it handed back (device-side list).  With BFA_FLAG_DIRECT_ONLY the
     // chain is not launched at all and such utterances are flagged instead.
     const bool use_direct = L.direct && fast;
-    const bool direct_only = use_direct && (p->reserved & BFA_FLAG_DIRECT_ONLY) != 0;
+    const bool logits = row_lse != nullptr;          // bfa_align_batch_logits: the one-kernel pass only, whatever it cannot finish is flagged
+    if (logits && !use_direct) return BFA_E_UNSUPPORTED;
+    const bool direct_only = use_direct && ((p->reserved & BFA_FLAG_DIRECT_ONLY) != 0 || logits);
     int* deferred = use_direct && !direct_only ? (int*)(ws + L.off_deferred) : nullptr;
     int32_t* uflag = use_direct && !direct_only ? (int32_t*)(ws + L.off_uflag) : nullptr;
     if (!direct_only) CUDA_TRY(cudaMemsetAsync(counters, 0, 64, st));
@@ -450,13 +486,14 @@ int bfa_align_batch(const BfaParams* p, const BfaShape* shape, const float* logp
         da.pscr_lp = spec ? (float*)(ws + L.off_pscr_lp) : nullptr;
         da.pscr_gs = spec ? (unsigned char*)(ws + L.off_pscr_gs) : nullptr;
         da.tpitch = L.d_tpitch; da.ncap = L.d_ncap; da.nslots = d.nsmid; da.direct_only = direct_only ? 1 : 0;
+        da.row_lse = row_lse;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         {
             std::lock_guard<std::mutex> lk(g_prof.mu);
             if (g_prof.on && (g_prof.calls++ % (unsigned)g_prof.every) == 0) { e0 = g_prof.get(); e1 = g_prof.get(); }
         }
         if (e0) cudaEventRecord(e0, st);
-        direct_launch(da, !boost, d.sms, st, direct_only && (p->reserved & BFA_FLAG_PIPELINED) != 0);
+        direct_launch(da, !boost, d.sms, st, direct_only && (p->reserved & BFA_FLAG_PIPELINED) != 0, logits);
         LAUNCH_CHECK();
         if (e0) {
             cudaEventRecord(e1, st);

@@ -125,6 +125,7 @@ struct Band3Args {
     int ncap;                  // phonemes per utterance the shared event / stamp arrays hold (>= max_N of the batch)
     int nslots;                // SM slots the per-SM scratch and slabs were sized for (> every %smid)
     int direct_only;           // no planner chain follows: utterances that do not qualify get status BFA_ST_DEFERRED
+    float* row_lse;            // logits mode (LOGITS instantiations): [total_frames] log(sum(exp(row))) of every row of the utterances run here
 };
 
 template <int G>
@@ -218,6 +219,11 @@ __device__ __forceinline__ unsigned long long b3_add2(unsigned long long a, unsi
 __device__ __forceinline__ unsigned long long b3_fma2(unsigned long long a, float s, unsigned long long c) {   // a * (s, s) + c
     unsigned long long r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b3_pack2(s, s)), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long b3_fma2v(unsigned long long a, unsigned long long b, unsigned long long c) {   // a * b + c, lane by lane
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -431,10 +437,15 @@ __device__ __forceinline__ void band3_pair_sync(uint32_t bar0, uint32_t& phase, 
     __syncwarp();
 }
 
-template <int CT>
+template <int CT, bool LOGITS>
 __device__ __noinline__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair, size_t R, int seg0, int which, int lane, bool have_spec);
 
-template <int G, int CT, bool DIRECT>
+// LOGITS (direct mode only): the rows hold un-normalised logits.  Boosting re-normalises every row (:51-54), so emissions, path,
+// timestamps and DP score are the same whatever constant a row is shifted by; only the confidences (utils.py:81, exp of the
+// ORIGINAL log-probabilities) need the row's own log-sum-exp.  The reduction carries it along: with e_c = 2^(x_c log2e + kk_c) the
+// boosted sum is sum(e_c) and the plain one sum(e_c * 2^(-kk_c)), and 2^(-kk_c) is 1 for a target class and exp(boost) otherwise,
+// i.e. 1 + kk_c * MSC -- two more packed FMAs per pair of classes.  It is written out per frame (Band3Args::row_lse).
+template <int G, int CT, bool DIRECT, bool LOGITS = false>
 __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int first, int n_valid, unsigned char* smem_pair, uint32_t& phase, bool not_first,
                              int lane, uint64_t pol, int pair, float* pscr_lp, unsigned char* pscr_gs) {
     constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
@@ -453,6 +464,9 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
     const int blank = a.p.blank_id;
     const float boostv = a.p.boost_factor;
     const bool warp_stats = k.warp_stats;
+    static_assert(!LOGITS || DIRECT, "logits are taken by the direct kernel only");
+    const float MSC = (LOGITS && boostv != 0.0f) ? (1.0f - expf(boostv)) / (boostv * LOG2E) : 0.0f;   // 2^(-kk) = 1 + kk * MSC for kk in {0, -boost log2e}
+    const unsigned long long ONE2 = b3_pack2(1.0f, 1.0f);
 
     // ---- per-utterance tables (built before the first bulk copies are issued: behind them these small loads would queue
     //      for microseconds): target classes (bytes) and the class weights of the fused log-sum-exp:
@@ -539,17 +553,21 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
             const float* rowp = k.stage_buf + st * k.stage_floats + seg * k.seg_stride + k.lead + l8 * C;
             const int t_row = c * B3_ROWS + l8;
             float lnS = 0.f;
+            float lnS0 = 0.f;                        // logits mode: log-sum-exp of the raw row
             if (warp_stats) {
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;      // logits mode: the plain sums
                 float best = -INFINITY;                  // running max of the boosted values, class index in the low 7 mantissa bits
                 // the mask must live in a register for (v & mask) | class to be ONE three-input logic op (the class is the
                 // immediate); deriving it from a run-time value keeps ptxas from folding it back into a second immediate
                 const uint32_t tagmask = 0xffffff80u | ((uint32_t)a.C >> 16);
                 auto tag = [&](float v, int c) { return __uint_as_float((__float_as_uint(v) & tagmask) | (uint32_t)c); };
                 const float* kp = k.kk + seg * B3_KK2;
-                auto term = [&](float x, float kc, int c, float& acc) {
+                auto term = [&](float x, float kc, int c, float& acc, float& zacc) {
                     const float v = fmaf(x, LOG2E, kc);
-                    acc += b3_ex2(v);
+                    const float e = b3_ex2(v);
+                    acc += e;
+                    if constexpr (LOGITS) zacc = fmaf(e, fmaf(kc, MSC, 1.0f), zacc);
                     best = fmaxf(best, tag(v, c));
                 };
                 if (CT != 0 && (CT & 1) == 1) {
@@ -563,28 +581,33 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
                     const unsigned long long* x64 = reinterpret_cast<const unsigned long long*>(rowp + odd);
                     const float* kq = odd ? kp + B3_KK + B3_KSH + 1 : kp;                  // weights of the first paired class, 16-byte aligned
                     const ulonglong2* k128 = reinterpret_cast<const ulonglong2*>(kq);
-                    unsigned long long sA = 0ull, sB = 0ull;
-                    auto pair_term = [&](unsigned long long x, unsigned long long kc, int c, unsigned long long& acc2) {
+                    unsigned long long sA = 0ull, sB = 0ull, zA = 0ull, zB = 0ull;
+                    auto pair_term = [&](unsigned long long x, unsigned long long kc, int c, unsigned long long& acc2, unsigned long long& zacc2) {
                         const unsigned long long v = b3_fma2(x, LOG2E, kc);
                         float v0, v1;
                         b3_unpack2(v, v0, v1);
-                        acc2 = b3_add2(acc2, b3_pack2(b3_ex2(v0), b3_ex2(v1)));
+                        const unsigned long long e2 = b3_pack2(b3_ex2(v0), b3_ex2(v1));
+                        acc2 = b3_add2(acc2, e2);
+                        if constexpr (LOGITS) zacc2 = b3_fma2v(e2, b3_fma2(kc, MSC, ONE2), zacc2);
                         best = fmaxf(best, fmaxf(tag(v0, c), tag(v1, c + 1)));
                     };
                     constexpr int NP = (CT - 1) / 2;           // pairs
 #pragma unroll
                     for (int i = 0; i < NP / 2; ++i) {
                         const ulonglong2 kv = k128[i];
-                        pair_term(x64[2 * i], kv.x, 4 * i, sA);
-                        pair_term(x64[2 * i + 1], kv.y, 4 * i + 2, sB);
+                        pair_term(x64[2 * i], kv.x, 4 * i, sA, zA);
+                        pair_term(x64[2 * i + 1], kv.y, 4 * i + 2, sB, zB);
                     }
-                    if (NP & 1) pair_term(x64[NP - 1], reinterpret_cast<const unsigned long long*>(kq)[NP - 1], 2 * (NP - 1), sA);
+                    if (NP & 1) pair_term(x64[NP - 1], reinterpret_cast<const unsigned long long*>(kq)[NP - 1], 2 * (NP - 1), sA, zA);
                     b3_unpack2(sA, s0, s1);
                     b3_unpack2(sB, s2, s3);
+                    if constexpr (LOGITS) { b3_unpack2(zA, z0, z1); b3_unpack2(zB, z2, z3); }
                     {   // the single class: CT-1 (row on an even float) or 0 (row on an odd float)
                         const int cs1 = odd ? 0 : CT - 1;
                         const float v = fmaf(rowp[cs1], LOG2E, kp[cs1]);
-                        s0 += b3_ex2(v);
+                        const float e = b3_ex2(v);
+                        s0 += e;
+                        if constexpr (LOGITS) z0 = fmaf(e, fmaf(kp[cs1], MSC, 1.0f), z0);
                         best = fmaxf(best, tag(v, 127));
                     }
                     // tag -> class
@@ -598,40 +621,51 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
                     // the issue slots, not the FP pipe, are what this warp competes for
                     const unsigned long long* x64 = reinterpret_cast<const unsigned long long*>(rowp);
                     const ulonglong2* k128 = reinterpret_cast<const ulonglong2*>(kp);
-                    unsigned long long sA = 0ull, sB = 0ull;          // (s0, s1), (s2, s3)
-                    auto pair_term = [&](unsigned long long x, unsigned long long kc, int c, unsigned long long& acc2) {
+                    unsigned long long sA = 0ull, sB = 0ull, zA = 0ull, zB = 0ull;          // (s0, s1), (s2, s3)
+                    auto pair_term = [&](unsigned long long x, unsigned long long kc, int c, unsigned long long& acc2, unsigned long long& zacc2) {
                         const unsigned long long v = b3_fma2(x, LOG2E, kc);
                         float v0, v1;
                         b3_unpack2(v, v0, v1);
-                        acc2 = b3_add2(acc2, b3_pack2(b3_ex2(v0), b3_ex2(v1)));
+                        const unsigned long long e2 = b3_pack2(b3_ex2(v0), b3_ex2(v1));
+                        acc2 = b3_add2(acc2, e2);
+                        if constexpr (LOGITS) zacc2 = b3_fma2v(e2, b3_fma2(kc, MSC, ONE2), zacc2);
                         best = fmaxf(best, fmaxf(tag(v0, c), tag(v1, c + 1)));
                     };
 #pragma unroll
                     for (int i = 0; i < CT / 4; ++i) {
                         const ulonglong2 kv = k128[i];
-                        pair_term(x64[2 * i], kv.x, 4 * i, sA);
-                        pair_term(x64[2 * i + 1], kv.y, 4 * i + 2, sB);
+                        pair_term(x64[2 * i], kv.x, 4 * i, sA, zA);
+                        pair_term(x64[2 * i + 1], kv.y, 4 * i + 2, sB, zB);
                     }
-                    if (CT % 4) pair_term(x64[CT / 2 - 1], reinterpret_cast<const unsigned long long*>(kp)[CT / 2 - 1], CT - 2, sA);
+                    if (CT % 4) pair_term(x64[CT / 2 - 1], reinterpret_cast<const unsigned long long*>(kp)[CT / 2 - 1], CT - 2, sA, zA);
                     b3_unpack2(sA, s0, s1);
                     b3_unpack2(sB, s2, s3);
+                    if constexpr (LOGITS) { b3_unpack2(zA, z0, z1); b3_unpack2(zB, z2, z3); }
                 } else {
                     int i = 0;
                     for (; i + 4 <= C; i += 4) {
-                        term(rowp[i], kp[i], i, s0);
-                        term(rowp[i + 1], kp[i + 1], i + 1, s1);
-                        term(rowp[i + 2], kp[i + 2], i + 2, s2);
-                        term(rowp[i + 3], kp[i + 3], i + 3, s3);
+                        term(rowp[i], kp[i], i, s0, z0);
+                        term(rowp[i + 1], kp[i + 1], i + 1, s1, z1);
+                        term(rowp[i + 2], kp[i + 2], i + 2, s2, z2);
+                        term(rowp[i + 3], kp[i + 3], i + 3, s3, z3);
                     }
-                    for (; i < C; ++i) term(rowp[i], kp[i], i, s0);
+                    for (; i < C; ++i) term(rowp[i], kp[i], i, s0, z0);
                 }
                 lnS = b3_lg2((s0 + s1) + (s2 + s3)) * LN2;          // log sum exp(x + b - boost)
                 if (k.use_stats && t_row < T) lse_chk += lnS;       // any zero / overflowing / NaN sum leaves a non-finite trace
+                if constexpr (LOGITS) {
+                    lnS0 = b3_lg2((z0 + z1) + (z2 + z3)) * LN2;     // log sum exp(x)
+                    const int rel = t_row - o_trim;
+                    if (k.use_stats && t_row < T) {
+                        lse_chk += lnS0;
+                        if (rel >= 0 && rel < rel_hi) a.row_lse[o_out - o_trim + t_row] = lnS0;
+                    }
+                }
                 if (spec) {
                     const int cs = min((int)(__float_as_uint(best) & 127u), C - 1);
                     const int rel = t_row - o_trim;
                     if (rel >= 0 && rel < rel_hi) {
-                        plp_row[t_row] = rowp[cs];
+                        plp_row[t_row] = rowp[cs] - lnS0;            // (logits mode: the class's log-probability)
                         gcl_row[t_row] = (unsigned char)cs;
                     }
                 }
@@ -712,7 +746,7 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
         PH_RESET;
         band3_pair_sync(k.bar0, phase, lane);                  // the walk is done
         PH_T(0);
-        band3_direct_finish<CT>(a, smem_pair, R, 2, 1, lane, pscr_lp != nullptr);
+        band3_direct_finish<CT, LOGITS>(a, smem_pair, R, 2, 1, lane, pscr_lp != nullptr);
         PH_T(1);
         band3_pair_sync(k.bar0, phase, lane);                  // both warps are done with the task
         PH_T(2);
@@ -834,7 +868,7 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
 // ------------------------------------------------------------------------------------------------------------
 // DP warp: frame loop, decision records, back-trace, outputs.
 // ------------------------------------------------------------------------------------------------------------
-template <int G, int CT, bool EXACT, bool DIRECT>
+template <int G, int CT, bool EXACT, bool DIRECT, bool LOGITS = false>
 __device__ void band3_dp(const Band3Args& a, const Band3Args::Class& kc, int first, int n_valid, unsigned char* smem_pair, uint32_t* slab, uint32_t& phase,
                          int lane, int pair, const float* pscr_lp, const unsigned char* pscr_gs) {
     using S = Band3Shape<G>;
@@ -853,7 +887,7 @@ __device__ void band3_dp(const Band3Args& a, const Band3Args::Class& kc, int fir
         if (k.n_chunks == 0) {                         // nothing of this task runs here (no such utterances, or all left to the planner chain)
             if (a.p.reserved & BFA_FLAG_FILL_ONLY) return;
             band3_pair_sync(k.bar0, phase, lane);
-            band3_direct_finish<CT>(a, smem_pair, R, 0, 0, lane, pscr_lp != nullptr);
+            band3_direct_finish<CT, LOGITS>(a, smem_pair, R, 0, 0, lane, pscr_lp != nullptr);
             band3_pair_sync(k.bar0, phase, lane);
             return;
         }
@@ -1226,7 +1260,7 @@ __device__ void band3_dp(const Band3Args& a, const Band3Args::Class& kc, int fir
         __syncwarp();
         band3_pair_sync(k.bar0, phase, lane);                     // events and verdicts are in shared memory
         PH_T(9);
-        band3_direct_finish<CT>(a, smem_pair, R, 0, 0, lane, pscr_lp != nullptr);
+        band3_direct_finish<CT, LOGITS>(a, smem_pair, R, 0, 0, lane, pscr_lp != nullptr);
         PH_T(10);
         band3_pair_sync(k.bar0, phase, lane);                     // both warps are done with the task
         PH_T(12);
@@ -1356,7 +1390,7 @@ __device__ void band3_dp(const Band3Args& a, const Band3Args::Class& kc, int fir
 // BFA_ST_DEFERRED when no chain follows.
 // Not inlined on purpose: this is run-once code, and one copy shared by all fourteen warps of the CTA (which arrive here at about
 // the same time) keeps its instruction-cache misses to one warp's worth.
-template <int CT>
+template <int CT, bool LOGITS>
 __device__ __noinline__ void band3_direct_finish(const Band3Args& a, unsigned char* smem_pair, size_t R, int seg0, int which, int lane, bool have_spec) {
     const int C = CT ? CT : a.C;
     const Item* items = reinterpret_cast<const Item*>(smem_pair + band3_off_items(R));
@@ -1500,13 +1534,14 @@ __device__ __noinline__ void band3_direct_finish(const Band3Args& a, unsigned ch
                 cp_async_wait_all();
                 FIN_T(6);
                 __syncwarp();                                    // every lane's copies have landed
+                const float* rl = LOGITS ? a.row_lse + it.out_off : nullptr;   // logits mode: what arrived is a logit; the helper warp left the row's log-sum-exp
                 for (int q4 = 0; q4 < (T + 3) >> 2; q4 += 32) {
                     const int qq = q4 + lane;
                     if (qq < (T + 3) >> 2) {
                         const uint32_t nib = mnib[qq];
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if ((nib >> k) & 1u) lp_s[4 * qq + k] = expf(lp_s[4 * qq + k]);
+                            if ((nib >> k) & 1u) lp_s[4 * qq + k] = expf(lp_s[4 * qq + k] - (LOGITS ? rl[4 * qq + k] : 0.0f));
                     }
                 }
             }
@@ -1670,7 +1705,7 @@ __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_kernel(Band3Ar
 // its first write another grid could see (band3_direct_finish).  The fill's private scratch (decision records, confidence
 // inputs) is indexed by the PHYSICAL SM: a CTA of this kernel owns its SM's shared memory, so two launches never use the same
 // SM's scratch at the same time.
-template <int CT, bool EXACT>
+template <int CT, bool EXACT, bool LOGITS = false>
 __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_direct_kernel(const __grid_constant__ Band3Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1699,12 +1734,12 @@ __global__ void __launch_bounds__(B3_PAIRS * 64, 1) viterbi_band3_direct_kernel(
     uint32_t phase = 0;
     if (is_dp) {
         for (int q = blockIdx.x + gridDim.x * pair; q < n_tasks; q += gridDim.x * npairs)
-            band3_dp<3, CT, EXACT, true>(a, k, q, B3_UPW, smem_pair, slab, phase, lane, pair, pscr_lp, pscr_gs);
+            band3_dp<3, CT, EXACT, true, LOGITS>(a, k, q, B3_UPW, smem_pair, slab, phase, lane, pair, pscr_lp, pscr_gs);
     } else {
         const uint64_t pol = policy_evict_first();
         bool not_first = false;
         for (int q = blockIdx.x + gridDim.x * pair; q < n_tasks; q += gridDim.x * npairs) {
-            band3_helper<3, CT, true>(a, k, q, B3_UPW, smem_pair, phase, not_first, lane, pol, pair, pscr_lp, pscr_gs);
+            band3_helper<3, CT, true, LOGITS>(a, k, q, B3_UPW, smem_pair, phase, not_first, lane, pol, pair, pscr_lp, pscr_gs);
             not_first = true;
         }
     }

@@ -220,6 +220,27 @@ int bfa_stitch_log_softmax(int32_t B, int32_t n_windows, int32_t frames_per_wind
                            const float *window_weights, float *logp_out, int64_t out_pitch, void *stream);
 
 /*
+ * == F.log_softmax (core.py:898-899) + decode_alignments + _calculate_confidences in ONE kernel: the same call as
+ *    bfa_align_batch with BFA_FLAG_DIRECT_ONLY, on rows that hold the acoustic model's UN-NORMALISED logits.
+ *    Boosting re-normalises every row (forced_alignment.py:51-54), so emissions, path, timestamps and DP score do not
+ *    depend on a per-row shift; the confidences (utils.py:81: exp of the ORIGINAL log-probabilities) do, and the
+ *    kernel's row reduction carries the row's own log-sum-exp along for them.
+ *    Requires p->mode == BFA_MODE_FULL and p->boost_targets (BFA_E_UNSUPPORTED otherwise).
+ *  row_lse   [dev] float[total_frames] out: log(sum(exp(row))) of every frame of every utterance finished here
+ *            (utterance u at frame_off[u]); log-probabilities downstream are logits[f, c] - row_lse[f].
+ *    Utterances the one-kernel pass cannot finish (silence_id in the target while anchoring is on, dense strides, ...) come
+ *    back with status BFA_ST_DEFERRED: normalise those rows (bfa_stitch_log_softmax with frames_per_window = 0) and call
+ *    bfa_align_batch -- the Python facade does.
+ */
+int bfa_align_batch_logits(const BfaParams *p, const BfaShape *shape,
+                           const float *logits, const int64_t *row_off, const int32_t *T,
+                           const int32_t *tgt, const int64_t *tgt_off,
+                           int32_t *frame_ph, int32_t *frame_idx, const int64_t *frame_off,
+                           float *dp_final, int32_t *status,
+                           BfaStamp *stamps, float *conf, int32_t *n_stamps, float *row_lse,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
+/*
  * Host-buffer convenience entry (what a CPU-side caller binds): same semantics as bfa_align_batch
  * with every pointer a HOST pointer.  Copies inputs host->device in chunks of utterances on two
  * streams (copy of chunk i+1 overlaps the kernels of chunk i), runs the device pipeline, copies

@@ -254,6 +254,57 @@ def test_caller_owned_arena(bfa, dev):
             dec.align_batch(lp, row_off, [T] * B, Cc, tg, [N] * B, params=p, arena=bad)
 
 
+@pytest.mark.parametrize("Cc", [66, 67, 17, 30])
+def test_logits_in_one_kernel(bfa, orc, dev, Cc):
+    """bfa_align_batch_logits: un-normalised logits in (core.py:898-899 skipped).  Frames, timestamps and statuses must equal what
+    the ordinary call gives on log_softmax(logits) -- and the oracle on the same log-probabilities --, confidences and the DP
+    score agree to 1e-4, row_lse is the rows' log-sum-exp; utterances the one-kernel pass cannot take are flagged DEFERRED."""
+    from bfa_b200 import synth, _cabi
+    B, T, N = 512, 300, 24
+    lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=900 + Cc, peak=7.0, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    shift = (torch.randn(B, T, 1, generator=g) * 6.0 + 3.0).to(dev)        # per-row offsets: what makes log-probs "logits"
+    logits = (lp + shift).contiguous()
+    tgt = tgt.clone()
+    tgt[3, 5] = 0                                                           # silence_id in a target while anchoring is on -> not for this pass
+    tg = tgt.to(torch.int32).reshape(-1).contiguous()
+    dec = bfa.AlignmentUtils(Cc - 1, 0, silence_anchors=10, ignore_noise=True, truly_forced=True).viterbi_decoder
+    row_off = torch.arange(B, dtype=torch.int64, device=dev) * T * Cc
+    p = dec._params(True, True, True)
+    ref = dec.align_batch(lp, row_off, [T] * B, Cc, tg, [N] * B, params=p)
+    r = dec.align_batch(logits, row_off, [T] * B, Cc, tg, [N] * B, params=dec._params(True, True, True), logits=True)
+    torch.cuda.synchronize()
+    st = r.status[:B].cpu().numpy()
+    assert (st[3] & 7) == _cabi.ST_DEFERRED and int(((st & 7) == _cabi.ST_DEFERRED).sum()) == 1
+    keep = torch.ones(B, dtype=torch.bool, device=dev); keep[3] = False
+    # the two runs see emissions that differ in the last bit (x - lse against (x + s) - (lse + s)): an utterance may differ where
+    # two paths tie to 1e-6 of the score; anything else must be identical
+    same = ((r.frame_ph[: B * T] == ref.frame_ph[: B * T]) & (r.frame_idx[: B * T] == ref.frame_idx[: B * T])).view(B, T).all(1)
+    tied = keep & ~same
+    assert int(tied.sum()) <= 2, int(tied.sum())
+    assert torch.allclose(r.dp_final[:B][tied], ref.dp_final[:B][tied], rtol=2e-6, atol=0)
+    keep = keep & same
+    fk = keep.repeat_interleave(T)
+    assert torch.equal(r.frame_ph[: B * T][fk], ref.frame_ph[: B * T][fk]) and torch.equal(r.frame_idx[: B * T][fk], ref.frame_idx[: B * T][fk])
+    assert torch.equal(r.n_stamps[:B][keep], ref.n_stamps[:B][keep])
+    assert torch.equal(r.stamps[:B, :N][keep], ref.stamps[:B, :N][keep])
+    assert torch.allclose(r.conf[:B, :N][keep], ref.conf[:B, :N][keep], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(r.dp_final[:B][keep], ref.dp_final[:B][keep], rtol=1e-4, atol=1e-3)
+    lse = torch.logsumexp(logits.double(), dim=2).float().reshape(-1)
+    assert torch.allclose(r.row_lse[: B * T][fk], lse[fk], rtol=0, atol=2e-5)
+    # and against the oracle on the normalised rows (a sample)
+    po = orc.params(Cc - 1, 0)
+    import numpy as np
+    for u in [u for u in (0, 100, 511) if bool(keep[u])]:
+        o = orc.align_batch(po, lp[u].cpu().numpy().reshape(1, T, Cc), np.zeros(1, np.int64), np.asarray([T], np.int32), Cc,
+                            tgt[u].cpu().numpy().astype(np.int32), np.asarray([0, N], np.int64), max_stamps=r.max_stamps, n_threads=1)
+        assert np.array_equal(r.frame_ph[u * T:(u + 1) * T].cpu().numpy(), o["frame_ph"])
+        assert np.allclose(r.conf[u, :N].cpu().numpy(), o["conf"][0, :N], rtol=1e-4, atol=1e-6)
+    # no boosting: nothing re-normalises the rows -> refused
+    with pytest.raises(Exception):
+        dec.align_batch(logits, row_off, [T] * B, Cc, tg, [N] * B, params=dec._params(False, True, True), logits=True)
+
+
 # ---- near-ties: how often does the fused log-softmax flip a back-trace decision? -------------------------------
 @pytest.mark.parametrize("Cc,sil", [(66, 0), (67, 0), (17, 0), (67, 9)])
 def test_flip_rate_at_low_peaks(bfa, orc, dev, Cc, sil):
