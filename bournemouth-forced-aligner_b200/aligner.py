@@ -118,6 +118,18 @@ def exact_items_hint(T, N, params) -> int:
     return int(exact.sum())
 
 
+def log_softmax_rows(logits: torch.Tensor) -> torch.Tensor:
+    """F.log_softmax(logits, dim=2) (core.py:898-899) for a CUDA [B, T, C] tensor (bfa_stitch_log_softmax without windows)."""
+    if not logits.is_cuda:
+        raise ValueError("logits must be a CUDA tensor (there is no CPU path)")
+    x = logits if (logits.dtype == torch.float32 and logits.is_contiguous()) else logits.contiguous().float()
+    B, T, C_ = x.shape
+    out = torch.empty_like(x)
+    rc = _cabi.lib().bfa_stitch_log_softmax(B, 0, 0, C_, T, _ptr(x), T * C_, None, _ptr(out), T * C_, _stream(x.device))
+    _cabi.check(rc)
+    return out
+
+
 def direct_only_worthwhile(T, N, params) -> bool:
     """True when (nearly) every utterance of the batch is a plain stride-4 DP problem (forced_alignment.py:153: 4N+1 <= T), i.e.
     when launching only the direct kernel (BFA_FLAG_DIRECT_ONLY) will finish the batch.  The caller has already established that no
@@ -392,7 +404,7 @@ class AlignmentUtils:
             return [int(v) for v in x.tolist()]
         return [int(v) for v in x]
 
-    def _dense_prepare(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf):
+    def _dense_prepare(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf, input_is_logits=False):
         """Everything of a padded batch's alignment call that is not the call itself: lengths, flat targets, offsets and the batch
         plan on the device (small torch ops on the current stream), and the choice of launch sequence."""
         _require_cuda(log_probs, "log_probs")
@@ -426,7 +438,13 @@ class AlignmentUtils:
         tgt = seqs[mask].to(torch.int32).contiguous()
         row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T_max * C_)
         plan = self.viterbi_decoder.plan_batch(T, N, C_, params=params, device=dev)
-        return dict(r=None, lp=lp, row_off=row_off, T=T, N=N, C=C_, tgt=tgt, params=params, want_conf=want_conf, B=B, T_max=T_max, plan=plan)
+        # Un-normalised logits (core.py:898-899 not run by the caller): when the batch goes to the one-kernel pass and boosting is
+        # on, that kernel takes them as they are (bfa_align_batch_logits); otherwise they are normalised first, like the reference.
+        use_logits = bool(input_is_logits and (params.reserved & _cabi.FLAG_DIRECT_ONLY) and params.mode == _cabi.MODE_FULL and params.boost_targets)
+        if input_is_logits and not use_logits:
+            lp = log_softmax_rows(lp)
+        return dict(r=None, lp=lp, row_off=row_off, T=T, N=N, C=C_, tgt=tgt, params=params, want_conf=want_conf, B=B, T_max=T_max, plan=plan,
+                    logits=use_logits)
 
     def _dense_enqueue(self, h, after_sibling=False):
         """Enqueue the prepared call (kernels only, no host synchronisation).  after_sibling: the operation before this one in the
@@ -437,22 +455,25 @@ class AlignmentUtils:
         if after_sibling and (params.reserved & _cabi.FLAG_DIRECT_ONLY):
             params.reserved |= _cabi.FLAG_PIPELINED
         h["r"] = self.viterbi_decoder.align_batch(h["lp"], h["row_off"], h["T"], h["C"], h["tgt"], h["N"], params=params, want_stamps=True,
-                                                  want_conf=h["want_conf"], plan=h["plan"])
+                                                  want_conf=h["want_conf"], plan=h["plan"], logits=h.get("logits", False))
         return h
 
-    def _dense_launch(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf):
+    def _dense_launch(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf, input_is_logits=False):
         """Enqueue the alignment of a padded batch on the current stream and return without waiting for it: the first half of
         decode_alignments.  Two heads (core.py:900-920) can be launched back to back before either result is looked at."""
-        return self._dense_enqueue(self._dense_prepare(log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf))
+        return self._dense_enqueue(self._dense_prepare(log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf, input_is_logits))
 
     def _dense_finish(self, h):
         """Second half: wait for the statuses, repeat the call where the library asked for it, raise what the reference raises."""
         r, params, B, T, N = h["r"], h["params"], h["B"], h["T"], h["N"]
         again = lambda **kw: self.viterbi_decoder.align_batch(h["lp"], h["row_off"], T, h["C"], h["tgt"], N, params=params, want_stamps=True,
-                                                              want_conf=h["want_conf"], **kw)
+                                                              want_conf=h["want_conf"], logits=h.get("logits", False), **kw)
         st = r.status[:B].cpu().numpy()
         if ((st & 7) == _cabi.ST_DEFERRED).any():  # the one-kernel path handed utterances back: the full chain takes the batch
             params.reserved &= ~(_cabi.FLAG_DIRECT_ONLY | _cabi.FLAG_PIPELINED)
+            if h.get("logits"):                    # ... on normalised rows: the chain's stamp kernel reads log-probabilities
+                h["lp"] = log_softmax_rows(h["lp"])
+                h["logits"] = False
             r = again()
             st = r.status[:B].cpu().numpy()
         if (st & _cabi.ST_STAMP_OVERFLOW).any():   # more runs than the default stamp pitch (degenerate paths): use the safe pitch
@@ -465,32 +486,37 @@ class AlignmentUtils:
                           f"{_cabi.MAX_L} states and were not aligned (no timestamps returned for them); split such segments")
         self.last_result = r
         self.last_params_reserved = int(params.reserved)     # which path the batch finally took (FLAG_DIRECT_ONLY: one kernel)
+        # input_is_logits: what downstream steps (soft boundaries, confidences of moved stamps) need to form log-probabilities:
+        # either the rows' log-sum-exp (aligned straight from the logits; r.row_lse, packed like the frame labels) or the
+        # normalised copy the fallback made
+        self.last_row_lse = r.row_lse if h.get("logits") else None
+        self.last_log_probs = None if h.get("logits") else h["lp"]
         self.viterbi_decoder._raise_if_too_short(st, T, N)
         return r
 
-    def _dense_batch(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf):
-        return self._dense_finish(self._dense_launch(log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf))
+    def _dense_batch(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf, input_is_logits=False):
+        return self._dense_finish(self._dense_launch(log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf, input_is_logits))
 
     def decode_alignments_launch(self, log_probs, true_seqs, pred_lens=None, true_seqs_lens=None, boost_targets=True, enforce_minimum=True,
-                                 with_confidence=False):
+                                 with_confidence=False, input_is_logits=False):
         """decode_alignments split in two: this half only enqueues the kernels (no host synchronisation) and returns a handle for
         decode_alignments_finish.  core.py:900-920 aligns the phoneme head and the group head one after the other; with the two
         halves both heads are in flight before the host looks at either."""
         if (true_seqs is None) or (true_seqs_lens is None):
             raise ValueError("Phoneme sequences and lengths required for forced alignment")  # :878-879
         p = self.viterbi_decoder._params(boost_targets, enforce_minimum, self.silence_anchors > 0)
-        h = self._dense_launch(log_probs, true_seqs, pred_lens, true_seqs_lens, p, with_confidence)
+        h = self._dense_launch(log_probs, true_seqs, pred_lens, true_seqs_lens, p, with_confidence, input_is_logits)
         h["with_confidence"] = with_confidence
         return h
 
     def decode_alignments_prepare(self, log_probs, true_seqs, pred_lens=None, true_seqs_lens=None, boost_targets=True, enforce_minimum=True,
-                                  with_confidence=False):
+                                  with_confidence=False, input_is_logits=False):
         """decode_alignments_launch without the launch: a handle for decode_alignments_enqueue.  Preparing both heads of a batch
         first and enqueueing them afterwards puts the two alignment kernels next to each other in the stream."""
         if (true_seqs is None) or (true_seqs_lens is None):
             raise ValueError("Phoneme sequences and lengths required for forced alignment")  # :878-879
         p = self.viterbi_decoder._params(boost_targets, enforce_minimum, self.silence_anchors > 0)
-        h = self._dense_prepare(log_probs, true_seqs, pred_lens, true_seqs_lens, p, with_confidence)
+        h = self._dense_prepare(log_probs, true_seqs, pred_lens, true_seqs_lens, p, with_confidence, input_is_logits)
         h["with_confidence"] = with_confidence
         return h
 
@@ -501,14 +527,16 @@ class AlignmentUtils:
         return self._dense_finish(handle).stamp_lists(with_conf=handle["with_confidence"])
 
     def decode_alignments(self, log_probs, true_seqs=None, pred_lens=None, true_seqs_lens=None, forced_alignment=True,
-                          boost_targets=True, enforce_minimum=True, debug=False, with_confidence=False):
+                          boost_targets=True, enforce_minimum=True, debug=False, with_confidence=False, input_is_logits=False):
         """forced_alignment.py:856-928.  Returns list[B] of list[(phoneme, start, end, target_idx)].
-        with_confidence=True (extension) appends utils._calculate_confidences' score to each tuple."""
+        with_confidence=True (extension) appends utils._calculate_confidences' score to each tuple.
+        input_is_logits=True (extension): `log_probs` holds the acoustic model's un-normalised logits, i.e. the caller skipped
+        F.log_softmax (core.py:898-899); same results as on the normalised tensor (see bfa_align_batch_logits)."""
         if forced_alignment:
             if (true_seqs is None) or (true_seqs_lens is None):
                 raise ValueError("Phoneme sequences and lengths required for forced alignment")  # :878-879
             p = self.viterbi_decoder._params(boost_targets, enforce_minimum, self.silence_anchors > 0)
-            r = self._dense_batch(log_probs, true_seqs, pred_lens, true_seqs_lens, p, with_confidence)
+            r = self._dense_batch(log_probs, true_seqs, pred_lens, true_seqs_lens, p, with_confidence, input_is_logits)
             return r.stamp_lists(with_conf=with_confidence)
         # free decoding (:912-928): frame-wise argmax then assort; returns ONE flat list like the reference
         _require_cuda(log_probs, "log_probs")

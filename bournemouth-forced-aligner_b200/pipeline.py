@@ -26,7 +26,7 @@ from typing import Callable, List, Optional, Sequence
 import torch
 
 from . import _cabi
-from .aligner import AlignmentUtils, _calculate_confidences_batch, _ptr, _stream, extend_soft_boundaries_func
+from .aligner import AlignmentUtils, _calculate_confidences_batch, _ptr, _stream, extend_soft_boundaries_func, log_softmax_rows
 from .postprocess import convert_to_ms, ensure_target_coverage, post_process_segment
 
 
@@ -49,18 +49,6 @@ def stitch_log_softmax(window_logits: torch.Tensor, original_audio_length: int, 
         raise ValueError(f"stitch: window {W - 2} of {fpw} frames ends beyond the {total_frames} output frames")
     rc = _cabi.lib().bfa_stitch_log_softmax(B, W, fpw, C_, total_frames, _ptr(x), W * fpw * C_, _ptr(weights), _ptr(out),
                                             total_frames * C_, _stream(x.device))
-    _cabi.check(rc)
-    return out
-
-
-def log_softmax_rows(logits: torch.Tensor) -> torch.Tensor:
-    """F.log_softmax(logits, dim=2) (core.py:898-899) for a CUDA [B, T, C] tensor, through the same kernel."""
-    if not logits.is_cuda:
-        raise ValueError("logits must be a CUDA tensor (there is no CPU path)")
-    x = logits if (logits.dtype == torch.float32 and logits.is_contiguous()) else logits.contiguous().float()
-    B, T, C_ = x.shape
-    out = torch.empty_like(x)
-    rc = _cabi.lib().bfa_stitch_log_softmax(B, 0, 0, C_, T, _ptr(x), T * C_, None, _ptr(out), T * C_, _stream(x.device))
     _cabi.check(rc)
     return out
 

@@ -305,6 +305,38 @@ def test_logits_in_one_kernel(bfa, orc, dev, Cc):
         dec.align_batch(logits, row_off, [T] * B, Cc, tg, [N] * B, params=dec._params(False, True, True), logits=True)
 
 
+def test_decode_alignments_from_logits(bfa, dev):
+    """AlignmentUtils.decode_alignments(input_is_logits=True): the caller skips F.log_softmax (core.py:898-899).  Same lists as on
+    the normalised tensor -- through the one-kernel pass when the batch qualifies, through a normalising pass + the full chain when a
+    target holds silence_id (or the one-kernel pass hands utterances back)."""
+    from bfa_b200 import synth, _cabi
+    Cc, B, T, N = 67, 96, 260, 20
+    for case in ("plain", "sil", "one deferred", "handed back"):
+        lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=31, peak=8.0, sil_every=7 if case == "sil" else 0, sil_frames=14, device=dev)
+        tgt = tgt.cpu()
+        lens_t = torch.full((B,), T); lens_n = torch.full((B,), N)
+        if case == "one deferred":
+            lens_t[5] = 60            # 4 N + 1 > T: stride 3 -- the host-side check sends the batch to the full chain
+        if case == "handed back":
+            tgt[5, 3] = Cc - 1        # blank_id inside a target: the host-side check passes, the kernel hands the utterance back
+        logits = (lp + (torch.randn(B, T, 1, generator=torch.Generator().manual_seed(9)) * 5.0).to(dev)).contiguous()
+        au = bfa.AlignmentUtils(blank_id=Cc - 1, silence_id=0, silence_anchors=10, ignore_noise=True, truly_forced=True)
+        want = au.decode_alignments(lp, true_seqs=tgt, pred_lens=lens_t, true_seqs_lens=lens_n, with_confidence=True)
+        got = au.decode_alignments(logits, true_seqs=tgt, pred_lens=lens_t, true_seqs_lens=lens_n, with_confidence=True, input_is_logits=True)
+        one_kernel = bool(au.last_params_reserved & _cabi.FLAG_DIRECT_ONLY)
+        assert one_kernel == (case == "plain"), (case, au.last_params_reserved)
+        assert (au.last_row_lse is not None) == one_kernel and (au.last_log_probs is None) == one_kernel
+        if one_kernel:
+            lse = torch.logsumexp(logits.double(), dim=2).float().reshape(-1)
+            assert torch.allclose(au.last_row_lse[: B * T], lse, rtol=0, atol=2e-5)
+        else:
+            assert torch.allclose(au.last_log_probs, torch.log_softmax(logits, dim=2), rtol=0, atol=2e-5)
+        assert len(got) == B
+        for b in range(B):
+            assert [x[:4] for x in got[b]] == [x[:4] for x in want[b]], (case, b)
+            assert all(abs(x[4] - y[4]) <= 1e-4 * max(abs(y[4]), 1e-3) for x, y in zip(got[b], want[b])), (case, b)
+
+
 # ---- near-ties: how often does the fused log-softmax flip a back-trace decision? -------------------------------
 @pytest.mark.parametrize("Cc,sil", [(66, 0), (67, 0), (17, 0), (67, 9)])
 def test_flip_rate_at_low_peaks(bfa, orc, dev, Cc, sil):
