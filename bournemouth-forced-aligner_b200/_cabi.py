@@ -58,6 +58,8 @@ _SIGNATURES = {
     "bfa_viterbi_paths": (C.c_int, [C.POINTER(BfaParams), C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [_P] * 13
                           + [_P, C.c_size_t, _P]),
     "bfa_confidence_batch": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, _P, _P]),
+    "bfa_confidence_batch_lse": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
+    "bfa_soft_boundaries_batch_lse": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "bfa_alignment_score_batch": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "bfa_stitch_log_softmax": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, C.c_int64, _P]),
     "bfa_assort_batch": (C.c_int, [C.POINTER(BfaParams), C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),

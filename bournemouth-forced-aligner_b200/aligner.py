@@ -587,10 +587,20 @@ def _calculate_confidences(log_probs: torch.Tensor, framestamps):
     return [(f[0], max(0, int(f[1])), min(T, int(f[2])), f[3], f[4], c[i]) for i, f in enumerate(framestamps)]
 
 
-def _calculate_confidences_batch(log_probs: torch.Tensor, framestamps, pred_lens=None):
+def _lse_offsets(row_lse, T, dev):
+    """Offsets of the utterances inside a packed row_lse (AlignmentUtils.last_row_lse: utterance u at sum(T[:u]))."""
+    off = np.zeros(len(T), np.int64)
+    np.cumsum(np.asarray(T[:-1], np.int64), out=off[1:])
+    if int(off[-1]) + int(T[-1]) > row_lse.numel():
+        raise ValueError("row_lse is shorter than the frames of the batch")
+    return torch.from_numpy(off).to(dev)
+
+
+def _calculate_confidences_batch(log_probs: torch.Tensor, framestamps, pred_lens=None, row_lse=None):
     """utils._calculate_confidences (utils.py:70-113) for a whole batch in ONE launch: log_probs [B, T, C] (CUDA), framestamps
     list[B] of lists of 5-tuples -> list[B] of lists of 6-tuples.  The reference loops over the batch (core.py:936-937);
-    `pred_lens[b]` plays the role of `log_probs[b].shape[0]` when the batch is padded."""
+    `pred_lens[b]` plays the role of `log_probs[b].shape[0]` when the batch is padded.
+    row_lse (AlignmentUtils.last_row_lse after decode_alignments(input_is_logits=True)): `log_probs` holds un-normalised logits."""
     _require_cuda(log_probs, "log_probs")
     lp = log_probs if (log_probs.dtype == torch.float32 and log_probs.is_contiguous()) else log_probs.contiguous().float()
     B, T_max, C_ = lp.shape
@@ -614,18 +624,21 @@ def _calculate_confidences_batch(log_probs: torch.Tensor, framestamps, pred_lens
     T_d = torch.tensor(T, dtype=torch.int32, device=dev)
     row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T_max * C_)
     conf = torch.zeros((B, ms), dtype=torch.float32, device=dev)
+    lse_off = _lse_offsets(row_lse, T, dev) if row_lse is not None else None
     with torch.cuda.device(dev):
-        rc = _cabi.lib().bfa_confidence_batch(B, C_, _ptr(lp), _ptr(row_off), _ptr(T_d), _ptr(st_d), _ptr(n_d), ms, _ptr(conf), _stream(dev))
+        rc = _cabi.lib().bfa_confidence_batch_lse(B, C_, _ptr(lp), _ptr(row_off), _ptr(T_d), _ptr(st_d), _ptr(n_d), ms, _ptr(conf),
+                                                  _ptr(row_lse), _ptr(lse_off), _stream(dev))
     _cabi.check(rc)
     c = conf.cpu().numpy()
     return [[(f[0], max(0, int(f[1])), min(T[b], int(f[2])), f[3], f[4], float(c[b, i])) for i, f in enumerate(fs)]
             for b, fs in enumerate(framestamps)]
 
 
-def extend_soft_boundaries_func(log_probs: torch.Tensor, framestamps, boundary_softness=3, debug=False):
+def extend_soft_boundaries_func(log_probs: torch.Tensor, framestamps, boundary_softness=3, debug=False, row_lse=None, pred_lens=None):
     """PhonemeTimestampAligner.extend_soft_boundaries_func (core.py:682-809) as a free function: log_probs [B, T, C] (CUDA),
     framestamps list[B] of lists of 5-tuples (phoneme, start, end, target_idx, is_estimated) -> the same structure with the
-    stretched boundaries.  One kernel over the whole batch (bfa_soft_boundaries_batch)."""
+    stretched boundaries.  One kernel over the whole batch (bfa_soft_boundaries_batch).
+    row_lse (+ the pred_lens it was packed with): `log_probs` holds un-normalised logits, see _calculate_confidences_batch."""
     _require_cuda(log_probs, "log_probs")
     lp = log_probs if (log_probs.dtype == torch.float32 and log_probs.is_contiguous()) else log_probs.contiguous().float()
     B, T, C_ = lp.shape
@@ -641,9 +654,14 @@ def extend_soft_boundaries_func(log_probs: torch.Tensor, framestamps, boundary_s
     n_d = torch.tensor([len(f) for f in framestamps], dtype=torch.int32, device=dev)
     T_d = torch.full((B,), T, dtype=torch.int32, device=dev)
     row_off = torch.arange(B, dtype=torch.int64, device=dev) * (T * C_)
+    lse_off = None
+    if row_lse is not None:      # row_lse only covers the frames that were aligned: the stretch stops at each utterance's own length
+        Tl = [T] * B if pred_lens is None else [int(v) for v in (pred_lens.tolist() if hasattr(pred_lens, "tolist") else pred_lens)]
+        lse_off = _lse_offsets(row_lse, Tl, dev)
+        T_d = torch.tensor(Tl, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        rc = _cabi.lib().bfa_soft_boundaries_batch(B, C_, _ptr(lp), _ptr(row_off), _ptr(T_d), _ptr(st_d), _ptr(n_d), ms,
-                                                   int(boundary_softness), _stream(dev))
+        rc = _cabi.lib().bfa_soft_boundaries_batch_lse(B, C_, _ptr(lp), _ptr(row_off), _ptr(T_d), _ptr(st_d), _ptr(n_d), ms,
+                                                       int(boundary_softness), _ptr(row_lse), _ptr(lse_off), _stream(dev))
     _cabi.check(rc)
     out = st_d.cpu().numpy()
     return [[(f[0], int(out[b, i, 1]), int(out[b, i, 2]), f[3], f[4]) for i, f in enumerate(fs)] for b, fs in enumerate(framestamps)]

@@ -10,16 +10,17 @@ namespace bfa {
 // utils.py:84-111 for one stamp; sequential fp32 accumulation in frame order like the reference.
 // NB utils.py:89: avg_confidence is a VIEW of probs[start, ph]; the in-place += and /= also
 // rewrite that element, so the max of :107 runs over {avg, p[start+1 .. end-1]}.
-__device__ __forceinline__ float stamp_confidence(const float* lp, int T, int C, int ph, int start, int end) {
+// `lse` (optional): the rows hold un-normalised logits and lse[f] is row f's log-sum-exp (bfa_align_batch_logits' row_lse).
+__device__ __forceinline__ float stamp_confidence(const float* lp, int T, int C, int ph, int start, int end, const float* lse = nullptr) {
     int s = max(0, start), e = min(T, end);                     // :86-87
     if (s >= T || ph < 0 || ph >= C) return __int_as_float(0x7fc00000);   // the reference raises IndexError here (probs[start, ph], :89); never read out of bounds
-    float avg = expf(lp[(long long)s * C + ph]);                // :89
+    float avg = expf(lp[(long long)s * C + ph] - (lse ? lse[s] : 0.0f));   // :89
     if (s < e && ph < C) {                                      // :93
         const float half = avg / 2.0f;                          // :95
         int good = 1;
         float mx = 0.f;
         for (int f = s + 1; f < e; ++f) {                       // :99-103
-            float pr = expf(lp[(long long)f * C + ph]);
+            float pr = expf(lp[(long long)f * C + ph] - (lse ? lse[f] : 0.0f));
             mx = fmaxf(mx, pr);
             if (pr > half || pr > 0.1f) { avg += pr; ++good; }
         }
@@ -327,14 +328,16 @@ __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(As
 
 // stand-alone confidence entry (bfa_confidence_batch)
 __global__ void confidence_kernel(int B, int C, const float* logp, const long long* row_off, const int32_t* Tc,
-                                  const BfaStamp* stamps, const int32_t* n_stamps, int max_stamps, float* conf) {
+                                  const BfaStamp* stamps, const int32_t* n_stamps, int max_stamps, float* conf,
+                                  const float* row_lse, const long long* lse_off) {
     const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (u >= B) return;
     const float* lp = logp + row_off[u];
+    const float* lse = row_lse ? row_lse + lse_off[u] : nullptr;
     const int n = min(n_stamps[u], max_stamps);
     for (int i = lane; i < n; i += 32) {
         BfaStamp s = stamps[(size_t)u * max_stamps + i];
-        conf[(size_t)u * max_stamps + i] = stamp_confidence(lp, Tc[u], C, s.phoneme, s.start, s.end);
+        conf[(size_t)u * max_stamps + i] = stamp_confidence(lp, Tc[u], C, s.phoneme, s.start, s.end, lse);
     }
 }
 
@@ -346,7 +349,8 @@ __global__ void confidence_kernel(int B, int C, const float* logp, const long lo
 constexpr int SOFT_WARPS = 4;
 __global__ void __launch_bounds__(SOFT_WARPS * 32) soft_boundaries_kernel(int B, int C, const float* __restrict__ logp,
                                                                           const long long* row_off, const int32_t* T, BfaStamp* stamps,
-                                                                          const int32_t* n_stamps, int max_stamps, double t1, double t2) {
+                                                                          const int32_t* n_stamps, int max_stamps, double t1, double t2,
+                                                                          const float* __restrict__ row_lse, const long long* lse_off) {
     extern __shared__ double soft_thr[];                         // [SOFT_WARPS][max_stamps]: min(mean * t1, t1) per stamp
     const int u = blockIdx.x * SOFT_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (u >= B) return;
@@ -354,7 +358,8 @@ __global__ void __launch_bounds__(SOFT_WARPS * 32) soft_boundaries_kernel(int B,
     const int Tu = T[u], n = min(n_stamps[u], max_stamps);
     BfaStamp* st = stamps + (size_t)u * max_stamps;
     double* thr = soft_thr + (size_t)(threadIdx.x >> 5) * max_stamps;
-    auto prob = [&](int f, int ph) { return (double)expf(lp[(size_t)f * C + ph]); };
+    const float* lse = row_lse ? row_lse + lse_off[u] : nullptr;   // logits in: lse[f] = log-sum-exp of row f (bfa_align_batch_logits)
+    auto prob = [&](int f, int ph) { return (double)expf(lp[(size_t)f * C + ph] - (lse ? lse[f] : 0.0f)); };
     for (int i = lane; i < n; i += 32) {                         // mean probability over the ORIGINAL stamp (:710-716)
         const BfaStamp s = st[i];
         double m = 0.001;

@@ -723,19 +723,33 @@ int bfa_stitch_log_softmax(int32_t B, int32_t n_windows, int32_t frames_per_wind
     return BFA_OK;
 }
 
-int bfa_confidence_batch(int32_t B, int32_t C, const float* logp, const int64_t* row_off, const int32_t* T_conf,
-                         const BfaStamp* stamps, const int32_t* n_stamps, int32_t max_stamps, float* conf, void* stream) {
-    if (!logp || !row_off || !T_conf || !stamps || !n_stamps || !conf || C <= 0 || max_stamps <= 0) return BFA_E_INVALID;
+int bfa_confidence_batch_lse(int32_t B, int32_t C, const float* logits, const int64_t* row_off, const int32_t* T_conf,
+                             const BfaStamp* stamps, const int32_t* n_stamps, int32_t max_stamps, float* conf,
+                             const float* row_lse, const int64_t* lse_off, void* stream) {
+    if (!logits || !row_off || !T_conf || !stamps || !n_stamps || !conf || C <= 0 || max_stamps <= 0) return BFA_E_INVALID;
+    if ((row_lse == nullptr) != (lse_off == nullptr)) return BFA_E_INVALID;
     if (B <= 0) return B == 0 ? BFA_OK : BFA_E_INVALID;
-    confidence_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(B, C, logp, (const long long*)row_off, T_conf, stamps, n_stamps,
-                                                                     max_stamps, conf);
+    confidence_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(B, C, logits, (const long long*)row_off, T_conf, stamps, n_stamps,
+                                                                     max_stamps, conf, row_lse, (const long long*)lse_off);
     LAUNCH_CHECK();
     return BFA_OK;
 }
 
+int bfa_confidence_batch(int32_t B, int32_t C, const float* logp, const int64_t* row_off, const int32_t* T_conf,
+                         const BfaStamp* stamps, const int32_t* n_stamps, int32_t max_stamps, float* conf, void* stream) {
+    return bfa_confidence_batch_lse(B, C, logp, row_off, T_conf, stamps, n_stamps, max_stamps, conf, nullptr, nullptr, stream);
+}
+
 int bfa_soft_boundaries_batch(int32_t B, int32_t C, const float* logp, const int64_t* row_off, const int32_t* T, BfaStamp* stamps,
                               const int32_t* n_stamps, int32_t max_stamps, int32_t boundary_softness, void* stream) {
+    return bfa_soft_boundaries_batch_lse(B, C, logp, row_off, T, stamps, n_stamps, max_stamps, boundary_softness, nullptr, nullptr, stream);
+}
+
+int bfa_soft_boundaries_batch_lse(int32_t B, int32_t C, const float* logp, const int64_t* row_off, const int32_t* T, BfaStamp* stamps,
+                                  const int32_t* n_stamps, int32_t max_stamps, int32_t boundary_softness,
+                                  const float* row_lse, const int64_t* lse_off, void* stream) {
     if (!logp || !row_off || !T || !stamps || !n_stamps || C <= 0 || max_stamps <= 0) return BFA_E_INVALID;
+    if ((row_lse == nullptr) != (lse_off == nullptr)) return BFA_E_INVALID;
     if (B <= 0) return B == 0 ? BFA_OK : BFA_E_INVALID;
     const size_t smem = (size_t)SOFT_WARPS * max_stamps * sizeof(double);
     if (smem > 200 * 1024) return BFA_E_UNSUPPORTED;
@@ -744,7 +758,7 @@ int bfa_soft_boundaries_batch(int32_t B, int32_t C, const float* logp, const int
     if (rc) return rc;
     const double t1 = pow(10.0, -1.0 * 3.0), t2 = pow(10.0, -1.0 * (double)boundary_softness);   // core.py:699-701
     soft_boundaries_kernel<<<(B + SOFT_WARPS - 1) / SOFT_WARPS, SOFT_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        B, C, logp, (const long long*)row_off, T, stamps, n_stamps, max_stamps, t1, t2);
+        B, C, logp, (const long long*)row_off, T, stamps, n_stamps, max_stamps, t1, t2, row_lse, (const long long*)lse_off);
     LAUNCH_CHECK();
     return BFA_OK;
 }

@@ -275,6 +275,16 @@ int bfa_assort_batch(const BfaParams *p, int32_t B, const int32_t *T, const int6
 int bfa_soft_boundaries_batch(int32_t B, int32_t C, const float *logp, const int64_t *row_off, const int32_t *T, BfaStamp *stamps,
                               const int32_t *n_stamps, int32_t max_stamps, int32_t boundary_softness, void *stream);
 
+/* The two steps after bfa_align_batch_logits on the same un-normalised rows: row_lse is that call's output and lse_off[u] the
+ * offset of utterance u inside it (its frame_off); log-probabilities are formed on the fly as logits[f, c] - row_lse[f].
+ * row_lse == NULL (and lse_off == NULL): exactly bfa_soft_boundaries_batch / bfa_confidence_batch. */
+int bfa_soft_boundaries_batch_lse(int32_t B, int32_t C, const float *logits, const int64_t *row_off, const int32_t *T, BfaStamp *stamps,
+                                  const int32_t *n_stamps, int32_t max_stamps, int32_t boundary_softness,
+                                  const float *row_lse, const int64_t *lse_off, void *stream);
+int bfa_confidence_batch_lse(int32_t B, int32_t C, const float *logits, const int64_t *row_off, const int32_t *T_conf,
+                             const BfaStamp *stamps, const int32_t *n_stamps, int32_t max_stamps, float *conf,
+                             const float *row_lse, const int64_t *lse_off, void *stream);
+
 /* Measurement hook: when enabled, bfa_align_batch / bfa_viterbi_paths bracket the dominant kernel
  * (the Viterbi fill+back-trace) with CUDA events on the launch stream; bfa_profile_read waits for
  * them and returns the summed device time and the number of launches since the previous read.

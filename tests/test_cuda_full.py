@@ -337,6 +337,29 @@ def test_decode_alignments_from_logits(bfa, dev):
             assert all(abs(x[4] - y[4]) <= 1e-4 * max(abs(y[4]), 1e-3) for x, y in zip(got[b], want[b])), (case, b)
 
 
+def test_downstream_steps_from_logits(bfa, dev):
+    """Soft boundaries and confidences on un-normalised logits + row_lse (bfa_*_batch_lse) equal the same steps on
+    log_softmax(logits): the chain core.py:925-937 runs after decode_alignments, without ever materialising the log-probabilities."""
+    from bfa_b200 import synth
+    Cc, B, T, N = 67, 40, 300, 22
+    lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=77, peak=6.0, device=dev)
+    logits = (lp + (torch.randn(B, T, 1, generator=torch.Generator().manual_seed(3)) * 4.0 - 2.0).to(dev)).contiguous()
+    lens_t = torch.full((B,), T); lens_n = torch.full((B,), N)
+    au = bfa.AlignmentUtils(blank_id=Cc - 1, silence_id=0, silence_anchors=10, ignore_noise=True, truly_forced=True)
+    got = au.decode_alignments(logits, true_seqs=tgt.cpu(), pred_lens=lens_t, true_seqs_lens=lens_n, input_is_logits=True)
+    rl = au.last_row_lse
+    assert rl is not None
+    st5 = [[(p, s, e, i, False) for (p, s, e, i) in fs] for fs in got]
+    soft_a = bfa.extend_soft_boundaries_func(logits, st5, boundary_softness=3, row_lse=rl, pred_lens=lens_t)
+    soft_b = bfa.extend_soft_boundaries_func(lp, st5, boundary_softness=3)
+    assert soft_a == soft_b and soft_a != st5          # identical, and the step did move boundaries
+    conf_a = bfa._calculate_confidences_batch(logits, soft_a, pred_lens=lens_t, row_lse=rl)
+    conf_b = bfa._calculate_confidences_batch(lp, soft_b, pred_lens=lens_t)
+    for fa, fb in zip(conf_a, conf_b):
+        assert [x[:5] for x in fa] == [x[:5] for x in fb]
+        assert all(abs(x[5] - y[5]) <= 1e-4 * max(abs(y[5]), 1e-3) for x, y in zip(fa, fb))
+
+
 # ---- near-ties: how often does the fused log-softmax flip a back-trace decision? -------------------------------
 @pytest.mark.parametrize("Cc,sil", [(66, 0), (67, 0), (17, 0), (67, 9)])
 def test_flip_rate_at_low_peaks(bfa, orc, dev, Cc, sil):
