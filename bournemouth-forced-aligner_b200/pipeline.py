@@ -105,17 +105,26 @@ class PhonemeTimestampAligner:
         self.stats.clear()
 
     # ---- the post-acoustic half of extract_timestamps_from_segment_batch --------------------------------------------------------
-    def _prepare(self, utils, log_probs, seqs, seq_lens, spectral_lens):
+    def _prepare(self, utils, log_probs, seqs, seq_lens, spectral_lens, input_is_logits=False):
         return utils.decode_alignments_prepare(log_probs, true_seqs=seqs, pred_lens=spectral_lens, true_seqs_lens=seq_lens,         # :902-922
-                                               boost_targets=self.boost_targets, enforce_minimum=self.enforce_minimum)
+                                               boost_targets=self.boost_targets, enforce_minimum=self.enforce_minimum,
+                                               input_is_logits=input_is_logits)
 
-    def _finish(self, utils, handle, log_probs, seqs, seq_lens, spectral_lens, wav_lens, offsets, silence):
+    def _finish(self, utils, handle, log_probs, seqs, seq_lens, spectral_lens, wav_lens, offsets, silence, input_is_logits=False):
         frames = utils.decode_alignments_finish(handle)
         frames = ensure_target_coverage(seqs, frames, seq_lens=seq_lens, _silence_class=silence,                               # :925-926
                                         ensure_completeness=self.ensure_completeness, stats=self.stats)
+        lse_kw = {}
+        if input_is_logits:
+            # aligned straight from the logits: the steps below form log-probabilities from the rows' log-sum-exp on the fly;
+            # otherwise the facade normalised the batch on its way to the full chain and that copy is used
+            if utils.last_row_lse is not None:
+                lse_kw = dict(row_lse=utils.last_row_lse, pred_lens=spectral_lens)
+            else:
+                log_probs = utils.last_log_probs
         if self.extend_soft_boundaries:                                                                                        # :928-931
-            frames = extend_soft_boundaries_func(log_probs, frames, boundary_softness=self.boundary_softness)
-        frames = _calculate_confidences_batch(log_probs, frames)                                                               # :936-937 (padded rows, like log_probs[b])
+            frames = extend_soft_boundaries_func(log_probs, frames, boundary_softness=self.boundary_softness, **lse_kw)
+        frames = _calculate_confidences_batch(log_probs, frames, **lse_kw)                                                     # :936-937 (padded rows, like log_probs[b])
         out = []
         for b, fs in enumerate(frames):
             off = offsets[b] if isinstance(offsets, (list, tuple)) else offsets
@@ -125,27 +134,33 @@ class PhonemeTimestampAligner:
 
     def timestamps_from_posteriors(self, log_probs_p: torch.Tensor, ph_seqs: torch.Tensor, ph_seq_lens, spectral_lens, wav_lens,
                                    start_offset_times=0.0, log_probs_g: Optional[torch.Tensor] = None,
-                                   grp_seqs: Optional[torch.Tensor] = None) -> List[dict]:
+                                   grp_seqs: Optional[torch.Tensor] = None, input_is_logits: bool = False) -> List[dict]:
         """log_probs_p [B, T, C_p] (CUDA, log-softmaxed like core.py:898), ph_seqs [B, S] padded targets, ph_seq_lens / spectral_lens /
         wav_lens per utterance.  Returns the reference's `timestamp_dicts` (core.py:958-964): 8-tuples
         (id, start_frame, end_frame, target_idx, is_estimated, confidence, start_ms, end_ms) per head.
-        Both heads are enqueued on the device before the host waits for either (core.py:900-922 runs them one after the other)."""
+        Both heads are enqueued on the device before the host waits for either (core.py:900-922 runs them one after the other).
+        input_is_logits=True: the tensors hold the acoustic model's un-normalised logits (core.py:898-899 skipped); a batch without
+        silence_id in its targets is then aligned, stretched and scored without the log-probabilities ever being written."""
         groups = log_probs_g is not None and grp_seqs is not None
         # both heads are prepared (targets, offsets, plans on the device) before either alignment is enqueued: the two alignment
         # kernels sit next to each other in the stream and the second may start while the first drains
-        hp = self._prepare(self.alignment_utils_p, log_probs_p, ph_seqs, ph_seq_lens, spectral_lens)
-        hg = self._prepare(self.alignment_utils_g, log_probs_g, grp_seqs, ph_seq_lens, spectral_lens) if groups else None
+        lg = input_is_logits and self.boost_targets
+        if input_is_logits and not lg:       # without boosting nothing re-normalises the rows: do what the reference does first
+            log_probs_p = log_softmax_rows(log_probs_p)
+            log_probs_g = log_softmax_rows(log_probs_g) if groups else log_probs_g
+        hp = self._prepare(self.alignment_utils_p, log_probs_p, ph_seqs, ph_seq_lens, spectral_lens, lg)
+        hg = self._prepare(self.alignment_utils_g, log_probs_g, grp_seqs, ph_seq_lens, spectral_lens, lg) if groups else None
         self.alignment_utils_p.decode_alignments_enqueue(hp)
         if groups:
             self.alignment_utils_g.decode_alignments_enqueue(hg, after_sibling=True)
         ph = self._finish(self.alignment_utils_p, hp, log_probs_p, ph_seqs, ph_seq_lens, spectral_lens, wav_lens, start_offset_times,
-                          self.silence_class)
+                          self.silence_class, lg)
         gr = (self._finish(self.alignment_utils_g, hg, log_probs_g, grp_seqs, ph_seq_lens, spectral_lens, wav_lens, start_offset_times,
-                           self.silence_group) if groups else [None] * len(ph))
+                           self.silence_group, lg) if groups else [None] * len(ph))
         return [{"phoneme_timestamps": ph[b], "group_timestamps": gr[b]} for b in range(len(ph))]
 
     # ---- acoustic side (injected) ------------------------------------------------------------------------------------------------
-    def _log_posteriors(self, wavs, wav_lens, extract_embeddings):
+    def _log_posteriors(self, wavs, wav_lens, extract_embeddings, keep_logits=False):
         """`_cupe_prediction_batch` (core.py:370-460) + log_softmax (:898-899): from the injected provider."""
         if self.posterior_provider is None:
             raise AssertionError("posterior provider is not set (the reference asserts that the CUPE extractor is loaded, core.py:890)")
@@ -155,11 +170,14 @@ class PhonemeTimestampAligner:
                       window_size_ms=r["window_size_ms"], stride_ms=r["stride_ms"])
             lp_p = stitch_log_softmax(r["window_logits_class"].to(self.device), **kw)
             lp_g = stitch_log_softmax(r["window_logits_group"].to(self.device), **kw) if r.get("window_logits_group") is not None else None
-            return lp_p, lp_g, r["spectral_lens"]
+            return lp_p, lp_g, r["spectral_lens"], False
         logits_class, logits_group, _emb, spectral_lens = r
+        if keep_logits:                  # the aligner takes the stitched logits as they are (timestamps_from_posteriors(input_is_logits=True))
+            f32 = lambda t: t.to(self.device).contiguous().float()
+            return f32(logits_class), (f32(logits_group) if logits_group is not None else None), spectral_lens, True
         lp_p = log_softmax_rows(logits_class.to(self.device))
         lp_g = log_softmax_rows(logits_group.to(self.device)) if logits_group is not None else None
-        return lp_p, lp_g, spectral_lens
+        return lp_p, lp_g, spectral_lens, False
 
     def _map_phonemes_to_groups(self, phoneme_sequence):                                  # :1048-1059
         return torch.tensor([self.phoneme_id_to_group_id.get(int(p), self.blank_group) for p in phoneme_sequence], dtype=torch.long)
@@ -185,11 +203,12 @@ class PhonemeTimestampAligner:
                 max_len = max(m.size(0) for m in mapped)
                 group_sequences = torch.stack([m if m.size(0) == max_len else torch.nn.functional.pad(m, (0, max_len - m.size(0)), value=self.blank_group)
                                                for m in mapped], dim=0)
-        log_probs_p, log_probs_g, spectral_lens = self._log_posteriors(wavs, wav_lens, extract_embeddings)
+        log_probs_p, log_probs_g, spectral_lens, are_logits = self._log_posteriors(wavs, wav_lens, extract_embeddings, keep_logits=True)
         spectral_lens = [int(v) for v in (spectral_lens.tolist() if isinstance(spectral_lens, torch.Tensor) else spectral_lens)]
         # the reference aligns the group head whatever do_groups says (:914-922); its result is dropped by process_segments then
         dicts = self.timestamps_from_posteriors(log_probs_p, phoneme_sequences, torch.tensor(ph_seq_lens, dtype=torch.long), spectral_lens,
-                                                wav_lens, start_offset_times, log_probs_g, group_sequences if log_probs_g is not None else None)
+                                                wav_lens, start_offset_times, log_probs_g, group_sequences if log_probs_g is not None else None,
+                                                input_is_logits=are_logits)
         for d in dicts:
             if d["group_timestamps"] is None:
                 d["group_timestamps"] = []
@@ -203,7 +222,7 @@ class PhonemeTimestampAligner:
             ph_seq_lens = [len(seq) for seq in phoneme_sequences]
             max_len = max(len(seq) for seq in phoneme_sequences)
             phoneme_sequences = torch.tensor([list(seq) + [self.blank_class] * (max_len - len(seq)) for seq in phoneme_sequences], dtype=torch.long)
-        log_probs_p, _, spectral_lens = self._log_posteriors(wavs, wav_lens, False)
+        log_probs_p, _, spectral_lens, _ = self._log_posteriors(wavs, wav_lens, False)
         spectral_lens = [int(v) for v in (spectral_lens.tolist() if isinstance(spectral_lens, torch.Tensor) else spectral_lens)]
         frames = self.alignment_utils_p.decode_alignments_simple(log_probs_p, true_seqs=phoneme_sequences.to(self.device),
                                                                  pred_lens=torch.tensor(spectral_lens, dtype=torch.long),

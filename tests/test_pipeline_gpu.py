@@ -72,6 +72,27 @@ def test_process_sentence_api_vs_reference(bfa, dev, name):
     assert [a.total_segments_processed, a.total_segments_failed, a.total_segments_bad, a.perfect_matches] == case["counters"]
 
 
+def test_process_sentence_takes_the_logits_path(bfa, dev):
+    """Text without punctuation (no silence_id in the targets): both heads are aligned straight from the provider's logits (one
+    kernel each, core.py:898-899 never run; soft boundaries and confidences from logits + row_lse).  Same record as when the
+    provider's logits are normalised first and everything runs on log-probabilities."""
+    from bfa_b200 import synth
+    import bfa_b200.pipeline as pl
+    case = json.loads((GOLD / "sentence.json").read_text())["sentence"]
+    text = "a plain sentence without any pause marks in it at all"
+    a, prov, wavs = _aligner(bfa, case)
+    got = a.process_sentence(text, wavs[0], do_groups=True)
+    assert a.alignment_utils_p.last_row_lse is not None and a.alignment_utils_g.last_row_lse is not None
+    assert a.alignment_utils_p.last_log_probs is None
+    b, prov_b, _ = _aligner(bfa, case)
+    keep = b._log_posteriors
+    b._log_posteriors = lambda w, wl, e, keep_logits=False: keep(w, wl, e, keep_logits=False)      # normalise first, like the reference
+    want = b.process_sentence(text, wavs[0], do_groups=True)
+    assert b.alignment_utils_p.last_row_lse is None
+    _same(json.loads(json.dumps(got)), json.loads(json.dumps(want)))
+    assert len(got["segments"][0]["phoneme_ts"]) > 10
+
+
 def test_process_segments_argument_errors(bfa, dev):
     from bfa_b200 import synth
     a = bfa.PhonemeTimestampAligner(posterior_provider=lambda w, l: None, phonemizer=synth.FakePhonemizer())
