@@ -593,6 +593,41 @@ def main():
                          "roofline": {"algorithmic_bytes": alg2, "achieved": alg2 / (ms2 / 1e3) / 1e9, "frac": alg2 / (ms2 / 1e3) / 1e9 / peak, "unit": "GB/s",
                                       "of": "both kernels, CUDA events around 10 steps"},
                          "items": {"exact_kernel": 0, "window_24_40_64": [0, 0, 0]}})
+        # the same C = 67 head from un-normalised LOGITS (core.py:898-899 not run): one kernel (bfa_align_batch_logits), next to what the
+        # reference's order of operations costs here -- a log-softmax pass over [B, T, C] (read + write) and then the kernel
+        from bfa_b200.aligner import log_softmax_rows
+        lg67 = lp67 + 3.0                                                  # any per-row shift: the kernel never sees normalised rows
+        tg67_32 = tg67.to(torch.int32).reshape(-1).contiguous()
+        p67 = hinted(au67.viterbi_decoder, True)
+        plan67 = au67.viterbi_decoder.plan_batch(Ts, Ns, 67, params=p67, device=dev)
+        rl = [None, None]
+
+        def from_logits():
+            rl[0] = au67.viterbi_decoder.align_batch(lg67, row_off67, Ts, 67, tg67_32, Ns, params=p67, plan=plan67, out=rl[0], logits=True)
+
+        p67s = au67.viterbi_decoder._params(True, True, True)              # not BFA_FLAG_PIPELINED: its rows are written by the kernel right before it
+        p67s.reserved |= _cabi.HINT_NO_SIL | _cabi.FLAG_DIRECT_ONLY
+        plan67s = au67.viterbi_decoder.plan_batch(Ts, Ns, 67, params=p67s, device=dev)
+
+        def softmax_then_align():
+            rl[1] = au67.viterbi_decoder.align_batch(log_softmax_rows(lg67), row_off67, Ts, 67, tg67_32, Ns, params=p67s, plan=plan67s, out=rl[1])
+        row_off67 = torch.arange(B, dtype=torch.int64, device=dev) * (T * 67)
+        for f in (from_logits, softmax_then_align):
+            for _ in range(4):
+                f()
+        torch.cuda.synchronize()
+        ms_l, ms_s = time_steps(torch, from_logits, 10), time_steps(torch, softmax_then_align, 10)
+        same = bool(torch.equal(rl[0].frame_ph, rl[1].frame_ph)) and int((rl[0].status[:B] & 7 != 0).sum()) == 0
+        alg67 = algorithmic_bytes(Ts, Ns, 67)
+        variants.append({"name": "metric shape at C=67 from un-normalised logits, one kernel per step (bfa_align_batch_logits: F.log_softmax of core.py:898-899 never run)",
+                         "B": B, "C": 67, "frames": B * T, "ms_per_step": ms_l, "value": B * T / (ms_l / 1e3), "unit": "frames/s",
+                         "launches_per_step": 1.0, "all_finished": same,
+                         "log_softmax_pass_then_kernel_ms": ms_s, "frames_identical_to_that": same,
+                         "roofline": {"algorithmic_bytes": alg67 + 4 * B * T, "achieved": (alg67 + 4 * B * T) / (ms_l / 1e3) / 1e9,
+                                      "frac": (alg67 + 4 * B * T) / (ms_l / 1e3) / 1e9 / peak, "unit": "GB/s",
+                                      "of": "the kernel (rows read once, frame labels + row_lse written), CUDA events around 10 steps"},
+                         "items": {"exact_kernel": 0, "window_24_40_64": [0, 0, 0]}})
+        del lg67, rl
         del lp67, lp17, h67, h17
         torch.cuda.empty_cache()
         # SIL at every 10th target (what punctuation does to real targets): silence anchoring really runs -- row statistics for the
