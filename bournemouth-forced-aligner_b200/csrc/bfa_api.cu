@@ -718,7 +718,16 @@ int bfa_stitch_log_softmax(int32_t B, int32_t n_windows, int32_t frames_per_wind
     a.in = window_logits; a.weights = window_weights; a.out = logp_out; a.in_pitch_b = in_pitch; a.out_pitch_b = out_pitch;
     const long long rows = (long long)B * total_frames;
     const int grid = (int)std::min((rows + STITCH_WARPS - 1) / STITCH_WARPS, (long long)d.sms * 8);
-    stitch_log_softmax_kernel<<<grid, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    if (frames_per_window == 0 && rows < (1LL << 31)) {
+        const long long units = (rows + LS_ROWS - 1) / LS_ROWS;
+        const int g2 = (int)std::min((units + STITCH_WARPS - 1) / STITCH_WARPS, (long long)d.sms * 8);
+        if (C <= 32) log_softmax_rows_kernel<1><<<g2, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+        else if (C <= 64) log_softmax_rows_kernel<2><<<g2, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+        else if (C <= 96) log_softmax_rows_kernel<3><<<g2, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+        else log_softmax_rows_kernel<MAX_WORDS><<<g2, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    } else {
+        stitch_log_softmax_kernel<<<grid, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    }
     LAUNCH_CHECK();
     return BFA_OK;
 }

@@ -20,6 +20,55 @@ struct StitchArgs {
 // operation by operation (product, then sum in ascending window order, :147-166; weight_sum + 1e-8, :169); the
 // log-softmax is max-subtracted like torch's.
 constexpr int STITCH_WARPS = 8;
+// Plain log-softmax of [B, total_frames, C] logits (no windows): the same arithmetic as the stitched path below (max-subtracted,
+// expf / logf, classes dealt to the lanes), but one row per warp and iteration keeps only C * 4 bytes per warp in flight --
+// far too little to cover HBM latency.  Here every warp takes LS_ROWS rows per iteration, all their loads issued before the
+// first reduction.
+// NW = 32-class words per row that are compiled in (C <= 32 NW): lanes do not issue predicated-off work for classes that do not exist.
+constexpr int LS_ROWS = 4;
+template <int NW>
+__global__ void __launch_bounds__(STITCH_WARPS * 32) log_softmax_rows_kernel(const __grid_constant__ StitchArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)a.B * a.total_frames;
+    const long long nw = (long long)gridDim.x * STITCH_WARPS;
+    for (long long r0 = ((long long)blockIdx.x * STITCH_WARPS + (threadIdx.x >> 5)) * LS_ROWS; r0 < rows; r0 += nw * LS_ROWS) {
+        float v[LS_ROWS][NW];
+#pragma unroll
+        for (int r = 0; r < LS_ROWS; ++r) {
+            const unsigned row = (unsigned)min(r0 + r, rows - 1);            // rows < 2^31 (checked by the caller): 32-bit division
+            const unsigned b = row / (unsigned)a.total_frames, f = row - b * (unsigned)a.total_frames;
+            const float* src = a.in + (long long)b * a.in_pitch_b + (long long)f * a.C;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                const int c = lane + 32 * i;
+                v[r][i] = c < a.C ? __ldcs(src + c) : -INFINITY;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < LS_ROWS; ++r) {
+            if (r0 + r >= rows) break;
+            const unsigned row = (unsigned)(r0 + r);
+            const unsigned b = row / (unsigned)a.total_frames, f = row - b * (unsigned)a.total_frames;
+            float m = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) m = fmaxf(m, v[r][i]);
+            m = warp_max(m);
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < NW; ++i)
+                if (lane + 32 * i < a.C) s += expf(v[r][i] - m);
+            s = warp_sum(s);
+            const float ls = logf(s);
+            float* dst = a.out + (long long)b * a.out_pitch_b + (long long)f * a.C;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                const int c = lane + 32 * i;
+                if (c < a.C) dst[c] = (v[r][i] - m) - ls;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(STITCH_WARPS * 32) stitch_log_softmax_kernel(const __grid_constant__ StitchArgs a) {
     const int lane = threadIdx.x & 31;
     const long long rows = (long long)a.B * a.total_frames;
