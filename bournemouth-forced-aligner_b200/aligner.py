@@ -440,7 +440,10 @@ class AlignmentUtils:
         plan = self.viterbi_decoder.plan_batch(T, N, C_, params=params, device=dev)
         # Un-normalised logits (core.py:898-899 not run by the caller): when the batch goes to the one-kernel pass and boosting is
         # on, that kernel takes them as they are (bfa_align_batch_logits); otherwise they are normalised first, like the reference.
-        use_logits = bool(input_is_logits and (params.reserved & _cabi.FLAG_DIRECT_ONLY) and params.mode == _cabi.MODE_FULL and params.boost_targets)
+        #   (... or to the planner chain with its silence pass, which then also leaves the rows' log-sum-exp behind)
+        chain_ok = may_segment and not (params.reserved & _cabi.HINT_NO_SIL) and 0 <= params.silence_id < C_
+        use_logits = bool(input_is_logits and params.mode == _cabi.MODE_FULL and params.boost_targets
+                          and ((params.reserved & _cabi.FLAG_DIRECT_ONLY) or chain_ok))
         if input_is_logits and not use_logits:
             lp = log_softmax_rows(lp)
         return dict(r=None, lp=lp, row_off=row_off, T=T, N=N, C=C_, tgt=tgt, params=params, want_conf=want_conf, B=B, T_max=T_max, plan=plan,
@@ -471,7 +474,7 @@ class AlignmentUtils:
         st = r.status[:B].cpu().numpy()
         if ((st & 7) == _cabi.ST_DEFERRED).any():  # the one-kernel path handed utterances back: the full chain takes the batch
             params.reserved &= ~(_cabi.FLAG_DIRECT_ONLY | _cabi.FLAG_PIPELINED)
-            if h.get("logits"):                    # ... on normalised rows: the chain's stamp kernel reads log-probabilities
+            if h.get("logits"):                    # ... on normalised rows (no silence pass runs in this configuration to supply row_lse)
                 h["lp"] = log_softmax_rows(h["lp"])
                 h["logits"] = False
             r = again()

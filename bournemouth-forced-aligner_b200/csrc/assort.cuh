@@ -35,15 +35,15 @@ __device__ __forceinline__ float stamp_confidence(const float* lp, int T, int C,
 
 // Same as stamp_confidence, but lp[f, ph] comes from the per-frame array the Viterbi kernels gathered
 // (valid because every frame of a stamp was assigned the stamp's phoneme).
-__device__ __forceinline__ float stamp_confidence_path(const float* plp, int T, int start, int end) {
+__device__ __forceinline__ float stamp_confidence_path(const float* plp, int T, int start, int end, const float* lse = nullptr) {
     int s = max(0, start), e = min(T, end);
-    float avg = expf(plp[s]);
+    float avg = expf(plp[s] - (lse ? lse[s] : 0.0f));
     if (s < e) {
         const float half = avg / 2.0f;
         int good = 1;
         float mx = 0.f;
         for (int f = s + 1; f < e; ++f) {
-            float pr = expf(plp[f]);
+            float pr = expf(plp[f] - (lse ? lse[f] : 0.0f));
             mx = fmaxf(mx, pr);
             if (pr > half || pr > 0.1f) { avg += pr; ++good; }
         }
@@ -104,6 +104,7 @@ struct AssortArgs {
     int32_t* n_stamps;
     const float* path_lp;   // per-frame gathered lp (or null: gather from logp)
     const int32_t* uflag;   // when non-null: utterances with uflag[u] != 0 were finished (stamps included) by the direct kernel
+    const float* row_lse;   // logits in: [total_frames] log-sum-exp of the rows (silprob_kernel<true>), subtracted where a value is exponentiated; or null
 };
 
 __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(AssortArgs a) {
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(As
     const int32_t* ph = a.frame_ph + fo;
     const int32_t* ix = a.frame_idx + fo;
     const float* plp = a.path_lp ? a.path_lp + fo : nullptr;
+    const float* lse = a.row_lse ? a.row_lse + fo : nullptr;
     // Stage the utterance's per-frame arrays in shared memory with independent coalesced loads (all in flight at
     // once), exponentiating the confidence inputs on the way in (one frame per lane instead of one stamp per lane);
     // the run-length scan and the per-stamp confidence loops below then never wait on global memory.
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(As
                 if (t < T) {
                     v_ph[j] = ph[t];
                     v_ix[j] = ix[t];
-                    if (plp) v_lp[j] = plp[t];
+                    if (plp) v_lp[j] = plp[t] - (lse ? lse[t] : 0.0f);
                 }
             }
 #pragma unroll
@@ -319,8 +321,8 @@ __global__ void __launch_bounds__(ASSORT_WARPS * 32) assort_confidence_kernel(As
         if (a.conf) {
             float cf;
             if (pr_s && s.phoneme < a.C) cf = stamp_confidence_prob(pr_s, T, s.start, s.end);
-            else if (plp && s.phoneme < a.C) cf = stamp_confidence_path(plp, T, s.start, s.end);
-            else cf = stamp_confidence(lp, T, a.C, s.phoneme, s.start, s.end);
+            else if (plp && s.phoneme < a.C) cf = stamp_confidence_path(plp, T, s.start, s.end, lse);
+            else cf = stamp_confidence(lp, T, a.C, s.phoneme, s.start, s.end, lse);
             a.conf[(size_t)u * a.max_stamps + i] = cf;
         }
     }

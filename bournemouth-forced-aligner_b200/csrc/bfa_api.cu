@@ -197,7 +197,8 @@ int device_info(DeviceInfo& out) {
         CUDA_TRY(cudaFuncSetAttribute(assort_confidence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)assort_smem(ASSORT_TS_MAX, ASSORT_SS_MAX)));
         CUDA_TRY(cudaFuncSetAttribute(soft_boundaries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(silprob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BAND_SMEM_MAX));
+        CUDA_TRY(cudaFuncSetAttribute(silprob_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BAND_SMEM_MAX));
+        CUDA_TRY(cudaFuncSetAttribute(silprob_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BAND_SMEM_MAX));
         const int band_smem_max = BAND_SMEM_MAX;
         d.band_ok = band_set_attr(band_smem_max) == cudaSuccess;
         if (!d.band_ok) (void)cudaGetLastError();   // do not leave a sticky error behind: the exact kernel still runs
@@ -461,9 +462,12 @@ static int align_impl(const BfaParams* p, const BfaShape* shape, const float* lo
     // confidences); the planner chain below then only sees what it handed back (device-side list).  With BFA_FLAG_DIRECT_ONLY the
     // chain is not launched at all and such utterances are flagged instead.
     const bool use_direct = L.direct && fast;
-    const bool logits = row_lse != nullptr;          // bfa_align_batch_logits: the one-kernel pass only, whatever it cannot finish is flagged
-    if (logits && !use_direct) return BFA_E_UNSUPPORTED;
-    const bool direct_only = use_direct && ((p->reserved & BFA_FLAG_DIRECT_ONLY) != 0 || logits);
+    // bfa_align_batch_logits.  The planner chain can follow when its silence pass runs (it reads every row of the chain's utterances
+    // and leaves their log-sum-exp behind for the stamp kernel); otherwise only the one-kernel pass runs and flags what it cannot finish.
+    const bool logits = row_lse != nullptr;
+    const bool chain_logits = logits && L.want_sil && shape->max_T > 0 && p->silence_id < C && (!(stamps && conf) || path_lp != nullptr);
+    if (logits && !use_direct && !chain_logits) return BFA_E_UNSUPPORTED;
+    const bool direct_only = use_direct && ((p->reserved & BFA_FLAG_DIRECT_ONLY) != 0 || (logits && !chain_logits));
     int* deferred = use_direct && !direct_only ? (int*)(ws + L.off_deferred) : nullptr;
     int32_t* uflag = use_direct && !direct_only ? (int32_t*)(ws + L.off_uflag) : nullptr;
     if (!direct_only) CUDA_TRY(cudaMemsetAsync(counters, 0, 64, st));
@@ -513,11 +517,13 @@ static int align_impl(const BfaParams* p, const BfaShape* shape, const float* lo
         sa.logp = logp; sa.row_off = (const long long*)row_off; sa.T = T; sa.tgt = tgt; sa.tgt_off = (const long long*)tgt_off;
         sa.frame_off = (const long long*)frame_off; sa.D = sild; sa.deferred = deferred; sa.n_deferred = counters + 13;
         sa.tmask = tmask; sa.units = (int2*)(ws + L.off_silunits); sa.n_units = counters + 14;
+        sa.row_lse = chain_logits ? row_lse : nullptr; sa.list_all = chain_logits ? 1 : 0;
         launch_maybe_pdl(silunits_kernel, (B + 7) / 8, 256, 0, st, sa, use_direct);
         LAUNCH_CHECK();
         const long long units = (long long)shape->total_frames / SS_CHUNK + B;      // upper bound; the real count stays on the device
         const int grid = (int)std::max(1LL, std::min((long long)d.sms, (units + SS_WARPS - 1) / SS_WARPS));
-        launch_maybe_pdl(silprob_kernel, grid, SS_WARPS * 32, ss_smem_per_warp(C, sa.nst) * SS_WARPS, st, sa, false);
+        if (chain_logits) launch_maybe_pdl(silprob_kernel<true>, grid, SS_WARPS * 32, ss_smem_per_warp(C, sa.nst) * SS_WARPS, st, sa, false);
+        else launch_maybe_pdl(silprob_kernel<false>, grid, SS_WARPS * 32, ss_smem_per_warp(C, sa.nst) * SS_WARPS, st, sa, false);
         LAUNCH_CHECK();
     }
     PlanArgs pa;
@@ -632,7 +638,7 @@ static int align_impl(const BfaParams* p, const BfaShape* shape, const float* lo
         aa.p = *p; aa.B = B; aa.C = C; aa.max_stamps = shape->max_stamps; aa.logp = logp; aa.row_off = (const long long*)row_off;
         aa.T = T; aa.frame_off = (const long long*)frame_off; aa.frame_ph = frame_ph; aa.frame_idx = frame_idx;
         aa.status = status; aa.stamps = stamps; aa.conf = conf; aa.n_stamps = n_stamps; aa.path_lp = path_lp;
-        aa.uflag = uflag;
+        aa.uflag = uflag; aa.row_lse = chain_logits ? row_lse : nullptr;
         aa.ts = shape->max_N < 32768 ? assort_ts(shape->max_T) : 0;   // staged frames pack (idx, phoneme) into 16 + 16 bits
         aa.ss = assort_ss(shape->max_stamps);
         cudaEvent_t ae0 = nullptr, ae1 = nullptr;
@@ -882,7 +888,7 @@ int bfa_assort_batch(const BfaParams* p, int32_t B, const int32_t* T, const int6
     AssortArgs aa;
     aa.p = *p; aa.B = B; aa.C = 0; aa.max_stamps = max_stamps; aa.logp = nullptr; aa.row_off = nullptr; aa.T = T;
     aa.frame_off = (const long long*)frame_off; aa.frame_ph = frame_ph; aa.frame_idx = frame_idx; aa.status = status;
-    aa.stamps = stamps; aa.conf = nullptr; aa.n_stamps = n_stamps; aa.path_lp = nullptr; aa.uflag = nullptr;
+    aa.stamps = stamps; aa.conf = nullptr; aa.n_stamps = n_stamps; aa.path_lp = nullptr; aa.uflag = nullptr; aa.row_lse = nullptr;
     aa.ts = 0; aa.ss = assort_ss(max_stamps);     // utterance lengths are only known on the device here: frames are read in place
     assort_confidence_kernel<<<(B + ASSORT_WARPS - 1) / ASSORT_WARPS, ASSORT_WARPS * 32, assort_smem(aa.ts, aa.ss), (cudaStream_t)stream>>>(aa);
     LAUNCH_CHECK();

@@ -41,6 +41,10 @@ struct SilArgs {
     int* n_units;
     const int* deferred;       // when non-null: only the utterances deferred[0 .. *n_deferred) (what the direct kernel left)
     const int* n_deferred;
+    // logits in (bfa_align_batch_logits, planner chain): this pass reads every row of every utterance the chain works on anyway
+    // (list_all: also those without silence_id in the target) and leaves the rows' plain log-sum-exp behind for the stamp kernel
+    float* row_lse;            // [total_frames] or null
+    int list_all;
 };
 
 __host__ __device__ inline size_t ss_stage_bytes(int C) { return C <= B3_KK ? ((size_t)SS_ROWS * C + SS_PAD) * 4 : 0; }
@@ -71,7 +75,7 @@ __device__ __noinline__ float ss_exact_prob(Row row, Wt is_target, int C, int si
 // the planner itself when it was told (wrongly) that no target holds silence_id.  Same results, not HBM speed.
 // mw = the utterance's target-class mask words.
 __device__ __noinline__ void ss_gather_rows(const BfaParams& p, int C, const float* base, int rows_u, double* Dout, int lane,
-                                            const uint32_t* mw, bool sil_tgt) {
+                                            const uint32_t* mw, bool sil_tgt, float* lse_out = nullptr) {
     const bool boost = p.boost_targets != 0;
     const int sil = p.silence_id;
     uint32_t tbits = 0;
@@ -88,6 +92,10 @@ __device__ __noinline__ void ss_gather_rows(const BfaParams& p, int C, const flo
                 const float* row = base + (long long)(b * SS_ROWS + r) * C;
                 const float2 s = row_stats_warp([&](int c) { return row[c]; }, C, lane, tbits, p.boost_factor);
                 if (lane == r) { m = s.x; ls = s.y; }
+                if (lse_out) {                                                // logits in: the plain log-sum-exp of the row
+                    const float2 s0 = row_stats_warp([&](int c) { return row[c]; }, C, lane, 0u, 0.0f);
+                    if (lane == r) lse_out[b * SS_ROWS + r] = s0.x + s0.y;
+                }
             }
         }
         float pr = 0.f;
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(256) silunits_kernel(const __grid_constant__ S
     const int u = a.deferred ? a.deferred[ui] : ui;
     const int Tu = a.T[u];
     const TgtInfo ti = target_info(a.tgt, a.tgt_off[u], a.tgt_off[u + 1], a.C, a.p.blank_id, a.p.silence_id, lane, s_mask[warp]);
-    if (!ti.has_sil || Tu <= 0) return;
+    if ((!ti.has_sil && !a.list_all) || Tu <= 0) return;
     if (lane < MAX_WORDS) a.tmask[(size_t)u * MAX_WORDS + lane] = s_mask[warp][lane];
     const int n = (Tu + SS_CHUNK - 1) >> SS_CHUNK_SHIFT;
     int base = 0;
@@ -128,8 +136,10 @@ __global__ void __launch_bounds__(256) silunits_kernel(const __grid_constant__ S
     for (int i = lane; i < n; i += 32) a.units[base + i] = make_int2(u, i);
 }
 
+// LG: logits in -- the reduction also carries the plain sum (2^(-kk) = 1 + kk * MSC, see viterbi_band3.cuh) and row_lse is written.
+template <bool LG>
 __global__ void __launch_bounds__(SS_WARPS * 32, 1) silprob_kernel(const __grid_constant__ SilArgs a) {
-    constexpr float LOG2E = 1.4426950408889634f;
+    constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
     extern __shared__ __align__(128) unsigned char ss_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = a.C, nst = a.nst;
@@ -154,6 +164,7 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 1) silprob_kernel(const __grid_
     const int gw = blockIdx.x * SS_WARPS + warp, nw = gridDim.x * SS_WARPS;
     const uint64_t pol = policy_evict_first();
     const float min_p = expf(p.min_log_prob);
+    const float MSC = (LG && p.boost_factor != 0.0f) ? (1.0f - expf(p.boost_factor)) / (p.boost_factor * LOG2E) : 0.0f;
     uint32_t phase = 0;
 
     for (int unit = gw; unit < total; unit += nw) {
@@ -169,6 +180,7 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 1) silprob_kernel(const __grid_
         const long long ro = a.row_off[u];
         const float* base = a.logp + ro + (long long)r0 * C;
         double* Dout = a.D + a.frame_off[u] + r0;
+        float* Lout = LG ? a.row_lse + a.frame_off[u] + r0 : nullptr;
         const int lead = (int)(((unsigned long long)(a.logp + ro) & 15ull) >> 2);     // 128*C bytes per copy: every copy of the utterance has this lead-in
         const bool staged = nst > 0 && boost && (lead == 0 || ro >= lead);
         double carry = 0.0;
@@ -207,6 +219,12 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 1) silprob_kernel(const __grid_
                 if (t < rows_u) {
                     const float* rowp = stage + (size_t)st * stage_floats + lead + lane * C;
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;         // LG: the plain sums
+                    auto term = [&](float x, float kc, float& acc, float& zacc) {
+                        const float e = b3_ex2(fmaf(x, LOG2E, kc));
+                        acc += e;
+                        if constexpr (LG) zacc = fmaf(e, fmaf(kc, MSC, 1.0f), zacc);
+                    };
                     if (vec2) {
                         const float2* x2 = reinterpret_cast<const float2*>(rowp);
                         const float4* k4 = reinterpret_cast<const float4*>(kk);
@@ -215,31 +233,44 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 1) silprob_kernel(const __grid_
                         for (int i = 0; i < n4; ++i) {
                             const float2 xa = x2[2 * i], xb = x2[2 * i + 1];
                             const float4 kv = k4[i];
-                            s0 += b3_ex2(fmaf(xa.x, LOG2E, kv.x));
-                            s1 += b3_ex2(fmaf(xa.y, LOG2E, kv.y));
-                            s2 += b3_ex2(fmaf(xb.x, LOG2E, kv.z));
-                            s3 += b3_ex2(fmaf(xb.y, LOG2E, kv.w));
+                            term(xa.x, kv.x, s0, z0);
+                            term(xa.y, kv.y, s1, z1);
+                            term(xb.x, kv.z, s2, z2);
+                            term(xb.y, kv.w, s3, z3);
                         }
                         if (C & 2) {
                             const float2 xa = x2[2 * n4];
-                            s0 += b3_ex2(fmaf(xa.x, LOG2E, kk[4 * n4]));
-                            s1 += b3_ex2(fmaf(xa.y, LOG2E, kk[4 * n4 + 1]));
+                            term(xa.x, kk[4 * n4], s0, z0);
+                            term(xa.y, kk[4 * n4 + 1], s1, z1);
                         }
                     } else {
                         int i = 0;
 #pragma unroll 2
                         for (; i + 4 <= C; i += 4) {
-                            s0 += b3_ex2(fmaf(rowp[i], LOG2E, kk[i]));
-                            s1 += b3_ex2(fmaf(rowp[i + 1], LOG2E, kk[i + 1]));
-                            s2 += b3_ex2(fmaf(rowp[i + 2], LOG2E, kk[i + 2]));
-                            s3 += b3_ex2(fmaf(rowp[i + 3], LOG2E, kk[i + 3]));
+                            term(rowp[i], kk[i], s0, z0);
+                            term(rowp[i + 1], kk[i + 1], s1, z1);
+                            term(rowp[i + 2], kk[i + 2], s2, z2);
+                            term(rowp[i + 3], kk[i + 3], s3, z3);
                         }
-                        for (; i < C; ++i) s0 += b3_ex2(fmaf(rowp[i], LOG2E, kk[i]));
+                        for (; i < C; ++i) term(rowp[i], kk[i], s0, z0);
                     }
                     const float S = (s0 + s1) + (s2 + s3);
                     if (S > 0.f && S < 3.0e38f) pr = b3_ex2(fmaf(rowp[sil], LOG2E, kk[sil])) / S;
                     else pr = ss_exact_prob([&](int c) { return rowp[c]; }, [&](int c) { return kk[c] == 0.0f; }, C, sil, p.boost_factor);
                     if (p.enforce_minimum && sil_tgt) pr = fmaxf(pr, min_p);   // :75-81, exp is monotone
+                    if constexpr (LG) {
+                        const float Z = (z0 + z1) + (z2 + z3);
+                        float l0;
+                        if (Z > 0.f && Z < 3.0e38f) l0 = b3_lg2(Z) * LN2;
+                        else {                                               // the slow, exact way (max-subtracted)
+                            float m = -INFINITY;
+                            for (int c = 0; c < C; ++c) m = fmaxf(m, rowp[c]);
+                            float sz = 0.f;
+                            for (int c = 0; c < C; ++c) sz += expf(rowp[c] - m);
+                            l0 = m + logf(sz);
+                        }
+                        Lout[t] = l0;
+                    }
                 }
                 __syncwarp();                                                 // every lane has read its row: the stage may be refilled
                 if (b + nst < nblk) issue(b + nst);
@@ -254,7 +285,7 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 1) silprob_kernel(const __grid_
                 carry = __shfl_sync(FULL, v, 31);
             }
         } else {
-            ss_gather_rows(p, C, base, rows_u, Dout, lane, mw, sil_tgt);
+            ss_gather_rows(p, C, base, rows_u, Dout, lane, mw, sil_tgt, Lout);
         }
     }
 }

@@ -258,7 +258,8 @@ def test_caller_owned_arena(bfa, dev):
 def test_logits_in_one_kernel(bfa, orc, dev, Cc):
     """bfa_align_batch_logits: un-normalised logits in (core.py:898-899 skipped).  Frames, timestamps and statuses must equal what
     the ordinary call gives on log_softmax(logits) -- and the oracle on the same log-probabilities --, confidences and the DP
-    score agree to 1e-4, row_lse is the rows' log-sum-exp; utterances the one-kernel pass cannot take are flagged DEFERRED."""
+    score agree to 1e-4, row_lse is the rows' log-sum-exp; an utterance the one-kernel pass cannot take goes through the planner
+    chain (still on the logits), or is flagged DEFERRED under BFA_FLAG_DIRECT_ONLY."""
     from bfa_b200 import synth, _cabi
     B, T, N = 512, 300, 24
     lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=900 + Cc, peak=7.0, device=dev)
@@ -274,9 +275,17 @@ def test_logits_in_one_kernel(bfa, orc, dev, Cc):
     ref = dec.align_batch(lp, row_off, [T] * B, Cc, tg, [N] * B, params=p)
     r = dec.align_batch(logits, row_off, [T] * B, Cc, tg, [N] * B, params=dec._params(True, True, True), logits=True)
     torch.cuda.synchronize()
-    st = r.status[:B].cpu().numpy()
+    # utterance 3 goes to the planner chain -- on the logits as well: the chain's silence pass supplies its row_lse
+    assert torch.equal(r.status[:B] & 7, ref.status[:B] & 7) and int(r.status[3] & 7) != _cabi.ST_DEFERRED
+    pd = dec._params(True, True, True)
+    pd.reserved |= _cabi.FLAG_DIRECT_ONLY              # the one-kernel pass alone: what it cannot take is flagged
+    rd = dec.align_batch(logits, row_off, [T] * B, Cc, tg, [N] * B, params=pd, logits=True)
+    st = rd.status[:B].cpu().numpy()
     assert (st[3] & 7) == _cabi.ST_DEFERRED and int(((st & 7) == _cabi.ST_DEFERRED).sum()) == 1
-    keep = torch.ones(B, dtype=torch.bool, device=dev); keep[3] = False
+    others = torch.ones(B, dtype=torch.bool, device=dev); others[3] = False
+    assert torch.equal(rd.frame_ph[: B * T][others.repeat_interleave(T)], r.frame_ph[: B * T][others.repeat_interleave(T)])
+    assert torch.equal(rd.conf[:B, :N][others], r.conf[:B, :N][others])
+    keep = torch.ones(B, dtype=torch.bool, device=dev)
     # the two runs see emissions that differ in the last bit (x - lse against (x + s) - (lse + s)): an utterance may differ where
     # two paths tie to 1e-6 of the score; anything else must be identical
     same = ((r.frame_ph[: B * T] == ref.frame_ph[: B * T]) & (r.frame_idx[: B * T] == ref.frame_idx[: B * T])).view(B, T).all(1)
@@ -307,8 +316,8 @@ def test_logits_in_one_kernel(bfa, orc, dev, Cc):
 
 def test_decode_alignments_from_logits(bfa, dev):
     """AlignmentUtils.decode_alignments(input_is_logits=True): the caller skips F.log_softmax (core.py:898-899).  Same lists as on
-    the normalised tensor -- through the one-kernel pass when the batch qualifies, through a normalising pass + the full chain when a
-    target holds silence_id (or the one-kernel pass hands utterances back)."""
+    the normalised tensor -- through the one-kernel pass when the batch qualifies, through the planner chain on the logits when targets
+    hold silence_id (the silence pass reads every row anyway and leaves row_lse), through a normalising pass otherwise."""
     from bfa_b200 import synth, _cabi
     Cc, B, T, N = 67, 96, 260, 20
     for case in ("plain", "sil", "one deferred", "handed back"):
@@ -325,8 +334,12 @@ def test_decode_alignments_from_logits(bfa, dev):
         got = au.decode_alignments(logits, true_seqs=tgt, pred_lens=lens_t, true_seqs_lens=lens_n, with_confidence=True, input_is_logits=True)
         one_kernel = bool(au.last_params_reserved & _cabi.FLAG_DIRECT_ONLY)
         assert one_kernel == (case == "plain"), (case, au.last_params_reserved)
-        assert (au.last_row_lse is not None) == one_kernel and (au.last_log_probs is None) == one_kernel
-        if one_kernel:
+        # "sil" goes through the planner chain ON THE LOGITS (its silence pass supplies row_lse); "one deferred" (no silence_id
+        # anywhere: that pass is not run) is normalised first, "handed back" started as a one-kernel call and is repeated on
+        # normalised rows
+        from_logits = case in ("plain", "sil")
+        assert (au.last_row_lse is not None) == from_logits and (au.last_log_probs is None) == from_logits
+        if from_logits:
             lse = torch.logsumexp(logits.double(), dim=2).float().reshape(-1)
             assert torch.allclose(au.last_row_lse[: B * T], lse, rtol=0, atol=2e-5)
         else:
