@@ -314,6 +314,41 @@ def test_logits_in_one_kernel(bfa, orc, dev, Cc):
         dec.align_batch(logits, row_off, [T] * B, Cc, tg, [N] * B, params=dec._params(False, True, True), logits=True)
 
 
+@pytest.mark.parametrize("Cc,sil_every", [(66, 10), (67, 9), (17, 5), (80, 10)])
+def test_logits_through_the_planner_chain(bfa, dev, Cc, sil_every):
+    """Targets with silence_id (what punctuation does): silence-anchored segmentation, list-mode banded kernel / exact kernel and
+    the stamp kernel all run on the un-normalised logits, the silence pass leaves row_lse.  Everything must equal the same call on
+    log_softmax(logits).  C = 80 takes the paths without the staged row reduction (class table of 72) and without banded kernels."""
+    from bfa_b200 import synth, _cabi
+    B, T = 384, 600
+    N = 40 if Cc > 20 else 14
+    lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=1200 + Cc, peak=9.0, sil_every=sil_every, sil_frames=15, device=dev)
+    tgt[::7, 1] = 1                                   # (some variety: utterances stay SIL-bearing)
+    shift = (torch.randn(B, T, 1, generator=torch.Generator().manual_seed(2)) * 7.0 - 4.0).to(dev)
+    logits = (lp + shift).contiguous()
+    tg = tgt.to(torch.int32).reshape(-1).contiguous()
+    dec = bfa.AlignmentUtils(Cc - 1, 0, silence_anchors=10, ignore_noise=True, truly_forced=True).viterbi_decoder
+    row_off = torch.arange(B, dtype=torch.int64, device=dev) * T * Cc
+    ref = dec.align_batch(lp, row_off, [T] * B, Cc, tg, [N] * B, params=dec._params(True, True, True))
+    for flags in (0, _cabi.FLAG_NO_DIRECT):
+        p = dec._params(True, True, True)
+        p.reserved |= flags
+        r = dec.align_batch(logits, row_off, [T] * B, Cc, tg, [N] * B, params=p, logits=True)
+        torch.cuda.synchronize()
+        assert torch.equal(r.status[:B] & 7, ref.status[:B] & 7)
+        assert int(((r.status[:B] & 7) == _cabi.ST_SEGMENTED).sum()) > B // 2          # anchoring really ran
+        same = ((r.frame_ph[: B * T] == ref.frame_ph[: B * T]) & (r.frame_idx[: B * T] == ref.frame_idx[: B * T])).view(B, T).all(1)
+        assert int((~same).sum()) <= 2, int((~same).sum())                              # last-bit ties, see test_logits_in_one_kernel
+        ns = ref.n_stamps[:B]
+        assert torch.equal(r.n_stamps[:B][same], ns[same])
+        ms = r.stamps.shape[1]
+        valid = (torch.arange(ms, device=dev)[None, :] < ns[:, None]) & same[:, None]
+        assert torch.equal(r.stamps[:B][valid], ref.stamps[:B][valid])
+        assert torch.allclose(r.conf[:B][valid], ref.conf[:B][valid], rtol=1e-4, atol=1e-6)
+        lse = torch.logsumexp(logits.double(), dim=2).float().reshape(-1)
+        assert torch.allclose(r.row_lse[: B * T], lse, rtol=0, atol=3e-5)
+
+
 def test_decode_alignments_from_logits(bfa, dev):
     """AlignmentUtils.decode_alignments(input_is_logits=True): the caller skips F.log_softmax (core.py:898-899).  Same lists as on
     the normalised tensor -- through the one-kernel pass when the batch qualifies, through the planner chain on the logits when targets
