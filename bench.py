@@ -636,6 +636,33 @@ def main():
         w = dict(lp=lpv, row_off=row_off, Ts=Ts, Ns=Ns, tgt=tgv.to(torch.int32).reshape(-1).contiguous())
         variants.append(run_variant(torch, lib, dec, dev, "metric shape with silence_id at every 10th target (anchoring on, no hints, full chain)", w, Cc,
                                     hinted(dec, False), peak))
+        # the same batch as un-normalised logits: the chain runs on them as they are (the silence pass also leaves row_lse), next to
+        # what the reference's order costs here: a log-softmax pass over [B, T, C], then the chain
+        from bfa_b200.aligner import log_softmax_rows as _lsr
+        lgv = lpv + 2.0
+        pl_ = hinted(dec, False)
+        plan_l = dec.plan_batch(Ts, Ns, Cc, params=pl_, device=dev)
+        rr = [None, None]
+
+        def sil_from_logits():
+            rr[0] = dec.align_batch(lgv, row_off, Ts, Cc, w["tgt"], Ns, params=pl_, plan=plan_l, out=rr[0], logits=True)
+
+        def sil_softmax_first():
+            rr[1] = dec.align_batch(_lsr(lgv), row_off, Ts, Cc, w["tgt"], Ns, params=pl_, plan=plan_l, out=rr[1])
+        for f in (sil_from_logits, sil_softmax_first):
+            for _ in range(3):
+                f()
+        torch.cuda.synchronize()
+        ms_a, ms_b = time_steps(torch, sil_from_logits, 10), time_steps(torch, sil_softmax_first, 10)
+        same_f = float((rr[0].frame_ph == rr[1].frame_ph).float().mean())
+        algs = algorithmic_bytes(Ts, Ns, Cc) + 4 * B * T
+        variants.append({"name": "metric shape with silence_id at every 10th target, from un-normalised logits (full chain on the logits, silence pass leaves row_lse)",
+                         "B": B, "C": Cc, "frames": B * T, "ms_per_step": ms_a, "value": B * T / (ms_a / 1e3), "unit": "frames/s",
+                         "launches_per_step": 7.0, "log_softmax_pass_then_chain_ms": ms_b, "frame_labels_equal_fraction": same_f,
+                         "roofline": {"algorithmic_bytes": algs, "achieved": algs / (ms_a / 1e3) / 1e9, "frac": algs / (ms_a / 1e3) / 1e9 / peak,
+                                      "unit": "GB/s", "of": "the whole step (every kernel of the call), CUDA events around 10 steps"},
+                         "items": {"exact_kernel": 0, "window_24_40_64": [0, 0, 0]}})
+        del lgv, rr
         psil = hinted(dec, False)
         psil.reserved |= _cabi.FLAG_NO_DIRECT        # what the facade sets when the host-side targets (nearly) all hold silence_id
         variants.append(run_variant(torch, lib, dec, dev, "metric shape with silence_id at every 10th target, one-kernel pass skipped (BFA_FLAG_NO_DIRECT)", w, Cc,

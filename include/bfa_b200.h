@@ -220,17 +220,19 @@ int bfa_stitch_log_softmax(int32_t B, int32_t n_windows, int32_t frames_per_wind
                            const float *window_weights, float *logp_out, int64_t out_pitch, void *stream);
 
 /*
- * == F.log_softmax (core.py:898-899) + decode_alignments + _calculate_confidences in ONE kernel: the same call as
- *    bfa_align_batch with BFA_FLAG_DIRECT_ONLY, on rows that hold the acoustic model's UN-NORMALISED logits.
+ * == F.log_softmax (core.py:898-899) + decode_alignments + _calculate_confidences without the log-softmax pass: the same call
+ *    as bfa_align_batch on rows that hold the acoustic model's UN-NORMALISED logits.
  *    Boosting re-normalises every row (forced_alignment.py:51-54), so emissions, path, timestamps and DP score do not
  *    depend on a per-row shift; the confidences (utils.py:81: exp of the ORIGINAL log-probabilities) do, and the
  *    kernel's row reduction carries the row's own log-sum-exp along for them.
  *    Requires p->mode == BFA_MODE_FULL and p->boost_targets (BFA_E_UNSUPPORTED otherwise).
- *  row_lse   [dev] float[total_frames] out: log(sum(exp(row))) of every frame of every utterance finished here
+ *  row_lse   [dev] float[total_frames] out: log(sum(exp(row))) of every frame of every utterance finished by this call
  *            (utterance u at frame_off[u]); log-probabilities downstream are logits[f, c] - row_lse[f].
- *    Utterances the one-kernel pass cannot finish (silence_id in the target while anchoring is on, dense strides, ...) come
- *    back with status BFA_ST_DEFERRED: normalise those rows (bfa_stitch_log_softmax with frames_per_window = 0) and call
- *    bfa_align_batch -- the Python facade does.
+ *    The planner chain follows as in bfa_align_batch whenever its silence pass runs (silence anchoring on, silence_id < C, no
+ *    BFA_HINT_NO_SIL): that pass reads every row of the chain's utterances anyway and leaves their row_lse behind, the stamp
+ *    kernel subtracts it where it exponentiates.  Otherwise (and under BFA_FLAG_DIRECT_ONLY) only the one-kernel pass runs and
+ *    utterances it cannot finish come back with status BFA_ST_DEFERRED: normalise the rows (bfa_stitch_log_softmax with
+ *    frames_per_window = 0) and call bfa_align_batch -- the Python facade does.
  */
 int bfa_align_batch_logits(const BfaParams *p, const BfaShape *shape,
                            const float *logits, const int64_t *row_off, const int32_t *T,
