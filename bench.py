@@ -81,7 +81,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -117,7 +117,8 @@ class ClockSampler:
                         reasons.add(n)
             return sm, mx, reasons
         # samples taken while the GPU was under load: from the start of the pre-warm loop to the end of the timed region
-        loaded = [x for x in self.lines if (t_from is None or x[0] >= t_from) and (t_to is None or x[0] <= t_to + 0.11)]
+        # (the first 40 ms after the load starts are the clock's ramp from idle: not part of the window)
+        loaded = [x for x in self.lines if (t_from is None or x[0] >= t_from + 0.04) and (t_to is None or x[0] <= t_to + 0.03)]
         sm, mx, reasons = digest(loaded if loaded else self.lines)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons), "window": "pre-warm loop + warm-up + timed region"}
