@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 1) silprob_kernel(const __grid_
                     auto term = [&](float x, float kc, float& acc, float& zacc) {
                         const float e = b3_ex2(fmaf(x, LOG2E, kc));
                         acc += e;
-                        if constexpr (LG) zacc = fmaf(e, fmaf(kc, MSC, 1.0f), zacc);
+                        if constexpr (LG) zacc = fmaf(e, kc, zacc);
                     };
                     if (vec2) {
                         const float2* x2 = reinterpret_cast<const float2*>(rowp);
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 1) silprob_kernel(const __grid_
                     else pr = ss_exact_prob([&](int c) { return rowp[c]; }, [&](int c) { return kk[c] == 0.0f; }, C, sil, p.boost_factor);
                     if (p.enforce_minimum && sil_tgt) pr = fmaxf(pr, min_p);   // :75-81, exp is monotone
                     if constexpr (LG) {
-                        const float Z = (z0 + z1) + (z2 + z3);
+                        const float Z = fmaf(MSC, (z0 + z1) + (z2 + z3), S);     // sum(e (1 + kk MSC)) = S + MSC sum(e kk)
                         float l0;
                         if (Z > 0.f && Z < 3.0e38f) l0 = b3_lg2(Z) * LN2;
                         else {                                               // the slow, exact way (max-subtracted)

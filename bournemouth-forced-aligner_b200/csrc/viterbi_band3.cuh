@@ -443,8 +443,9 @@ __device__ __noinline__ void band3_direct_finish(const Band3Args& a, unsigned ch
 // LOGITS (direct mode only): the rows hold un-normalised logits.  Boosting re-normalises every row (:51-54), so emissions, path,
 // timestamps and DP score are the same whatever constant a row is shifted by; only the confidences (utils.py:81, exp of the
 // ORIGINAL log-probabilities) need the row's own log-sum-exp.  The reduction carries it along: with e_c = 2^(x_c log2e + kk_c) the
-// boosted sum is sum(e_c) and the plain one sum(e_c * 2^(-kk_c)), and 2^(-kk_c) is 1 for a target class and exp(boost) otherwise,
-// i.e. 1 + kk_c * MSC -- two more packed FMAs per pair of classes.  It is written out per frame (Band3Args::row_lse).
+// boosted sum is S = sum(e_c) and the plain one sum(e_c * 2^(-kk_c)), and 2^(-kk_c) is 1 for a target class and exp(boost) otherwise,
+// i.e. 1 + kk_c * MSC: the plain sum is S + MSC * sum(e_c * kk_c) -- one more packed FMA per pair of classes.  It is written out per
+// frame (Band3Args::row_lse).
 template <int G, int CT, bool DIRECT, bool LOGITS = false>
 __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int first, int n_valid, unsigned char* smem_pair, uint32_t& phase, bool not_first,
                              int lane, uint64_t pol, int pair, float* pscr_lp, unsigned char* pscr_gs) {
@@ -466,7 +467,6 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
     const bool warp_stats = k.warp_stats;
     static_assert(!LOGITS || DIRECT, "logits are taken by the direct kernel only");
     const float MSC = (LOGITS && boostv != 0.0f) ? (1.0f - expf(boostv)) / (boostv * LOG2E) : 0.0f;   // 2^(-kk) = 1 + kk * MSC for kk in {0, -boost log2e}
-    const unsigned long long ONE2 = b3_pack2(1.0f, 1.0f);
 
     // ---- per-utterance tables (built before the first bulk copies are issued: behind them these small loads would queue
     //      for microseconds): target classes (bytes) and the class weights of the fused log-sum-exp:
@@ -567,7 +567,7 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
                     const float v = fmaf(x, LOG2E, kc);
                     const float e = b3_ex2(v);
                     acc += e;
-                    if constexpr (LOGITS) zacc = fmaf(e, fmaf(kc, MSC, 1.0f), zacc);
+                    if constexpr (LOGITS) zacc = fmaf(e, kc, zacc);
                     best = fmaxf(best, tag(v, c));
                 };
                 if (CT != 0 && (CT & 1) == 1) {
@@ -588,7 +588,7 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
                         b3_unpack2(v, v0, v1);
                         const unsigned long long e2 = b3_pack2(b3_ex2(v0), b3_ex2(v1));
                         acc2 = b3_add2(acc2, e2);
-                        if constexpr (LOGITS) zacc2 = b3_fma2v(e2, b3_fma2(kc, MSC, ONE2), zacc2);
+                        if constexpr (LOGITS) zacc2 = b3_fma2v(e2, kc, zacc2);
                         best = fmaxf(best, fmaxf(tag(v0, c), tag(v1, c + 1)));
                     };
                     constexpr int NP = (CT - 1) / 2;           // pairs
@@ -607,7 +607,7 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
                         const float v = fmaf(rowp[cs1], LOG2E, kp[cs1]);
                         const float e = b3_ex2(v);
                         s0 += e;
-                        if constexpr (LOGITS) z0 = fmaf(e, fmaf(kp[cs1], MSC, 1.0f), z0);
+                        if constexpr (LOGITS) z0 = fmaf(e, kp[cs1], z0);
                         best = fmaxf(best, tag(v, 127));
                     }
                     // tag -> class
@@ -628,7 +628,7 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
                         b3_unpack2(v, v0, v1);
                         const unsigned long long e2 = b3_pack2(b3_ex2(v0), b3_ex2(v1));
                         acc2 = b3_add2(acc2, e2);
-                        if constexpr (LOGITS) zacc2 = b3_fma2v(e2, b3_fma2(kc, MSC, ONE2), zacc2);
+                        if constexpr (LOGITS) zacc2 = b3_fma2v(e2, kc, zacc2);
                         best = fmaxf(best, fmaxf(tag(v0, c), tag(v1, c + 1)));
                     };
 #pragma unroll
@@ -654,7 +654,8 @@ __device__ void band3_helper(const Band3Args& a, const Band3Args::Class& kc, int
                 lnS = b3_lg2((s0 + s1) + (s2 + s3)) * LN2;          // log sum exp(x + b - boost)
                 if (k.use_stats && t_row < T) lse_chk += lnS;       // any zero / overflowing / NaN sum leaves a non-finite trace
                 if constexpr (LOGITS) {
-                    lnS0 = b3_lg2((z0 + z1) + (z2 + z3)) * LN2;     // log sum exp(x)
+                    // sum(e_c 2^(-kk_c)) = sum(e_c (1 + kk_c MSC)) = S + MSC sum(e_c kk_c): ONE more packed FMA per pair of classes
+                    lnS0 = b3_lg2(fmaf(MSC, (z0 + z1) + (z2 + z3), (s0 + s1) + (s2 + s3))) * LN2;     // log sum exp(x)
                     const int rel = t_row - o_trim;
                     if (k.use_stats && t_row < T) {
                         lse_chk += lnS0;
