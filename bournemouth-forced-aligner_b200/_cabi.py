@@ -39,7 +39,7 @@ class BfaShape(C.Structure):
 
 
 class BfaError(RuntimeError):
-    pass
+    code = None        # the library's return code when the error came from a C-ABI call
 
 
 _P = C.c_void_p
@@ -109,7 +109,9 @@ def check(rc: int, host: bool = False):
     if rc == BFA_E_CUDA:
         detail = (l.bfa_host_last_error() if host else l.bfa_last_cuda_error()).decode()
         msg = f"{msg}: {detail}"
-    raise BfaError(f"libbfa_b200: {msg} (code {rc})")
+    err = BfaError(f"libbfa_b200: {msg} (code {rc})")
+    err.code = rc
+    raise err
 
 
 def default_params(blank_id: int, silence_id) -> BfaParams:

@@ -457,8 +457,18 @@ class AlignmentUtils:
         params = h["params"]
         if after_sibling and (params.reserved & _cabi.FLAG_DIRECT_ONLY):
             params.reserved |= _cabi.FLAG_PIPELINED
-        h["r"] = self.viterbi_decoder.align_batch(h["lp"], h["row_off"], h["T"], h["C"], h["tgt"], h["N"], params=params, want_stamps=True,
-                                                  want_conf=h["want_conf"], plan=h["plan"], logits=h.get("logits", False))
+        run = lambda: self.viterbi_decoder.align_batch(h["lp"], h["row_off"], h["T"], h["C"], h["tgt"], h["N"], params=params, want_stamps=True,
+                                                       want_conf=h["want_conf"], plan=h["plan"], logits=h.get("logits", False))
+        try:
+            h["r"] = run()
+        except BfaError as e:
+            # logits in, but neither the one-kernel pass nor a chain with a silence pass is available for this shape (more than 72
+            # classes without silence_id in the batch, ...): normalise first, like the reference
+            if not (h.get("logits") and e.code == _cabi.BFA_E_UNSUPPORTED):
+                raise
+            h["lp"] = log_softmax_rows(h["lp"])
+            h["logits"] = False
+            h["r"] = run()
         return h
 
     def _dense_launch(self, log_probs, true_seqs, pred_lens, true_seqs_lens, params, want_conf, input_is_logits=False):

@@ -349,6 +349,23 @@ def test_logits_through_the_planner_chain(bfa, dev, Cc, sil_every):
         assert torch.allclose(r.row_lse[: B * T], lse, rtol=0, atol=3e-5)
 
 
+def test_logits_fall_back_when_no_pass_can_take_them(bfa, dev):
+    """80 classes (beyond the banded kernels' class table) and no silence_id in the batch: neither the one-kernel pass nor a silence
+    pass exists for this shape; the C entry says BFA_E_UNSUPPORTED and the facade normalises first.  Same lists either way."""
+    from bfa_b200 import synth
+    Cc, B, T, N = 80, 24, 200, 12
+    lp, tgt, _ = synth.planted_batch(B, T, N, Cc, seed=5, peak=8.0, device=dev)
+    logits = (lp + 2.5).contiguous()
+    au = bfa.AlignmentUtils(blank_id=Cc - 1, silence_id=0, silence_anchors=10, ignore_noise=True, truly_forced=True)
+    lens_t = torch.full((B,), T); lens_n = torch.full((B,), N)
+    want = au.decode_alignments(lp, true_seqs=tgt.cpu(), pred_lens=lens_t, true_seqs_lens=lens_n, with_confidence=True)
+    got = au.decode_alignments(logits, true_seqs=tgt.cpu(), pred_lens=lens_t, true_seqs_lens=lens_n, with_confidence=True, input_is_logits=True)
+    assert au.last_row_lse is None and au.last_log_probs is not None
+    for b in range(B):
+        assert [x[:4] for x in got[b]] == [x[:4] for x in want[b]]
+        assert all(abs(x[4] - y[4]) <= 1e-4 * max(abs(y[4]), 1e-3) for x, y in zip(got[b], want[b]))
+
+
 def test_decode_alignments_from_logits(bfa, dev):
     """AlignmentUtils.decode_alignments(input_is_logits=True): the caller skips F.log_softmax (core.py:898-899).  Same lists as on
     the normalised tensor -- through the one-kernel pass when the batch qualifies, through the planner chain on the logits when targets
