@@ -1,5 +1,6 @@
-import sys, torch
-sys.path.insert(0, "/root/repo")
+"""Development: device time of log_softmax_rows (the window-less case of bfa_stitch_log_softmax) against torch."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bfa_b200
 for C in (67, 17, 66):
     x = torch.randn(4096, 600, C, device="cuda")
