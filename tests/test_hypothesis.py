@@ -176,3 +176,68 @@ def test_cuda_vs_oracle_drawn_batches(bfa, orc, dev, B, Cc, Tmax, dens, sil_ever
         if n:
             np.testing.assert_array_equal(r.stamps[b, :n, 1].cpu().numpy(), o["stamps"]["start"][b][:n])
             np.testing.assert_allclose(r.conf[b, :n].cpu().numpy(), o["conf"][b, :n], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.gpu
+@settings(max_examples=20, **SET)
+@given(st.integers(1, 24), st.sampled_from([9, 17, 30, 66, 67, 72, 80]), st.integers(8, 420), st.sampled_from([0.03, 0.1, 0.2, 0.26, 0.5, 1.0]),
+       st.sampled_from([0, 4, 9]), st.sampled_from([0, 3, 10]), st.sampled_from([0, 64, 128]), st.integers(0, 10_000))
+def test_logits_equal_log_probs_drawn_batches(bfa, dev, B, Cc, Tmax, dens, sil_every, anchors, flags, seed):
+    """bfa_align_batch_logits on ragged, packed batches (rows on every 16-byte residue; every stride, T == N, silence layouts,
+    with the one-kernel pass alone / skipped / followed by the chain): whatever the call finishes must equal the ordinary call on
+    the normalised rows -- statuses, frame labels, stamps bit for bit (an utterance may differ on a last-bit tie of the DP score),
+    confidences to 1e-4, row_lse to 3e-5 -- and what it cannot take must come back flagged (or the call refused), never wrong."""
+    from bfa_b200 import synth, _cabi
+    from bfa_b200._cabi import BfaError
+    rng = np.random.default_rng(seed)
+    utts = []
+    for b in range(B):
+        T = int(rng.integers(max(2, Tmax // 4), Tmax + 1))
+        N = max(1, min(int(T * dens), 120))
+        l, t, _ = synth.planted_batch(1, T, N, Cc, seed=seed * 37 + b, peak=9.0, sil_every=sil_every, sil_frames=12)
+        utts.append((l[0], t[0]))
+    flat, row_off, Ts, tg, Ns = synth.pack_ragged(utts, Cc, align_floats=1)
+    n_tot = int(sum(Ts))
+    # per-row shifts (what makes the rows "logits"), applied row by row on the packed buffer
+    logit = flat.clone()
+    g = torch.Generator().manual_seed(seed)
+    for b in range(B):
+        o = int(row_off[b])
+        rows = logit[o:o + Ts[b] * Cc].view(Ts[b], Cc)
+        rows += torch.randn(Ts[b], 1, generator=g) * 5.0 + 1.0
+    dec = bfa.AlignmentUtils(Cc - 1, 0, silence_anchors=anchors).viterbi_decoder
+    ref = dec.align_batch(flat.to(dev), row_off.to(dev), Ts, Cc, tg.to(dev), Ns, params=dec._params(True, True, anchors > 0))
+    p = dec._params(True, True, anchors > 0)
+    p.reserved |= flags                                    # 0 | BFA_FLAG_DIRECT_ONLY | BFA_FLAG_NO_DIRECT
+    try:
+        r = dec.align_batch(logit.to(dev), row_off.to(dev), Ts, Cc, tg.to(dev), Ns, params=p, logits=True)
+    except BfaError as e:
+        assert e.code == _cabi.BFA_E_UNSUPPORTED           # no pass can take logits for this shape: said so, nothing computed
+        return
+    torch.cuda.synchronize()
+    st_r, st_g = ref.status[:B].cpu().numpy(), r.status[:B].cpu().numpy()
+    done = (st_g & 7) != _cabi.ST_DEFERRED
+    np.testing.assert_array_equal((st_g & 15)[done], (st_r & 15)[done])
+    fo = np.zeros(B + 1, np.int64); np.cumsum(np.asarray(Ts, np.int64), out=fo[1:])
+    fph_r, fix_r = ref.frame_ph.cpu().numpy(), ref.frame_idx.cpu().numpy()
+    fph_g, fix_g = r.frame_ph.cpu().numpy(), r.frame_idx.cpu().numpy()
+    lse = r.row_lse.cpu().numpy()
+    ties = 0
+    for b in np.nonzero(done)[0]:
+        if (st_g[b] & 7) == 2:                             # TOO_SHORT: no frames
+            continue
+        a, e = int(fo[b]), int(fo[b + 1])
+        if not (np.array_equal(fph_g[a:e], fph_r[a:e]) and np.array_equal(fix_g[a:e], fix_r[a:e])):
+            ties += 1
+            assert abs(float(r.dp_final[b]) - float(ref.dp_final[b])) <= 4e-6 * max(1.0, abs(float(ref.dp_final[b])))
+            continue
+        n = int(ref.n_stamps[b])
+        assert int(r.n_stamps[b]) == n
+        if n:
+            assert torch.equal(r.stamps[b, :n], ref.stamps[b, :n])
+            np.testing.assert_allclose(r.conf[b, :n].cpu().numpy(), ref.conf[b, :n].cpu().numpy(), rtol=1e-4, atol=1e-6)
+        if (st_g[b] & 7) in (0, 4) and Ns[b] > 0:          # rows were read by a pass that leaves row_lse
+            o = int(row_off[b])
+            want = torch.logsumexp(logit[o:o + Ts[b] * Cc].view(Ts[b], Cc).double(), dim=1).numpy()
+            np.testing.assert_allclose(lse[a:e], want, rtol=0, atol=3e-5)
+    assert ties <= 1
