@@ -732,7 +732,10 @@ int bfa_stitch_log_softmax(int32_t B, int32_t n_windows, int32_t frames_per_wind
         else if (C <= 96) log_softmax_rows_kernel<3><<<g2, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
         else log_softmax_rows_kernel<MAX_WORDS><<<g2, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     } else {
-        stitch_log_softmax_kernel<<<grid, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+        if (C <= 32) stitch_log_softmax_kernel<1><<<grid, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+        else if (C <= 64) stitch_log_softmax_kernel<2><<<grid, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+        else if (C <= 96) stitch_log_softmax_kernel<3><<<grid, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+        else stitch_log_softmax_kernel<MAX_WORDS><<<grid, STITCH_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     }
     LAUNCH_CHECK();
     return BFA_OK;

@@ -69,26 +69,28 @@ __global__ void __launch_bounds__(STITCH_WARPS * 32) log_softmax_rows_kernel(con
     }
 }
 
+// NW: 32-class words compiled in (C <= 32 NW), as in log_softmax_rows_kernel.
+template <int NW>
 __global__ void __launch_bounds__(STITCH_WARPS * 32) stitch_log_softmax_kernel(const __grid_constant__ StitchArgs a) {
     const int lane = threadIdx.x & 31;
     const long long rows = (long long)a.B * a.total_frames;
     const long long nw = (long long)gridDim.x * STITCH_WARPS;
     for (long long row = (long long)blockIdx.x * STITCH_WARPS + (threadIdx.x >> 5); row < rows; row += nw) {
         const int b = (int)(row / a.total_frames), f = (int)(row % a.total_frames);
-        float v[MAX_WORDS];
+        float v[NW];
         if (a.fpw == 0) {
             const float* src = a.in + (long long)b * a.in_pitch_b + (long long)f * a.C;
 #pragma unroll
-            for (int i = 0; i < MAX_WORDS; ++i) {
+            for (int i = 0; i < NW; ++i) {
                 const int c = lane + 32 * i;
                 v[i] = c < a.C ? src[c] : -INFINITY;
             }
         } else {
             // windows i with i*sf <= f < i*sf + fpw, ascending (at most 3: fpw = 2 sf or 2 sf + 1)
             const int i1 = f / a.sf;
-            float acc[MAX_WORDS];
+            float acc[NW];
 #pragma unroll
-            for (int i = 0; i < MAX_WORDS; ++i) acc[i] = 0.0f;
+            for (int i = 0; i < NW; ++i) acc[i] = 0.0f;
             float ws = 0.0f;
 #pragma unroll
             for (int d = 2; d >= 0; --d) {
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(STITCH_WARPS * 32) stitch_log_softmax_kernel(c
                 const float w = a.weights[off];
                 const float* src = a.in + (long long)b * a.in_pitch_b + ((long long)wi * a.fpw + off) * a.C;
 #pragma unroll
-                for (int i = 0; i < MAX_WORDS; ++i) {
+                for (int i = 0; i < NW; ++i) {
                     const int c = lane + 32 * i;
                     if (c < a.C) acc[i] = __fadd_rn(acc[i], __fmul_rn(src[c], w));      // combined += logits * w  (:152 / :166)
                 }
@@ -106,21 +108,21 @@ __global__ void __launch_bounds__(STITCH_WARPS * 32) stitch_log_softmax_kernel(c
             }
             const float den = __fadd_rn(ws, 1e-8f);                                      // :169
 #pragma unroll
-            for (int i = 0; i < MAX_WORDS; ++i) v[i] = (lane + 32 * i < a.C) ? __fdiv_rn(acc[i], den) : -INFINITY;
+            for (int i = 0; i < NW; ++i) v[i] = (lane + 32 * i < a.C) ? __fdiv_rn(acc[i], den) : -INFINITY;
         }
         float m = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < MAX_WORDS; ++i) m = fmaxf(m, v[i]);
+        for (int i = 0; i < NW; ++i) m = fmaxf(m, v[i]);
         m = warp_max(m);
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < MAX_WORDS; ++i)
+        for (int i = 0; i < NW; ++i)
             if (lane + 32 * i < a.C) s += expf(v[i] - m);
         s = warp_sum(s);
         const float ls = logf(s);
         float* dst = a.out + (long long)b * a.out_pitch_b + (long long)f * a.C;
 #pragma unroll
-        for (int i = 0; i < MAX_WORDS; ++i) {
+        for (int i = 0; i < NW; ++i) {
             const int c = lane + 32 * i;
             if (c < a.C) dst[c] = (v[i] - m) - ls;
         }
